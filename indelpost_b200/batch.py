@@ -1,0 +1,129 @@
+"""Batched aligner: the new entry point that the sswpy-compatible layer adds.
+
+`BatchAligner` owns one swb_ctx (= one GPU).  `align()` takes the SoA arrays of include/swb200.h's
+swb_batch as numpy arrays and returns (results, cigar_arena) with results a structured array of
+RESULT_DTYPE (every s_align field of reference ssw.h:55-66)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def dna_score_matrix(match_score: int = 2, mismatch_penalty: int = 2) -> np.ndarray:
+    """sswpy.pyx:306-336 buildDNAScoreMatrix: 5x5, +match on the ACGT diagonal, -mismatch elsewhere,
+    0 for anything involving N.  The arguments are narrowed to uint8 then int8 like the reference does."""
+    m = np.zeros(25, dtype=np.int8)
+    ms = np.array([match_score & 0xFF], dtype=np.uint8).view(np.int8)[0]
+    mm = np.array([(-(mismatch_penalty & 0xFF)) & 0xFF], dtype=np.uint8).view(np.int8)[0]
+    for i in range(4):
+        for j in range(4):
+            m[i * 5 + j] = ms if i == j else mm
+    return m
+
+
+def _c(a, dtype):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class BatchAligner:
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        self.ctx = self.lib.swb_create(int(device))
+        if not self.ctx:
+            raise L.SwbError(self.lib.swb_last_error(None).decode())
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.swb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def _make_batch(self, reads, read_off, read_len, windows, win_off, win_len, pair_read, pair_win, gap_open, gap_ext,
+                    ref_beg=None, ref_len=None, mask_len=None, mat=None, n=5, score_size=2, flag=1, filters=0, filterd=0,
+                    seq_encoding=L.SWB_SEQ_CODES):
+        arrs = dict(
+            reads=_c(reads, np.int8), read_off=_c(read_off, np.int64), read_len=_c(read_len, np.int32),
+            windows=_c(windows, np.int8), win_off=_c(win_off, np.int64), win_len=_c(win_len, np.int32),
+            pair_read=_c(pair_read, np.int32), pair_win=_c(pair_win, np.int32),
+            ref_beg=_c(ref_beg, np.int32), ref_len=_c(ref_len, np.int32),
+            gap_open=_c(gap_open, np.uint8), gap_ext=_c(gap_ext, np.uint8), mask_len=_c(mask_len, np.int32),
+            mat=_c(mat if mat is not None else dna_score_matrix(), np.int8),
+        )
+        b = L.SwbBatch()
+        b.n_pairs = int(arrs["pair_read"].shape[0])
+        b.n_reads = int(arrs["read_len"].shape[0])
+        b.n_windows = int(arrs["win_len"].shape[0])
+        b.seq_encoding = int(seq_encoding)
+        for k, a in arrs.items():
+            setattr(b, k, a.ctypes.data if a is not None and a.size else (a.ctypes.data if a is not None else None))
+        b.n = int(n)
+        b.score_size = int(score_size)
+        b.flag = int(flag)
+        b.filters = int(filters)
+        b.filterd = int(filterd)
+        return b, arrs
+
+    def _err(self):
+        return self.lib.swb_last_error(self.ctx).decode()
+
+    def align(self, *args, cigar_cap: int | None = None, **kw):
+        """one-shot: host arrays in, (results, cigar_arena) out (H2D + kernels + D2H)"""
+        b, keep = self._make_batch(*args, **kw)
+        n = b.n_pairs
+        res = np.zeros(n, dtype=L.RESULT_DTYPE)
+        cap = int(cigar_cap if cigar_cap is not None else max(64, 16 * n))
+        used = C.c_int64(0)
+        while True:
+            arena = np.zeros(cap, dtype=np.uint32)
+            rc = self.lib.swb_align_batch(self.ctx, C.byref(b), res.ctypes.data, arena.ctypes.data, cap, C.byref(used))
+            if rc == -2:
+                cap = int(used.value) + 64
+                continue
+            if rc != 0:
+                raise L.SwbError(self._err())
+            return res, arena[: used.value]
+
+    # split form (device-resident timing)
+    def upload(self, *args, **kw):
+        b, keep = self._make_batch(*args, **kw)
+        self._keep = (b, keep)
+        if self.lib.swb_upload(self.ctx, C.byref(b)) != 0:
+            raise L.SwbError(self._err())
+        return b.n_pairs
+
+    def compute(self):
+        if self.lib.swb_compute(self.ctx) != 0:
+            raise L.SwbError(self._err())
+
+    def download(self, n_pairs: int, cigar_cap: int | None = None):
+        res = np.zeros(n_pairs, dtype=L.RESULT_DTYPE)
+        cap = int(cigar_cap if cigar_cap is not None else max(64, 16 * n_pairs))
+        used = C.c_int64(0)
+        while True:
+            arena = np.zeros(cap, dtype=np.uint32)
+            rc = self.lib.swb_download(self.ctx, res.ctypes.data, arena.ctypes.data, cap, C.byref(used))
+            if rc == -2:
+                cap = int(used.value) + 64
+                continue
+            if rc != 0:
+                raise L.SwbError(self._err())
+            return res, arena[: used.value]
+
+    def timing(self) -> dict:
+        t = L.SwbTiming()
+        self.lib.swb_get_timing(self.ctx, C.byref(t))
+        return t.as_dict()

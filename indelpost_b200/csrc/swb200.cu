@@ -1,0 +1,535 @@
+// swb200.cu — libswb200: host pipeline + C ABI (include/swb200.h).
+//
+// One swb_ctx per GPU: a stream, timing events and grow-only device buffers.  A batch moves through
+//   upload  : one cudaMemcpyAsync per input array (tables + per-pair arrays)
+//   prepare : encode/validate sequences, derive per-pair pointers, seed the job lists
+//   forward : score / end position / sub-optimal score        (ssw.c:842-871)
+//   reverse : begin position                                   (ssw.c:875-891)
+//   band    : banded DP + traceback -> CIGAR, in doubling rounds (ssw.c:897-916)
+//   download: results + CIGAR arena
+// Stage-to-stage hand-over is through device-side job lists (append with warp-aggregated atomics), so
+// the host only synchronises to read the few counters that size the next launch.
+// There is no CPU implementation behind any entry point: without a usable GPU every call fails.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <algorithm>
+
+#include "swb_common.cuh"
+#include "swb_exact.cuh"
+#include "swb_band.cuh"
+
+#define SWB_VERSION "swb200 0.1 (sm_100a)"
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+
+// one warp per sequence: ASCII -> code (in place) and range check; bad[s] = 1 if any code is outside [0, n)
+__global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int n, int ascii, uint8_t* bad)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nseq) return;
+    int8_t* s = blob + off[w];
+    const int L = len[w];
+    bool b = false;
+    for (int i = lane; i < L; i += 32) {
+        int c = s[i];
+        if (ascii) { c = swb_dna_code((unsigned char)c); s[i] = (int8_t)c; }
+        if (c < 0 || c >= n) b = true;
+    }
+    b = __any_sync(0xffffffffu, b);
+    if (lane == 0) bad[w] = b ? 1 : 0;
+}
+
+__global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_bad, int32_t p0, int32_t p1)
+{
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    swb_result r;
+    r.score1 = 0; r.score2 = 0; r.ref_begin1 = -1; r.ref_end1 = 0; r.read_begin1 = -1; r.read_end1 = 0;
+    r.ref_end2 = 0; r.cigar_len = 0; r.flag = 0; r.status = SWB_OK; r.cigar_off = 0;
+    const int ri = d.pair_read[p], wi = d.pair_win[p];
+    bool ok = ri >= 0 && ri < d.n_reads && wi >= 0 && wi < d.n_windows;
+    int rl = 0, wl = 0, rb = 0;
+    if (ok) {
+        rl = d.read_len[ri];
+        rb = d.ref_beg ? d.ref_beg[p] : 0;
+        wl = d.ref_len ? d.ref_len[p] : d.win_len[wi] - rb;
+        ok = rl > 0 && wl > 0 && rb >= 0 && (long long)rb + wl <= d.win_len[wi] && !read_bad[ri] && !win_bad[wi];
+    }
+    if (ok && d.score_size != 0 && d.score_size != 1 && d.score_size != 2) ok = false;   // ssw.c:856-859: no profile
+    d.p_mode[p] = 0;
+    d.t_bw[p] = 0; d.t_best[p] = 0;
+    if (!ok) {
+        r.status = SWB_ERR_BAD_INPUT;
+        d.p_roff[p] = 0; d.p_woff[p] = 0; d.p_rlen[p] = 0; d.p_wlen[p] = 0; d.p_mask[p] = 0;
+        d.res[p] = r;
+        return;
+    }
+    d.p_roff[p] = d.read_off[ri];
+    d.p_woff[p] = d.win_off[wi] + rb;
+    d.p_rlen[p] = rl;
+    d.p_wlen[p] = wl;
+    d.p_mask[p] = d.mask_len ? d.mask_len[p] : (rl / 2 < 15 ? 15 : rl / 2);      // sswpy.pyx:209-211
+    d.res[p] = r;
+    if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
+    else list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT };
+
+struct swb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT];
+    std::string err;
+    SwbDev d;
+    bool have_batch = false, computed = false;
+    // device buffers
+    DevBuf b_reads, b_read_off, b_read_len, b_windows, b_win_off, b_win_len;
+    DevBuf b_pair_read, b_pair_win, b_ref_beg, b_ref_len, b_go, b_ge, b_mask, b_mat;
+    DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
+    DevBuf b_tbw, b_tbest, b_rbad, b_wbad;
+    int32_t* h_counters = nullptr;              // pinned mirror of counters
+    unsigned long long* h_bump = nullptr;       // pinned mirror of bump
+    swb_timing tm;
+    int smem_optin = 0;
+    int n_sm = 0;
+    int64_t chunk_pairs = 0;
+};
+
+static std::string g_create_err;
+static std::mutex g_mu;
+
+#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
+
+extern "C" int swb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* swb_version(void) { return SWB_VERSION; }
+
+extern "C" swb_ctx* swb_create(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("no CUDA device usable: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + " (libswb200 has no CPU fallback)";
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return nullptr; }
+    if (prop.major != 10) {
+        g_create_err = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; libswb200 is built for sm_100a only";
+        return nullptr;
+    }
+    swb_ctx* c = new swb_ctx();
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    memset(&c->d, 0, sizeof c->d);
+    memset(&c->tm, 0, sizeof c->tm);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_err = std::string("cannot create stream: ") + cudaGetErrorString(cudaGetLastError());
+        delete c; return nullptr;
+    }
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+    cudaMallocHost((void**)&c->h_counters, 16 * sizeof(int32_t));
+    cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long));
+    // opt in to large dynamic shared memory for the exact kernels
+    cudaFuncSetAttribute(k_exact<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(k_exact<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(k_exact<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(k_exact<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    return c;
+}
+
+extern "C" void swb_destroy(swb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* all[] = { &c->b_reads, &c->b_read_off, &c->b_read_len, &c->b_windows, &c->b_win_off, &c->b_win_len, &c->b_pair_read, &c->b_pair_win,
+                      &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
+                      &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
+                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad };
+    for (DevBuf* b : all) b->release();
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
+    cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char* swb_last_error(const swb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" void* swb_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)(bytes > 0 ? bytes : 1)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void swb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" void swb_encode_dna(const char* ascii, int8_t* codes, int64_t len) {
+    for (int64_t i = 0; i < len; ++i) codes[i] = swb_dna_code((unsigned char)ascii[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload
+// ------------------------------------------------------------------------------------------------
+
+template <typename T>
+static int up(swb_ctx* c, DevBuf& b, const T* src, size_t count, T** dst) {
+    if (!src) { *dst = nullptr; return 0; }
+    CUDA_TRY(c, b.ensure(count * sizeof(T) + 16));
+    if (count) CUDA_TRY(c, cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    c->tm.h2d_bytes += (int64_t)(count * sizeof(T));
+    *dst = reinterpret_cast<T*>(b.p);
+    return 0;
+}
+
+extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
+    if (!c) return -1;
+    c->err.clear();
+    c->have_batch = false; c->computed = false;
+    if (!b || b->n_pairs < 0 || b->n_reads < 0 || b->n_windows < 0) { c->err = "bad batch header"; return -1; }
+    if (b->n < 1 || b->n > SWB_MAX_N || !b->mat) { c->err = "substitution matrix edge n must be in [1, 32]"; return -1; }
+    if (b->n_pairs && (!b->pair_read || !b->pair_win || !b->gap_open || !b->gap_ext)) { c->err = "missing per-pair arrays"; return -1; }
+    if ((b->n_reads && (!b->reads || !b->read_off || !b->read_len)) || (b->n_windows && (!b->windows || !b->win_off || !b->win_len))) { c->err = "missing sequence tables"; return -1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    SwbDev& d = c->d;
+    memset(&c->tm, 0, sizeof c->tm);
+
+    // table extents (host scan of the small length arrays; also the max lengths that size shared memory)
+    int64_t reads_bytes = 0, win_bytes = 0; int32_t max_rl = 0, max_wl = 0;
+    for (int32_t i = 0; i < b->n_reads; ++i) {
+        if (b->read_len[i] < 0 || b->read_off[i] < 0) { c->err = "negative read offset/length"; return -1; }
+        reads_bytes = std::max<int64_t>(reads_bytes, b->read_off[i] + b->read_len[i]); max_rl = std::max(max_rl, b->read_len[i]);
+    }
+    for (int32_t i = 0; i < b->n_windows; ++i) {
+        if (b->win_len[i] < 0 || b->win_off[i] < 0) { c->err = "negative window offset/length"; return -1; }
+        win_bytes = std::max<int64_t>(win_bytes, b->win_off[i] + b->win_len[i]); max_wl = std::max(max_wl, b->win_len[i]);
+    }
+
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D0], c->stream));
+    const size_t np = (size_t)b->n_pairs;
+    if (up(c, c->b_reads, b->reads, (size_t)reads_bytes, &d.reads)) return -1;
+    if (up(c, c->b_read_off, b->read_off, (size_t)b->n_reads, &d.read_off)) return -1;
+    if (up(c, c->b_read_len, b->read_len, (size_t)b->n_reads, &d.read_len)) return -1;
+    if (up(c, c->b_windows, b->windows, (size_t)win_bytes, &d.windows)) return -1;
+    if (up(c, c->b_win_off, b->win_off, (size_t)b->n_windows, &d.win_off)) return -1;
+    if (up(c, c->b_win_len, b->win_len, (size_t)b->n_windows, &d.win_len)) return -1;
+    if (up(c, c->b_pair_read, b->pair_read, np, &d.pair_read)) return -1;
+    if (up(c, c->b_pair_win, b->pair_win, np, &d.pair_win)) return -1;
+    if (up(c, c->b_ref_beg, b->ref_beg, np, &d.ref_beg)) return -1;
+    if (up(c, c->b_ref_len, b->ref_len, np, &d.ref_len)) return -1;
+    if (up(c, c->b_go, b->gap_open, np, &d.gap_open)) return -1;
+    if (up(c, c->b_ge, b->gap_ext, np, &d.gap_ext)) return -1;
+    if (up(c, c->b_mask, b->mask_len, np, &d.mask_len)) return -1;
+    if (up(c, c->b_mat, b->mat, (size_t)b->n * b->n, &d.mat)) return -1;
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], c->stream));
+
+    d.n_pairs = b->n_pairs; d.n_reads = b->n_reads; d.n_windows = b->n_windows;
+    d.n = b->n; d.score_size = b->score_size; d.flag = b->flag; d.filters = b->filters; d.filterd = b->filterd;
+    d.seq_encoding = b->seq_encoding;
+    d.max_rlen = max_rl; d.max_wlen = max_wl;
+    int bias = 0;
+    for (int i = 0; i < b->n * b->n; ++i) if (b->mat[i] < bias) bias = b->mat[i];       // ssw.c:795-797
+    d.bias = (b->score_size == 0 || b->score_size == 2) ? std::abs(bias) : 0;
+    c->have_batch = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute
+// ------------------------------------------------------------------------------------------------
+
+static int read_counters(swb_ctx* c) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->d.counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_bump, c->d.bump, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+template <int MODE, int DIR>
+static int launch_exact(swb_ctx* c, int listSlot, int cntSlot, int upperBound) {
+    if (upperBound <= 0) return 0;
+    const SwbDev& d = c->d;
+    const int W = MODE ? 8 : 16;
+    const int segAlloc = (d.max_rlen + W - 1) / W;
+    const int per = exact_smem_per_group(MODE, d.n, d.max_rlen);
+    int groups = 128 / W;                                   // groups per block at 128 threads
+    while (groups > 32 / W && (size_t)groups * per > (size_t)c->smem_optin) groups /= 2;
+    if ((size_t)groups * per > (size_t)c->smem_optin) { c->err = "read too long for the exact kernel's shared-memory profile"; return -1; }
+    const int threads = groups * W;
+    const int blocks = (upperBound + groups - 1) / groups;
+    k_exact<MODE, DIR><<<blocks, threads, (size_t)groups * per, c->stream>>>(d, d.list[listSlot], d.counters + cntSlot, segAlloc, per);
+    c->tm.n_launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int swb_compute(swb_ctx* c) {
+    if (!c) return -1;
+    if (!c->have_batch) { c->err = "swb_compute: no batch uploaded"; return -1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    SwbDev& d = c->d;
+    const size_t np = (size_t)d.n_pairs;
+    swb_timing& tm = c->tm;
+    tm.ms_total = tm.ms_prepare = tm.ms_forward = tm.ms_reverse = tm.ms_traceback = 0;
+    tm.cells_forward = tm.cells_reverse = tm.cells_band = 0; tm.n_fast = tm.n_exact = 0; tm.n_launches = 0;
+
+    // workspace
+    CUDA_TRY(c, c->b_roff.ensure(np * 8 + 16));   d.p_roff = (int64_t*)c->b_roff.p;
+    CUDA_TRY(c, c->b_woff.ensure(np * 8 + 16));   d.p_woff = (int64_t*)c->b_woff.p;
+    CUDA_TRY(c, c->b_rlen.ensure(np * 4 + 16));   d.p_rlen = (int32_t*)c->b_rlen.p;
+    CUDA_TRY(c, c->b_wlen.ensure(np * 4 + 16));   d.p_wlen = (int32_t*)c->b_wlen.p;
+    CUDA_TRY(c, c->b_pmask.ensure(np * 4 + 16));  d.p_mask = (int32_t*)c->b_pmask.p;
+    CUDA_TRY(c, c->b_mode.ensure(np + 16));       d.p_mode = (uint8_t*)c->b_mode.p;
+    CUDA_TRY(c, c->b_res.ensure(np * sizeof(swb_result) + 16)); d.res = (swb_result*)c->b_res.p;
+    CUDA_TRY(c, c->b_lists.ensure(6 * (np + 32) * 4));
+    for (int i = 0; i < 6; ++i) d.list[i] = (int32_t*)c->b_lists.p + (size_t)i * (np + 32);
+    CUDA_TRY(c, c->b_counters.ensure(16 * 4));    d.counters = (int32_t*)c->b_counters.p;
+    CUDA_TRY(c, c->b_bump.ensure(2 * 8));         d.bump = (unsigned long long*)c->b_bump.p;
+    CUDA_TRY(c, c->b_tbw.ensure(np * 4 + 16));    d.t_bw = (int32_t*)c->b_tbw.p;
+    CUDA_TRY(c, c->b_tbest.ensure(np * 4 + 16));  d.t_best = (int32_t*)c->b_tbest.p;
+    CUDA_TRY(c, c->b_rbad.ensure((size_t)d.n_reads + 16));
+    CUDA_TRY(c, c->b_wbad.ensure((size_t)d.n_windows + 16));
+    d.colmax_stride = (d.max_wlen + 7) & ~7;
+    CUDA_TRY(c, c->b_colmax.ensure(np * (size_t)d.colmax_stride * 2 + 16)); d.colmax = (uint16_t*)c->b_colmax.p;
+    {
+        // direction-byte scratch: enough for a typical band on every pair; pairs that do not fit are
+        // deferred to the next round by the kernel itself
+        size_t want = std::max<size_t>((size_t)64 << 20, np * (size_t)(d.max_rlen + 8) * 12);
+        want = std::min<size_t>(want, (size_t)8 << 30);
+        if (c->b_band.cap < want) CUDA_TRY(c, c->b_band.ensure(want));
+        d.band = (uint8_t*)c->b_band.p; d.band_cap = (int64_t)c->b_band.cap;
+        size_t cw = std::max<size_t>(4096, np * 16);
+        if (c->b_cigar.cap < cw * 4) CUDA_TRY(c, c->b_cigar.ensure(cw * 4));
+        d.cigar = (uint32_t*)c->b_cigar.p; d.cigar_cap = (int64_t)(c->b_cigar.cap / 4);
+    }
+
+    cudaStream_t s = c->stream;
+    CUDA_TRY(c, cudaMemsetAsync(d.counters, 0, 16 * 4, s));
+    CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 16, s));
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_START], s));
+
+    // ---- prepare ------------------------------------------------------------------------------
+    if (d.n_reads) { k_encode_validate<<<(d.n_reads + 3) / 4, 128, 0, s>>>(d.reads, d.read_off, d.read_len, d.n_reads, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p); tm.n_launches++; }
+    if (d.n_windows) { k_encode_validate<<<(d.n_windows + 3) / 4, 128, 0, s>>>(d.windows, d.win_off, d.win_len, d.n_windows, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p); tm.n_launches++; }
+    d.seq_encoding = SWB_SEQ_CODES;                         // tables are codes from now on (repeat computes must not re-encode)
+    if (np) { k_prepare<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, 0, (int32_t)np); tm.n_launches++; }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
+
+    // ---- forward (ssw.c:842-860): 8-bit pass, then 16-bit pass for the pairs that overflowed ----
+    if (launch_exact<0, 0>(c, LIST_BYTE_FWD, CNT_BYTE_FWD, (int)np)) return -1;
+    if (launch_exact<1, 0>(c, LIST_WORD_FWD, CNT_WORD_FWD, (int)np)) return -1;
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_FWD], s));
+
+    // ---- reverse (ssw.c:875-891) ----------------------------------------------------------------
+    if (launch_exact<0, 1>(c, LIST_BYTE_REV, CNT_BYTE_REV, (int)np)) return -1;
+    if (launch_exact<1, 1>(c, LIST_WORD_REV, CNT_WORD_REV, (int)np)) return -1;
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));
+
+    // ---- banded DP + traceback rounds (ssw.c:897-916) ----------------------------------------------
+    if (read_counters(c)) return -1;
+    tm.n_exact = c->h_counters[CNT_BYTE_FWD] + c->h_counters[CNT_WORD_FWD];
+    int cur = LIST_BAND, curCnt = CNT_BAND, nxt = LIST_BAND_NEXT, nxtCnt = CNT_BAND_NEXT;
+    int njobs = c->h_counters[curCnt];
+    int round = 0, stalls = 0;
+    while (njobs > 0) {
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + nxtCnt, 0, 4, s));
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
+        CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
+        const int blocks = (njobs + 127) / 128;
+        k_band<true><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + curCnt, d.list[nxt], d.counters + nxtCnt, round);
+        k_band<false><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + curCnt, d.list[nxt], d.counters + nxtCnt, round);
+        tm.n_launches += 2;
+        CUDA_TRY(c, cudaGetLastError());
+        if (read_counters(c)) return -1;
+        const int next = c->h_counters[nxtCnt];
+        if (c->h_counters[CNT_BAND_OVERFLOW] == njobs) {
+            // nothing fitted: the scratch is smaller than a single band; grow it
+            if (++stalls > 8 || c->b_band.cap >= ((size_t)64 << 30)) { c->err = "banded traceback scratch exhausted"; return -1; }
+            size_t want = c->b_band.cap * 4;
+            CUDA_TRY(c, c->b_band.ensure(want));
+            d.band = (uint8_t*)c->b_band.p; d.band_cap = (int64_t)c->b_band.cap;
+        }
+        std::swap(cur, nxt); std::swap(curCnt, nxtCnt);
+        njobs = next;
+        ++round;
+        if (round > 64) { c->err = "banded traceback did not converge"; return -1; }
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND], s));
+    if (read_counters(c)) return -1;
+    if (c->h_counters[CNT_CIGAR_OVERFLOW] > 0) {
+        // device arena too small: grow to the exact requirement and redo (rare; the default is 16 ops/pair)
+        size_t need = (size_t)c->h_bump[1] + 1024;
+        CUDA_TRY(c, c->b_cigar.ensure(need * 4));
+        return swb_compute(c);
+    }
+    cudaEventElapsedTime(&tm.ms_prepare, c->ev[EV_START], c->ev[EV_PREP]);
+    cudaEventElapsedTime(&tm.ms_forward, c->ev[EV_PREP], c->ev[EV_FWD]);
+    cudaEventElapsedTime(&tm.ms_reverse, c->ev[EV_FWD], c->ev[EV_REV]);
+    cudaEventElapsedTime(&tm.ms_traceback, c->ev[EV_REV], c->ev[EV_BAND]);
+    cudaEventElapsedTime(&tm.ms_total, c->ev[EV_START], c->ev[EV_BAND]);
+    memcpy(&tm.cells_forward, c->h_counters + CNT_CELLS_FWD, 8);
+    memcpy(&tm.cells_reverse, c->h_counters + CNT_CELLS_REV, 8);
+    memcpy(&tm.cells_band, c->h_counters + CNT_CELLS_BAND, 8);
+    c->computed = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// download
+// ------------------------------------------------------------------------------------------------
+
+extern "C" int swb_download(swb_ctx* c, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used) {
+    if (!c) return -1;
+    if (!c->computed) { c->err = "swb_download: nothing computed"; return -1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const SwbDev& d = c->d;
+    const int64_t used = (int64_t)c->h_bump[1];
+    if (cigar_used) *cigar_used = used;
+    if (used > cigar_cap || (used > 0 && !cigar_arena)) { c->err = "cigar arena too small"; return -2; }
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_D2H0], c->stream));
+    if (d.n_pairs) CUDA_TRY(c, cudaMemcpyAsync(results, d.res, (size_t)d.n_pairs * sizeof(swb_result), cudaMemcpyDeviceToHost, c->stream));
+    if (used) CUDA_TRY(c, cudaMemcpyAsync(cigar_arena, d.cigar, (size_t)used * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_D2H1], c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->tm.d2h_bytes = (int64_t)d.n_pairs * (int64_t)sizeof(swb_result) + used * 4;
+    cudaEventElapsedTime(&c->tm.ms_d2h, c->ev[EV_D2H0], c->ev[EV_D2H1]);
+    cudaEventElapsedTime(&c->tm.ms_h2d, c->ev[EV_H2D0], c->ev[EV_H2D1]);
+    return 0;
+}
+
+extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used) {
+    int rc = swb_upload(c, b);
+    if (rc) return rc;
+    rc = swb_compute(c);
+    if (rc) return rc;
+    return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);
+}
+
+extern "C" int swb_get_timing(const swb_ctx* c, swb_timing* out) {
+    if (!c || !out) return -1;
+    *out = c->tm;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference-compatible single-pair interface (ssw.h:86-139)
+// ------------------------------------------------------------------------------------------------
+
+struct _profile {            // what sswpy.pyx:59-64 declares: read, mat, readLen, n, bias
+    const int8_t* read;
+    const int8_t* mat;
+    int32_t readLen;
+    int32_t n;
+    uint8_t bias;
+    int8_t score_size;
+};
+
+static swb_ctx* g_default_ctx = nullptr;
+static std::mutex g_align_mu;
+
+static swb_ctx* default_ctx() {
+    if (!g_default_ctx) {
+        int dev = 0;
+        const char* e = getenv("SWB200_DEVICE");
+        if (e) dev = atoi(e);
+        g_default_ctx = swb_create(dev);
+    }
+    return g_default_ctx;
+}
+
+extern "C" s_profile* ssw_init(const int8_t* read, const int32_t readLen, const int8_t* mat, const int32_t n, const int8_t score_size) {
+    s_profile* p = (s_profile*)calloc(1, sizeof(s_profile));
+    p->read = read; p->mat = mat; p->readLen = readLen; p->n = n; p->score_size = score_size;     // aliases caller memory like ssw.c:803-804
+    p->bias = 0;
+    if (score_size == 0 || score_size == 2) {
+        int bias = 0;
+        for (int i = 0; i < n * n; ++i) if (mat[i] < bias) bias = mat[i];
+        p->bias = (uint8_t)std::abs(bias);
+    }
+    return p;
+}
+
+extern "C" void init_destroy(s_profile* p) { free(p); }
+
+extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t refLen, const uint8_t weight_gapO, const uint8_t weight_gapE,
+                              const uint8_t flag, const uint16_t filters, const int32_t filterd, const int32_t maskLen) {
+    std::lock_guard<std::mutex> lk(g_align_mu);
+    if (!prof) { fprintf(stderr, "Please call the function ssw_init before ssw_align.\n"); return nullptr; }
+    swb_ctx* c = default_ctx();
+    if (!c) { fprintf(stderr, "libswb200: %s\n", swb_last_error(nullptr)); return nullptr; }
+    if (maskLen < 15) fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");   // ssw.c:837-839
+    if (prof->score_size != 0 && prof->score_size != 1 && prof->score_size != 2) {
+        fprintf(stderr, "Please call the function ssw_init before ssw_align.\n");                                                         // ssw.c:856-859
+        return nullptr;
+    }
+    swb_batch b; memset(&b, 0, sizeof b);
+    int64_t zero = 0; int32_t rl = prof->readLen, wl = refLen, idx0 = 0, ml = maskLen;
+    uint8_t go = weight_gapO, ge = weight_gapE;
+    b.n_pairs = 1; b.n_reads = 1; b.n_windows = 1; b.seq_encoding = SWB_SEQ_CODES;
+    b.reads = prof->read; b.read_off = &zero; b.read_len = &rl;
+    b.windows = ref; b.win_off = &zero; b.win_len = &wl;
+    b.pair_read = &idx0; b.pair_win = &idx0; b.gap_open = &go; b.gap_ext = &ge; b.mask_len = &ml;
+    b.mat = prof->mat; b.n = prof->n; b.score_size = prof->score_size; b.flag = flag; b.filters = filters; b.filterd = filterd;
+    swb_result r; int64_t used = 0;
+    std::vector<uint32_t> arena((size_t)rl + (size_t)wl + 8);
+    int rc = swb_align_batch(c, &b, &r, arena.data(), (int64_t)arena.size(), &used);
+    if (rc) { fprintf(stderr, "libswb200: %s\n", swb_last_error(c)); return nullptr; }
+    if (r.status == SWB_ERR_BYTE_ONLY) {
+        fprintf(stderr, "Please set 2 to the score_size parameter of the function ssw_init, otherwise the alignment results will be incorrect.\n");   // ssw.c:849
+        return nullptr;
+    }
+    if (r.status != SWB_OK) { fprintf(stderr, "libswb200: invalid input (empty sequence or code outside the matrix)\n"); return nullptr; }
+    s_align* a = (s_align*)calloc(1, sizeof(s_align));
+    a->score1 = r.score1; a->score2 = r.score2; a->ref_begin1 = r.ref_begin1; a->ref_end1 = r.ref_end1;
+    a->read_begin1 = r.read_begin1; a->read_end1 = r.read_end1; a->ref_end2 = r.ref_end2; a->flag = r.flag;
+    a->cigar = nullptr; a->cigarLen = 0;
+    if (r.cigar_len > 0) {
+        a->cigar = (uint32_t*)malloc((size_t)r.cigar_len * 4);
+        memcpy(a->cigar, arena.data() + r.cigar_off, (size_t)r.cigar_len * 4);
+        a->cigarLen = r.cigar_len;
+    }
+    return a;
+}
+
+extern "C" void align_destroy(s_align* a) { if (a) { free(a->cigar); free(a); } }
+
+// ssw.h:171-190
+extern "C" char swb_cigar_int_to_op(uint32_t v) { return (v & 0xfU) > 8 ? 'M' : "MIDNSHP=X"[v & 0xfU]; }
+extern "C" uint32_t swb_cigar_int_to_len(uint32_t v) { return v >> 4; }
+extern "C" uint32_t swb_to_cigar_int(uint32_t length, char op) {
+    uint32_t code = 0;
+    switch (op) { case 'M': code = 0; break; case 'I': code = 1; break; case 'D': code = 2; break; case 'N': code = 3; break;
+                  case 'S': code = 4; break; case 'H': code = 5; break; case 'P': code = 6; break; case '=': code = 7; break; case 'X': code = 8; break; default: code = 0; }
+    return (length << 4) | code;
+}

@@ -1,0 +1,77 @@
+// swb_common.cuh — shared device/host definitions of libswb200 (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/swb200.h"
+
+#define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident batch ("workspace").  One per context, grown on demand.
+// Layout in HBM: structure-of-arrays indexed by pair; sequences stay in their de-duplicated
+// tables (codes, 1 byte/base) and every pair points into them, so a locus' window is uploaded once.
+// ---------------------------------------------------------------------------------------------
+struct SwbDev {
+    // tables
+    int8_t*  reads;     int64_t* read_off; int32_t* read_len;
+    int8_t*  windows;   int64_t* win_off;  int32_t* win_len;
+    // raw per-pair inputs
+    int32_t* pair_read; int32_t* pair_win; int32_t* ref_beg; int32_t* ref_len;   // ref_beg/ref_len may be null
+    uint8_t* gap_open;  uint8_t* gap_ext;  int32_t* mask_len;                    // mask_len may be null
+    int8_t*  mat;       // n*n
+    // derived per-pair (k_prepare)
+    int64_t* p_roff;    // read start in reads[]
+    int64_t* p_woff;    // window start (incl. ref_beg) in windows[]
+    int32_t* p_rlen;
+    int32_t* p_wlen;
+    int32_t* p_mask;
+    uint8_t* p_mode;    // 0: result is byte-mode, 1: word-mode (set by the forward stage)
+    // results
+    swb_result* res;
+    // job lists (indices of pairs) + counters
+    int32_t* list[6];
+    int32_t* counters;  // [16]
+    // per-pair column maxima scratch for the sub-optimal score (u16, stride = max window length)
+    uint16_t* colmax;   int32_t colmax_stride;
+    // banded traceback scratch + CIGAR arena
+    uint8_t*  band;     int64_t band_cap;
+    uint32_t* cigar;    int64_t cigar_cap;
+    unsigned long long* bump;   // [0]: band scratch bump pointer, [1]: cigar arena bump pointer
+    int32_t*  t_bw;     // current band width per pair (banded rounds)
+    int32_t*  t_best;   // running DP maximum per pair (not reset between widenings, ssw.c:600,661)
+
+    int32_t n_pairs, n_reads, n_windows;
+    int32_t n;          // matrix edge
+    int32_t bias;       // |min(mat)| (ssw.c:795-799)
+    int8_t  score_size; uint8_t flag; uint16_t filters; int32_t filterd;
+    int32_t seq_encoding;
+    int32_t max_rlen, max_wlen;
+};
+
+// counters[] slots
+enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3, CNT_BAND = 4, CNT_BAND_NEXT = 5,
+       CNT_CELLS_FWD = 6, CNT_CELLS_REV = 8, CNT_CELLS_BAND = 10, CNT_BAND_OVERFLOW = 12, CNT_CIGAR_OVERFLOW = 13 };
+// list[] slots
+enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_BAND = 4, LIST_BAND_NEXT = 5 };
+
+__device__ __forceinline__ void list_push(int32_t* list, int32_t* counter, int32_t v) {
+    // warp-aggregated append
+    unsigned m = __activemask();
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    list[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = v;
+}
+
+// sswpy.pyx:16-29 DNA_BASE_LUT
+__host__ __device__ __forceinline__ int8_t swb_dna_code(unsigned char c) {
+    switch (c) {
+        case 'A': case 'a': case 'U': case 'u': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
