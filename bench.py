@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — SW GCUPS / reads realigned per second of the batched realignment hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): P = 1 M read x window pairs per GPU, 150-bp reads vs 400-bp
+windows, score + coordinates + CIGAR (flag=1), (go, ge) = (3, 1), match 3 / mismatch 2, one planted
+event per read (1/3 none, 1/3 deletion 1-10 bp, 1/3 insertion 1-10 bp) and 1 % substitutions, synthetic.
+GCUPS := sum(readLen * windowLen) / seconds / 1e9 (one nominal forward matrix per pair).
+
+A "step" is one pass of the whole hot path (prepare, forward, reverse, banded traceback) over the batch.
+  value : inputs already resident in HBM when the timed region starts (swb_upload done; K x swb_compute)
+  e2e   : the same through the one-shot C-ABI call swb_align_batch with pinned HOST buffers:
+          H2D of every input + kernels + D2H of results and CIGARs inside the timed region
+Multi-GPU (torchrun, one rank per GPU): the pairs shard across ranks with no collective in the data
+path (weak scaling: every rank aligns its own P pairs); torch.distributed is only the barrier and the
+max-over-ranks of the timed region.
+
+--impl reference times the reference's own ssw.c (oracle/_ref, compiled from /root/reference by
+oracle/Makefile) on the host cores with one thread per core on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "sw_gcups"
+UNIT = "GCUPS"
+READ_LEN, WIN_LEN = 150, 400
+
+
+def workload_config(pairs, n_gpus):
+    return {
+        "workload": "cfg2: 1M read x window pairs per GPU, 150bp reads vs 400bp windows, score+coords+CIGAR (flag=1), go=3 ge=1, match=3 mismatch=2",
+        "pairs_per_gpu": pairs,
+        "read_len": READ_LEN,
+        "window_len": WIN_LEN,
+        "distinct_windows": True,
+        "parallelism": f"pair-sharded x{n_gpus}, no collective",
+        "l2_policy": "inputs (~550 MB/GPU) larger than the 126 MB L2; no explicit flush",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                if t0 <= ts <= t1 + 0.2:
+                    sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            if t0 <= ts <= t1 + 0.2:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the reference's own ssw.c when oracle/_ref is present, else the oracle port)
+# ----------------------------------------------------------------------------------------------
+def cpu_align_parallel(batch, n_threads):
+    """time ref_align_batch / orc_align_batch over `batch`, pairs split evenly over n_threads threads
+    (ctypes releases the GIL, each thread runs the C loop on its own core)."""
+    import swbtest as T
+
+    if T.have_ref():
+        kind = "reference"
+        chk = T.reference()
+        parts = np.array_split(np.arange(batch.n_pairs), n_threads)
+        subs = [(int(p[0]), int(p.shape[0])) for p in parts if p.shape[0]]
+        run = lambda fc: chk.align_batch(batch, fc[0], fc[1])
+    else:
+        kind = "port"
+        chk = T.oracle()
+        parts = np.array_split(np.arange(batch.n_pairs), n_threads)
+        subs = [batch.subset(p) for p in parts if p.shape[0]]
+        run = lambda sb: chk.align_batch(sb)
+    from concurrent.futures import ThreadPoolExecutor
+
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    os.dup2(devnull, 2)  # the reference prints warnings on stderr
+    try:
+        with ThreadPoolExecutor(max_workers=n_threads) as ex:
+            t0 = time.perf_counter()
+            list(ex.map(run, subs))
+            dt = time.perf_counter() - t0
+    finally:
+        os.dup2(saved, 2)
+        os.close(devnull)
+        os.close(saved)
+    return dt, kind
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    import swbtest as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    sample_pairs = max(cores * 250, min(args.pairs, cores * 1500))
+    b = T.make_pairs_fast(sample_pairs, READ_LEN, WIN_LEN, seed=1234)
+    for _ in range(args.warmup):
+        cpu_align_parallel(b.subset(np.arange(min(sample_pairs, cores * 100))), cores)
+    times = []
+    kind = "reference"
+    for _ in range(args.steps):
+        dt, kind = cpu_align_parallel(b, cores)
+        times.append(dt)
+    tot = float(sum(times))
+    gcups = b.cells() * args.steps / tot / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16 (SSE2)",
+        "data": "synthetic", "config": workload_config(args.pairs, args.gpus),
+        "reads_per_s": sample_pairs * args.steps / tot,
+        "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample_pairs} pairs of the cfg2 workload per step, split evenly over {cores} threads (unmodified ssw.c: ssw_init+ssw_align+destroy per pair)"},
+        "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def dpx_peak():
+    """measured DPX/ALU-pipe peak (profiles/dpx_peak.json, from tools/dpx_microbench on this pool's B200)"""
+    p = os.path.join(ROOT, "profiles", "dpx_peak.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {"lanes_per_clk_per_sm": 64.0, "sm_mhz": 1965.0, "sms": 148, "instr_per_cell_pair": 6, "source": "fallback (nominal)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import swbtest as T
+    from indelpost_b200 import BatchAligner
+    from indelpost_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libswb200 has no CPU fallback)")
+    dev = local if world > 1 else 0
+    torch.cuda.set_device(dev)
+    al = BatchAligner(dev)
+
+    b = T.make_pairs_fast(args.pairs, READ_LEN, WIN_LEN, seed=1000 + rank)
+    cells = b.cells()
+
+    # pinned host staging for every input array (the batched entry point's contract)
+    def pin(a):
+        buf = L.PinnedBuffer(a.nbytes)
+        v = buf.view(a.dtype, a.size)
+        v[:] = a.reshape(-1)
+        return buf, v
+
+    keep = []
+    arrs = {}
+    for k in ("reads", "read_off", "read_len", "windows", "win_off", "win_len", "pair_read", "pair_win", "gap_open", "gap_ext"):
+        buf, v = pin(getattr(b, k))
+        keep.append(buf)
+        arrs[k] = v
+    args_pos = [arrs[k] for k in ("reads", "read_off", "read_len", "windows", "win_off", "win_len", "pair_read", "pair_win", "gap_open", "gap_ext")]
+    kw = dict(mat=b.mat, n=5, score_size=2, flag=1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident leg --------------------------------------------------------------------------
+    n = al.upload(*args_pos, **kw)
+    for _ in range(args.warmup):
+        al.compute()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    t0 = time.perf_counter()
+    ev_ms = 0.0
+    stage = {"ms_prepare": 0.0, "ms_forward": 0.0, "ms_reverse": 0.0, "ms_traceback": 0.0}
+    launches = 0
+    tm = {}
+    for _ in range(args.steps):
+        al.compute()
+        tm = al.timing()
+        ev_ms += tm["ms_total"]
+        for k in stage:
+            stage[k] += tm[k]
+        launches += tm["n_launches"]
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    dt = t1 - t0
+    res, arena = al.download(n)
+
+    # ---- end-to-end leg (pinned host buffers -> results on host) ---------------------------------
+    for _ in range(min(2, args.warmup)):
+        al.align(*args_pos, **kw)
+    barrier()
+    e0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        res2, arena2 = al.align(*args_pos, **kw)
+        t = al.timing()
+        h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
+    barrier()
+    e1 = time.perf_counter()
+    dte = e1 - e0
+
+    if world > 1:
+        tt = torch.tensor([dt, dte], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dte = float(tt[0]), float(tt[1])
+        cc = torch.tensor([float(cells)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        total_cells = float(cc[0])
+    else:
+        total_cells = float(cells)
+
+    if rank == 0:
+        # sanity: results are real (spot-check against the CPU checker on a few pairs)
+        sub = b.subset(np.arange(0, args.pairs, max(1, args.pairs // 64))[:64])
+        ro, ao = (T.reference() if T.have_ref() else T.oracle()).align_batch(sub)
+        idx = np.arange(0, args.pairs, max(1, args.pairs // 64))[:64]
+        r_sub = res[idx].view(T.RESULT_DTYPE)
+        for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len", "flag"):
+            assert (r_sub[f] == ro[f]).all(), f"bench sanity check failed on {f}"
+
+        value = total_cells * args.steps / dt / 1e9
+        e2e = total_cells * args.steps / dte / 1e9
+        pk = dpx_peak()
+        peak_gcups = pk["lanes_per_clk_per_sm"] * pk["sms"] * pk["sm_mhz"] * 1e6 * 2 / pk["instr_per_cell_pair"] / 1e9
+        # dominant kernel family = forward sweep; algorithmic cells per launch = sum(readLen*winLen) of this rank
+        fwd_ms = stage["ms_forward"] / args.steps
+        achieved = cells / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
+        alg_bytes = int(h2d)  # every input byte is read once by the sweep
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback"
+        cores = host_cores()
+        sample_pairs = cores * 600
+        sb = T.make_pairs_fast(sample_pairs, READ_LEN, WIN_LEN, seed=77)
+        cdt, kind = cpu_align_parallel(sb, cores)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s16x2 (DPX) / u8+s16 striped emulation", "data": "synthetic", "config": workload_config(args.pairs, world),
+            "reads_per_s": args.pairs * world * args.steps / dt,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "reads_per_s": args.pairs * world * args.steps / dte,
+                    "ms_per_step": 1e3 * dte / args.steps},
+            "gpu_launches": int(launches),
+            "device_event_ms_per_step": ev_ms / args.steps,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "path_split": {"n_fast": int(tm.get("n_fast", 0)), "n_exact": int(tm.get("n_exact", 0))},
+            "roofline": {"bound": "dpx", "kernel": "forward sweep (score/end/sub-optimal)", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
+                         "frac": achieved / peak_gcups if peak_gcups else None, "traffic": None,
+                         "peak_source": pk.get("source", "profiles/dpx_peak.json"),
+                         "hbm": {"achieved_gbs": alg_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                                 "note": "algorithmic bytes = inputs read once (~0.009 B per cell): the path is integer-issue bound, not HBM bound"}},
+            "cpu_baseline": {"value": sb.cells() / cdt / 1e9, "unit": UNIT, "cores": cores, "kind": kind, "reads_per_s": sample_pairs / cdt,
+                             "sample": f"{sample_pairs} pairs of the same workload, split evenly over {cores} threads"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

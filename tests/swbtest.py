@@ -408,3 +408,52 @@ def compare(res_a, arena_a, res_b, arena_b, what="", limit=5):
             lines.append(f"pair {p}:\n   A={a}\n   B={b}")
         raise AssertionError(f"{what}: {nbad}/{res_a.shape[0]} pairs differ\n" + "\n".join(lines))
     return True
+
+
+def make_pairs_fast(n_pairs: int, read_len: int = 150, win_len: int = 400, *, seed: int = 1, reads_per_window: int = 1,
+                    max_indel: int = 10, sub_rate: float = 0.01, go: int = 3, ge: int = 1, match: int = 3, mismatch: int = 2,
+                    chunk: int = 65536) -> Batch:
+    """Vectorised config-2 generator for bench-sized batches (1 M pairs in a few seconds): fixed read
+    and window lengths, per pair one planted event (1/3 none, 1/3 deletion, 1/3 insertion of
+    1..max_indel bp) plus substitutions — the same distribution as make_pairs()."""
+    rng = np.random.default_rng(seed)
+    n_windows = (n_pairs + reads_per_window - 1) // reads_per_window
+    windows = rng.integers(0, 4, size=(n_windows, win_len), dtype=np.int8)
+    reads = np.empty((n_pairs, read_len), dtype=np.int8)
+    pair_win = (np.arange(n_pairs) // reads_per_window).astype(np.int32)
+    L = read_len
+    k = np.arange(L, dtype=np.int32)[None, :]
+    for c0 in range(0, n_pairs, chunk):
+        c1 = min(n_pairs, c0 + chunk)
+        m = c1 - c0
+        kind = rng.integers(0, 3, size=m)
+        ev = rng.integers(1, max_indel + 1, size=m).astype(np.int32) if max_indel > 0 else np.zeros(m, np.int32)
+        ev = np.where(kind == 0, 0, ev)
+        ev = np.where(kind == 2, np.minimum(ev, L - 2), ev)
+        span = np.where(kind == 1, L + ev, np.where(kind == 2, L - ev, L)).astype(np.int32)
+        start = (rng.random(m) * (win_len - span + 1)).astype(np.int32)
+        cut = (1 + rng.random(m) * (np.where(kind == 2, span, L) - 1)).astype(np.int32)
+        cut = np.maximum(1, np.minimum(cut, np.where(kind == 2, span, L) - 1))
+        is_del = (kind == 1)[:, None]
+        is_ins = (kind == 2)[:, None]
+        evc = ev[:, None]
+        cutc = cut[:, None]
+        # source index in the window for every read position
+        src = start[:, None] + k + np.where(is_del & (k >= cutc), evc, 0) - np.where(is_ins & (k >= cutc + evc), evc, 0)
+        src = np.clip(src, 0, win_len - 1)
+        r = windows[pair_win[c0:c1, None], src]
+        inserted = is_ins & (k >= cutc) & (k < cutc + evc)
+        rnd = rng.integers(0, 4, size=(m, L), dtype=np.int8)
+        r = np.where(inserted, rnd, r)
+        if sub_rate > 0:
+            sub = rng.random((m, L)) < sub_rate
+            r = np.where(sub, (r + 1 + (rnd % 3)) % 4, r)
+        reads[c0:c1] = r.astype(np.int8)
+    roff = (np.arange(n_pairs, dtype=np.int64) * L)
+    woff = (np.arange(n_windows, dtype=np.int64) * win_len)
+    return Batch(
+        np.ascontiguousarray(reads.reshape(-1)), roff, np.full(n_pairs, L, dtype=np.int32),
+        np.ascontiguousarray(windows.reshape(-1)), woff, np.full(n_windows, win_len, dtype=np.int32),
+        np.arange(n_pairs, dtype=np.int32), pair_win,
+        np.full(n_pairs, go, dtype=np.uint8), np.full(n_pairs, ge, dtype=np.uint8), mat=dna_matrix(match, mismatch),
+    )
