@@ -20,6 +20,8 @@
 #include "swb_common.cuh"
 #include "swb_exact.cuh"
 #include "swb_band.cuh"
+#include "swb_fast.cuh"
+#include "swb_cert.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
 
@@ -30,19 +32,22 @@
 // one warp per sequence: ASCII -> code (in place) and range check; bad[s] = 1 if any code is outside [0, n)
 __global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int n, int ascii, uint8_t* bad)
 {
+    // bad[s]: bit0 = code outside [0, n) (invalid input), bit1 = some code >= 4 (not usable by the DPX fast path as a window)
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nseq) return;
     int8_t* s = blob + off[w];
     const int L = len[w];
-    bool b = false;
+    bool b = false, hi = false;
     for (int i = lane; i < L; i += 32) {
         int c = s[i];
         if (ascii) { c = swb_dna_code((unsigned char)c); s[i] = (int8_t)c; }
         if (c < 0 || c >= n) b = true;
+        if (c >= 4) hi = true;
     }
     b = __any_sync(0xffffffffu, b);
-    if (lane == 0) bad[w] = b ? 1 : 0;
+    hi = __any_sync(0xffffffffu, hi);
+    if (lane == 0) bad[w] = (b ? 1 : 0) | (hi ? 2 : 0);
 }
 
 __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_bad, int32_t p0, int32_t p1)
@@ -59,10 +64,10 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         rl = d.read_len[ri];
         rb = d.ref_beg ? d.ref_beg[p] : 0;
         wl = d.ref_len ? d.ref_len[p] : d.win_len[wi] - rb;
-        ok = rl > 0 && wl > 0 && rb >= 0 && (long long)rb + wl <= d.win_len[wi] && !read_bad[ri] && !win_bad[wi];
+        ok = rl > 0 && wl > 0 && rb >= 0 && (long long)rb + wl <= d.win_len[wi] && !(read_bad[ri] & 1) && !(win_bad[wi] & 1);
     }
     if (ok && d.score_size != 0 && d.score_size != 1 && d.score_size != 2) ok = false;   // ssw.c:856-859: no profile
-    d.p_mode[p] = 0;
+    d.p_mode[p] = 0; d.p_state[p] = 0;
     d.t_bw[p] = 0; d.t_best[p] = 0;
     if (!ok) {
         r.status = SWB_ERR_BAD_INPUT;
@@ -76,7 +81,19 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
     d.p_wlen[p] = wl;
     d.p_mask[p] = d.mask_len ? d.mask_len[p] : (rl / 2 < 15 ? 15 : rl / 2);      // sswpy.pyx:209-211
     d.res[p] = r;
-    if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
+    // ---- route: DPX fast path when the striped result is provably plain Gotoh, else exact emulation
+    const int go = d.gap_open[p], ge = d.gap_ext[p];
+    const int lp16 = (rl + 15) & ~15;
+    const bool fast = d.fast_ok && go > ge && !(win_bad[wi] & 2) && lp16 <= 32 * SWB_NBUCKETS && wl <= d.fast_max_cols &&
+                      (long long)d.max_score * rl <= FAST_MAX_SCORE;
+    if (fast) {
+        // which padding the result will be reported in: 16-bit semantics if the 8-bit pass can overflow at all
+        const bool wordSem = d.score_size == 1 || (d.max_score * rl + d.bias >= 255);
+        d.p_mode[p] = wordSem ? 1 : 0;
+        const int b = (lp16 + 31) / 32 - 1;
+        list_push(d.list[LIST_FAST_FWD + b], d.counters + CNT_FAST_FWD + b, p);
+    }
+    else if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
     else list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
 }
 
@@ -111,7 +128,7 @@ struct swb_ctx {
     DevBuf b_reads, b_read_off, b_read_len, b_windows, b_win_off, b_win_len;
     DevBuf b_pair_read, b_pair_win, b_ref_beg, b_ref_len, b_go, b_ge, b_mask, b_mat;
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
-    DevBuf b_tbw, b_tbest, b_rbad, b_wbad;
+    DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state;
     int32_t* h_counters = nullptr;              // pinned mirror of counters
     unsigned long long* h_bump = nullptr;       // pinned mirror of bump
     swb_timing tm;
@@ -160,7 +177,7 @@ extern "C" swb_ctx* swb_create(int device) {
         delete c; return nullptr;
     }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
-    cudaMallocHost((void**)&c->h_counters, 16 * sizeof(int32_t));
+    cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t));
     cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long));
     // opt in to large dynamic shared memory for the exact kernels
     cudaFuncSetAttribute(k_exact<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
@@ -177,7 +194,7 @@ extern "C" void swb_destroy(swb_ctx* c) {
     DevBuf* all[] = { &c->b_reads, &c->b_read_off, &c->b_read_len, &c->b_windows, &c->b_win_off, &c->b_win_len, &c->b_pair_read, &c->b_pair_win,
                       &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
                       &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
-                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad };
+                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state };
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
@@ -260,6 +277,10 @@ extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
     int bias = 0;
     for (int i = 0; i < b->n * b->n; ++i) if (b->mat[i] < bias) bias = b->mat[i];       // ssw.c:795-797
     d.bias = (b->score_size == 0 || b->score_size == 2) ? std::abs(bias) : 0;
+    int mx = 0; bool small = true;
+    for (int i = 0; i < b->n * b->n; ++i) { mx = std::max<int>(mx, b->mat[i]); if (b->mat[i] > 7 || b->mat[i] < -7) small = false; }
+    d.max_score = mx;
+    d.fast_ok = (small && b->n >= 4 && mx > 0 && (b->score_size == 1 || b->score_size == 2) && !getenv("SWB200_NO_FAST")) ? 1 : 0;
     c->have_batch = true;
     return 0;
 }
@@ -268,15 +289,25 @@ extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
 // compute
 // ------------------------------------------------------------------------------------------------
 
+// SWB200_DEBUG_SYNC=1: synchronise after every stage and name the one that faulted
+static int stage_check(swb_ctx* c, const char* name) {
+    static const bool dbg = getenv("SWB200_DEBUG_SYNC") != nullptr;
+    if (!dbg) return 0;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { c->err = std::string("stage ") + name + ": " + cudaGetErrorString(e); fprintf(stderr, "libswb200: %s\n", c->err.c_str()); return -1; }
+    return 0;
+}
+
 static int read_counters(swb_ctx* c) {
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->d.counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->d.counters, SWB_NCOUNTERS * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_bump, c->d.bump, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 template <int MODE, int DIR>
-static int launch_exact(swb_ctx* c, int listSlot, int cntSlot, int upperBound) {
+static int launch_exact(swb_ctx* c, int listSlot, int upperBound) {
     if (upperBound <= 0) return 0;
     const SwbDev& d = c->d;
     const int W = MODE ? 8 : 16;
@@ -287,9 +318,93 @@ static int launch_exact(swb_ctx* c, int listSlot, int cntSlot, int upperBound) {
     if ((size_t)groups * per > (size_t)c->smem_optin) { c->err = "read too long for the exact kernel's shared-memory profile"; return -1; }
     const int threads = groups * W;
     const int blocks = (upperBound + groups - 1) / groups;
-    k_exact<MODE, DIR><<<blocks, threads, (size_t)groups * per, c->stream>>>(d, d.list[listSlot], d.counters + cntSlot, segAlloc, per);
+    k_exact<MODE, DIR><<<blocks, threads, (size_t)groups * per, c->stream>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per);
     c->tm.n_launches++;
     CUDA_TRY(c, cudaGetLastError());
+    return stage_check(c, MODE ? (DIR ? "exact word rev" : "exact word fwd") : (DIR ? "exact byte rev" : "exact byte fwd"));
+}
+
+// fast-path launch geometry: groups of FAST_G threads, 10 bytes of shared memory per column per group
+static int fast_col_alloc(const SwbDev& d) { return (std::max(d.max_wlen, 8) + 7) & ~7; }
+
+template <int R, int DIR>
+static int launch_fast_one(swb_ctx* c, int bucket, int upperBoundPairs) {
+    const SwbDev& d = c->d;
+    const int colAlloc = fast_col_alloc(d);
+    const size_t per = (size_t)colAlloc * 10;
+    int groups = 128 / FAST_G;
+    while (groups > 2 && groups * per > (size_t)c->smem_optin - 1024) groups /= 2;
+    const int threads = groups * FAST_G;
+    const int ngroups = (upperBoundPairs + 1) / 2;
+    const int blocks = (ngroups + groups - 1) / groups;
+    static bool attr_set[2][SWB_NBUCKETS] = {};
+    if (!attr_set[DIR][bucket]) {
+        cudaFuncSetAttribute(k_fast<R, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
+        attr_set[DIR][bucket] = true;
+    }
+    const int slot = (DIR ? LIST_FAST_REV : LIST_FAST_FWD) + bucket;
+    k_fast<R, DIR><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc);
+    c->tm.n_launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return stage_check(c, DIR ? "fast rev" : "fast fwd");
+}
+
+template <int DIR>
+static int launch_fast(swb_ctx* c, const int* counts) {
+    // one launch per non-empty read-length bucket (R = 2*(bucket+1) rows per thread)
+    for (int b = 0; b < SWB_NBUCKETS; ++b) {
+        const int n = counts[b];
+        if (n <= 0) continue;
+        int rc = 0;
+        switch (b) {
+            case 0: rc = launch_fast_one<2, DIR>(c, b, n); break;
+            case 1: rc = launch_fast_one<4, DIR>(c, b, n); break;
+            case 2: rc = launch_fast_one<6, DIR>(c, b, n); break;
+            case 3: rc = launch_fast_one<8, DIR>(c, b, n); break;
+            case 4: rc = launch_fast_one<10, DIR>(c, b, n); break;
+            case 5: rc = launch_fast_one<12, DIR>(c, b, n); break;
+            case 6: rc = launch_fast_one<14, DIR>(c, b, n); break;
+            case 7: rc = launch_fast_one<16, DIR>(c, b, n); break;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// banded DP + traceback in doubling rounds over d.list[LIST_BAND] (ssw.c:897-916)
+static int run_band_rounds(swb_ctx* c) {
+    SwbDev& d = c->d;
+    cudaStream_t s = c->stream;
+    if (read_counters(c)) return -1;
+    int cur = LIST_BAND, nxt = LIST_BAND_NEXT;
+    int njobs = c->h_counters[cur];
+    int round = 0, stalls = 0;
+    while (njobs > 0) {
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4, s));
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
+        CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
+        const int blocks = (njobs + 127) / 128;
+        k_band<true><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
+        k_band<false><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
+        c->tm.n_launches += 2;
+        CUDA_TRY(c, cudaGetLastError());
+        if (stage_check(c, "band")) return -1;
+        if (read_counters(c)) return -1;
+        const int next = c->h_counters[nxt];
+        if (c->h_counters[CNT_BAND_OVERFLOW] == njobs) {
+            // nothing fitted: the scratch is smaller than a single band; grow it
+            if (++stalls > 8 || c->b_band.cap >= ((size_t)64 << 30)) { c->err = "banded traceback scratch exhausted"; return -1; }
+            size_t want = c->b_band.cap * 4;
+            CUDA_TRY(c, c->b_band.ensure(want));
+            d.band = (uint8_t*)c->b_band.p; d.band_cap = (int64_t)c->b_band.cap;
+        }
+        std::swap(cur, nxt);
+        njobs = next;
+        if (++round > 64) { c->err = "banded traceback did not converge"; return -1; }
+    }
+    // leave LIST_BAND empty for a later phase
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND, 0, 4, s));
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND_NEXT, 0, 4, s));
     return 0;
 }
 
@@ -310,10 +425,11 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, c->b_wlen.ensure(np * 4 + 16));   d.p_wlen = (int32_t*)c->b_wlen.p;
     CUDA_TRY(c, c->b_pmask.ensure(np * 4 + 16));  d.p_mask = (int32_t*)c->b_pmask.p;
     CUDA_TRY(c, c->b_mode.ensure(np + 16));       d.p_mode = (uint8_t*)c->b_mode.p;
+    CUDA_TRY(c, c->b_state.ensure(np + 16));      d.p_state = (uint8_t*)c->b_state.p;
     CUDA_TRY(c, c->b_res.ensure(np * sizeof(swb_result) + 16)); d.res = (swb_result*)c->b_res.p;
-    CUDA_TRY(c, c->b_lists.ensure(6 * (np + 32) * 4));
-    for (int i = 0; i < 6; ++i) d.list[i] = (int32_t*)c->b_lists.p + (size_t)i * (np + 32);
-    CUDA_TRY(c, c->b_counters.ensure(16 * 4));    d.counters = (int32_t*)c->b_counters.p;
+    CUDA_TRY(c, c->b_lists.ensure((size_t)SWB_NLISTS * (np + 32) * 4));
+    for (int i = 0; i < SWB_NLISTS; ++i) d.list[i] = (int32_t*)c->b_lists.p + (size_t)i * (np + 32);
+    CUDA_TRY(c, c->b_counters.ensure(SWB_NCOUNTERS * 4)); d.counters = (int32_t*)c->b_counters.p;
     CUDA_TRY(c, c->b_bump.ensure(2 * 8));         d.bump = (unsigned long long*)c->b_bump.p;
     CUDA_TRY(c, c->b_tbw.ensure(np * 4 + 16));    d.t_bw = (int32_t*)c->b_tbw.p;
     CUDA_TRY(c, c->b_tbest.ensure(np * 4 + 16));  d.t_best = (int32_t*)c->b_tbest.p;
@@ -321,6 +437,8 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, c->b_wbad.ensure((size_t)d.n_windows + 16));
     d.colmax_stride = (d.max_wlen + 7) & ~7;
     CUDA_TRY(c, c->b_colmax.ensure(np * (size_t)d.colmax_stride * 2 + 16)); d.colmax = (uint16_t*)c->b_colmax.p;
+    // the fast path keeps 10 bytes per window column per lane-pair in shared memory
+    d.fast_max_cols = (c->smem_optin - 1024) / 2 / 10;
     {
         // direction-byte scratch: enough for a typical band on every pair; pairs that do not fit are
         // deferred to the next round by the kernel itself
@@ -334,7 +452,7 @@ extern "C" int swb_compute(swb_ctx* c) {
     }
 
     cudaStream_t s = c->stream;
-    CUDA_TRY(c, cudaMemsetAsync(d.counters, 0, 16 * 4, s));
+    CUDA_TRY(c, cudaMemsetAsync(d.counters, 0, SWB_NCOUNTERS * 4, s));
     CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 16, s));
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_START], s));
 
@@ -344,46 +462,46 @@ extern "C" int swb_compute(swb_ctx* c) {
     d.seq_encoding = SWB_SEQ_CODES;                         // tables are codes from now on (repeat computes must not re-encode)
     if (np) { k_prepare<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, 0, (int32_t)np); tm.n_launches++; }
     CUDA_TRY(c, cudaGetLastError());
+    if (stage_check(c, "prepare")) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
+    if (read_counters(c)) return -1;                        // bucket sizes for the fast path launches
+    int fwdCounts[SWB_NBUCKETS]; int nFastTotal = 0;
+    for (int b = 0; b < SWB_NBUCKETS; ++b) { fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; nFastTotal += fwdCounts[b]; }
 
-    // ---- forward (ssw.c:842-860): 8-bit pass, then 16-bit pass for the pairs that overflowed ----
-    if (launch_exact<0, 0>(c, LIST_BYTE_FWD, CNT_BYTE_FWD, (int)np)) return -1;
-    if (launch_exact<1, 0>(c, LIST_WORD_FWD, CNT_WORD_FWD, (int)np)) return -1;
+    // ---- forward (ssw.c:842-860) --------------------------------------------------------------------
+    //   fast path: one 16-bit Gotoh sweep per pair (pairs it cannot decide are appended to the exact lists)
+    //   exact path: 8-bit pass, then 16-bit pass for the pairs that overflowed
+    if (launch_fast<0>(c, fwdCounts)) return -1;
+    if (launch_exact<0, 0>(c, LIST_BYTE_FWD, (int)np)) return -1;
+    if (launch_exact<1, 0>(c, LIST_WORD_FWD, (int)np)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_FWD], s));
 
     // ---- reverse (ssw.c:875-891) ----------------------------------------------------------------
-    if (launch_exact<0, 1>(c, LIST_BYTE_REV, CNT_BYTE_REV, (int)np)) return -1;
-    if (launch_exact<1, 1>(c, LIST_WORD_REV, CNT_WORD_REV, (int)np)) return -1;
+    if (launch_fast<1>(c, fwdCounts)) return -1;            // rev bucket sizes are bounded by the fwd ones
+    if (launch_exact<0, 1>(c, LIST_BYTE_REV, (int)np)) return -1;
+    if (launch_exact<1, 1>(c, LIST_WORD_REV, (int)np)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));
 
-    // ---- banded DP + traceback rounds (ssw.c:897-916) ----------------------------------------------
-    if (read_counters(c)) return -1;
-    tm.n_exact = c->h_counters[CNT_BYTE_FWD] + c->h_counters[CNT_WORD_FWD];
-    int cur = LIST_BAND, curCnt = CNT_BAND, nxt = LIST_BAND_NEXT, nxtCnt = CNT_BAND_NEXT;
-    int njobs = c->h_counters[curCnt];
-    int round = 0, stalls = 0;
-    while (njobs > 0) {
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + nxtCnt, 0, 4, s));
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
-        CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
-        const int blocks = (njobs + 127) / 128;
-        k_band<true><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + curCnt, d.list[nxt], d.counters + nxtCnt, round);
-        k_band<false><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + curCnt, d.list[nxt], d.counters + nxtCnt, round);
-        tm.n_launches += 2;
+    // ---- banded DP + traceback (ssw.c:897-916) -----------------------------------------------------
+    if (run_band_rounds(c)) return -1;
+
+    // ---- overflow certificate for provisionally accepted 16-bit results; exact 8-bit pass for the rest ----
+    if (nFastTotal > 0 && d.score_size == 2) {
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_FWD, 0, 4, s));
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_REV, 0, 4, s));
+        k_certify<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np);
+        tm.n_launches++;
         CUDA_TRY(c, cudaGetLastError());
+        if (stage_check(c, "certify")) return -1;
         if (read_counters(c)) return -1;
-        const int next = c->h_counters[nxtCnt];
-        if (c->h_counters[CNT_BAND_OVERFLOW] == njobs) {
-            // nothing fitted: the scratch is smaller than a single band; grow it
-            if (++stalls > 8 || c->b_band.cap >= ((size_t)64 << 30)) { c->err = "banded traceback scratch exhausted"; return -1; }
-            size_t want = c->b_band.cap * 4;
-            CUDA_TRY(c, c->b_band.ensure(want));
-            d.band = (uint8_t*)c->b_band.p; d.band_cap = (int64_t)c->b_band.cap;
+        const int nverify = c->h_counters[CNT_BYTE_FWD];
+        if (nverify > 0) {
+            if (launch_exact<0, 0>(c, LIST_BYTE_FWD, nverify)) return -1;     // confirms the overflow, or produces the byte-mode result
+            if (launch_exact<0, 1>(c, LIST_BYTE_REV, nverify)) return -1;
+            if (run_band_rounds(c)) return -1;
         }
-        std::swap(cur, nxt); std::swap(curCnt, nxtCnt);
-        njobs = next;
-        ++round;
-        if (round > 64) { c->err = "banded traceback did not converge"; return -1; }
     }
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND], s));
     if (read_counters(c)) return -1;
@@ -401,6 +519,8 @@ extern "C" int swb_compute(swb_ctx* c) {
     memcpy(&tm.cells_forward, c->h_counters + CNT_CELLS_FWD, 8);
     memcpy(&tm.cells_reverse, c->h_counters + CNT_CELLS_REV, 8);
     memcpy(&tm.cells_band, c->h_counters + CNT_CELLS_BAND, 8);
+    tm.n_fast = c->h_counters[CNT_FAST_DONE] - c->h_counters[CNT_VERIFY_BYTE];
+    tm.n_exact = c->h_counters[CNT_EXACT_JOBS];
     c->computed = true;
     return 0;
 }

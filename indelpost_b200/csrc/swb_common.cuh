@@ -6,6 +6,9 @@
 #include "../../include/swb200.h"
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
+#define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
+#define SWB_NLISTS 24
+#define SWB_NCOUNTERS 64
 
 // ---------------------------------------------------------------------------------------------
 // Device-resident batch ("workspace").  One per context, grown on demand.
@@ -26,12 +29,13 @@ struct SwbDev {
     int32_t* p_rlen;
     int32_t* p_wlen;
     int32_t* p_mask;
-    uint8_t* p_mode;    // 0: result is byte-mode, 1: word-mode (set by the forward stage)
+    uint8_t* p_mode;    // 0: result is byte-mode, 1: word-mode (semantic chosen by k_prepare for the fast path, final mode after forward)
+    uint8_t* p_state;   // PST_* flags
     // results
     swb_result* res;
     // job lists (indices of pairs) + counters
-    int32_t* list[6];
-    int32_t* counters;  // [16]
+    int32_t* list[SWB_NLISTS];
+    int32_t* counters;  // [SWB_NCOUNTERS]
     // per-pair column maxima scratch for the sub-optimal score (u16, stride = max window length)
     uint16_t* colmax;   int32_t colmax_stride;
     // banded traceback scratch + CIGAR arena
@@ -47,18 +51,28 @@ struct SwbDev {
     int8_t  score_size; uint8_t flag; uint16_t filters; int32_t filterd;
     int32_t seq_encoding;
     int32_t max_rlen, max_wlen;
+    int32_t max_score;  // max(mat): bound on the score gained per read base
+    int32_t fast_ok;    // batch-level eligibility of the DPX fast path (matrix range, n >= 4, score_size)
+    int32_t fast_max_cols;
 };
 
-// counters[] slots
+// list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
+enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_BAND = 4, LIST_BAND_NEXT = 5,
+       LIST_FAST_FWD = 8, LIST_FAST_REV = 16 };
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3, CNT_BAND = 4, CNT_BAND_NEXT = 5,
-       CNT_CELLS_FWD = 6, CNT_CELLS_REV = 8, CNT_CELLS_BAND = 10, CNT_BAND_OVERFLOW = 12, CNT_CIGAR_OVERFLOW = 13 };
-// list[] slots
-enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_BAND = 4, LIST_BAND_NEXT = 5 };
+       CNT_FAST_FWD = 8, CNT_FAST_REV = 16,
+       CNT_CELLS_FWD = 32, CNT_CELLS_REV = 34, CNT_CELLS_BAND = 36, CNT_BAND_OVERFLOW = 38, CNT_CIGAR_OVERFLOW = 39,
+       CNT_FAST_DONE = 40, CNT_CERT_FAIL = 41, CNT_VERIFY_BYTE = 42, CNT_EXACT_JOBS = 43 };
+// p_state flags
+enum { PST_FAST = 1,        // forward result produced by the DPX fast path
+       PST_NEED_CERT = 2,   // word-mode result accepted provisionally: the 8-bit pass still has to be shown to overflow
+       PST_HAVE_WORD = 4 }; // 16-bit result already in place: the exact 8-bit pass only verifies the overflow
 
 __device__ __forceinline__ void list_push(int32_t* list, int32_t* counter, int32_t v) {
-    // warp-aggregated append
-    unsigned m = __activemask();
-    int leader = __ffs(m) - 1;
+    // warp-aggregated append; lanes are grouped by destination list (one call site may feed several lists)
+    const unsigned act = __activemask();
+    const unsigned m = __match_any_sync(act, (unsigned long long)(uintptr_t)counter);
+    const int leader = __ffs(m) - 1;
     int base = 0;
     if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, __popc(m));
     base = __shfl_sync(m, base, leader);

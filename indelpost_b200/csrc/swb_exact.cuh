@@ -38,7 +38,6 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
     typedef ExactTraits<MODE> TR;
     typedef typename TR::elem elem;
     constexpr int W = TR::W;
-    constexpr int GPW = 32 / W;                       // groups per warp
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -189,6 +188,7 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
     }
 
     if (!valid) return;
+    const unsigned GM = (W == 32) ? FULL : (((1u << W) - 1u) << (gw * W));   // from here on groups may diverge: group-scoped shuffles only
 
     // ---- smallest read index holding the maximum in the best column (ssw.c:341-349 / 543-551) --
     int end_read = rl - 1;
@@ -196,7 +196,7 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
         if ((int)Hb[j * W + gl] == best) { const int r = j + gl * segLen; if (r < end_read) end_read = r; }
     }
 #pragma unroll
-    for (int o = W / 2; o > 0; o >>= 1) end_read = min(end_read, __shfl_xor_sync(FULL, end_read, o, W));
+    for (int o = W / 2; o > 0; o >>= 1) end_read = min(end_read, __shfl_xor_sync(GM, end_read, o, W));
 
     if (gl == 0) {
         atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + (DIR ? CNT_CELLS_REV : CNT_CELLS_FWD)), (unsigned long long)cells * 1ull);
@@ -207,7 +207,7 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
         // ---- sub-optimal score: first strict maximum outside the mask (ssw.c:366-379 / 568-581) ----
         int s2 = 0, r2 = 0;
         if (!overflow) {
-            __syncwarp();
+            __syncwarp(GM);
             const int edgeL = max(end_ref - maskLen, 0);
             const int edgeR = min(end_ref + maskLen, cols) + (MODE ? 0 : 1);
             int bv = 0, bi = 0x7fffffff;
@@ -219,17 +219,22 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
             }
 #pragma unroll
             for (int o = W / 2; o > 0; o >>= 1) {
-                const int ov = __shfl_xor_sync(FULL, bv, o, W), oi = __shfl_xor_sync(FULL, bi, o, W);
+                const int ov = __shfl_xor_sync(GM, bv, o, W), oi = __shfl_xor_sync(GM, bi, o, W);
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
             if (bv > 0) { s2 = bv; r2 = bi; }
         }
         if (gl == 0) {
+            atomicAdd(d.counters + CNT_EXACT_JOBS, 1);
             if (MODE == 0 && overflow) {
                 // 8-bit pass overflowed (ssw.c:358, 844-852)
-                if (d.score_size == 2) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
+                if (d.p_state[p] & PST_HAVE_WORD) { /* verification only: the 16-bit result already stored stands */ }
+                else if (d.score_size == 2) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
                 else { r.status = SWB_ERR_BYTE_ONLY; }
             } else {
+                if (d.p_state[p] & PST_HAVE_WORD) atomicAdd(d.counters + CNT_VERIFY_BYTE, 1);   // the provisional 16-bit result was wrong: redo in 8-bit semantics
+                d.p_state[p] = 0;
+                r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.cigar_off = 0; r.flag = 0;
                 r.score1 = (uint16_t)best; r.ref_end1 = end_ref; r.read_end1 = end_read;
                 if (maskLen >= 15) { r.score2 = (uint16_t)s2; r.ref_end2 = r2; }      // ssw.c:864-870
                 else { r.score2 = 0; r.ref_end2 = -1; }

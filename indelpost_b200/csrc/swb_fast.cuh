@@ -1,0 +1,288 @@
+// swb_fast.cuh — DPX (s16x2) inter-sequence Smith-Waterman sweep for the pairs whose striped result is
+// provably plain Gotoh on the zero-padded read:
+//     gap_open > gap_extension, window without N, |mat| <= 7, maxScore*readLen <= 1023, readLen <= G*R.
+//
+// Work decomposition
+//   * the two 16-bit lanes of every register hold two DIFFERENT alignments (A in the low half, B in
+//     the high half): every DPX instruction updates two cells;
+//   * a group of G threads owns one such lane-pair; thread g keeps rows g*R .. g*R+R-1 of BOTH reads in
+//     registers (H, E, the per-row score table, the per-row key offset) and the group sweeps the window
+//     as a wavefront: at step t thread g is on column t-g and receives (H, F, column-best) of the row
+//     above from thread g-1 by __shfl_up.  No shared memory in the inner loop except one 16-bit selector
+//     per column.
+//   * substitution scores come from ONE PRMT per cell pair: each row holds a 4-byte table
+//     {s(A),s(C),s(G),s(T)} per read (two registers), the per-column selector picks the two bytes named by
+//     the two windows' bases and sign-extends them into the two 16-bit lanes.
+//
+// Number representation: every DP value is stored as 16*v + 0x4000 in its lane.
+//   * the bias keeps lanes positive, so `x - gap` is a plain 32-bit IADD (FMA pipe) with no borrow
+//     between lanes, leaving the ALU pipe to the DPX instructions (measured: 64 lanes/clk/SM each,
+//     profiles/dpx_microbench_r01.md);
+//   * the factor 16 leaves 4 tag bits: key = value - rowInThread orders cells by (score desc, row asc),
+//     which is exactly ssw.c's "smallest read index holding the maximum" rule (ssw.c:341-349,543-551);
+//     rows beyond the padded read get key offset 0x4000 and can never win.
+// Column maxima (needed for the sub-optimal score, ssw.c:366-379 / 568-581) are carried down the
+// wavefront as (value, row) and stored per column in shared memory by the last thread; best score, first
+// best column (ssw.c:325-333 / 530-534), mask rule and the reverse pass' "first column whose maximum
+// equals score1" (ssw.c:337/539) are resolved by a short scan after the sweep.
+#pragma once
+#include "swb_common.cuh"
+
+#define FAST_C      0x4000            // lane bias
+#define FAST_CPACK  0x40004000u
+#define FAST_SCALE  16
+#define FAST_G      16                // threads per lane-pair
+#define FAST_MAX_SCORE 1023           // (32767 - 0x4000) / 16
+
+__device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b) { uint32_t d; asm("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+// raw PRMT (default mode): selector nibble bit 3 = replicate the sign of the selected byte.  The __byte_perm intrinsic
+// masks the selector with 0x7777 and cannot express that.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
+// per-lane (= per alignment) parameters resolved at kernel start
+struct FastLane {
+    const int8_t* read; const int8_t* ref;
+    int L, Lp, ncols, go, ge, mask, target;   // Lp: rows that count (read padded to 8 or 16, ssw.c:169/391)
+    int p;                                    // pair index (-1: lane unused)
+};
+
+// job list entry j -> pairs (jobs[2j], jobs[2j+1]); an odd tail is paired with itself
+template <int R, int DIR>
+__global__ void __launch_bounds__(128)
+k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc)
+{
+    constexpr int G = FAST_G;
+    constexpr int BKT = R / 2 - 1;                               // read-length bucket this instantiation serves
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_rowtab[SWB_MAX_N];
+
+    const int npairs = *njobs_ptr;
+    const int ngroups = (npairs + 1) >> 1;
+    const int groupsPerBlock = blockDim.x / G;
+    if (blockIdx.x * groupsPerBlock >= ngroups) return;
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G;
+    const int groupInBlock = threadIdx.x / G;
+    const int grp = blockIdx.x * groupsPerBlock + groupInBlock;
+    const bool valid = grp < ngroups;
+
+    // per-read-base score table: byte nt = 16 * mat[nt][rb]  (qP_word's profile cell, ssw.c:402, scaled)
+    if (threadIdx.x < d.n) {
+        uint32_t t = 0;
+        for (int nt = 0; nt < 4; ++nt) t |= (uint32_t)(uint8_t)(int8_t)(FAST_SCALE * d.mat[nt * d.n + threadIdx.x]) << (8 * nt);
+        s_rowtab[threadIdx.x] = t;
+    }
+
+    FastLane ln[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        FastLane& q = ln[s];
+        q.p = -1; q.L = 0; q.Lp = 0; q.ncols = 0; q.go = 1; q.ge = 0; q.mask = 15; q.target = -1; q.read = nullptr; q.ref = nullptr;
+        if (valid) {
+            int idx = 2 * grp + s;
+            if (idx >= npairs) idx = 2 * grp;                   // odd tail: duplicate lane A (its result is written once)
+            const int p = jobs[idx];
+            q.p = (s == 1 && 2 * grp + 1 >= npairs) ? -1 : p;
+            q.read = d.reads + d.p_roff[p];
+            q.ref = d.windows + d.p_woff[p];
+            q.go = d.gap_open[p]; q.ge = d.gap_ext[p]; q.mask = d.p_mask[p];
+            const int pad = d.p_mode[p] ? 8 : 16;               // p_mode is the semantic chosen by k_classify: 1 word, 0 byte
+            if (DIR == 0) { q.L = d.p_rlen[p]; q.ncols = d.p_wlen[p]; }
+            else {
+                const swb_result& r = d.res[p];
+                q.L = r.read_end1 + 1; q.ncols = r.ref_end1 + 1; q.target = r.score1;
+            }
+            q.Lp = (q.L + pad - 1) / pad * pad;
+        }
+    }
+    __syncthreads();
+
+    // ---- shared memory: per group, per column: selector (u16), column best value (u32), its row (u32) ----
+    unsigned char* gbase = smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * 10);
+    uint32_t* colv = reinterpret_cast<uint32_t*>(gbase);
+    uint32_t* colr = colv + colAlloc;
+    uint16_t* selS = reinterpret_cast<uint16_t*>(colr + colAlloc);
+
+    const int maxcols = max(ln[0].ncols, ln[1].ncols);
+    for (int c = g; c < maxcols; c += G) {
+        int bA = 0, bB = 0;
+        if (c < ln[0].ncols) bA = DIR ? ln[0].ref[ln[0].ncols - 1 - c] : ln[0].ref[c];
+        if (c < ln[1].ncols) bB = DIR ? ln[1].ref[ln[1].ncols - 1 - c] : ln[1].ref[c];
+        // PRMT selector: byte0 = tabA[bA], byte1 = sign(byte0), byte2 = tabB[bB], byte3 = sign(byte2)
+        selS[c] = (uint16_t)(0xC480u | (uint32_t)(bA & 3) * 0x11u | (uint32_t)(bB & 3) * 0x1100u);
+    }
+
+    // ---- per-row registers -------------------------------------------------------------------------
+    uint32_t H[R], E[R], tA[R], tB[R], dk[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int r = g * R + k;
+        uint32_t a = 0, b = 0;
+        if (r < ln[0].L) a = s_rowtab[DIR ? ln[0].read[ln[0].L - 1 - r] : ln[0].read[r]];
+        if (r < ln[1].L) b = s_rowtab[DIR ? ln[1].read[ln[1].L - 1 - r] : ln[1].read[r]];
+        tA[k] = a; tB[k] = b;
+        dk[k] = pack2(r < ln[0].Lp ? k : FAST_C, r < ln[1].Lp ? k : FAST_C);
+        H[k] = FAST_CPACK; E[k] = FAST_CPACK;
+    }
+    const uint32_t goP = pack2(FAST_SCALE * ln[0].go, FAST_SCALE * ln[1].go);
+    const uint32_t ngeP = pack2(-FAST_SCALE * ln[0].ge, -FAST_SCALE * ln[1].ge);
+    const uint32_t rowBase = pack2(g * R, g * R);
+    __syncwarp();
+
+    // warp-uniform step count
+    int nsteps = maxcols + G - 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(FULL, nsteps, o));
+    if (!valid) nsteps = max(nsteps, 0);
+
+    uint32_t outH = FAST_CPACK, outF = FAST_CPACK, outV = 0, outRow = 0, prevInH = FAST_CPACK;
+    const uint32_t targetV = pack2(ln[0].target >= 0 ? FAST_SCALE * ln[0].target + FAST_C : 0x7fff, ln[1].target >= 0 ? FAST_SCALE * ln[1].target + FAST_C : 0x7fff);
+    bool done = false;                                         // reverse pass: both lanes have hit their target
+
+    for (int t = 0; t < nsteps; ++t) {
+        uint32_t inH = __shfl_up_sync(FULL, outH, 1, G);
+        uint32_t inF = __shfl_up_sync(FULL, outF, 1, G);
+        uint32_t inV = __shfl_up_sync(FULL, outV, 1, G);
+        uint32_t inRow = __shfl_up_sync(FULL, outRow, 1, G);
+        if (g == 0) { inH = FAST_CPACK; inF = FAST_CPACK; inV = 0; inRow = 0; }
+        const int c = t - g;
+        if (c >= 0 && c < maxcols && !done) {
+            const uint32_t sel = selS[c];
+            uint32_t F = inF, hd = prevInH, cm = 0;
+            prevInH = inH;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const uint32_t s = prmt(tA[k], tB[k], sel);
+                uint32_t h = __viaddmax_s16x2(hd, s, E[k]);                  // max(Hdiag + s, E)
+                h = __vimax3_s16x2(h, F, FAST_CPACK);                        // max(., F, 0)
+                hd = H[k]; H[k] = h;
+                const uint32_t key = h - dk[k];                              // FMA-pipe IADD, no lane borrow
+                const uint32_t hg = h - goP;
+                E[k] = __viaddmax_s16x2(E[k], ngeP, hg);                     // max(E - ge, H - go)
+                F = __viaddmax_s16x2(F, ngeP, hg);                           // max(F - ge, H - go)
+                cm = vmax2(cm, key);
+            }
+            outH = H[R - 1]; outF = F;
+            // local column best -> (value, absolute row); merge with the rows above (they win ties)
+            const uint32_t lv = (cm + 0x000F000Fu) & 0xFFF0FFF0u;
+            const uint32_t lrow = lv - cm + rowBase;
+            const uint32_t x = (inV | 0x80008000u) - lv;                     // lane bit15 set <=> inV >= lv
+            const uint32_t keep = prmt(x, 0u, 0xBB99u);                 // 0xFFFF in lanes where the upstream value stays
+            outV = vmax2(inV, lv);
+            outRow = (inRow & keep) | (lrow & ~keep);
+            if (g == G - 1) { colv[c] = outV; colr[c] = outRow; }
+        }
+        if (DIR == 1 && (t & 31) == 31) {
+            // every 32 steps: have both lanes of this group seen a column whose maximum equals score1?
+            __syncwarp();
+            bool hitA = ln[0].p < 0 && ln[1].p < 0, hitB = true;
+            const int hi = min(t - (G - 1), maxcols - 1);
+            bool a = false, b = false;
+            for (int c2 = g; c2 <= hi; c2 += G) {
+                const uint32_t v = colv[c2] ^ targetV;
+                if (c2 < ln[0].ncols && (v & 0xffffu) == 0) a = true;
+                if (c2 < ln[1].ncols && (v >> 16) == 0) b = true;
+            }
+            const unsigned ba = __ballot_sync(FULL, a), bb = __ballot_sync(FULL, b);
+            const unsigned gm = ((1u << G) - 1u) << ((lane / G) * G);
+            hitA = hitA || (ba & gm) != 0 || ln[0].p < 0 || hi >= ln[0].ncols - 1;
+            hitB = (bb & gm) != 0 || ln[1].p < 0 || hi >= ln[1].ncols - 1;
+            done = !valid || (hitA && hitB);
+            if (__all_sync(FULL, done)) break;
+        }
+    }
+    __syncwarp();
+    if (!valid) return;
+
+    // ---- post-sweep scans (per lane) -------------------------------------------------------------------
+    const unsigned GM = ((1u << G) - 1u) << ((lane / G) * G);      // shuffles below are group-scoped: the two groups of a warp may diverge
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const FastLane& q = ln[s];
+        if (q.p < 0) continue;
+        const int sh = 16 * s;
+        const int p = q.p;
+        swb_result& r = d.res[p];
+        const bool wordSem = d.p_mode[p] != 0;
+        if (DIR == 0) {
+            // best score and first column reaching it
+            int bv = 0, bc = 0x7fffffff;
+            for (int c = g; c < q.ncols; c += G) {
+                const int v = (int)((colv[c] >> sh) & 0xffffu);
+                if (v > bv) { bv = v; bc = c; }
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const int ov = __shfl_xor_sync(GM, bv, o, G), oc = __shfl_xor_sync(GM, bc, o, G);
+                if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+            }
+            const int T = bv > FAST_C ? (bv - FAST_C) / FAST_SCALE : 0;
+            int end_ref, end_read;
+            if (T > 0) { end_ref = bc; end_read = min((int)((colr[bc] >> sh) & 0xffffu), q.L - 1); }
+            else { end_ref = wordSem ? 0 : -1; end_read = 0; }                      // ssw.c:427 / 220
+            // sub-optimal score outside the mask (ssw.c:366-379 byte, 568-581 word)
+            const int edgeL = max(end_ref - q.mask, 0);
+            const int edgeR = min(end_ref + q.mask, q.ncols) + (wordSem ? 0 : 1);
+            int sv = FAST_C, si = 0x7fffffff;
+            for (int c = g; c < q.ncols; c += G) {
+                if (c < edgeL || c >= edgeR) {
+                    const int v = (int)((colv[c] >> sh) & 0xffffu);
+                    if (v > sv) { sv = v; si = c; }
+                }
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const int ov = __shfl_xor_sync(GM, sv, o, G), oi = __shfl_xor_sync(GM, si, o, G);
+                if (ov > sv || (ov == sv && oi < si)) { sv = ov; si = oi; }
+            }
+            const int s2 = sv > FAST_C ? (sv - FAST_C) / FAST_SCALE : 0;
+            const int r2 = s2 > 0 ? si : 0;
+            if (g == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + CNT_CELLS_FWD), (unsigned long long)q.Lp * q.ncols);
+                const int limit = 255 - d.bias;                                    // 8-bit pass overflows at max + bias >= 255 (ssw.c:327)
+                bool accept;
+                if (wordSem) accept = d.score_size == 1 || T >= limit;            // else the result is a byte-mode one: exact path decides
+                else accept = T < limit && T < 128 + q.go + q.ge;                  // safe zone of the signed lazy-F test
+                if (!accept) {
+                    d.p_mode[p] = 0; d.p_state[p] = 0;
+                    list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
+                } else {
+                    r.score1 = (uint16_t)T; r.ref_end1 = end_ref; r.read_end1 = end_read;
+                    if (q.mask >= 15) { r.score2 = (uint16_t)s2; r.ref_end2 = r2; } else { r.score2 = 0; r.ref_end2 = -1; }
+                    d.p_state[p] = (wordSem && d.score_size == 2) ? (PST_FAST | PST_NEED_CERT) : PST_FAST;
+                    atomicAdd(d.counters + CNT_FAST_DONE, 1);
+                    const bool scoreOnly = d.flag == 0 || (d.flag == 2 && T < (int)d.filters);     // ssw.c:872
+                    if (!scoreOnly) list_push(d.list[LIST_FAST_REV + BKT], d.counters + CNT_FAST_REV + BKT, p);
+                }
+            }
+        } else {
+            // first column (scanning away from ref_end1) whose maximum equals score1 (ssw.c:337 / 539)
+            const int tv = (int)((targetV >> sh) & 0xffffu);
+            int hc = 0x7fffffff;
+            for (int c = g; c < q.ncols; c += G) {
+                const int v = (int)((colv[c] >> sh) & 0xffffu);
+                if (v == tv) { hc = c; break; }
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) hc = min(hc, __shfl_xor_sync(GM, hc, o, G));
+            if (g == 0) {
+                if (hc == 0x7fffffff || q.target <= 0) {
+                    // no column reaches score1 (or score 0 corner): let the exact path reproduce ssw.c literally
+                    const int md = d.p_mode[p];
+                    d.p_state[p] &= ~PST_FAST;
+                    list_push(d.list[md ? LIST_WORD_REV : LIST_BYTE_REV], d.counters + (md ? CNT_WORD_REV : CNT_BYTE_REV), p);
+                } else {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + CNT_CELLS_REV), (unsigned long long)q.Lp * (hc + 1));
+                    r.ref_begin1 = r.ref_end1 - hc;                                 // ssw.c:885-886
+                    r.read_begin1 = r.read_end1 - (int)((colr[hc] >> sh) & 0xffffu);
+                    const int f = d.flag;
+                    const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
+                                         ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));
+                    if (!noCigar) list_push(d.list[LIST_BAND], d.counters + CNT_BAND, p);
+                }
+            }
+        }
+    }
+}

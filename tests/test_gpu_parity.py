@@ -122,3 +122,29 @@ def test_c_abi_single_pair_entry_points():
         assert cg == [int(v) for v in ao[int(ro["cigar_off"][p]) : int(ro["cigar_off"][p]) + int(ro["cigar_len"][p])]]
         lib.align_destroy(a)
         lib.init_destroy(prof)
+
+
+@pytest.mark.parametrize("cfg", [FUZZ[0], FUZZ[2], FUZZ[3]], ids=["150x400", "mixed", "short"])
+def test_gpu_exact_path_alone_matches_oracle(cfg, monkeypatch):
+    """the exact striped-emulation kernels must stay bit-exact on inputs the DPX fast path normally takes"""
+    from gpuutil import gpu_align
+
+    monkeypatch.setenv("SWB200_NO_FAST", "1")
+    b = T.make_pairs(**{**cfg, "n_pairs": 1500})
+    ro, ao = T.oracle().align_batch(b)
+    rg, ag, tm = gpu_align(b)
+    assert tm["n_fast"] == 0
+    T.compare(rg, ag, ro, ao, what=f"exact-only gpu vs oracle {cfg}")
+
+
+def test_gpu_fast_path_is_used_for_the_headline_workload():
+    from gpuutil import gpu_align
+
+    b = T.make_pairs_fast(20000, 150, 400, seed=5)
+    rg, ag, tm = gpu_align(b)
+    assert tm["n_fast"] > 0.9 * b.n_pairs, tm
+    sub = np.arange(0, b.n_pairs, 10)
+    ro, ao = T.oracle().align_batch(b.subset(sub))
+    rs = rg[sub].copy()
+    # re-base cigar offsets of the subset for the comparison
+    T.compare(rs, ag, ro, ao, what="fast path vs oracle (cfg2)")
