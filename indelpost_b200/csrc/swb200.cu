@@ -184,6 +184,7 @@ extern "C" swb_ctx* swb_create(int device) {
     cudaFuncSetAttribute(k_exact<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(k_exact<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(k_exact<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+    cudaFuncSetAttribute(k_band<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWB_BAND_SMEM);
     return c;
 }
 
@@ -383,9 +384,9 @@ static int run_band_rounds(swb_ctx* c) {
         CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
-        const int blocks = (njobs + 127) / 128;
-        k_band<true><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
-        k_band<false><<<blocks, 128, 0, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
+        const int blocks = (njobs + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
+        k_band<true><<<blocks, SWB_BAND_THREADS, SWB_BAND_SMEM, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
+        k_band<false><<<blocks, SWB_BAND_THREADS, 0, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
         c->tm.n_launches += 2;
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "band")) return -1;

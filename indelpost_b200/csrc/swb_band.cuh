@@ -7,28 +7,32 @@
 // When the band is wider than the matrix those details decide what a cell reads as its upper neighbour,
 // so a "clean" formulation would not be bit-exact.
 //
-// Direction information (3 bytes per cell in the reference) is packed into one byte per cell and kept in
-// a global scratch arena; each thread bump-allocates (2w+1)*readLen bytes.  Band doubling is done in
+// Direction information (3 bytes per cell in the reference) is packed into 4 bits per cell, 8 cells per
+// 32-bit word, and kept in a global scratch arena (one word store per 8 cells instead of a 32-byte sector
+// per cell); each thread bump-allocates ceil((2w+1)/8)*4*readLen bytes.  The three rolling rows live in
+// shared memory laid out [slot][thread], which is bank-conflict free whatever slot each thread touches.  Band doubling is done in
 // rounds: a pair whose DP maximum is still below score1 is re-queued with twice the width (about 0.5 %
 // of realistic pairs).  The traceback is walked twice (count, then emit) so the CIGAR
 // can be written, already reversed, straight into the output arena.
 #pragma once
 #include "swb_common.cuh"
 
-#define SWB_BAND_LOCAL_BW 32                         // bands up to this half-width keep their rows in local memory
+#define SWB_BAND_LOCAL_BW 16                         // bands up to this half-width keep their rows in shared memory
 #define SWB_BAND_LOCAL_W (2 * SWB_BAND_LOCAL_BW + 4)
+#define SWB_BAND_THREADS 128
+#define SWB_BAND_SMEM (3 * SWB_BAND_LOCAL_W * SWB_BAND_THREADS * 4)
 
 __device__ __forceinline__ int band_x(int w, int i) { int x = i - w; return x > 0 ? x : 0; }
 
 struct BandGeom {
-    int w, width_d, refLen, readLen;
+    int w, width_d, strideW, refLen, readLen;           // strideW: 32-bit words per band row
     __device__ __forceinline__ int beg(int i) const { int b = i - w; return b > 0 ? b : 0; }
     __device__ __forceinline__ int end(int i) const { int e = i + w; return e < refLen - 1 ? e : refLen - 1; }
 };
 
 // value the reference would read at direction_line[set_d(i, j, state)] (ssw.c:680-681); 0 = not a
 // computed cell (the reference reads uninitialised memory there; we report a traceback error)
-__device__ __forceinline__ int band_dir_at(const uint8_t* dir, const BandGeom& g, int i, int j, int state) {
+__device__ __forceinline__ int band_dir_at(const uint32_t* dir, const BandGeom& g, int i, int j, int state) {
     int x = j - band_x(g.w, i);
     int ii = i, st = state;
     if (x < 0 || x >= g.width_d) {
@@ -40,7 +44,7 @@ __device__ __forceinline__ int band_dir_at(const uint8_t* dir, const BandGeom& g
     }
     const int jj = x + band_x(g.w, ii);
     if (jj < g.beg(ii) || jj > g.end(ii)) return 0;
-    const int b = dir[(size_t)ii * g.width_d + x];
+    const int b = (int)((dir[(size_t)ii * g.strideW + (x >> 3)] >> (4 * (x & 7))) & 15u);
     const int de = 2 + (b & 1), df = 4 + ((b >> 1) & 1);
     if (st == 0) return de;
     if (st == 1) return df;
@@ -49,7 +53,7 @@ __device__ __forceinline__ int band_dir_at(const uint8_t* dir, const BandGeom& g
 }
 
 // walk the traceback; if out != nullptr write the ops reversed into out[0..total)
-__device__ __forceinline__ int band_traceback(const uint8_t* dir, const BandGeom& g, uint32_t* out, int total) {
+__device__ __forceinline__ int band_traceback(const uint32_t* dir, const BandGeom& g, uint32_t* out, int total) {
     int i = g.readLen - 1, j = g.refLen - 1;
     int e = 0, l = 0, state = 2;
     int op = 0, prev_op = 0;                           // 0 M, 1 I, 2 D  (BAM op codes)
@@ -80,8 +84,14 @@ __device__ __forceinline__ int band_traceback(const uint8_t* dir, const BandGeom
     return l;
 }
 
+// rolling-row accessor: shared memory [slot][thread] (LOCAL) or a private global array (wide bands)
+template <bool LOCAL> struct BandRow {
+    int* p;
+    __device__ __forceinline__ int& operator[](int u) const { return LOCAL ? p[u * SWB_BAND_THREADS] : p[u]; }
+};
+
 template <bool LOCAL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SWB_BAND_THREADS)
 k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int32_t* nextList, int32_t* nextCount, int round)
 {
     const int njobs = *njobs_ptr;
@@ -98,7 +108,7 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     else { bw = d.t_bw[p]; best = d.t_best[p]; }
     const bool wantLocal = bw <= SWB_BAND_LOCAL_BW;
     if (wantLocal != LOCAL) return;                    // the other instantiation handles it
-    g.w = bw; g.width_d = 2 * bw + 1;
+    g.w = bw; g.width_d = 2 * bw + 1; g.strideW = (g.width_d + 7) >> 3;
     const int width = 2 * bw + 3;
     const int len = g.refLen > g.readLen ? g.refLen : g.readLen;
     const int score = r.score1;
@@ -111,10 +121,10 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     const int8_t* ref = d.windows + d.p_woff[p] + (ubRef ? 0 : r.ref_begin1);
     const int8_t* read = d.reads + d.p_roff[p] + (r.read_begin1 < 0 ? 0 : r.read_begin1);
 
-    // ---- scratch: direction bytes (+ the three row buffers when the band is too wide for local memory)
-    const long long dirBytes = (long long)g.width_d * (g.readLen > 0 ? g.readLen : 1);
+    // ---- scratch: packed direction words (+ the three rolling rows when the band is too wide for shared memory)
+    const long long dirBytes = (long long)g.strideW * 4 * (g.readLen > 0 ? g.readLen : 1);
     const long long rowBytes = LOCAL ? 0 : 3ll * (width + 1) * 4;
-    const long long need = ((dirBytes + 3) & ~3ll) + rowBytes;
+    const long long need = dirBytes + rowBytes;
     d.t_bw[p] = bw; d.t_best[p] = best;
     const unsigned long long off = atomicAdd(&d.bump[0], (unsigned long long)need);
     if ((long long)off + need > d.band_cap) {          // out of scratch: retry in the next round
@@ -122,16 +132,19 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         list_push(nextList, nextCount, p);
         return;
     }
-    uint8_t* dir = d.band + off;
-    int lh[LOCAL ? SWB_BAND_LOCAL_W : 1], le[LOCAL ? SWB_BAND_LOCAL_W : 1], lc[LOCAL ? SWB_BAND_LOCAL_W : 1];
-    int* hPrev; int* ePrev; int* hCur;
-    if (LOCAL) { hPrev = lh; ePrev = le; hCur = lc; }
-    else {
-        hPrev = reinterpret_cast<int*>(dir + ((dirBytes + 3) & ~3ll));
-        ePrev = hPrev + (width + 1); hCur = ePrev + (width + 1);
+    uint32_t* dir = reinterpret_cast<uint32_t*>(d.band + off);
+    extern __shared__ int band_smem[];
+    BandRow<LOCAL> hPrev, ePrev, hCur;
+    if (LOCAL) {
+        hPrev.p = band_smem + threadIdx.x;
+        ePrev.p = hPrev.p + SWB_BAND_LOCAL_W * SWB_BAND_THREADS;
+        hCur.p = ePrev.p + SWB_BAND_LOCAL_W * SWB_BAND_THREADS;
+    } else {
+        hPrev.p = reinterpret_cast<int*>(d.band + off + dirBytes);
+        ePrev.p = hPrev.p + (width + 1); hCur.p = ePrev.p + (width + 1);
     }
     // the reference's buffers are realloc'ed across widenings and not cleared; every slot it reads is
-    // written first within an iteration except where it reads uninitialised memory — start from zeros
+    // written first within an iteration except where it reads uninitialised memory -- start from zeros
     for (int j = 0; j <= width; ++j) { hPrev[j] = 0; ePrev[j] = 0; hCur[j] = 0; }
 
     long long cells = 0;
@@ -141,7 +154,8 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         int f = 0, u = 0;
         hPrev[0] = 0; ePrev[0] = 0; hPrev[edge] = 0; ePrev[edge] = 0; hCur[0] = 0;     // ssw.c:633
         const int xi = band_x(bw, i), xp = band_x(bw, i - 1);
-        uint8_t* line = dir + (size_t)i * g.width_d;
+        uint32_t* line = dir + (size_t)i * g.strideW;
+        uint32_t word = 0;
         const int rb = read[i];
         for (int j = beg; j <= end; ++j) {
             u = j - xi + 1;                            // set_u(u, w, i, j)
@@ -166,8 +180,11 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             hCur[u] = h;
             if (h > best) best = h;                    // ssw.c:661
             const int sel = gmax <= m ? 0 : (e1 > f1 ? 1 : 2);       // ssw.c:663-664
-            line[j - xi] = (uint8_t)(bitE | (bitF << 1) | (sel << 2));
+            const int x = j - xi;
+            word |= (uint32_t)(bitE | (bitF << 1) | (sel << 2)) << (4 * (x & 7));
+            if ((x & 7) == 7) { line[x >> 3] = word; word = 0; }
         }
+        if (end >= beg && ((end - xi) & 7) != 7) line[(end - xi) >> 3] = word;
         cells += end - beg + 1;
         for (int j = 1; j <= u; ++j) hPrev[j] = hCur[j];             // ssw.c:666
     }

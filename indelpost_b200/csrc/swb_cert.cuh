@@ -10,6 +10,19 @@
 // walk the CIGAR, keep a running (Kadane) score that restarts after every insertion.  Pairs without a
 // certificate are re-run through the exact 8-bit emulation (k_exact<0,0>), which either confirms the
 // overflow or yields the byte-mode result.
+//
+// Insertions the running score may continue across (everything else restarts it):
+//  (a) the gap opens and ends inside ONE striped segment (rows r with the same r / segLen, segLen =
+//      ceil(readLen/16), ssw.c:169): the main loop carries vF through those rows (ssw.c:294-295), the
+//      lazy loop is not involved;
+//  (b) every value of the chain is >= 128 + go.  The lazy loop goes on while some lane has
+//      (int8)(vF - ge) > (int8)(H - go) (ssw.c:309-311) with H >= vF (ssw.c:306); a live chain is mis-seen
+//      only if vF - ge >= 128 > H - go, i.e. only for vF in [128 + ge, 127 + go].  The vF a lane carries is
+//      the maximum over all paths, hence >= the value on our path; if ours never drops below 128 + go
+//      neither does the true one, both operands of the test are >= 128 and the signed compare orders
+//      them correctly.
+// A deletion right after an insertion also restarts: E is computed from H before the lazy correction
+// (ssw.c:287-291, 301).
 #pragma once
 #include "swb_common.cuh"
 
@@ -29,6 +42,8 @@ __global__ void k_certify(SwbDev d, int32_t p0, int32_t p1)
         const int go = d.gap_open[p], ge = d.gap_ext[p], n = d.n;
         const uint32_t* cg = d.cigar + r.cigar_off;
         int i = r.read_begin1, j = r.ref_begin1, S = 0;
+        const int segLen = (L + 15) / 16;
+        bool afterIns = false;
         for (int k = 0; k < r.cigar_len && !ok; ++k) {
             const int len = (int)(cg[k] >> 4), op = (int)(cg[k] & 15);
             if (op == 0) {
@@ -38,13 +53,21 @@ __global__ void k_certify(SwbDev d, int32_t p0, int32_t p1)
                     if (S >= limit) { ok = true; break; }
                 }
             } else if (op == 2) {           // deletion = horizontal gap (E): stays inside the F-free recurrence
+                if (afterIns) S = 0;
                 S -= go + (len - 1) * ge;
                 if (S < 0) S = 0;
                 j += len;
-            } else {                        // insertion = vertical gap (F): restart
-                S = 0;
+            } else {                        // insertion = vertical gap (F) over read rows i .. i+len-1, opened from row i-1
+                const int last = S - go - (len - 1) * ge;
+                const bool sameSeg = i >= 1 && (i - 1) / segLen == (i + len - 1) / segLen;
+                const bool above = last >= 128 + go;
+                if (sameSeg || above) { S = last; if (S < 0) S = 0; }
+                else S = 0;
+                afterIns = true;
                 i += len;
+                continue;
             }
+            afterIns = false;
         }
     }
     if (ok) { d.p_state[p] = st & ~PST_NEED_CERT; return; }

@@ -19,8 +19,10 @@
 //     between lanes, leaving the ALU pipe to the DPX instructions (measured: 64 lanes/clk/SM each,
 //     profiles/dpx_microbench_r01.md);
 //   * the factor 16 leaves 4 tag bits: key = value - rowInThread orders cells by (score desc, row asc),
-//     which is exactly ssw.c's "smallest read index holding the maximum" rule (ssw.c:341-349,543-551);
-//     rows beyond the padded read get key offset 0x4000 and can never win.
+//     which is exactly ssw.c's "smallest read index holding the maximum" rule (ssw.c:341-349,543-551).
+//   * rows are END-aligned: the padded read occupies the last Lp of the G*R row slots of its lane; the
+//     slots before it get a table of -128 for every base, which pins their H to 0 (= the H[-1][.] = 0
+//     boundary of row 0), so there are no dead rows and the key offset of row k is the immediate k.
 // Column maxima (needed for the sub-optimal score, ssw.c:366-379 / 568-581) are carried down the
 // wavefront as (value, row) and stored per column in shared memory by the last thread; best score, first
 // best column (ssw.c:325-333 / 530-534), mask rule and the reverse pass' "first column whose maximum
@@ -43,7 +45,7 @@ __device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo
 // per-lane (= per alignment) parameters resolved at kernel start
 struct FastLane {
     const int8_t* read; const int8_t* ref;
-    int L, Lp, ncols, go, ge, mask, target;   // Lp: rows that count (read padded to 8 or 16, ssw.c:169/391)
+    int L, Lp, off, ncols, go, ge, mask, target;   // Lp: rows that count (read padded to 8 or 16, ssw.c:169/391); off = G*R - Lp
     int p;                                    // pair index (-1: lane unused)
 };
 
@@ -79,7 +81,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         FastLane& q = ln[s];
-        q.p = -1; q.L = 0; q.Lp = 0; q.ncols = 0; q.go = 1; q.ge = 0; q.mask = 15; q.target = -1; q.read = nullptr; q.ref = nullptr;
+        q.p = -1; q.L = 0; q.Lp = 0; q.off = G * R; q.ncols = 0; q.go = 1; q.ge = 0; q.mask = 15; q.target = -1; q.read = nullptr; q.ref = nullptr;
         if (valid) {
             int idx = 2 * grp + s;
             if (idx >= npairs) idx = 2 * grp;                   // odd tail: duplicate lane A (its result is written once)
@@ -95,6 +97,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                 q.L = r.read_end1 + 1; q.ncols = r.ref_end1 + 1; q.target = r.score1;
             }
             q.Lp = (q.L + pad - 1) / pad * pad;
+            q.off = G * R - q.Lp;
         }
     }
     __syncthreads();
@@ -114,21 +117,24 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         selS[c] = (uint16_t)(0xC480u | (uint32_t)(bA & 3) * 0x11u | (uint32_t)(bB & 3) * 0x1100u);
     }
 
-    // ---- per-row registers -------------------------------------------------------------------------
-    uint32_t H[R], E[R], tA[R], tB[R], dk[R];
+    // ---- per-row registers (slot g*R+k of the lane holds read row slot - off) -------------------------
+    uint32_t H[R], E[R], tA[R], tB[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        const int r = g * R + k;
-        uint32_t a = 0, b = 0;
-        if (r < ln[0].L) a = s_rowtab[DIR ? ln[0].read[ln[0].L - 1 - r] : ln[0].read[r]];
-        if (r < ln[1].L) b = s_rowtab[DIR ? ln[1].read[ln[1].L - 1 - r] : ln[1].read[r]];
+        const int rA = g * R + k - ln[0].off, rB = g * R + k - ln[1].off;
+        uint32_t a = 0, b = 0;                                   // pad rows score 0 against everything (ssw.c:402)
+        if (rA < 0) a = 0x80808080u; else if (rA < ln[0].L) a = s_rowtab[DIR ? ln[0].read[ln[0].L - 1 - rA] : ln[0].read[rA]];
+        if (rB < 0) b = 0x80808080u; else if (rB < ln[1].L) b = s_rowtab[DIR ? ln[1].read[ln[1].L - 1 - rB] : ln[1].read[rB]];
         tA[k] = a; tB[k] = b;
-        dk[k] = pack2(r < ln[0].Lp ? k : FAST_C, r < ln[1].Lp ? k : FAST_C);
         H[k] = FAST_CPACK; E[k] = FAST_CPACK;
     }
-    const uint32_t goP = pack2(FAST_SCALE * ln[0].go, FAST_SCALE * ln[1].go);
-    const uint32_t ngeP = pack2(-FAST_SCALE * ln[0].ge, -FAST_SCALE * ln[1].ge);
-    const uint32_t rowBase = pack2(g * R, g * R);
+    uint32_t goP = pack2(FAST_SCALE * ln[0].go, FAST_SCALE * ln[1].go);
+    uint32_t ngeP = pack2(-FAST_SCALE * ln[0].ge, -FAST_SCALE * ln[1].ge);
+    uint32_t rowBase = pack2(g * R, g * R);
+    // keep the loop invariants in registers (ptxas otherwise rematerialises them every step)
+    asm volatile("" : "+r"(goP), "+r"(ngeP), "+r"(rowBase));
+#pragma unroll
+    for (int k = 0; k < R; ++k) asm volatile("" : "+r"(tA[k]), "+r"(tB[k]));
     __syncwarp();
 
     // warp-uniform step count
@@ -155,14 +161,13 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 const uint32_t s = prmt(tA[k], tB[k], sel);
-                uint32_t h = __viaddmax_s16x2(hd, s, E[k]);                  // max(Hdiag + s, E)
-                h = __vimax3_s16x2(h, F, FAST_CPACK);                        // max(., F, 0)
+                uint32_t h = __viaddmax_s16x2(hd, s, E[k]);                      // max(Hdiag + s, E)
+                h = __vimax3_s16x2(h, F, FAST_CPACK);                            // max(., F, 0)
                 hd = H[k]; H[k] = h;
-                const uint32_t key = h - dk[k];                              // FMA-pipe IADD, no lane borrow
-                const uint32_t hg = h - goP;
-                E[k] = __viaddmax_s16x2(E[k], ngeP, hg);                     // max(E - ge, H - go)
-                F = __viaddmax_s16x2(F, ngeP, hg);                           // max(F - ge, H - go)
-                cm = vmax2(cm, key);
+                cm = __viaddmax_s16x2(h, (uint32_t)((-k) & 0xffff) * 0x00010001u, cm);      // column best over keys (value - rowInThread)
+                const uint32_t hg = h - goP;                                     // FMA-pipe IADD; no lane borrow: h >= 0x4000 > 16*go
+                E[k] = __viaddmax_s16x2(E[k], ngeP, hg);                         // max(E - ge, H - go)
+                F = __viaddmax_s16x2(F, ngeP, hg);                               // max(F - ge, H - go)
             }
             outH = H[R - 1]; outF = F;
             // local column best -> (value, absolute row); merge with the rows above (they win ties)
@@ -220,7 +225,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             }
             const int T = bv > FAST_C ? (bv - FAST_C) / FAST_SCALE : 0;
             int end_ref, end_read;
-            if (T > 0) { end_ref = bc; end_read = min((int)((colr[bc] >> sh) & 0xffffu), q.L - 1); }
+            if (T > 0) { end_ref = bc; end_read = min((int)((colr[bc] >> sh) & 0xffffu) - q.off, q.L - 1); }
             else { end_ref = wordSem ? 0 : -1; end_read = 0; }                      // ssw.c:427 / 220
             // sub-optimal score outside the mask (ssw.c:366-379 byte, 568-581 word)
             const int edgeL = max(end_ref - q.mask, 0);
@@ -276,7 +281,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                 } else {
                     atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + CNT_CELLS_REV), (unsigned long long)q.Lp * (hc + 1));
                     r.ref_begin1 = r.ref_end1 - hc;                                 // ssw.c:885-886
-                    r.read_begin1 = r.read_end1 - (int)((colr[hc] >> sh) & 0xffffu);
+                    r.read_begin1 = r.read_end1 - ((int)((colr[hc] >> sh) & 0xffffu) - q.off);
                     const int f = d.flag;
                     const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
                                          ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));

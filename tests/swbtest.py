@@ -457,3 +457,55 @@ def make_pairs_fast(n_pairs: int, read_len: int = 150, win_len: int = 400, *, se
         np.arange(n_pairs, dtype=np.int32), pair_win,
         np.full(n_pairs, go, dtype=np.uint8), np.full(n_pairs, ge, dtype=np.uint8), mat=dna_matrix(match, mismatch),
     )
+
+
+def make_overflow_zone_pairs(n_pairs: int, seed: int = 1) -> Batch:
+    """Targeted stress for the 8-bit/16-bit escalation decision (ssw.c:842-847): reads whose best
+    alignment needs an insertion placed where the running score is around 128 (the zone in which the
+    signed lazy-F exit test of ssw.c:311 can drop a vertical gap), so that whether the 8-bit pass
+    overflows depends on that quirk.  Mixed gap penalties from indelPost's grid."""
+    rng = np.random.default_rng(seed)
+    grid = [(3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0)]
+    wins, reads, go, ge = [], [], [], []
+    for p in range(n_pairs):
+        wl = int(rng.integers(250, 420))
+        W = rng.integers(0, 4, size=wl, dtype=np.int8)
+        L = int(rng.integers(86, 170))
+        q = int(rng.integers(30, min(100, L - 10)))           # insertion point: left flank score ~ 3q
+        k = int(rng.integers(1, 14))
+        span = L - k
+        start = int(rng.integers(0, wl - span))
+        ins = rng.integers(0, 4, size=k, dtype=np.int8)
+        r = np.concatenate([W[start:start + q], ins, W[start + q:start + span]]).astype(np.int8)
+        nsub = int(rng.integers(0, 4))
+        for _ in range(nsub):
+            x = int(rng.integers(0, r.shape[0]))
+            r[x] = (r[x] + 1 + rng.integers(0, 3)) % 4
+        if rng.random() < 0.2:                                 # second event
+            x = int(rng.integers(5, r.shape[0] - 5))
+            r = np.concatenate([r[:x], r[x + int(rng.integers(1, 4)):]]) if rng.random() < 0.5 else np.concatenate([r[:x], rng.integers(0, 4, size=int(rng.integers(1, 4)), dtype=np.int8), r[x:]])
+        g = grid[int(rng.integers(0, 6))]
+        wins.append(W); reads.append(r.astype(np.int8)); go.append(g[0]); ge.append(g[1])
+    idx = np.arange(n_pairs, dtype=np.int32)
+    b = batch_from_lists(reads, wins, idx, idx, go, ge)
+    b.mat = dna_matrix(3, 2)
+    return b
+
+
+def oracle_parallel(b: Batch, threads: int = 8):
+    """oracle over a batch using several threads (ctypes releases the GIL)"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    parts = [p for p in np.array_split(np.arange(b.n_pairs), threads) if p.shape[0]]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        outs = list(ex.map(lambda p: oracle().align_batch(b.subset(p)), parts))
+    res = np.concatenate([o[0] for o in outs])
+    shift = 0
+    arenas = []
+    pos = 0
+    for (r, a), p in zip(outs, parts):
+        res["cigar_off"][pos:pos + p.shape[0]] += shift
+        shift += a.shape[0]
+        pos += p.shape[0]
+        arenas.append(a)
+    return res, np.concatenate(arenas) if arenas else np.zeros(0, np.uint32)

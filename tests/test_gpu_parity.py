@@ -148,3 +148,16 @@ def test_gpu_fast_path_is_used_for_the_headline_workload():
     rs = rg[sub].copy()
     # re-base cigar offsets of the subset for the comparison
     T.compare(rs, ag, ro, ao, what="fast path vs oracle (cfg2)")
+
+
+@pytest.mark.parametrize("seed", [301, 302])
+def test_gpu_overflow_decision_stress(seed):
+    """the provisional 16-bit results of the fast path must survive ssw.c's 8-bit-first escalation rule on
+    inputs built to sit in the zone where the 8-bit pass' signed lazy-F test misbehaves"""
+    from gpuutil import gpu_align
+
+    b = T.make_overflow_zone_pairs(24000, seed=seed)
+    ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+    rg, ag, tm = gpu_align(b)
+    T.compare(rg, ag, ro, ao, what=f"overflow-zone stress seed={seed}")
+    assert tm["n_fast"] > 0
