@@ -20,7 +20,9 @@
 #define SWB_BAND_LOCAL_BW 16                         // bands up to this half-width keep their rows in shared memory
 #define SWB_BAND_LOCAL_W (2 * SWB_BAND_LOCAL_BW + 4)
 #define SWB_BAND_THREADS 128
-#define SWB_BAND_SMEM (3 * SWB_BAND_LOCAL_W * SWB_BAND_THREADS * 4)
+#define SWB_BAND_REFRING 64                           // circular buffer of window bases per thread (>= band width)
+#define SWB_BAND_SMEM (3 * SWB_BAND_LOCAL_W * SWB_BAND_THREADS * 2 + SWB_BAND_REFRING * SWB_BAND_THREADS)
+#define SWB_BAND_MAX16 30000                          // largest score the 16-bit shared-memory rows may hold
 
 __device__ __forceinline__ int band_x(int w, int i) { int x = i - w; return x > 0 ? x : 0; }
 
@@ -85,10 +87,9 @@ __device__ __forceinline__ int band_traceback(const uint32_t* dir, const BandGeo
 }
 
 // rolling-row accessor: shared memory [slot][thread] (LOCAL) or a private global array (wide bands)
-template <bool LOCAL> struct BandRow {
-    int* p;
-    __device__ __forceinline__ int& operator[](int u) const { return LOCAL ? p[u * SWB_BAND_THREADS] : p[u]; }
-};
+template <bool LOCAL> struct BandRow;
+template <> struct BandRow<true>  { short* p; __device__ __forceinline__ short& operator[](int u) const { return p[u * SWB_BAND_THREADS]; } };
+template <> struct BandRow<false> { int* p;   __device__ __forceinline__ int& operator[](int u) const { return p[u]; } };
 
 template <bool LOCAL>
 __global__ void __launch_bounds__(SWB_BAND_THREADS)
@@ -106,7 +107,7 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     int bw, best;
     if (round == 0 || d.t_bw[p] == 0) { int dl = g.refLen - g.readLen; bw = (dl < 0 ? -dl : dl) + 1; best = 0; }
     else { bw = d.t_bw[p]; best = d.t_best[p]; }
-    const bool wantLocal = bw <= SWB_BAND_LOCAL_BW;
+    const bool wantLocal = bw <= SWB_BAND_LOCAL_BW && (long long)d.max_score * (g.readLen > 0 ? g.readLen : 1) <= SWB_BAND_MAX16;
     if (wantLocal != LOCAL) return;                    // the other instantiation handles it
     g.w = bw; g.width_d = 2 * bw + 1; g.strideW = (g.width_d + 7) >> 3;
     const int width = 2 * bw + 3;
@@ -133,23 +134,31 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         return;
     }
     uint32_t* dir = reinterpret_cast<uint32_t*>(d.band + off);
-    extern __shared__ int band_smem[];
+    extern __shared__ __align__(16) unsigned char band_smem[];
     BandRow<LOCAL> hPrev, ePrev, hCur;
-    if (LOCAL) {
-        hPrev.p = band_smem + threadIdx.x;
+    unsigned char* refRing = nullptr;                  // LOCAL: window bases of the current band, slot = column & 63
+    if constexpr (LOCAL) {
+        hPrev.p = reinterpret_cast<short*>(band_smem) + threadIdx.x;
         ePrev.p = hPrev.p + SWB_BAND_LOCAL_W * SWB_BAND_THREADS;
         hCur.p = ePrev.p + SWB_BAND_LOCAL_W * SWB_BAND_THREADS;
+        refRing = band_smem + 3 * SWB_BAND_LOCAL_W * SWB_BAND_THREADS * 2 + threadIdx.x;
     } else {
         hPrev.p = reinterpret_cast<int*>(d.band + off + dirBytes);
         ePrev.p = hPrev.p + (width + 1); hCur.p = ePrev.p + (width + 1);
     }
+    // substitution scores of one read base against every window base, packed 8 x int8 (n <= 8)
+    const bool packRow = n <= 8;
     // the reference's buffers are realloc'ed across widenings and not cleared; every slot it reads is
     // written first within an iteration except where it reads uninitialised memory -- start from zeros
     for (int j = 0; j <= width; ++j) { hPrev[j] = 0; ePrev[j] = 0; hCur[j] = 0; }
 
     long long cells = 0;
+    int ringHi = -1;                                   // last window column already in refRing
     for (int i = 0; i < g.readLen; ++i) {              // ssw.c:628-667
         const int beg = g.beg(i), end = g.end(i);
+        if constexpr (LOCAL) {
+            for (; ringHi < end; ) { ++ringHi; refRing[(ringHi & (SWB_BAND_REFRING - 1)) * SWB_BAND_THREADS] = (unsigned char)(ubRef ? 0 : ref[ringHi]); }
+        }
         int edge = end + 1 < width - 1 ? end + 1 : width - 1;
         int f = 0, u = 0;
         hPrev[0] = 0; ePrev[0] = 0; hPrev[edge] = 0; ePrev[edge] = 0; hCur[0] = 0;     // ssw.c:633
@@ -157,6 +166,8 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         uint32_t* line = dir + (size_t)i * g.strideW;
         uint32_t word = 0;
         const int rb = read[i];
+        unsigned long long rowTab = 0;
+        if (packRow) { for (int nt = 0; nt < n; ++nt) rowTab |= (unsigned long long)(uint8_t)mat[nt * n + rb] << (8 * nt); }
         for (int j = beg; j <= end; ++j) {
             u = j - xi + 1;                            // set_u(u, w, i, j)
             const int up = j - xp + 1;                 // set_u(e, w, i-1, j)
@@ -165,7 +176,7 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             int a = i == 0 ? -go : hPrev[up] - go;     // ssw.c:644-648
             int b = i == 0 ? -ge : ePrev[up] - ge;
             const int ev = a > b ? a : b;
-            ePrev[u] = ev;
+            ePrev[u] = (LOCAL ? (short)ev : ev);
             const int bitE = a > b ? 1 : 0;
             a = hCur[lf] - go;                         // ssw.c:650-653
             b = f - ge;
@@ -174,10 +185,13 @@ k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             const int e1 = ev > 0 ? ev : 0;            // ssw.c:655-659
             const int f1 = f > 0 ? f : 0;
             const int gmax = e1 > f1 ? e1 : f1;
-            const int rc = ubRef ? 0 : ref[j];
-            const int m = hPrev[dg] + mat[rc * n + rb];
+            int rc;
+            if constexpr (LOCAL) rc = refRing[(j & (SWB_BAND_REFRING - 1)) * SWB_BAND_THREADS];
+            else rc = ubRef ? 0 : ref[j];
+            const int sc = packRow ? (int)(int8_t)(rowTab >> (8 * rc)) : (int)mat[rc * n + rb];
+            const int m = hPrev[dg] + sc;
             const int h = gmax > m ? gmax : m;
-            hCur[u] = h;
+            hCur[u] = (LOCAL ? (short)h : h);
             if (h > best) best = h;                    // ssw.c:661
             const int sel = gmax <= m ? 0 : (e1 > f1 ? 1 : 2);       // ssw.c:663-664
             const int x = j - xi;
