@@ -241,7 +241,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     ev_ms = 0.0
-    stage = {"ms_prepare": 0.0, "ms_forward": 0.0, "ms_reverse": 0.0, "ms_traceback": 0.0}
+    stage = {"ms_prepare": 0.0, "ms_forward": 0.0, "ms_reverse": 0.0, "ms_traceback": 0.0, "ms_band_round0": 0.0, "ms_band_rest": 0.0, "ms_certify": 0.0}
     launches = 0
     tm = {}
     for _ in range(args.steps):

@@ -153,6 +153,10 @@ typedef struct {
     int64_t n_launches;      /* kernels launched                                  */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    float   ms_band_round0;  /* first banded-DP round (all pairs at their initial band width)   */
+    float   ms_band_rest;    /* band-doubling rounds                                             */
+    float   ms_certify;      /* overflow certificate + exact 8-bit verification of the remainder */
+    int32_t band_rounds;
 } swb_timing;
 
 int         swb_device_count(void);

@@ -19,9 +19,9 @@
 
 #include "swb_common.cuh"
 #include "swb_exact.cuh"
+#include "swb_cert.cuh"
 #include "swb_band.cuh"
 #include "swb_fast.cuh"
-#include "swb_cert.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
 
@@ -115,11 +115,12 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_COUNT };
+enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_BAND_R0, EV_BAND_ALL, EV_COUNT };
 
 struct swb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev[EV_COUNT];
     std::string err;
     SwbDev d;
@@ -177,6 +178,8 @@ extern "C" swb_ctx* swb_create(int device) {
         delete c; return nullptr;
     }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+    cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t));
     cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long));
     // opt in to large dynamic shared memory for the exact kernels
@@ -184,7 +187,8 @@ extern "C" swb_ctx* swb_create(int device) {
     cudaFuncSetAttribute(k_exact<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(k_exact<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(k_exact<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-    cudaFuncSetAttribute(k_band<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWB_BAND_SMEM);
+    cudaFuncSetAttribute(k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS));
+    cudaFuncSetAttribute(k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS));
     return c;
 }
 
@@ -200,6 +204,7 @@ extern "C" void swb_destroy(swb_ctx* c) {
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
     delete c;
 }
 
@@ -281,6 +286,7 @@ extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
     int mx = 0; bool small = true;
     for (int i = 0; i < b->n * b->n; ++i) { mx = std::max<int>(mx, b->mat[i]); if (b->mat[i] > 7 || b->mat[i] < -7) small = false; }
     d.max_score = mx;
+    { const char* o = getenv("SWB200_OPT"); d.opt = o ? atoi(o) : 0; }
     d.fast_ok = (small && b->n >= 4 && mx > 0 && (b->score_size == 1 || b->score_size == 2) && !getenv("SWB200_NO_FAST")) ? 1 : 0;
     c->have_batch = true;
     return 0;
@@ -372,27 +378,46 @@ static int launch_fast(swb_ctx* c, const int* counts) {
     return 0;
 }
 
-// banded DP + traceback in doubling rounds over d.list[LIST_BAND] (ssw.c:897-916)
-static int run_band_rounds(swb_ctx* c) {
+// banded DP + traceback (ssw.c:897-916) over the four band-class lists; a launch round per class, repeated only
+// for pairs the kernel re-queued (scratch exhausted, or band outgrew the shared-memory rows)
+static int run_band_rounds(swb_ctx* c, bool record) {
     SwbDev& d = c->d;
     cudaStream_t s = c->stream;
     if (read_counters(c)) return -1;
     int cur = LIST_BAND, nxt = LIST_BAND_NEXT;
-    int njobs = c->h_counters[cur];
     int round = 0, stalls = 0;
-    while (njobs > 0) {
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4, s));
+    for (;;) {
+        int njobs[SWB_NBANDCLASS], total = 0;
+        for (int k = 0; k < SWB_NBANDCLASS; ++k) { njobs[k] = c->h_counters[cur + k]; total += njobs[k]; }
+        if (total <= 0) break;
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
-        const int blocks = (njobs + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
-        k_band<true><<<blocks, SWB_BAND_THREADS, SWB_BAND_SMEM, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
-        k_band<false><<<blocks, SWB_BAND_THREADS, 0, s>>>(d, d.list[cur], d.counters + cur, d.list[nxt], d.counters + nxt, round);
-        c->tm.n_launches += 2;
+        // the rare wide classes go to the side stream so their long, latency-bound threads overlap the bulk
+        const bool side = njobs[3] > 0 || njobs[4] > 0;
+        if (side) {
+            CUDA_TRY(c, cudaEventRecord(c->ev_fork, s));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            if (njobs[4] > 0) { k_band<0, SWB_BAND_THREADS><<<(njobs[4] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, SWB_BAND_THREADS, 0, c->stream2>>>(d, cur, 4, 4); c->tm.n_launches++; }
+            if (njobs[3] > 0) {
+                k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS><<<(njobs[3] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, SWB_BAND_MID_THREADS,
+                                                                  band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS), c->stream2>>>(d, cur, 3, 3);
+                c->tm.n_launches++;
+            }
+            CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
+        }
+        int blocks = 0;
+        for (int k = 0; k < 3; ++k) blocks += (njobs[k] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
+        if (blocks > 0) {
+            k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS><<<blocks, SWB_BAND_THREADS, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS), s>>>(d, cur, 0, 2);
+            c->tm.n_launches++;
+        }
+        if (side) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "band")) return -1;
+        if (record && round == 0) CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_R0], s));
         if (read_counters(c)) return -1;
-        const int next = c->h_counters[nxt];
-        if (c->h_counters[CNT_BAND_OVERFLOW] == njobs) {
+        if (c->h_counters[CNT_BAND_OVERFLOW] >= total) {
             // nothing fitted: the scratch is smaller than a single band; grow it
             if (++stalls > 8 || c->b_band.cap >= ((size_t)64 << 30)) { c->err = "banded traceback scratch exhausted"; return -1; }
             size_t want = c->b_band.cap * 4;
@@ -400,12 +425,13 @@ static int run_band_rounds(swb_ctx* c) {
             d.band = (uint8_t*)c->b_band.p; d.band_cap = (int64_t)c->b_band.cap;
         }
         std::swap(cur, nxt);
-        njobs = next;
+        c->tm.band_rounds++;
         if (++round > 64) { c->err = "banded traceback did not converge"; return -1; }
     }
-    // leave LIST_BAND empty for a later phase
-    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND, 0, 4, s));
-    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND_NEXT, 0, 4, s));
+    if (record && round == 0) CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_R0], s));
+    // leave both list sets empty for a later phase
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND, 0, 4 * SWB_NBANDCLASS, s));
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND_NEXT, 0, 4 * SWB_NBANDCLASS, s));
     return 0;
 }
 
@@ -484,24 +510,24 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));
 
     // ---- banded DP + traceback (ssw.c:897-916) -----------------------------------------------------
-    if (run_band_rounds(c)) return -1;
+    tm.band_rounds = 0;
+    if (run_band_rounds(c, true)) return -1;
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_ALL], s));
 
-    // ---- overflow certificate for provisionally accepted 16-bit results; exact 8-bit pass for the rest ----
+    // ---- provisional 16-bit results without an overflow certificate (k_band queued them): exact 8-bit pass ----
     if (nFastTotal > 0 && d.score_size == 2) {
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_FWD, 0, 4, s));
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_REV, 0, 4, s));
-        k_certify<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np);
+        // pairs whose CIGAR was not requested (flag / filters) never reached the inline certificate: sweep the flags
+        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np);
         tm.n_launches++;
         CUDA_TRY(c, cudaGetLastError());
-        if (stage_check(c, "certify")) return -1;
         if (read_counters(c)) return -1;
-        const int nverify = c->h_counters[CNT_BYTE_FWD];
+        const int nverify = c->h_counters[LIST_VERIFY];
         if (nverify > 0) {
-            if (launch_exact<0, 0>(c, LIST_BYTE_FWD, nverify)) return -1;     // confirms the overflow, or produces the byte-mode result
+            CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));
+            CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
+            if (launch_exact<0, 0>(c, LIST_VERIFY, nverify)) return -1;       // confirms the overflow, or produces the byte-mode result
             if (launch_exact<0, 1>(c, LIST_BYTE_REV, nverify)) return -1;
-            if (run_band_rounds(c)) return -1;
+            if (run_band_rounds(c, false)) return -1;
         }
     }
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND], s));
@@ -517,6 +543,9 @@ extern "C" int swb_compute(swb_ctx* c) {
     cudaEventElapsedTime(&tm.ms_reverse, c->ev[EV_FWD], c->ev[EV_REV]);
     cudaEventElapsedTime(&tm.ms_traceback, c->ev[EV_REV], c->ev[EV_BAND]);
     cudaEventElapsedTime(&tm.ms_total, c->ev[EV_START], c->ev[EV_BAND]);
+    cudaEventElapsedTime(&tm.ms_band_round0, c->ev[EV_REV], c->ev[EV_BAND_R0]);
+    cudaEventElapsedTime(&tm.ms_band_rest, c->ev[EV_BAND_R0], c->ev[EV_BAND_ALL]);
+    cudaEventElapsedTime(&tm.ms_certify, c->ev[EV_BAND_ALL], c->ev[EV_BAND]);
     memcpy(&tm.cells_forward, c->h_counters + CNT_CELLS_FWD, 8);
     memcpy(&tm.cells_reverse, c->h_counters + CNT_CELLS_REV, 8);
     memcpy(&tm.cells_band, c->h_counters + CNT_CELLS_BAND, 8);

@@ -10,19 +10,27 @@
 // Direction information (3 bytes per cell in the reference) is packed into 4 bits per cell, 8 cells per
 // 32-bit word, and kept in a global scratch arena (one word store per 8 cells instead of a 32-byte sector
 // per cell); each thread bump-allocates ceil((2w+1)/8)*4*readLen bytes.  The three rolling rows live in
-// shared memory laid out [slot][thread], which is bank-conflict free whatever slot each thread touches.  Band doubling is done in
-// rounds: a pair whose DP maximum is still below score1 is re-queued with twice the width (about 0.5 %
-// of realistic pairs).  The traceback is walked twice (count, then emit) so the CIGAR
+// shared memory laid out [slot][thread], which is bank-conflict free whatever slot each thread touches.  Band doubling
+// (ssw.c:668-669) happens inside the kernel with a fresh scratch allocation; a pair is only re-queued for a
+// later launch when the scratch arena is exhausted or its band outgrows the shared-memory rows.  Jobs are
+// bucketed by band-width class so the threads of a warp run bands of similar width.  The traceback is walked twice (count, then emit) so the CIGAR
 // can be written, already reversed, straight into the output arena.
 #pragma once
 #include "swb_common.cuh"
+#include "swb_cert.cuh"
 
-#define SWB_BAND_LOCAL_BW 16                         // bands up to this half-width keep their rows in shared memory
-#define SWB_BAND_LOCAL_W (2 * SWB_BAND_LOCAL_BW + 4)
+// Instantiations: BW = largest half-width whose rolling rows fit the shared-memory layout (0 = rows in global
+// memory, any width), T = threads per block, RING = circular buffer of window bases per thread (>= band width).
+//   k_band<16, 128>  : classes 0-2 (the bulk)          k_band<112, 32> : class 3, bands up to 225 wide
+//   k_band<0, 128>   : anything wider (global rows; latency bound, rare)
+#define SWB_BAND_LOCAL_BW 16
+#define SWB_BAND_MID_BW 112
 #define SWB_BAND_THREADS 128
-#define SWB_BAND_REFRING 64                           // circular buffer of window bases per thread (>= band width)
-#define SWB_BAND_SMEM (3 * SWB_BAND_LOCAL_W * SWB_BAND_THREADS * 2 + SWB_BAND_REFRING * SWB_BAND_THREADS)
+#define SWB_BAND_MID_THREADS 32
 #define SWB_BAND_MAX16 30000                          // largest score the 16-bit shared-memory rows may hold
+__host__ __device__ constexpr int band_rows_w(int BW) { return 2 * BW + 4; }
+__host__ __device__ constexpr int band_ring(int BW) { return BW <= 16 ? 64 : 256; }
+__host__ __device__ constexpr int band_smem_bytes(int BW, int T) { return BW == 0 ? 0 : 3 * band_rows_w(BW) * T * 2 + band_ring(BW) * T; }
 
 __device__ __forceinline__ int band_x(int w, int i) { int x = i - w; return x > 0 ? x : 0; }
 
@@ -87,134 +95,168 @@ __device__ __forceinline__ int band_traceback(const uint32_t* dir, const BandGeo
 }
 
 // rolling-row accessor: shared memory [slot][thread] (LOCAL) or a private global array (wide bands)
-template <bool LOCAL> struct BandRow;
-template <> struct BandRow<true>  { short* p; __device__ __forceinline__ short& operator[](int u) const { return p[u * SWB_BAND_THREADS]; } };
-template <> struct BandRow<false> { int* p;   __device__ __forceinline__ int& operator[](int u) const { return p[u]; } };
+template <bool LOCAL, int T> struct BandRow;
+template <int T> struct BandRow<true, T>  { short* p; __device__ __forceinline__ short& operator[](int u) const { return p[u * T]; } };
+template <int T> struct BandRow<false, T> { int* p;   __device__ __forceinline__ int& operator[](int u) const { return p[u]; } };
 
-template <bool LOCAL>
-__global__ void __launch_bounds__(SWB_BAND_THREADS)
-k_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int32_t* nextList, int32_t* nextCount, int round)
+template <int BW, int T>
+__global__ void __launch_bounds__(T)
+k_band(SwbDev d, int listBase, int firstClass, int lastClass)
 {
-    const int njobs = *njobs_ptr;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= njobs) return;
-    const int p = jobs[t];
+    constexpr bool LOCAL = BW > 0;
+    constexpr int ROWS_W = band_rows_w(BW);
+    constexpr int RING = band_ring(BW);
+    __shared__ unsigned long long s_rowTab[8];         // per read base: its scores against every window base, 8 x int8 (n <= 8)
+    if (d.n <= 8 && threadIdx.x < d.n) {
+        unsigned long long tab = 0;
+        for (int nt = 0; nt < d.n; ++nt) tab |= (unsigned long long)(uint8_t)d.mat[nt * d.n + threadIdx.x] << (8 * nt);
+        s_rowTab[threadIdx.x] = tab;
+    }
+    __syncthreads();
+    // one launch serves the classes firstClass..lastClass, widest first (blocks are scheduled in order, so the long
+    // threads start first and the short ones fill the tail); thread t indexes the concatenation of their lists
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = -1;
+    for (int k = lastClass; k >= firstClass; --k) {
+        // each class starts at a block boundary so a block never mixes classes
+        const int nk = d.counters[listBase + k];
+        const int padded = (nk + T - 1) / T * T;
+        if (t < padded) { if (t < nk) p = d.list[listBase + k][t]; break; }
+        t -= padded;
+    }
+    if (p < 0) return;
     swb_result& r = d.res[p];
 
     BandGeom g;
     g.refLen = r.ref_end1 - r.ref_begin1 + 1;          // ssw.c:897-899
     g.readLen = r.read_end1 - r.read_begin1 + 1;
     int bw, best;
-    if (round == 0 || d.t_bw[p] == 0) { int dl = g.refLen - g.readLen; bw = (dl < 0 ? -dl : dl) + 1; best = 0; }
-    else { bw = d.t_bw[p]; best = d.t_best[p]; }
-    const bool wantLocal = bw <= SWB_BAND_LOCAL_BW && (long long)d.max_score * (g.readLen > 0 ? g.readLen : 1) <= SWB_BAND_MAX16;
-    if (wantLocal != LOCAL) return;                    // the other instantiation handles it
-    g.w = bw; g.width_d = 2 * bw + 1; g.strideW = (g.width_d + 7) >> 3;
-    const int width = 2 * bw + 3;
+    if (d.t_bw[p] == 0) { int dl = g.refLen - g.readLen; bw = (dl < 0 ? -dl : dl) + 1; best = 0; }
+    else { bw = d.t_bw[p]; best = d.t_best[p]; }       // re-queued: resume with the saved width and running maximum
     const int len = g.refLen > g.readLen ? g.refLen : g.readLen;
     const int score = r.score1;
     const int go = d.gap_open[p], ge = d.gap_ext[p];
     const int n = d.n;
     const int8_t* mat = d.mat;
+    const bool fits16 = (long long)d.max_score * (g.readLen > 0 ? g.readLen : 1) <= SWB_BAND_MAX16;
     // score1 == 0 in byte mode leaves ref_begin1 == -1 and the reference reads ref[-1] (undefined);
     // the 1x1 problem it then solves gives "1M" whatever that byte is
     const bool ubRef = r.ref_begin1 < 0;
     const int8_t* ref = d.windows + d.p_woff[p] + (ubRef ? 0 : r.ref_begin1);
     const int8_t* read = d.reads + d.p_roff[p] + (r.read_begin1 < 0 ? 0 : r.read_begin1);
+    const bool packRow = n <= 8;                       // substitution scores of one read base vs every window base in 8 x int8
 
-    // ---- scratch: packed direction words (+ the three rolling rows when the band is too wide for shared memory)
-    const long long dirBytes = (long long)g.strideW * 4 * (g.readLen > 0 ? g.readLen : 1);
-    const long long rowBytes = LOCAL ? 0 : 3ll * (width + 1) * 4;
-    const long long need = dirBytes + rowBytes;
-    d.t_bw[p] = bw; d.t_best[p] = best;
-    const unsigned long long off = atomicAdd(&d.bump[0], (unsigned long long)need);
-    if ((long long)off + need > d.band_cap) {          // out of scratch: retry in the next round
-        atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
-        list_push(nextList, nextCount, p);
-        return;
-    }
-    uint32_t* dir = reinterpret_cast<uint32_t*>(d.band + off);
     extern __shared__ __align__(16) unsigned char band_smem[];
-    BandRow<LOCAL> hPrev, ePrev, hCur;
-    unsigned char* refRing = nullptr;                  // LOCAL: window bases of the current band, slot = column & 63
+    BandRow<LOCAL, T> hPrev, ePrev, hCur;
+    unsigned char* refRing = nullptr;                  // LOCAL: window bases of the current band, slot = column & (RING-1)
     if constexpr (LOCAL) {
         hPrev.p = reinterpret_cast<short*>(band_smem) + threadIdx.x;
-        ePrev.p = hPrev.p + SWB_BAND_LOCAL_W * SWB_BAND_THREADS;
-        hCur.p = ePrev.p + SWB_BAND_LOCAL_W * SWB_BAND_THREADS;
-        refRing = band_smem + 3 * SWB_BAND_LOCAL_W * SWB_BAND_THREADS * 2 + threadIdx.x;
-    } else {
-        hPrev.p = reinterpret_cast<int*>(d.band + off + dirBytes);
-        ePrev.p = hPrev.p + (width + 1); hCur.p = ePrev.p + (width + 1);
+        ePrev.p = hPrev.p + ROWS_W * T;
+        hCur.p = ePrev.p + ROWS_W * T;
+        refRing = band_smem + 3 * ROWS_W * T * 2 + threadIdx.x;
     }
-    // substitution scores of one read base against every window base, packed 8 x int8 (n <= 8)
-    const bool packRow = n <= 8;
-    // the reference's buffers are realloc'ed across widenings and not cleared; every slot it reads is
-    // written first within an iteration except where it reads uninitialised memory -- start from zeros
-    for (int j = 0; j <= width; ++j) { hPrev[j] = 0; ePrev[j] = 0; hCur[j] = 0; }
-
+    uint32_t* dir = nullptr;
     long long cells = 0;
-    int ringHi = -1;                                   // last window column already in refRing
-    for (int i = 0; i < g.readLen; ++i) {              // ssw.c:628-667
-        const int beg = g.beg(i), end = g.end(i);
-        if constexpr (LOCAL) {
-            for (; ringHi < end; ) { ++ringHi; refRing[(ringHi & (SWB_BAND_REFRING - 1)) * SWB_BAND_THREADS] = (unsigned char)(ubRef ? 0 : ref[ringHi]); }
-        }
-        int edge = end + 1 < width - 1 ? end + 1 : width - 1;
-        int f = 0, u = 0;
-        hPrev[0] = 0; ePrev[0] = 0; hPrev[edge] = 0; ePrev[edge] = 0; hCur[0] = 0;     // ssw.c:633
-        const int xi = band_x(bw, i), xp = band_x(bw, i - 1);
-        uint32_t* line = dir + (size_t)i * g.strideW;
-        uint32_t word = 0;
-        const int rb = read[i];
-        unsigned long long rowTab = 0;
-        if (packRow) { for (int nt = 0; nt < n; ++nt) rowTab |= (unsigned long long)(uint8_t)mat[nt * n + rb] << (8 * nt); }
-        for (int j = beg; j <= end; ++j) {
-            u = j - xi + 1;                            // set_u(u, w, i, j)
-            const int up = j - xp + 1;                 // set_u(e, w, i-1, j)
-            const int lf = u - 1;                      // set_u(b, w, i, j-1)
-            const int dg = up - 1;                     // set_u(d, w, i-1, j-1)
-            int a = i == 0 ? -go : hPrev[up] - go;     // ssw.c:644-648
-            int b = i == 0 ? -ge : ePrev[up] - ge;
-            const int ev = a > b ? a : b;
-            ePrev[u] = (LOCAL ? (short)ev : ev);
-            const int bitE = a > b ? 1 : 0;
-            a = hCur[lf] - go;                         // ssw.c:650-653
-            b = f - ge;
-            f = a > b ? a : b;
-            const int bitF = a > b ? 1 : 0;
-            const int e1 = ev > 0 ? ev : 0;            // ssw.c:655-659
-            const int f1 = f > 0 ? f : 0;
-            const int gmax = e1 > f1 ? e1 : f1;
-            int rc;
-            if constexpr (LOCAL) rc = refRing[(j & (SWB_BAND_REFRING - 1)) * SWB_BAND_THREADS];
-            else rc = ubRef ? 0 : ref[j];
-            const int sc = packRow ? (int)(int8_t)(rowTab >> (8 * rc)) : (int)mat[rc * n + rb];
-            const int m = hPrev[dg] + sc;
-            const int h = gmax > m ? gmax : m;
-            hCur[u] = (LOCAL ? (short)h : h);
-            if (h > best) best = h;                    // ssw.c:661
-            const int sel = gmax <= m ? 0 : (e1 > f1 ? 1 : 2);       // ssw.c:663-664
-            const int x = j - xi;
-            word |= (uint32_t)(bitE | (bitF << 1) | (sel << 2)) << (4 * (x & 7));
-            if ((x & 7) == 7) { line[x >> 3] = word; word = 0; }
-        }
-        if (end >= beg && ((end - xi) & 7) != 7) line[(end - xi) >> 3] = word;
-        cells += end - beg + 1;
-        for (int j = 1; j <= u; ++j) hPrev[j] = hCur[j];             // ssw.c:666
-    }
-    atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + CNT_CELLS_BAND), (unsigned long long)cells);
 
-    if (best < score && bw * 2 <= len) {               // ssw.c:668-669: widen and redo
-        d.t_bw[p] = bw * 2; d.t_best[p] = best;
-        list_push(nextList, nextCount, p);
-        return;
+    for (;;) {                                         // band widening loop, ssw.c:612-669
+        if (LOCAL && (bw > BW || !fits16)) {
+            // outgrew this instantiation's shared-memory rows: continue in the next wider one
+            d.t_bw[p] = bw; d.t_best[p] = best;
+            const int c = (BW == SWB_BAND_LOCAL_BW && fits16) ? 3 : 4;
+            list_push(d.list[LIST_BAND_NEXT + c], d.counters + CNT_BAND_NEXT + c, p);
+            warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
+            return;
+        }
+        g.w = bw; g.width_d = 2 * bw + 1; g.strideW = (g.width_d + 7) >> 3;
+        const int width = 2 * bw + 3;
+        // ---- scratch: packed direction words (+ the three rolling rows when they do not live in shared memory)
+        const long long dirBytes = (long long)g.strideW * 4 * (g.readLen > 0 ? g.readLen : 1);
+        const long long rowBytes = LOCAL ? 0 : 3ll * (width + 1) * 4;
+        const long long need = dirBytes + rowBytes;
+        const unsigned long long off = warp_bump(&d.bump[0], (unsigned long long)need);
+        if ((long long)off + need > d.band_cap) {      // out of scratch: retry in a later launch
+            d.t_bw[p] = bw; d.t_best[p] = best;
+            atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
+            const int c = BW == 0 ? 4 : (BW == SWB_BAND_MID_BW ? 3 : band_class(bw));
+            list_push(d.list[LIST_BAND_NEXT + c], d.counters + CNT_BAND_NEXT + c, p);
+            warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
+            return;
+        }
+        dir = reinterpret_cast<uint32_t*>(d.band + off);
+        if constexpr (!LOCAL) {
+            hPrev.p = reinterpret_cast<int*>(d.band + off + dirBytes);
+            ePrev.p = hPrev.p + (width + 1); hCur.p = ePrev.p + (width + 1);
+        }
+        // the reference's buffers are realloc'ed across widenings and not cleared; every slot it reads is
+        // written first within an iteration except where it reads uninitialised memory -- start from zeros
+        for (int j = 0; j <= width; ++j) { hPrev[j] = 0; ePrev[j] = 0; hCur[j] = 0; }
+
+        int ringHi = -1;                               // last window column already in refRing
+        int rbNext = g.readLen > 0 ? read[0] : 0;      // software prefetch: next row's read base and the next window base
+        int refNext = (!ubRef && g.refLen > 0) ? ref[0] : 0;
+        for (int i = 0; i < g.readLen; ++i) {          // ssw.c:628-667
+            const int beg = g.beg(i), end = g.end(i);
+            if constexpr (LOCAL) {
+                for (; ringHi < end; ) {
+                    ++ringHi;
+                    refRing[(ringHi & (RING - 1)) * T] = (unsigned char)refNext;
+                    refNext = (!ubRef && ringHi + 1 < g.refLen) ? ref[ringHi + 1] : 0;
+                }
+            }
+            int edge = end + 1 < width - 1 ? end + 1 : width - 1;
+            int f = 0, u = 0;
+            hPrev[0] = 0; ePrev[0] = 0; hPrev[edge] = 0; ePrev[edge] = 0; hCur[0] = 0;     // ssw.c:633
+            const int xi = band_x(bw, i), xp = band_x(bw, i - 1);
+            uint32_t* line = dir + (size_t)i * g.strideW;
+            uint32_t word = 0;
+            const int rb = rbNext;
+            rbNext = i + 1 < g.readLen ? read[i + 1] : 0;
+            const unsigned long long rowTab = packRow ? s_rowTab[rb] : 0ull;
+            for (int j = beg; j <= end; ++j) {
+                u = j - xi + 1;                        // set_u(u, w, i, j)
+                const int up = j - xp + 1;             // set_u(e, w, i-1, j)
+                const int lf = u - 1;                  // set_u(b, w, i, j-1)
+                const int dg = up - 1;                 // set_u(d, w, i-1, j-1)
+                int a = i == 0 ? -go : hPrev[up] - go; // ssw.c:644-648
+                int b = i == 0 ? -ge : ePrev[up] - ge;
+                const int ev = a > b ? a : b;
+                ePrev[u] = (LOCAL ? (short)ev : ev);
+                const int bitE = a > b ? 1 : 0;
+                a = hCur[lf] - go;                     // ssw.c:650-653
+                b = f - ge;
+                f = a > b ? a : b;
+                const int bitF = a > b ? 1 : 0;
+                const int e1 = ev > 0 ? ev : 0;        // ssw.c:655-659
+                const int f1 = f > 0 ? f : 0;
+                const int gmax = e1 > f1 ? e1 : f1;
+                int rc;
+                if constexpr (LOCAL) rc = refRing[(j & (RING - 1)) * T];
+                else rc = ubRef ? 0 : ref[j];
+                const int sc = packRow ? (int)(int8_t)(rowTab >> (8 * rc)) : (int)mat[rc * n + rb];
+                const int m = hPrev[dg] + sc;
+                const int h = gmax > m ? gmax : m;
+                hCur[u] = (LOCAL ? (short)h : h);
+                if (h > best) best = h;                // ssw.c:661
+                const int sel = gmax <= m ? 0 : (e1 > f1 ? 1 : 2);       // ssw.c:663-664
+                const int x = j - xi;
+                word |= (uint32_t)(bitE | (bitF << 1) | (sel << 2)) << (4 * (x & 7));
+                if ((x & 7) == 7) { line[x >> 3] = word; word = 0; }
+            }
+            if (end >= beg && ((end - xi) & 7) != 7) line[(end - xi) >> 3] = word;
+            cells += end - beg + 1;
+            for (int j = 1; j <= u; ++j) hPrev[j] = hCur[j];             // ssw.c:666
+        }
+        if (best < score && bw * 2 <= len) { bw *= 2; continue; }       // ssw.c:668-669: widen and redo
+        break;
     }
+    warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
 
     // ---- traceback: count, allocate, emit ---------------------------------------------------------
     const int l = band_traceback(dir, g, nullptr, 0);
     if (l < 0) { r.flag = 1; r.cigar_len = 0; r.cigar_off = 0; return; }      // ssw.c:911
-    const unsigned long long coff = atomicAdd(&d.bump[1], (unsigned long long)l);
+    const unsigned long long coff = warp_bump(&d.bump[1], (unsigned long long)l);
     r.cigar_len = l; r.cigar_off = (int64_t)coff;
     if ((long long)coff + l > d.cigar_cap) { atomicAdd(d.counters + CNT_CIGAR_OVERFLOW, 1); return; }
     band_traceback(dir, g, d.cigar + coff, l);
+    if (d.opt & 1) certify_pair(d, p);                 // SWB200_OPT bit0: certificate inline (default: k_certify_rest, a cheaper separate pass)
 }

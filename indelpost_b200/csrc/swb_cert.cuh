@@ -26,16 +26,16 @@
 #pragma once
 #include "swb_common.cuh"
 
-__global__ void k_certify(SwbDev d, int32_t p0, int32_t p1)
+// returns true if the pair's provisional 16-bit result is certified (or needs no certificate); otherwise flags it
+// PST_HAVE_WORD and queues it for the exact 8-bit pass.  Called by the thread that just emitted the CIGAR.
+__device__ __forceinline__ void certify_pair(const SwbDev& d, int p)
 {
-    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= p1) return;
     const int st = d.p_state[p];
     if (!(st & PST_NEED_CERT)) return;
     const swb_result& r = d.res[p];
     const int limit = 255 - d.bias;
     bool ok = false;
-    if (r.cigar_len > 0 && r.ref_begin1 >= 0 && r.read_begin1 >= 0) {
+    if (r.cigar_len > 0 && r.ref_begin1 >= 0 && r.read_begin1 >= 0 && r.cigar_off + r.cigar_len <= d.cigar_cap) {
         const int8_t* read = d.reads + d.p_roff[p];
         const int8_t* ref = d.windows + d.p_woff[p];
         const int L = d.p_rlen[p], nc = d.p_wlen[p];
@@ -73,5 +73,13 @@ __global__ void k_certify(SwbDev d, int32_t p0, int32_t p1)
     if (ok) { d.p_state[p] = st & ~PST_NEED_CERT; return; }
     d.p_state[p] = (st & ~PST_NEED_CERT) | PST_HAVE_WORD;
     atomicAdd(d.counters + CNT_CERT_FAIL, 1);
-    list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
+    list_push(d.list[LIST_VERIFY], d.counters + LIST_VERIFY, p);
+}
+
+// pairs that still carry PST_NEED_CERT after the band stage (no CIGAR requested or traceback failed)
+__global__ void k_certify_rest(SwbDev d, int32_t p0, int32_t p1)
+{
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    certify_pair(d, p);
 }

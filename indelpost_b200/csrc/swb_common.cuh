@@ -7,7 +7,7 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 24
+#define SWB_NLISTS 36
 #define SWB_NCOUNTERS 64
 
 // ---------------------------------------------------------------------------------------------
@@ -54,15 +54,17 @@ struct SwbDev {
     int32_t max_score;  // max(mat): bound on the score gained per read base
     int32_t fast_ok;    // batch-level eligibility of the DPX fast path (matrix range, n >= 4, score_size)
     int32_t fast_max_cols;
+    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
-enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_BAND = 4, LIST_BAND_NEXT = 5,
-       LIST_FAST_FWD = 8, LIST_FAST_REV = 16 };
-enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3, CNT_BAND = 4, CNT_BAND_NEXT = 5,
-       CNT_FAST_FWD = 8, CNT_FAST_REV = 16,
-       CNT_CELLS_FWD = 32, CNT_CELLS_REV = 34, CNT_CELLS_BAND = 36, CNT_BAND_OVERFLOW = 38, CNT_CIGAR_OVERFLOW = 39,
-       CNT_FAST_DONE = 40, CNT_CERT_FAIL = 41, CNT_VERIFY_BYTE = 42, CNT_EXACT_JOBS = 43 };
+#define SWB_NBANDCLASS 5         // band jobs are bucketed by half-width: 1 | 2-4 | 5-16 | 17-112 (32-thread blocks) | wider (global-memory rows)
+enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4,
+       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 29 };
+enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
+       CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 29,
+       CNT_CELLS_FWD = 40, CNT_CELLS_REV = 42, CNT_CELLS_BAND = 44, CNT_BAND_OVERFLOW = 46, CNT_CIGAR_OVERFLOW = 47,
+       CNT_FAST_DONE = 48, CNT_CERT_FAIL = 49, CNT_VERIFY_BYTE = 50, CNT_EXACT_JOBS = 51 };
 // p_state flags
 enum { PST_FAST = 1,        // forward result produced by the DPX fast path
        PST_NEED_CERT = 2,   // word-mode result accepted provisionally: the 8-bit pass still has to be shown to overflow
@@ -77,6 +79,43 @@ __device__ __forceinline__ void list_push(int32_t* list, int32_t* counter, int32
     if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, __popc(m));
     base = __shfl_sync(m, base, leader);
     list[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = v;
+}
+
+// warp-aggregated bump allocation: the active lanes of a warp get consecutive ranges from ONE atomicAdd
+__device__ __forceinline__ unsigned long long warp_bump(unsigned long long* ptr, unsigned long long need) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    unsigned long long pre = 0, tot = 0;
+    for (unsigned rest = m; rest; rest &= rest - 1) {
+        const int src = __ffs(rest) - 1;
+        const unsigned long long v = __shfl_sync(m, need, src);
+        if (src < lane) pre += v;
+        tot += v;
+    }
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(ptr, tot);
+    base = __shfl_sync(m, base, leader);
+    return base + pre;
+}
+
+// warp-aggregated 64-bit statistics counter
+__device__ __forceinline__ void warp_count(int32_t* counter64, unsigned long long v) {
+    const unsigned m = __activemask();
+    unsigned long long tot = 0;
+    for (unsigned rest = m; rest; rest &= rest - 1) tot += __shfl_sync(m, v, __ffs(rest) - 1);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(reinterpret_cast<unsigned long long*>(counter64), tot);
+}
+
+// band job class from the half-width (see SWB_NBANDCLASS)
+__host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : (bw <= 4 ? 1 : (bw <= 16 ? 2 : (bw <= 112 ? 3 : 4))); }
+
+// queue a pair for the banded traceback in the class of its initial band width |refLen - readLen| + 1 (ssw.c:899)
+__device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_result& r) {
+    int dl = (r.ref_end1 - r.ref_begin1) - (r.read_end1 - r.read_begin1);
+    const int bw = (dl < 0 ? -dl : dl) + 1;
+    const int c = band_class(bw);
+    list_push(d.list[LIST_BAND + c], d.counters + CNT_BAND + c, p);
 }
 
 // sswpy.pyx:16-29 DNA_BASE_LUT

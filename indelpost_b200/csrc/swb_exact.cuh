@@ -233,7 +233,7 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
                 else { r.status = SWB_ERR_BYTE_ONLY; }
             } else {
                 if (d.p_state[p] & PST_HAVE_WORD) atomicAdd(d.counters + CNT_VERIFY_BYTE, 1);   // the provisional 16-bit result was wrong: redo in 8-bit semantics
-                d.p_state[p] = 0;
+                d.p_state[p] = 0; d.t_bw[p] = 0; d.t_best[p] = 0;
                 r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.cigar_off = 0; r.flag = 0;
                 r.score1 = (uint16_t)best; r.ref_end1 = end_ref; r.read_end1 = end_read;
                 if (maskLen >= 15) { r.score2 = (uint16_t)s2; r.ref_end2 = r2; }      // ssw.c:864-870
@@ -251,7 +251,7 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
             const int f = d.flag;
             const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
                                  ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));   // ssw.c:894
-            if (!noCigar) list_push(d.list[LIST_BAND], d.counters + CNT_BAND, p);
+            if (!noCigar) push_band(d, p, r);
         }
     }
 }

@@ -245,7 +245,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             const int s2 = sv > FAST_C ? (sv - FAST_C) / FAST_SCALE : 0;
             const int r2 = s2 > 0 ? si : 0;
             if (g == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + CNT_CELLS_FWD), (unsigned long long)q.Lp * q.ncols);
+                warp_count(d.counters + CNT_CELLS_FWD, (unsigned long long)q.Lp * q.ncols);
                 const int limit = 255 - d.bias;                                    // 8-bit pass overflows at max + bias >= 255 (ssw.c:327)
                 bool accept;
                 if (wordSem) accept = d.score_size == 1 || T >= limit;            // else the result is a byte-mode one: exact path decides
@@ -257,7 +257,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     r.score1 = (uint16_t)T; r.ref_end1 = end_ref; r.read_end1 = end_read;
                     if (q.mask >= 15) { r.score2 = (uint16_t)s2; r.ref_end2 = r2; } else { r.score2 = 0; r.ref_end2 = -1; }
                     d.p_state[p] = (wordSem && d.score_size == 2) ? (PST_FAST | PST_NEED_CERT) : PST_FAST;
-                    atomicAdd(d.counters + CNT_FAST_DONE, 1);
+                    { const unsigned am = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am) - 1) atomicAdd(d.counters + CNT_FAST_DONE, __popc(am)); }
                     const bool scoreOnly = d.flag == 0 || (d.flag == 2 && T < (int)d.filters);     // ssw.c:872
                     if (!scoreOnly) list_push(d.list[LIST_FAST_REV + BKT], d.counters + CNT_FAST_REV + BKT, p);
                 }
@@ -279,13 +279,13 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     d.p_state[p] &= ~PST_FAST;
                     list_push(d.list[md ? LIST_WORD_REV : LIST_BYTE_REV], d.counters + (md ? CNT_WORD_REV : CNT_BYTE_REV), p);
                 } else {
-                    atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + CNT_CELLS_REV), (unsigned long long)q.Lp * (hc + 1));
+                    warp_count(d.counters + CNT_CELLS_REV, (unsigned long long)q.Lp * (hc + 1));
                     r.ref_begin1 = r.ref_end1 - hc;                                 // ssw.c:885-886
                     r.read_begin1 = r.read_end1 - ((int)((colr[hc] >> sh) & 0xffffu) - q.off);
                     const int f = d.flag;
                     const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
                                          ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));
-                    if (!noCigar) list_push(d.list[LIST_BAND], d.counters + CNT_BAND, p);
+                    if (!noCigar) push_band(d, p, r);
                 }
             }
         }
