@@ -39,11 +39,32 @@ class BatchAligner:
             raise L.SwbError(self.lib.swb_last_error(None).decode())
         self.device = device
         self._keep = None
+        self._res_pin = None      # pinned output staging, grown on demand and reused across calls
+        self._arena_pin = None
+
+    def _out_buffers(self, n: int, cap: int):
+        """pinned (cudaMallocHost) result / CIGAR buffers: D2H into pageable numpy memory would be staged and
+        synchronous, which serialises the pipelined swb_align_batch"""
+        need_r = max(1, n) * L.RESULT_DTYPE.itemsize
+        if self._res_pin is None or self._res_pin.nbytes < need_r:
+            if self._res_pin is not None:
+                self._res_pin.close()
+            self._res_pin = L.PinnedBuffer(need_r + need_r // 8)
+        need_a = max(64, cap) * 4
+        if self._arena_pin is None or self._arena_pin.nbytes < need_a:
+            if self._arena_pin is not None:
+                self._arena_pin.close()
+            self._arena_pin = L.PinnedBuffer(need_a + need_a // 8)
+        return self._res_pin.view(L.RESULT_DTYPE, n), self._arena_pin.view(np.uint32, self._arena_pin.nbytes // 4)
 
     def close(self):
         if getattr(self, "ctx", None):
             self.lib.swb_destroy(self.ctx)
             self.ctx = None
+        for b in ("_res_pin", "_arena_pin"):
+            if getattr(self, b, None) is not None:
+                getattr(self, b).close()
+                setattr(self, b, None)
 
     def __del__(self):
         try:
@@ -80,22 +101,26 @@ class BatchAligner:
     def _err(self):
         return self.lib.swb_last_error(self.ctx).decode()
 
-    def align(self, *args, cigar_cap: int | None = None, **kw):
-        """one-shot: host arrays in, (results, cigar_arena) out (H2D + kernels + D2H)"""
+    def align(self, *args, cigar_cap: int | None = None, copy: bool = True, **kw):
+        """one-shot: host arrays in, (results, cigar_arena) out (H2D + kernels + D2H).
+
+        Outputs land in pinned buffers owned by the aligner; with copy=False the returned arrays are views
+        of those buffers, valid until the next call on this aligner."""
         b, keep = self._make_batch(*args, **kw)
         n = b.n_pairs
-        res = np.zeros(n, dtype=L.RESULT_DTYPE)
-        cap = int(cigar_cap if cigar_cap is not None else max(64, 16 * n))
+        cap = int(cigar_cap if cigar_cap is not None else max(64, 8 * n))
         used = C.c_int64(0)
         while True:
-            arena = np.zeros(cap, dtype=np.uint32)
+            res, arena = self._out_buffers(n, cap)
+            cap = arena.shape[0]
             rc = self.lib.swb_align_batch(self.ctx, C.byref(b), res.ctypes.data, arena.ctypes.data, cap, C.byref(used))
             if rc == -2:
                 cap = int(used.value) + 64
                 continue
             if rc != 0:
                 raise L.SwbError(self._err())
-            return res, arena[: used.value]
+            a = arena[: used.value]
+            return (res.copy(), a.copy()) if copy else (res, a)
 
     # split form (device-resident timing)
     def upload(self, *args, **kw):

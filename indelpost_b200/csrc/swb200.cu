@@ -16,6 +16,9 @@
 #include <vector>
 #include <mutex>
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <climits>
 
 #include "swb_common.cuh"
 #include "swb_exact.cuh"
@@ -30,13 +33,13 @@
 // ------------------------------------------------------------------------------------------------
 
 // one warp per sequence: ASCII -> code (in place) and range check; bad[s] = 1 if any code is outside [0, n)
-__global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int n, int ascii, uint8_t* bad)
+__global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int n, int ascii, uint8_t* bad, int64_t byte_base)
 {
     // bad[s]: bit0 = code outside [0, n) (invalid input), bit1 = some code >= 4 (not usable by the DPX fast path as a window)
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nseq) return;
-    int8_t* s = blob + off[w];
+    int8_t* s = blob + (off[w] - byte_base);
     const int L = len[w];
     bool b = false, hi = false;
     for (int i = lane; i < L; i += 32) {
@@ -57,8 +60,10 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
     swb_result r;
     r.score1 = 0; r.score2 = 0; r.ref_begin1 = -1; r.ref_end1 = 0; r.read_begin1 = -1; r.read_end1 = 0;
     r.ref_end2 = 0; r.cigar_len = 0; r.flag = 0; r.status = SWB_OK; r.cigar_off = 0;
-    const int ri = d.pair_read[p], wi = d.pair_win[p];
-    bool ok = ri >= 0 && ri < d.n_reads && wi >= 0 && wi < d.n_windows;
+    const int riAbs = d.pair_read[p], wiAbs = d.pair_win[p];
+    const int ri = riAbs - d.ridx_base, wi = wiAbs - d.widx_base;      // position inside the uploaded table slices
+    bool ok = riAbs >= 0 && riAbs < d.n_reads_total && wiAbs >= 0 && wiAbs < d.n_windows_total &&
+              ri >= 0 && ri < d.n_reads && wi >= 0 && wi < d.n_windows;
     int rl = 0, wl = 0, rb = 0;
     if (ok) {
         rl = d.read_len[ri];
@@ -75,8 +80,8 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         d.res[p] = r;
         return;
     }
-    d.p_roff[p] = d.read_off[ri];
-    d.p_woff[p] = d.win_off[wi] + rb;
+    d.p_roff[p] = d.read_off[ri] - d.rbyte_base;
+    d.p_woff[p] = d.win_off[wi] - d.wbyte_base + rb;
     d.p_rlen[p] = rl;
     d.p_wlen[p] = wl;
     d.p_mask[p] = d.mask_len ? d.mask_len[p] : (rl / 2 < 15 ? 15 : rl / 2);      // sswpy.pyx:209-211
@@ -136,6 +141,8 @@ struct swb_ctx {
     int smem_optin = 0;
     int n_sm = 0;
     int64_t chunk_pairs = 0;
+    swb_ctx* sibling = nullptr;                 // second lane, created on demand by the pipelined swb_align_batch
+    bool pipelined_last = false;
 };
 
 static std::string g_create_err;
@@ -194,6 +201,7 @@ extern "C" swb_ctx* swb_create(int device) {
 
 extern "C" void swb_destroy(swb_ctx* c) {
     if (!c) return;
+    if (c->sibling) { swb_destroy(c->sibling); c->sibling = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* all[] = { &c->b_reads, &c->b_read_off, &c->b_read_len, &c->b_windows, &c->b_win_off, &c->b_win_len, &c->b_pair_read, &c->b_pair_win,
@@ -235,7 +243,21 @@ static int up(swb_ctx* c, DevBuf& b, const T* src, size_t count, T** dst) {
     return 0;
 }
 
+// chunk view of a batch: `b` is already sliced (table pointers/counts and per-pair pointers offset); the bases tell
+// the kernels how to translate the caller's indices / byte offsets into the slice
+struct ChunkView { int32_t ridx_base = 0, widx_base = 0, n_reads_total = 0, n_windows_total = 0; int64_t rbyte_base = 0, wbyte_base = 0; bool sliced = false; };
+
+static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v);
+
 extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
+    if (!c) return -1;
+    c->pipelined_last = false;
+    ChunkView v;
+    if (b) { v.n_reads_total = b->n_reads; v.n_windows_total = b->n_windows; }
+    return upload_view(c, b, v);
+}
+
+static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v) {
     if (!c) return -1;
     c->err.clear();
     c->have_batch = false; c->computed = false;
@@ -250,12 +272,12 @@ extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
     // table extents (host scan of the small length arrays; also the max lengths that size shared memory)
     int64_t reads_bytes = 0, win_bytes = 0; int32_t max_rl = 0, max_wl = 0;
     for (int32_t i = 0; i < b->n_reads; ++i) {
-        if (b->read_len[i] < 0 || b->read_off[i] < 0) { c->err = "negative read offset/length"; return -1; }
-        reads_bytes = std::max<int64_t>(reads_bytes, b->read_off[i] + b->read_len[i]); max_rl = std::max(max_rl, b->read_len[i]);
+        if (b->read_len[i] < 0 || b->read_off[i] < v.rbyte_base) { c->err = "negative read offset/length"; return -1; }
+        reads_bytes = std::max<int64_t>(reads_bytes, b->read_off[i] - v.rbyte_base + b->read_len[i]); max_rl = std::max(max_rl, b->read_len[i]);
     }
     for (int32_t i = 0; i < b->n_windows; ++i) {
-        if (b->win_len[i] < 0 || b->win_off[i] < 0) { c->err = "negative window offset/length"; return -1; }
-        win_bytes = std::max<int64_t>(win_bytes, b->win_off[i] + b->win_len[i]); max_wl = std::max(max_wl, b->win_len[i]);
+        if (b->win_len[i] < 0 || b->win_off[i] < v.wbyte_base) { c->err = "negative window offset/length"; return -1; }
+        win_bytes = std::max<int64_t>(win_bytes, b->win_off[i] - v.wbyte_base + b->win_len[i]); max_wl = std::max(max_wl, b->win_len[i]);
     }
 
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D0], c->stream));
@@ -277,6 +299,8 @@ extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], c->stream));
 
     d.n_pairs = b->n_pairs; d.n_reads = b->n_reads; d.n_windows = b->n_windows;
+    d.ridx_base = v.ridx_base; d.widx_base = v.widx_base; d.n_reads_total = v.n_reads_total; d.n_windows_total = v.n_windows_total;
+    d.rbyte_base = v.rbyte_base; d.wbyte_base = v.wbyte_base;
     d.n = b->n; d.score_size = b->score_size; d.flag = b->flag; d.filters = b->filters; d.filterd = b->filterd;
     d.seq_encoding = b->seq_encoding;
     d.max_rlen = max_rl; d.max_wlen = max_wl;
@@ -484,8 +508,8 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_START], s));
 
     // ---- prepare ------------------------------------------------------------------------------
-    if (d.n_reads) { k_encode_validate<<<(d.n_reads + 3) / 4, 128, 0, s>>>(d.reads, d.read_off, d.read_len, d.n_reads, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p); tm.n_launches++; }
-    if (d.n_windows) { k_encode_validate<<<(d.n_windows + 3) / 4, 128, 0, s>>>(d.windows, d.win_off, d.win_len, d.n_windows, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p); tm.n_launches++; }
+    if (d.n_reads) { k_encode_validate<<<(d.n_reads + 3) / 4, 128, 0, s>>>(d.reads, d.read_off, d.read_len, d.n_reads, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p, d.rbyte_base); tm.n_launches++; }
+    if (d.n_windows) { k_encode_validate<<<(d.n_windows + 3) / 4, 128, 0, s>>>(d.windows, d.win_off, d.win_len, d.n_windows, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p, d.wbyte_base); tm.n_launches++; }
     d.seq_encoding = SWB_SEQ_CODES;                         // tables are codes from now on (repeat computes must not re-encode)
     if (np) { k_prepare<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, 0, (int32_t)np); tm.n_launches++; }
     CUDA_TRY(c, cudaGetLastError());
@@ -578,12 +602,133 @@ extern "C" int swb_download(swb_ctx* c, swb_result* results, uint32_t* cigar_are
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// one-shot entry: single pass for small batches, two-lane pipeline for large ones
+// ------------------------------------------------------------------------------------------------
+
+__global__ void k_rebase_cigar(swb_result* res, int32_t n, long long base)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n && res[p].cigar_len > 0) res[p].cigar_off += base;
+}
+
+struct ChunkPlan { int32_t p0 = 0, p1 = 0; swb_batch b; ChunkView v; };
+
+static void add_timing(swb_timing& a, const swb_timing& t) {
+    a.ms_total += t.ms_total; a.ms_prepare += t.ms_prepare; a.ms_forward += t.ms_forward; a.ms_reverse += t.ms_reverse;
+    a.ms_traceback += t.ms_traceback; a.ms_h2d += t.ms_h2d; a.ms_d2h += t.ms_d2h;
+    a.cells_forward += t.cells_forward; a.cells_reverse += t.cells_reverse; a.cells_band += t.cells_band;
+    a.n_fast += t.n_fast; a.n_exact += t.n_exact; a.n_launches += t.n_launches; a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes;
+    a.ms_band_round0 += t.ms_band_round0; a.ms_band_rest += t.ms_band_rest; a.ms_certify += t.ms_certify; a.band_rounds += t.band_rounds;
+}
+
+// Split the pairs into contiguous chunks, each with the slice of the read/window tables its pairs touch.  Callers that
+// emit pairs in locus order (all of indelPost's call sites) get disjoint or barely overlapping slices; if the
+// slices would re-upload much more than the tables themselves, the batch is not pipelined.
+static bool plan_chunks(const swb_batch* b, std::vector<ChunkPlan>& plans)
+{
+    const int64_t np = b->n_pairs;
+    const bool off = getenv("SWB200_NO_PIPELINE") != nullptr;
+    if (off || np < 524288 || b->n_reads <= 0 || b->n_windows <= 0) return false;
+    int64_t chunkPairs = 524288;          // per-chunk fixed latencies (host round trips, tail rounds) favour large chunks
+    if (const char* e = getenv("SWB200_CHUNK_PAIRS")) chunkPairs = std::max<int64_t>(16384, atoll(e));
+    const int nchunks = (int)std::max<int64_t>(2, (np + chunkPairs - 1) / chunkPairs);
+    int64_t total_r = 0, total_w = 0;
+    for (int32_t i = 0; i < b->n_reads; ++i) total_r = std::max<int64_t>(total_r, b->read_off[i] + std::max(b->read_len[i], 0));
+    for (int32_t i = 0; i < b->n_windows; ++i) total_w = std::max<int64_t>(total_w, b->win_off[i] + std::max(b->win_len[i], 0));
+    int64_t sliced = 0;
+    plans.assign(nchunks, ChunkPlan());
+    for (int k = 0; k < nchunks; ++k) {
+        ChunkPlan& pl = plans[k];
+        pl.p0 = (int32_t)(np * k / nchunks); pl.p1 = (int32_t)(np * (k + 1) / nchunks);
+        int32_t rlo = INT32_MAX, rhi = -1, wlo = INT32_MAX, whi = -1;
+        for (int32_t p = pl.p0; p < pl.p1; ++p) {
+            const int32_t r = b->pair_read[p], w = b->pair_win[p];
+            if (r >= 0 && r < b->n_reads) { rlo = std::min(rlo, r); rhi = std::max(rhi, r); }
+            if (w >= 0 && w < b->n_windows) { wlo = std::min(wlo, w); whi = std::max(whi, w); }
+        }
+        if (rhi < 0) { rlo = 0; rhi = -1; }
+        if (whi < 0) { wlo = 0; whi = -1; }
+        int64_t rb0 = INT64_MAX, rb1 = 0, wb0 = INT64_MAX, wb1 = 0;
+        for (int32_t i = rlo; i <= rhi; ++i) { rb0 = std::min<int64_t>(rb0, b->read_off[i]); rb1 = std::max<int64_t>(rb1, b->read_off[i] + std::max(b->read_len[i], 0)); }
+        for (int32_t i = wlo; i <= whi; ++i) { wb0 = std::min<int64_t>(wb0, b->win_off[i]); wb1 = std::max<int64_t>(wb1, b->win_off[i] + std::max(b->win_len[i], 0)); }
+        if (rhi < rlo) { rb0 = 0; rb1 = 0; }
+        if (whi < wlo) { wb0 = 0; wb1 = 0; }
+        if (rb0 < 0 || wb0 < 0) return false;
+        sliced += (rb1 - rb0) + (wb1 - wb0);
+        pl.b = *b;
+        pl.b.n_pairs = pl.p1 - pl.p0;
+        pl.b.n_reads = rhi - rlo + 1; pl.b.n_windows = whi - wlo + 1;
+        pl.b.reads = b->reads + rb0; pl.b.read_off = b->read_off + rlo; pl.b.read_len = b->read_len + rlo;
+        pl.b.windows = b->windows + wb0; pl.b.win_off = b->win_off + wlo; pl.b.win_len = b->win_len + wlo;
+        pl.b.pair_read = b->pair_read + pl.p0; pl.b.pair_win = b->pair_win + pl.p0;
+        pl.b.ref_beg = b->ref_beg ? b->ref_beg + pl.p0 : nullptr; pl.b.ref_len = b->ref_len ? b->ref_len + pl.p0 : nullptr;
+        pl.b.gap_open = b->gap_open + pl.p0; pl.b.gap_ext = b->gap_ext + pl.p0;
+        pl.b.mask_len = b->mask_len ? b->mask_len + pl.p0 : nullptr;
+        pl.v.sliced = true; pl.v.ridx_base = rlo; pl.v.widx_base = wlo; pl.v.rbyte_base = rb0; pl.v.wbyte_base = wb0;
+        pl.v.n_reads_total = b->n_reads; pl.v.n_windows_total = b->n_windows;
+    }
+    return sliced <= (total_r + total_w) + (total_r + total_w) / 2 + (1 << 20);
+}
+
 extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used) {
-    int rc = swb_upload(c, b);
-    if (rc) return rc;
-    rc = swb_compute(c);
-    if (rc) return rc;
-    return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);
+    if (!c) return -1;
+    std::vector<ChunkPlan> plans;
+    if (!b || !plan_chunks(b, plans)) {
+        int rc = swb_upload(c, b);
+        if (rc) return rc;
+        rc = swb_compute(c);
+        if (rc) return rc;
+        return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);
+    }
+    // ---- pipelined: two lanes (stream + workspace each) driven by two host threads, chunks alternate between them,
+    //      so one lane's H2D / D2H and host round trips overlap the other lane's kernels
+    if (!c->sibling) {
+        c->sibling = swb_create(c->device);
+        if (!c->sibling) { c->err = std::string("cannot create the second pipeline lane: ") + g_create_err; return -1; }
+    }
+    std::atomic<long long> arena_used(0);
+    std::atomic<int> failed(0);
+    std::string errs[2];
+    swb_timing acc[2]; memset(acc, 0, sizeof acc);
+    auto worker = [&](int li) {
+        swb_ctx* L = li ? c->sibling : c;
+        if (cudaSetDevice(L->device) != cudaSuccess) { failed = 1; errs[li] = "cudaSetDevice failed"; return; }
+        for (size_t k = (size_t)li; k < plans.size(); k += 2) {
+            if (failed.load()) return;
+            const ChunkPlan& pl = plans[k];
+            if (upload_view(L, &pl.b, pl.v) || swb_compute(L)) { failed = 1; errs[li] = L->err; return; }
+            const int32_t n = pl.p1 - pl.p0;
+            const long long used = (long long)L->h_bump[1];
+            const long long base = arena_used.fetch_add(used);
+            cudaStream_t s = L->stream;
+            bool ok = true;
+            ok = ok && cudaEventRecord(L->ev[EV_D2H0], s) == cudaSuccess;
+            if (n > 0 && base != 0) k_rebase_cigar<<<(n + 255) / 256, 256, 0, s>>>(L->d.res, n, base);
+            if (n > 0) ok = ok && cudaMemcpyAsync(results + pl.p0, L->d.res, (size_t)n * sizeof(swb_result), cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            if (used > 0 && base + used <= cigar_cap && cigar_arena)
+                ok = ok && cudaMemcpyAsync(cigar_arena + base, L->d.cigar, (size_t)used * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess;
+            ok = ok && cudaEventRecord(L->ev[EV_D2H1], s) == cudaSuccess;
+            ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
+            if (!ok) { failed = 1; errs[li] = std::string("download: ") + cudaGetErrorString(cudaGetLastError()); return; }
+            L->tm.d2h_bytes = (int64_t)n * (int64_t)sizeof(swb_result) + used * 4;
+            cudaEventElapsedTime(&L->tm.ms_d2h, L->ev[EV_D2H0], L->ev[EV_D2H1]);
+            cudaEventElapsedTime(&L->tm.ms_h2d, L->ev[EV_H2D0], L->ev[EV_H2D1]);
+            add_timing(acc[li], L->tm);
+        }
+    };
+    std::thread t1(worker, 1);
+    worker(0);
+    t1.join();
+    cudaSetDevice(c->device);
+    if (failed.load()) { c->err = !errs[0].empty() ? errs[0] : errs[1]; c->computed = false; return -1; }
+    memset(&c->tm, 0, sizeof c->tm);
+    add_timing(c->tm, acc[0]); add_timing(c->tm, acc[1]);
+    c->computed = false; c->have_batch = false;            // the lanes hold chunks, not the batch: swb_download is not valid after this call
+    const long long used = arena_used.load();
+    if (cigar_used) *cigar_used = used;
+    if (used > cigar_cap || (used > 0 && !cigar_arena)) { c->err = "cigar arena too small"; return -2; }
+    return 0;
 }
 
 extern "C" int swb_get_timing(const swb_ctx* c, swb_timing* out) {

@@ -54,6 +54,10 @@ struct SwbDev {
     int32_t max_score;  // max(mat): bound on the score gained per read base
     int32_t fast_ok;    // batch-level eligibility of the DPX fast path (matrix range, n >= 4, score_size)
     int32_t fast_max_cols;
+    // chunk view: the uploaded tables are slices of the caller's tables (pipelined swb_align_batch)
+    int32_t ridx_base, widx_base;     // first read / window index present in the slice
+    int32_t n_reads_total, n_windows_total;
+    int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
     int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass
 };
 

@@ -161,3 +161,27 @@ def test_gpu_overflow_decision_stress(seed):
     rg, ag, tm = gpu_align(b)
     T.compare(rg, ag, ro, ao, what=f"overflow-zone stress seed={seed}")
     assert tm["n_fast"] > 0
+
+
+def test_gpu_pipelined_batch_equals_single_pass(monkeypatch):
+    """large batches go through the two-lane chunked pipeline of swb_align_batch (table slices, index rebasing,
+    CIGAR arena stitched from chunks): results must equal the single-pass path and the oracle"""
+    from gpuutil import gpu_align
+
+    monkeypatch.setenv("SWB200_CHUNK_PAIRS", "70000")          # force several chunks on a test-sized batch
+    b = T.make_pairs_fast(600000, 100, 260, seed=9, reads_per_window=40)
+    # shuffle penalties a bit and add bad indices at chunk edges
+    b.gap_open[::7] = 5
+    b.gap_ext[::5] = 0
+    b.pair_read[12345] = -1
+    b.pair_win[250000] = b.n_windows + 3
+    assert b.n_pairs >= 524288
+    r1, a1, tm1 = gpu_align(b)
+    monkeypatch.setenv("SWB200_NO_PIPELINE", "1")
+    r0, a0, tm0 = gpu_align(b)
+    T.compare(r1, a1, r0, a0, what="pipelined vs single pass")
+    assert r1["status"][12345] == 2 and r1["status"][250000] == 2
+    sub = np.arange(0, b.n_pairs, 97)
+    sub = sub[(sub != 12345) & (sub != 250000)]
+    ro, ao = T.oracle_parallel(b.subset(sub), threads=min(16, os.cpu_count() or 1))
+    T.compare(r1[sub].copy(), a1, ro, ao, what="pipelined vs oracle")
