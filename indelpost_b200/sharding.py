@@ -1,0 +1,104 @@
+"""Host-side sharding of a pair batch over several GPUs.
+
+Pairs are independent and results return per pair, so multi-GPU needs no collective: the batch is cut into
+contiguous ranges with balanced DP work (sum of readLen * windowLen), each range goes to its own swb_ctx
+(one per device, one host thread each), and the per-shard results are stitched back in pair order with the CIGAR
+offsets rebased.  Contiguous ranges keep a locus' reads together, so its window is uploaded to one device only.
+
+`shard_bounds` / `stitch` are pure numpy and are what the torchrun path of bench.py and the gloo tests use;
+`MultiGpuAligner` is the in-process (threads) variant for one host driving several GPUs.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+def pair_cells(read_len, win_len, pair_read, pair_win, ref_len=None, ref_beg=None) -> np.ndarray:
+    """nominal DP cells of every pair: readLen * searched window length"""
+    rl = np.asarray(read_len, dtype=np.int64)[np.asarray(pair_read, dtype=np.int64).clip(0, max(len(read_len) - 1, 0))]
+    if ref_len is not None:
+        wl = np.asarray(ref_len, dtype=np.int64)
+    else:
+        wl = np.asarray(win_len, dtype=np.int64)[np.asarray(pair_win, dtype=np.int64).clip(0, max(len(win_len) - 1, 0))]
+        if ref_beg is not None:
+            wl = wl - np.asarray(ref_beg, dtype=np.int64)
+    return rl * np.maximum(wl, 0)
+
+
+def shard_bounds(cells: np.ndarray, n_shards: int) -> List[Tuple[int, int]]:
+    """contiguous [p0, p1) ranges whose cell sums are as equal as a contiguous cut allows"""
+    n = int(cells.shape[0])
+    n_shards = max(1, int(n_shards))
+    if n == 0:
+        return [(0, 0)] * n_shards
+    csum = np.cumsum(cells.astype(np.float64))
+    total = csum[-1]
+    cuts = [0]
+    for k in range(1, n_shards):
+        target = total * k / n_shards
+        cuts.append(int(np.searchsorted(csum, target, side="left")))
+    cuts.append(n)
+    cuts = np.maximum.accumulate(np.array(cuts))
+    return [(int(cuts[k]), int(cuts[k + 1])) for k in range(n_shards)]
+
+
+def stitch(parts: Sequence[Tuple[np.ndarray, np.ndarray]]) -> Tuple[np.ndarray, np.ndarray]:
+    """concatenate per-shard (results, cigar_arena) in shard order, rebasing cigar_off"""
+    res = [np.array(r, copy=True) for r, _ in parts]
+    base = 0
+    for r, (_, a) in zip(res, parts):
+        if r.shape[0]:
+            r["cigar_off"] = np.where(r["cigar_len"] > 0, r["cigar_off"] + base, r["cigar_off"])
+        base += int(a.shape[0])
+    arena = np.concatenate([a for _, a in parts]) if parts else np.zeros(0, np.uint32)
+    return (np.concatenate(res) if res else np.zeros(0, L.RESULT_DTYPE)), arena
+
+
+def slice_pairs(arrs: dict, p0: int, p1: int) -> dict:
+    """per-pair arrays restricted to [p0, p1); tables are passed whole (the library uploads only the slices a
+    chunk touches when it pipelines, and a shard's tables are small next to the DP work)"""
+    out = dict(arrs)
+    for k in ("pair_read", "pair_win", "gap_open", "gap_ext", "ref_beg", "ref_len", "mask_len"):
+        if out.get(k) is not None:
+            out[k] = np.ascontiguousarray(out[k][p0:p1])
+    return out
+
+
+class MultiGpuAligner:
+    """one BatchAligner per device, one host thread per device, no collective"""
+
+    def __init__(self, devices: Sequence[int]):
+        from .batch import BatchAligner
+
+        self.devices = list(devices)
+        self.aligners = [BatchAligner(d) for d in self.devices]
+        self.pool = ThreadPoolExecutor(max_workers=len(self.devices))
+
+    def close(self):
+        for a in self.aligners:
+            a.close()
+        self.pool.shutdown(wait=False)
+
+    def align(self, reads, read_off, read_len, windows, win_off, win_len, pair_read, pair_win, gap_open, gap_ext,
+              ref_beg=None, ref_len=None, mask_len=None, **kw):
+        arrs = dict(pair_read=np.asarray(pair_read, np.int32), pair_win=np.asarray(pair_win, np.int32),
+                    gap_open=np.asarray(gap_open, np.uint8), gap_ext=np.asarray(gap_ext, np.uint8),
+                    ref_beg=None if ref_beg is None else np.asarray(ref_beg, np.int32),
+                    ref_len=None if ref_len is None else np.asarray(ref_len, np.int32),
+                    mask_len=None if mask_len is None else np.asarray(mask_len, np.int32))
+        cells = pair_cells(read_len, win_len, arrs["pair_read"], arrs["pair_win"], arrs["ref_len"], arrs["ref_beg"])
+        bounds = shard_bounds(cells, len(self.aligners))
+
+        def run(k):
+            p0, p1 = bounds[k]
+            s = slice_pairs(arrs, p0, p1)
+            return self.aligners[k].align(reads, read_off, read_len, windows, win_off, win_len, s["pair_read"], s["pair_win"],
+                                          s["gap_open"], s["gap_ext"], ref_beg=s["ref_beg"], ref_len=s["ref_len"], mask_len=s["mask_len"], **kw)
+
+        parts = list(self.pool.map(run, range(len(self.aligners))))
+        return stitch(parts)

@@ -185,3 +185,22 @@ def test_gpu_pipelined_batch_equals_single_pass(monkeypatch):
     sub = sub[(sub != 12345) & (sub != 250000)]
     ro, ao = T.oracle_parallel(b.subset(sub), threads=min(16, os.cpu_count() or 1))
     T.compare(r1[sub].copy(), a1, ro, ao, what="pipelined vs oracle")
+
+
+def test_multi_gpu_aligner_shards_and_stitches():
+    """host-side sharding over several contexts (here: two contexts on the available device(s))"""
+    import torch
+
+    from indelpost_b200.sharding import MultiGpuAligner
+
+    ndev = max(1, torch.cuda.device_count())
+    devs = [0, 1 % ndev, 0][: 3 if ndev == 1 else 2]
+    b = T.make_pairs(3000, (40, 150), (100, 400), seed=81, reads_per_window=30, grid=True, n_rate=0.003)
+    m = MultiGpuAligner(devs)
+    try:
+        r, a = m.align(b.reads, b.read_off, b.read_len, b.windows, b.win_off, b.win_len, b.pair_read, b.pair_win, b.gap_open, b.gap_ext,
+                       mat=b.mat, n=b.n, score_size=2, flag=1)
+    finally:
+        m.close()
+    ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+    T.compare(r.view(T.RESULT_DTYPE), a, ro, ao, what="MultiGpuAligner vs oracle")
