@@ -134,7 +134,7 @@ struct swb_ctx {
     DevBuf b_reads, b_read_off, b_read_len, b_windows, b_win_off, b_win_len;
     DevBuf b_pair_read, b_pair_win, b_ref_beg, b_ref_len, b_go, b_ge, b_mask, b_mat;
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
-    DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state;
+    DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe;
     int32_t* h_counters = nullptr;              // pinned mirror of counters
     unsigned long long* h_bump = nullptr;       // pinned mirror of bump
     swb_timing tm;
@@ -207,7 +207,7 @@ extern "C" void swb_destroy(swb_ctx* c) {
     DevBuf* all[] = { &c->b_reads, &c->b_read_off, &c->b_read_len, &c->b_windows, &c->b_win_off, &c->b_win_len, &c->b_pair_read, &c->b_pair_win,
                       &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
                       &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
-                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state };
+                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe };
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
@@ -477,6 +477,7 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, c->b_pmask.ensure(np * 4 + 16));  d.p_mask = (int32_t*)c->b_pmask.p;
     CUDA_TRY(c, c->b_mode.ensure(np + 16));       d.p_mode = (uint8_t*)c->b_mode.p;
     CUDA_TRY(c, c->b_state.ensure(np + 16));      d.p_state = (uint8_t*)c->b_state.p;
+    CUDA_TRY(c, c->b_csafe.ensure(np * 4 + 16));  d.p_csafe = (int32_t*)c->b_csafe.p;
     CUDA_TRY(c, c->b_res.ensure(np * sizeof(swb_result) + 16)); d.res = (swb_result*)c->b_res.p;
     CUDA_TRY(c, c->b_lists.ensure((size_t)SWB_NLISTS * (np + 32) * 4));
     for (int i = 0; i < SWB_NLISTS; ++i) d.list[i] = (int32_t*)c->b_lists.p + (size_t)i * (np + 32);

@@ -15,6 +15,8 @@
 //  (a) the gap opens and ends inside ONE striped segment (rows r with the same r / segLen, segLen =
 //      ceil(readLen/16), ssw.c:169): the main loop carries vF through those rows (ssw.c:294-295), the
 //      lazy loop is not involved;
+//  (c) the gap sits in a window column before the first column whose maximum reaches 128+go+ge (recorded by the
+//      forward sweep): every F value of that column is < 128+ge, the signed test is exact there.
 //  (b) every value of the chain is >= 128 + go.  The lazy loop goes on while some lane has
 //      (int8)(vF - ge) > (int8)(H - go) (ssw.c:309-311) with H >= vF (ssw.c:306); a live chain is mis-seen
 //      only if vF - ge >= 128 > H - go, i.e. only for vF in [128 + ge, 127 + go].  The vF a lane carries is
@@ -43,6 +45,7 @@ __device__ __forceinline__ void certify_pair(const SwbDev& d, int p)
         const uint32_t* cg = d.cigar + r.cigar_off;
         int i = r.read_begin1, j = r.ref_begin1, S = 0;
         const int segLen = (L + 15) / 16;
+        const int csafe = d.p_csafe[p];
         bool afterIns = false;
         for (int k = 0; k < r.cigar_len && !ok; ++k) {
             const int len = (int)(cg[k] >> 4), op = (int)(cg[k] & 15);
@@ -61,7 +64,8 @@ __device__ __forceinline__ void certify_pair(const SwbDev& d, int p)
                 const int last = S - go - (len - 1) * ge;
                 const bool sameSeg = i >= 1 && (i - 1) / segLen == (i + len - 1) / segLen;
                 const bool above = last >= 128 + go;
-                if (sameSeg || above) { S = last; if (S < 0) S = 0; }
+                const bool lowCol = (j - 1) < csafe;          // the vertical gap runs in the column of the last matched cell
+                if (sameSeg || above || lowCol) { S = last; if (S < 0) S = 0; }
                 else S = 0;
                 afterIns = true;
                 i += len;

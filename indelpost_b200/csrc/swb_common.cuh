@@ -31,6 +31,7 @@ struct SwbDev {
     int32_t* p_mask;
     uint8_t* p_mode;    // 0: result is byte-mode, 1: word-mode (semantic chosen by k_prepare for the fast path, final mode after forward)
     uint8_t* p_state;   // PST_* flags
+    int32_t* p_csafe;   // fast path: first window column whose column maximum reaches 128+go+ge (wlen if none): up to there the 8-bit pass is exact Gotoh
     // results
     swb_result* res;
     // job lists (indices of pairs) + counters

@@ -242,6 +242,15 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                 const int ov = __shfl_xor_sync(GM, sv, o, G), oi = __shfl_xor_sync(GM, si, o, G);
                 if (ov > sv || (ov == sv && oi < si)) { sv = ov; si = oi; }
             }
+            // first column whose maximum reaches 128+go+ge: every F value before it is < 128+ge, so the signed lazy-F test
+            // (ssw.c:311) is correct there and the 8-bit pass is exact Gotoh up to that column (used by the certificate)
+            const int thr = FAST_C + FAST_SCALE * (128 + q.go + q.ge);
+            int cs = q.ncols;
+            for (int c = g; c < q.ncols; c += G) {
+                if ((int)((colv[c] >> sh) & 0xffffu) >= thr) { cs = c; break; }
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) cs = min(cs, __shfl_xor_sync(GM, cs, o, G));
             const int s2 = sv > FAST_C ? (sv - FAST_C) / FAST_SCALE : 0;
             const int r2 = s2 > 0 ? si : 0;
             if (g == 0) {
@@ -255,6 +264,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
                 } else {
                     r.score1 = (uint16_t)T; r.ref_end1 = end_ref; r.read_end1 = end_read;
+                    d.p_csafe[p] = cs;
                     if (q.mask >= 15) { r.score2 = (uint16_t)s2; r.ref_end2 = r2; } else { r.score2 = 0; r.ref_end2 = -1; }
                     d.p_state[p] = (wordSem && d.score_size == 2) ? (PST_FAST | PST_NEED_CERT) : PST_FAST;
                     { const unsigned am = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am) - 1) atomicAdd(d.counters + CNT_FAST_DONE, __popc(am)); }
