@@ -22,6 +22,7 @@
 
 #include "swb_common.cuh"
 #include "swb_exact.cuh"
+#include "swb_exact2.cuh"
 #include "swb_cert.cuh"
 #include "swb_band.cuh"
 #include "swb_fast.cuh"
@@ -347,6 +348,22 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound) {
     int groups = 128 / W;                                   // groups per block at 128 threads
     while (groups > 32 / W && (size_t)groups * per > (size_t)c->smem_optin) groups /= 2;
     if ((size_t)groups * per > (size_t)c->smem_optin) { c->err = "read too long for the exact kernel's shared-memory profile"; return -1; }
+    // packed variant (two SSE2 lanes per thread) whenever its 16-bit lanes cannot saturate; SWB200_OPT bit1 forces the scalar-lane kernel
+    const bool packed = !(d.opt & 2) && (MODE == 0 || (long long)d.max_score * d.max_rlen <= 32000);
+    if (packed) {
+        const int T2 = W / 2;
+        const int per2 = exact2_smem_per_group(MODE, d.n, d.max_rlen);
+        int g2 = 128 / T2;
+        while (g2 > 32 / T2 && (size_t)g2 * per2 > (size_t)c->smem_optin) g2 /= 2;
+        if ((size_t)g2 * per2 <= (size_t)c->smem_optin) {
+            static bool attr2[2][2] = {};
+            if (!attr2[MODE][DIR]) { cudaFuncSetAttribute(k_exact2<MODE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr2[MODE][DIR] = true; }
+            k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, c->stream>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2);
+            c->tm.n_launches++;
+            CUDA_TRY(c, cudaGetLastError());
+            return stage_check(c, MODE ? (DIR ? "exact2 word rev" : "exact2 word fwd") : (DIR ? "exact2 byte rev" : "exact2 byte fwd"));
+        }
+    }
     const int threads = groups * W;
     const int blocks = (upperBound + groups - 1) / groups;
     k_exact<MODE, DIR><<<blocks, threads, (size_t)groups * per, c->stream>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per);

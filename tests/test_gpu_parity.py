@@ -124,12 +124,16 @@ def test_c_abi_single_pair_entry_points():
         lib.init_destroy(prof)
 
 
-@pytest.mark.parametrize("cfg", [FUZZ[0], FUZZ[2], FUZZ[3]], ids=["150x400", "mixed", "short"])
-def test_gpu_exact_path_alone_matches_oracle(cfg, monkeypatch):
-    """the exact striped-emulation kernels must stay bit-exact on inputs the DPX fast path normally takes"""
+@pytest.mark.parametrize("scalar_lanes", [False, True], ids=["packed", "scalar"])
+@pytest.mark.parametrize("cfg", [FUZZ[0], FUZZ[2], FUZZ[3], FUZZ[9], FUZZ[10]], ids=["150x400", "mixed", "short", "go<ge", "go=ge=0"])
+def test_gpu_exact_path_alone_matches_oracle(cfg, scalar_lanes, monkeypatch):
+    """the exact striped-emulation kernels (packed two-lanes-per-thread variant and the scalar-lane one) must stay
+    bit-exact on inputs the DPX fast path normally takes"""
     from gpuutil import gpu_align
 
     monkeypatch.setenv("SWB200_NO_FAST", "1")
+    if scalar_lanes:
+        monkeypatch.setenv("SWB200_OPT", "2")
     b = T.make_pairs(**{**cfg, "n_pairs": 1500})
     ro, ao = T.oracle().align_batch(b)
     rg, ag, tm = gpu_align(b)
