@@ -125,8 +125,8 @@ enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0
 
 struct swb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
+    cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
     cudaEvent_t ev[EV_COUNT];
     std::string err;
     SwbDev d;
@@ -187,7 +187,9 @@ extern "C" swb_ctx* swb_create(int device) {
     }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
     cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
     cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t));
     cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long));
     // opt in to large dynamic shared memory for the exact kernels
@@ -213,7 +215,8 @@ extern "C" void swb_destroy(swb_ctx* c) {
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
     cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->stream3); cudaEventDestroy(c->ev_fork3);
+    cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); cudaEventDestroy(c->ev_join2);
     delete c;
 }
 
@@ -339,8 +342,9 @@ static int read_counters(swb_ctx* c) {
 }
 
 template <int MODE, int DIR>
-static int launch_exact(swb_ctx* c, int listSlot, int upperBound) {
+static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t st = nullptr) {
     if (upperBound <= 0) return 0;
+    if (!st) st = c->stream;
     const SwbDev& d = c->d;
     const int W = MODE ? 8 : 16;
     const int segAlloc = (d.max_rlen + W - 1) / W;
@@ -358,7 +362,7 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound) {
         if ((size_t)g2 * per2 <= (size_t)c->smem_optin) {
             static bool attr2[2][2] = {};
             if (!attr2[MODE][DIR]) { cudaFuncSetAttribute(k_exact2<MODE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr2[MODE][DIR] = true; }
-            k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, c->stream>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2);
+            k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2);
             c->tm.n_launches++;
             CUDA_TRY(c, cudaGetLastError());
             return stage_check(c, MODE ? (DIR ? "exact2 word rev" : "exact2 word fwd") : (DIR ? "exact2 byte rev" : "exact2 byte fwd"));
@@ -366,7 +370,7 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound) {
     }
     const int threads = groups * W;
     const int blocks = (upperBound + groups - 1) / groups;
-    k_exact<MODE, DIR><<<blocks, threads, (size_t)groups * per, c->stream>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per);
+    k_exact<MODE, DIR><<<blocks, threads, (size_t)groups * per, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per);
     c->tm.n_launches++;
     CUDA_TRY(c, cudaGetLastError());
     return stage_check(c, MODE ? (DIR ? "exact word rev" : "exact word fwd") : (DIR ? "exact byte rev" : "exact byte fwd"));
@@ -421,15 +425,17 @@ static int launch_fast(swb_ctx* c, const int* counts) {
 
 // banded DP + traceback (ssw.c:897-916) over the four band-class lists; a launch round per class, repeated only
 // for pairs the kernel re-queued (scratch exhausted, or band outgrew the shared-memory rows)
-static int run_band_rounds(swb_ctx* c, bool record) {
+static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, int* firstJobs = nullptr) {
     SwbDev& d = c->d;
     cudaStream_t s = c->stream;
     if (read_counters(c)) return -1;
-    int cur = LIST_BAND, nxt = LIST_BAND_NEXT;
+    int cur = firstBase, nxt = LIST_BAND_NEXT;
     int round = 0, stalls = 0;
+    if (firstJobs) *firstJobs = 0;
     for (;;) {
         int njobs[SWB_NBANDCLASS], total = 0;
         for (int k = 0; k < SWB_NBANDCLASS; ++k) { njobs[k] = c->h_counters[cur + k]; total += njobs[k]; }
+        if (round == 0 && firstJobs) *firstJobs = total;
         if (total <= 0) break;
         CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
@@ -470,8 +476,8 @@ static int run_band_rounds(swb_ctx* c, bool record) {
         if (++round > 64) { c->err = "banded traceback did not converge"; return -1; }
     }
     if (record && round == 0) CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_R0], s));
-    // leave both list sets empty for a later phase
-    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND, 0, 4 * SWB_NBANDCLASS, s));
+    // leave the list sets this call used empty for a later phase
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + firstBase, 0, 4 * SWB_NBANDCLASS, s));
     CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND_NEXT, 0, 4 * SWB_NBANDCLASS, s));
     return 0;
 }
@@ -551,25 +557,47 @@ extern "C" int swb_compute(swb_ctx* c) {
     if (launch_exact<1, 1>(c, LIST_WORD_REV, (int)np)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));
 
-    // ---- banded DP + traceback (ssw.c:897-916) -----------------------------------------------------
+    // ---- banded DP + traceback (ssw.c:897-916), overlapped with the overflow verification -----------------------
+    // phase 1: the pairs that can fail the certificate (provisional 16-bit result + net insertion), then the certificate
+    //          pass over them; their exact 8-bit verification is launched on the side stream (grid sized by an upper
+    //          bound, the kernel reads the real count) while
+    // phase 2: the bulk of the traceback runs on the main stream.
     tm.band_rounds = 0;
-    if (run_band_rounds(c, true)) return -1;
-    CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_ALL], s));
-
-    // ---- provisional 16-bit results without an overflow certificate (k_band queued them): exact 8-bit pass ----
-    if (nFastTotal > 0 && d.score_size == 2) {
-        // pairs whose CIGAR was not requested (flag / filters) never reached the inline certificate: sweep the flags
-        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np);
+    const bool certify = nFastTotal > 0 && d.score_size == 2;
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));      // consumed by the reverse stage; reused by the verification
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
+    int nFirst = 0;
+    if (run_band_rounds(c, false, LIST_BAND_FIRST, &nFirst)) return -1;
+    bool forked = false;
+    if (certify && nFirst > 0) {
+        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, LIST_VERIFY);
         tm.n_launches++;
         CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
+        if (launch_exact<0, 0>(c, LIST_VERIFY, nFirst, c->stream3)) return -1;     // confirms the overflow, or produces the byte-mode result
+        CUDA_TRY(c, cudaEventRecord(c->ev_join2, c->stream3));
+        forked = true;
+    }
+    if (run_band_rounds(c, true, LIST_BAND)) return -1;
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_ALL], s));
+    if (forked) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join2, 0));
+
+    // ---- leftovers: certificate for the pairs of phase 2 (rarely fails), byte-mode redo for verified pairs whose 8-bit
+    //      pass did not overflow (never observed in practice)
+    if (certify) {
+        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, LIST_VERIFY2);
+        tm.n_launches++;
+        CUDA_TRY(c, cudaGetLastError());
+        if (stage_check(c, "certify")) return -1;
         if (read_counters(c)) return -1;
-        const int nverify = c->h_counters[LIST_VERIFY];
-        if (nverify > 0) {
-            CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));
-            CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
-            if (launch_exact<0, 0>(c, LIST_VERIFY, nverify)) return -1;       // confirms the overflow, or produces the byte-mode result
-            if (launch_exact<0, 1>(c, LIST_BYTE_REV, nverify)) return -1;
-            if (run_band_rounds(c, false)) return -1;
+        const int nverify2 = c->h_counters[LIST_VERIFY2];
+        if (nverify2 > 0 && launch_exact<0, 0>(c, LIST_VERIFY2, nverify2)) return -1;
+        if (nverify2 > 0 && read_counters(c)) return -1;
+        const int nbyte = c->h_counters[CNT_BYTE_REV];
+        if (nbyte > 0) {
+            if (launch_exact<0, 1>(c, LIST_BYTE_REV, nbyte)) return -1;
+            if (run_band_rounds(c, false, LIST_BAND)) return -1;
         }
     }
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND], s));

@@ -62,13 +62,62 @@ __device__ __forceinline__ int band_dir_at(const uint32_t* dir, const BandGeom& 
     return sel == 0 ? 1 : (sel == 1 ? de : df);
 }
 
-// walk the traceback; if out != nullptr write the ops reversed into out[0..total)
-__device__ __forceinline__ int band_traceback(const uint32_t* dir, const BandGeom& g, uint32_t* out, int total) {
+// Walk the traceback (ssw.c:672-751).  The packed direction words of the row being visited are held in registers and
+// the row above is prefetched while the current row is processed (a step moves up by at most one row), so the walk is
+// not a chain of dependent L2 round trips.  Ops are produced last-to-first; the first `BAND_OPBUF` of them are kept in
+// registers so the common case needs a single walk: the caller allocates arena space for the returned count and
+// calls band_emit().  Returns the op count, or -1 for the reference's "Trace back error" (ssw.c:711-719).
+#define BAND_OPBUF 12
+#define BAND_ROWWORDS 5                               // words per band row held in registers (band width <= 40)
+
+struct BandOps { uint32_t op[BAND_OPBUF]; int n; };
+
+__device__ __forceinline__ void band_push(BandOps& o, uint32_t v, uint32_t* out, int total) {
+    if (o.n < BAND_OPBUF) {
+#pragma unroll
+        for (int q = 0; q < BAND_OPBUF; ++q) if (q == o.n) o.op[q] = v;      // register-indexed store
+    }
+    ++o.n;
+    if (out) out[total - o.n] = v;
+}
+
+template <bool REGROWS>
+__device__ __forceinline__ int band_traceback(const uint32_t* dir, const BandGeom& g, BandOps& ops, uint32_t* out, int total) {
     int i = g.readLen - 1, j = g.refLen - 1;
-    int e = 0, l = 0, state = 2;
+    int e = 0, state = 2;
     int op = 0, prev_op = 0;                           // 0 M, 1 I, 2 D  (BAM op codes)
+    ops.n = 0;
+    uint32_t cur[BAND_ROWWORDS], nxt[BAND_ROWWORDS];
+    int curRow = -1;
+    if (REGROWS && i >= 0) {
+#pragma unroll
+        for (int q = 0; q < BAND_ROWWORDS; ++q) cur[q] = q < g.strideW ? dir[(size_t)i * g.strideW + q] : 0u;
+#pragma unroll
+        for (int q = 0; q < BAND_ROWWORDS; ++q) nxt[q] = (q < g.strideW && i >= 1) ? dir[(size_t)(i - 1) * g.strideW + q] : 0u;
+        curRow = i;
+    }
     while (i >= 0 && j > 0) {                          // ssw.c:679
-        const int dv = band_dir_at(dir, g, i, j, state);
+        int dv;
+        const int x = j - band_x(g.w, i);
+        if (REGROWS && x >= 0 && x < g.width_d && j <= g.end(i)) {
+            if (curRow != i) {                         // moved up: rotate the prefetched row in (or reload after a fallback step), prefetch the next
+                const bool oneUp = curRow - 1 == i;
+#pragma unroll
+                for (int q = 0; q < BAND_ROWWORDS; ++q) cur[q] = oneUp ? nxt[q] : (q < g.strideW ? dir[(size_t)i * g.strideW + q] : 0u);
+#pragma unroll
+                for (int q = 0; q < BAND_ROWWORDS; ++q) nxt[q] = (q < g.strideW && i >= 1) ? dir[(size_t)(i - 1) * g.strideW + q] : 0u;
+                curRow = i;
+            }
+            uint32_t w = cur[0];
+#pragma unroll
+            for (int q = 1; q < BAND_ROWWORDS; ++q) if ((x >> 3) == q) w = cur[q];
+            const int b = (int)((w >> (4 * (x & 7))) & 15u);
+            const int de = 2 + (b & 1), df = 4 + ((b >> 1) & 1);
+            const int sel = (b >> 2) & 3;
+            dv = state == 0 ? de : (state == 1 ? df : (sel == 0 ? 1 : (sel == 1 ? de : df)));
+        } else {
+            dv = band_dir_at(dir, g, i, j, state);     // out-of-band corner cases, literal index arithmetic
+        }
         switch (dv) {
             case 1: --i; --j; state = 2; op = 0; break;
             case 2: --i;      state = 0; op = 1; break;
@@ -79,19 +128,17 @@ __device__ __forceinline__ int band_traceback(const uint32_t* dir, const BandGeo
         }
         if (op == prev_op) ++e;
         else {
-            ++l;
-            if (out) out[total - l] = ((uint32_t)e << 4) | (uint32_t)prev_op;
+            band_push(ops, ((uint32_t)e << 4) | (uint32_t)prev_op, out, total);
             prev_op = op; e = 1;
         }
     }
     if (op == 0) {                                     // ssw.c:734-751
-        ++l;
-        if (out) out[total - l] = ((uint32_t)(e + 1) << 4) | 0u;
+        band_push(ops, ((uint32_t)(e + 1) << 4) | 0u, out, total);
     } else {
-        l += 2;
-        if (out) { out[total - (l - 1)] = ((uint32_t)e << 4) | (uint32_t)op; out[total - l] = (1u << 4) | 0u; }
+        band_push(ops, ((uint32_t)e << 4) | (uint32_t)op, out, total);
+        band_push(ops, (1u << 4) | 0u, out, total);
     }
-    return l;
+    return ops.n;
 }
 
 // rolling-row accessor: shared memory [slot][thread] (LOCAL) or a private global array (wide bands)
@@ -251,12 +298,20 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass)
     }
     warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
 
-    // ---- traceback: count, allocate, emit ---------------------------------------------------------
-    const int l = band_traceback(dir, g, nullptr, 0);
-    if (l < 0) { r.flag = 1; r.cigar_len = 0; r.cigar_off = 0; return; }      // ssw.c:911
+    // ---- traceback: one walk (ops buffered in registers), allocate, emit reversed ---------------------------------
+    BandOps ops;
+    const bool regRows = g.strideW <= BAND_ROWWORDS;
+    const int l = regRows ? band_traceback<true>(dir, g, ops, nullptr, 0) : band_traceback<false>(dir, g, ops, nullptr, 0);
+    if (l < 0) { r.flag = 1; r.cigar_len = 0; r.cigar_off = 0; d.p_state[p] |= PST_BAND_DONE; return; }      // ssw.c:911
     const unsigned long long coff = warp_bump(&d.bump[1], (unsigned long long)l);
     r.cigar_len = l; r.cigar_off = (int64_t)coff;
     if ((long long)coff + l > d.cigar_cap) { atomicAdd(d.counters + CNT_CIGAR_OVERFLOW, 1); return; }
-    band_traceback(dir, g, d.cigar + coff, l);
-    if (d.opt & 1) certify_pair(d, p);                 // SWB200_OPT bit0: certificate inline (default: k_certify_rest, a cheaper separate pass)
+    if (l <= BAND_OPBUF) {
+#pragma unroll
+        for (int q = 0; q < BAND_OPBUF; ++q) if (q < l) d.cigar[coff + (l - 1 - q)] = ops.op[q];   // reverse (ssw.c:753-762)
+    } else {
+        // more ops than the register buffer holds: walk again, writing straight into the arena
+        if (regRows) band_traceback<true>(dir, g, ops, d.cigar + coff, l); else band_traceback<false>(dir, g, ops, d.cigar + coff, l);
+    }
+    d.p_state[p] |= PST_BAND_DONE;                     // the certificate pass (k_certify_rest) may now look at this pair
 }

@@ -30,10 +30,10 @@
 
 // returns true if the pair's provisional 16-bit result is certified (or needs no certificate); otherwise flags it
 // PST_HAVE_WORD and queues it for the exact 8-bit pass.  Called by the thread that just emitted the CIGAR.
-__device__ __forceinline__ void certify_pair(const SwbDev& d, int p)
+__device__ __forceinline__ void certify_pair(const SwbDev& d, int p, int verifyList)
 {
     const int st = d.p_state[p];
-    if (!(st & PST_NEED_CERT)) return;
+    if (!(st & PST_NEED_CERT) || !(st & PST_BAND_DONE)) return;
     const swb_result& r = d.res[p];
     const int limit = 255 - d.bias;
     bool ok = false;
@@ -77,13 +77,13 @@ __device__ __forceinline__ void certify_pair(const SwbDev& d, int p)
     if (ok) { d.p_state[p] = st & ~PST_NEED_CERT; return; }
     d.p_state[p] = (st & ~PST_NEED_CERT) | PST_HAVE_WORD;
     atomicAdd(d.counters + CNT_CERT_FAIL, 1);
-    list_push(d.list[LIST_VERIFY], d.counters + LIST_VERIFY, p);
+    list_push(d.list[verifyList], d.counters + verifyList, p);
 }
 
-// pairs that still carry PST_NEED_CERT after the band stage (no CIGAR requested or traceback failed)
-__global__ void k_certify_rest(SwbDev d, int32_t p0, int32_t p1)
+// certificate pass over the pairs whose traceback has finished (PST_BAND_DONE) and that still carry PST_NEED_CERT
+__global__ void k_certify_rest(SwbDev d, int32_t p0, int32_t p1, int verifyList)
 {
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
-    certify_pair(d, p);
+    certify_pair(d, p, verifyList);
 }

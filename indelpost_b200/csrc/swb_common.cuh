@@ -7,7 +7,7 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 36
+#define SWB_NLISTS 40
 #define SWB_NCOUNTERS 64
 
 // ---------------------------------------------------------------------------------------------
@@ -64,8 +64,8 @@ struct SwbDev {
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
 #define SWB_NBANDCLASS 5         // band jobs are bucketed by half-width: 1 | 2-4 | 5-16 | 17-112 (32-thread blocks) | wider (global-memory rows)
-enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4,
-       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 29 };
+enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
+       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 29, LIST_BAND_FIRST = 34 };
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 29,
        CNT_CELLS_FWD = 40, CNT_CELLS_REV = 42, CNT_CELLS_BAND = 44, CNT_BAND_OVERFLOW = 46, CNT_CIGAR_OVERFLOW = 47,
@@ -73,7 +73,8 @@ enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
 // p_state flags
 enum { PST_FAST = 1,        // forward result produced by the DPX fast path
        PST_NEED_CERT = 2,   // word-mode result accepted provisionally: the 8-bit pass still has to be shown to overflow
-       PST_HAVE_WORD = 4 }; // 16-bit result already in place: the exact 8-bit pass only verifies the overflow
+       PST_HAVE_WORD = 4,   // 16-bit result already in place: the exact 8-bit pass only verifies the overflow
+       PST_BAND_DONE = 8 }; // traceback finished (or no CIGAR requested): the certificate may look at the pair
 
 __device__ __forceinline__ void list_push(int32_t* list, int32_t* counter, int32_t v) {
     // warp-aggregated append; lanes are grouped by destination list (one call site may feed several lists)
@@ -120,7 +121,10 @@ __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_resu
     int dl = (r.ref_end1 - r.ref_begin1) - (r.read_end1 - r.read_begin1);
     const int bw = (dl < 0 ? -dl : dl) + 1;
     const int c = band_class(bw);
-    list_push(d.list[LIST_BAND + c], d.counters + CNT_BAND + c, p);
+    // provisional 16-bit results whose alignment has a net insertion are the only ones that can fail the overflow
+    // certificate (swb_cert.cuh): they are traced back first so their verification overlaps the rest of the stage
+    const int base = ((d.p_state[p] & PST_NEED_CERT) && dl < 0) ? LIST_BAND_FIRST : LIST_BAND;
+    list_push(d.list[base + c], d.counters + base + c, p);
 }
 
 // sswpy.pyx:16-29 DNA_BASE_LUT

@@ -251,7 +251,7 @@ k_exact(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ 
             const int f = d.flag;
             const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
                                  ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));   // ssw.c:894
-            if (!noCigar) push_band(d, p, r);
+            if (!noCigar) push_band(d, p, r); else d.p_state[p] |= PST_BAND_DONE;
         }
     }
 }

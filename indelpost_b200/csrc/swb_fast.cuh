@@ -270,6 +270,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     { const unsigned am = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am) - 1) atomicAdd(d.counters + CNT_FAST_DONE, __popc(am)); }
                     const bool scoreOnly = d.flag == 0 || (d.flag == 2 && T < (int)d.filters);     // ssw.c:872
                     if (!scoreOnly) list_push(d.list[LIST_FAST_REV + BKT], d.counters + CNT_FAST_REV + BKT, p);
+                    else d.p_state[p] |= PST_BAND_DONE;                            // no reverse pass / traceback will follow
                 }
             }
         } else {
@@ -295,7 +296,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     const int f = d.flag;
                     const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
                                          ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));
-                    if (!noCigar) push_band(d, p, r);
+                    if (!noCigar) push_band(d, p, r); else d.p_state[p] |= PST_BAND_DONE;
                 }
             }
         }
