@@ -315,6 +315,7 @@ static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v) {
     for (int i = 0; i < b->n * b->n; ++i) { mx = std::max<int>(mx, b->mat[i]); if (b->mat[i] > 7 || b->mat[i] < -7) small = false; }
     d.max_score = mx;
     { const char* o = getenv("SWB200_OPT"); d.opt = o ? atoi(o) : 0; }
+    d.one = 1;
     d.fast_ok = (small && b->n >= 4 && mx > 0 && (b->score_size == 1 || b->score_size == 2) && !getenv("SWB200_NO_FAST")) ? 1 : 0;
     c->have_batch = true;
     return 0;

@@ -59,6 +59,7 @@ struct SwbDev {
     int32_t ridx_base, widx_base;     // first read / window index present in the slice
     int32_t n_reads_total, n_windows_total;
     int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
+    int32_t one;        // always 1, but opaque to the compiler: x * one + c compiles to a real IMAD (FMA pipe) instead of an ALU-pipe add
     int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass
 };
 

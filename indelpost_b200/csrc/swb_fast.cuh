@@ -131,6 +131,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     uint32_t goP = pack2(FAST_SCALE * ln[0].go, FAST_SCALE * ln[1].go);
     uint32_t ngeP = pack2(-FAST_SCALE * ln[0].ge, -FAST_SCALE * ln[1].ge);
     uint32_t rowBase = pack2(g * R, g * R);
+    const uint32_t one = (uint32_t)d.one;
     // keep the loop invariants in registers (ptxas otherwise rematerialises them every step)
     asm volatile("" : "+r"(goP), "+r"(ngeP), "+r"(rowBase));
 #pragma unroll
@@ -159,15 +160,21 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             uint32_t F = inF, hd = prevInH, cm = 0;
             prevInH = inH;
 #pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const uint32_t s = prmt(tA[k], tB[k], sel);
-                uint32_t h = __viaddmax_s16x2(hd, s, E[k]);                      // max(Hdiag + s, E)
-                h = __vimax3_s16x2(h, F, FAST_CPACK);                            // max(., F, 0)
-                hd = H[k]; H[k] = h;
-                cm = __viaddmax_s16x2(h, (uint32_t)((-k) & 0xffff) * 0x00010001u, cm);      // column best over keys (value - rowInThread)
-                const uint32_t hg = h - goP;                                     // FMA-pipe IADD; no lane borrow: h >= 0x4000 > 16*go
-                E[k] = __viaddmax_s16x2(E[k], ngeP, hg);                         // max(E - ge, H - go)
-                F = __viaddmax_s16x2(F, ngeP, hg);                               // max(F - ge, H - go)
+            for (int k = 0; k < R; k += 2) {
+                uint32_t key[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int kk = k + u;
+                    const uint32_t s = prmt(tA[kk], tB[kk], sel);
+                    uint32_t h = __viaddmax_s16x2(hd, s, E[kk]);                 // max(Hdiag + s, E)
+                    h = __vimax3_s16x2(h, F, FAST_CPACK);                        // max(., F, 0)
+                    hd = H[kk]; H[kk] = h;
+                    key[u] = h * one - (uint32_t)(kk * 0x00010001);              // value - rowInThread: a true IMAD (FMA pipe), no lane borrow
+                    const uint32_t hg = h - goP;                                 // FMA-pipe IADD; no lane borrow: h >= 0x4000 > 16*go
+                    E[kk] = __viaddmax_s16x2(E[kk], ngeP, hg);                   // max(E - ge, H - go)
+                    F = __viaddmax_s16x2(F, ngeP, hg);                           // max(F - ge, H - go)
+                }
+                cm = __vimax3_s16x2(cm, key[0], key[1]);                         // column best over keys, two rows per ALU instruction
             }
             outH = H[R - 1]; outF = F;
             // local column best -> (value, absolute row); merge with the rows above (they win ties)
