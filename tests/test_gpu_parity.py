@@ -208,3 +208,52 @@ def test_multi_gpu_aligner_shards_and_stitches():
         m.close()
     ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
     T.compare(r.view(T.RESULT_DTYPE), a, ro, ao, what="MultiGpuAligner vs oracle")
+
+
+def _random_matrix_batch(n, seed, n_pairs=600, rl=(30, 140), wl=(80, 300), vmax=6):
+    rng = np.random.default_rng(seed)
+    mat = rng.integers(-vmax, 1, size=(n, n)).astype(np.int8)
+    mat = np.minimum(mat, mat.T)
+    for i in range(n):
+        mat[i, i] = rng.integers(1, vmax + 1)
+    wins, reads = [], []
+    for p in range(n_pairs):
+        W = rng.integers(0, n, size=int(rng.integers(wl[0], wl[1] + 1)), dtype=np.int8)
+        L = int(min(rng.integers(rl[0], rl[1] + 1), W.shape[0] - 5))
+        s = int(rng.integers(0, W.shape[0] - L))
+        r = W[s:s + L].copy()
+        m = rng.random(L) < 0.05
+        r[m] = rng.integers(0, n, size=int(m.sum()), dtype=np.int8)
+        if rng.random() < 0.4:
+            x = int(rng.integers(3, L - 3)); k = int(rng.integers(1, 6))
+            r = np.concatenate([r[:x], r[x + k:]]) if rng.random() < 0.5 else np.concatenate([r[:x], rng.integers(0, n, size=k, dtype=np.int8), r[x:]])
+        wins.append(W); reads.append(r.astype(np.int8))
+    idx = np.arange(n_pairs, dtype=np.int32)
+    b = T.batch_from_lists(reads, wins, idx, idx, rng.integers(2, 8, size=n_pairs), rng.integers(0, 3, size=n_pairs))
+    b.mat = mat.reshape(-1)
+    b.n = n
+    return b
+
+
+@pytest.mark.parametrize("n,vmax", [(4, 5), (5, 7), (8, 6), (21, 4), (5, 20)], ids=["n4", "n5", "n8", "n21-protein-like", "n5-big-scores"])
+def test_gpu_general_substitution_matrices(n, vmax):
+    """ssw_init takes any n x n matrix (ssw.h:86): fast path for |mat| <= 7 and windows of codes 0..3, exact path otherwise"""
+    from gpuutil import gpu_align
+
+    b = _random_matrix_batch(n, seed=400 + n + vmax, vmax=vmax)
+    ro, ao = T.oracle().align_batch(b)
+    rg, ag, _ = gpu_align(b)
+    T.compare(rg, ag, ro, ao, what=f"matrix n={n} vmax={vmax}")
+
+
+def test_gpu_long_reads_and_windows_beyond_fast_path_limits():
+    from gpuutil import gpu_align
+
+    cfgs = [dict(n_pairs=120, read_len=(257, 700), win_len=(800, 1500), seed=501, max_indel=30),      # reads longer than the fast path's 256 rows
+            dict(n_pairs=40, read_len=(100, 250), win_len=(12000, 14000), seed=502, max_indel=10),     # windows beyond its shared-memory column budget
+            dict(n_pairs=60, read_len=(342, 400), win_len=(500, 700), seed=503, max_indel=5)]          # max(mat)*L > 1023
+    for cfg in cfgs:
+        b = T.make_pairs(**cfg)
+        ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+        rg, ag, tm = gpu_align(b)
+        T.compare(rg, ag, ro, ao, what=f"long {cfg}")
