@@ -291,7 +291,10 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass)
             }
             if (end >= beg && ((end - xi) & 7) != 7) line[(end - xi) >> 3] = word;
             cells += end - beg + 1;
-            for (int j = 1; j <= u; ++j) hPrev[j] = hCur[j];             // ssw.c:666
+            // ssw.c:666 copies the row just computed (slots 1..u) into the previous-row buffer.  Every slot the next row
+            // reads is either one of those or is zeroed at its start (ssw.c:633), so exchanging the two buffers is
+            // equivalent and saves a shared-memory round trip per cell.
+            { auto* tp = hPrev.p; hPrev.p = hCur.p; hCur.p = tp; }
         }
         if (best < score && bw * 2 <= len) { bw *= 2; continue; }       // ssw.c:668-669: widen and redo
         break;
