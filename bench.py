@@ -297,7 +297,15 @@ def run_ours(args):
         # dominant kernel family = forward sweep; algorithmic cells per launch = sum(readLen*winLen) of this rank
         fwd_ms = stage["ms_forward"] / args.steps
         achieved = cells / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
-        alg_bytes = int(h2d)  # every input byte is read once by the sweep
+        alg_bytes = int(h2d) + args.pairs * 40  # every input byte is read once by the sweep, one 40-byte result record written per pair
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            k = tj["kernels"].get("k_fast_fwd")
+            if k:
+                traffic = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["pairs"] * args.pairs
+                traffic_src = tj["source"] + ": dram__bytes_read.sum + dram__bytes_write.sum of k_fast<10,0>, scaled per pair"
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"
@@ -320,7 +328,8 @@ def run_ours(args):
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "path_split": {"n_fast": int(tm.get("n_fast", 0)), "n_exact": int(tm.get("n_exact", 0))},
             "roofline": {"bound": "dpx", "kernel": "forward sweep (score/end/sub-optimal)", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
-                         "frac": achieved / peak_gcups if peak_gcups else None, "traffic": None,
+                         "frac": achieved / peak_gcups if peak_gcups else None, "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
                          "peak_source": pk.get("source", "profiles/dpx_peak.json"),
                          "hbm": {"achieved_gbs": alg_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                                  "note": "algorithmic bytes = inputs read once (~0.009 B per cell): the path is integer-issue bound, not HBM bound"}},
