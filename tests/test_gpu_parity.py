@@ -257,3 +257,18 @@ def test_gpu_long_reads_and_windows_beyond_fast_path_limits():
         ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
         rg, ag, tm = gpu_align(b)
         T.compare(rg, ag, ro, ao, what=f"long {cfg}")
+
+
+@pytest.mark.parametrize("flag,filters,filterd", [(0, 0, 0), (8, 0, 0), (2, 420, 0), (4, 0, 148), (6, 400, 150), (1, 0, 0), (9, 0, 0), (3, 430, 0)])
+def test_gpu_flag_and_filter_variants(flag, filters, filterd):
+    """ssw_align's flag bits (ssw.c:816-824, 872, 894): score only / begin positions only / CIGAR only above a score
+    filter or below a length filter.  Pairs that skip the traceback still have to pass the 8-bit/16-bit escalation check."""
+    from gpuutil import gpu_align
+
+    b = T.make_pairs(2500, (60, 150), 400, seed=600 + flag, max_indel=12, junk_tail=0.1)
+    b.flag, b.filters, b.filterd = flag, filters, filterd
+    ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+    rg, ag, _ = gpu_align(b)
+    T.compare(rg, ag, ro, ao, what=f"flag={flag} filters={filters} filterd={filterd}")
+    if flag in (2, 4, 6, 3):
+        assert 0 < int((ro["cigar_len"] > 0).sum()) < b.n_pairs      # the filters really split the batch
