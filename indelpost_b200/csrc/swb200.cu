@@ -98,6 +98,7 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         d.p_mode[p] = wordSem ? 1 : 0;
         const int b = (lp16 + 31) / 32 - 1;
         list_push(d.list[LIST_FAST_FWD + b], d.counters + CNT_FAST_FWD + b, p);
+        atomicMax(d.counters + CNT_FAST_MAXCOLS + b, wl);
     }
     else if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
     else list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
@@ -135,7 +136,8 @@ struct swb_ctx {
     DevBuf b_reads, b_read_off, b_read_len, b_windows, b_win_off, b_win_len;
     DevBuf b_pair_read, b_pair_win, b_ref_beg, b_ref_len, b_go, b_ge, b_mask, b_mat;
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
-    DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe;
+    DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe, b_fastcols;
+    int fastMaxCols[SWB_NBUCKETS] = {};
     int32_t* h_counters = nullptr;              // pinned mirror of counters
     unsigned long long* h_bump = nullptr;       // pinned mirror of bump
     swb_timing tm;
@@ -199,6 +201,7 @@ extern "C" swb_ctx* swb_create(int device) {
     cudaFuncSetAttribute(k_exact<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
     cudaFuncSetAttribute(k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS));
     cudaFuncSetAttribute(k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS));
+    cudaFuncSetAttribute(k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS));
     return c;
 }
 
@@ -210,7 +213,7 @@ extern "C" void swb_destroy(swb_ctx* c) {
     DevBuf* all[] = { &c->b_reads, &c->b_read_off, &c->b_read_len, &c->b_windows, &c->b_win_off, &c->b_win_len, &c->b_pair_read, &c->b_pair_win,
                       &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
                       &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
-                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe };
+                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe, &c->b_fastcols };
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
@@ -378,26 +381,40 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t s
 }
 
 // fast-path launch geometry: groups of FAST_G threads, 10 bytes of shared memory per column per group
-static int fast_col_alloc(const SwbDev& d) { return (std::max(d.max_wlen, 8) + 7) & ~7; }
+#define SWB_FAST_SMEM_COLS 1024     // windows longer than this keep their column bests in global memory
 
 template <int R, int DIR>
 static int launch_fast_one(swb_ctx* c, int bucket, int upperBoundPairs) {
-    const SwbDev& d = c->d;
-    const int colAlloc = fast_col_alloc(d);
-    const size_t per = (size_t)colAlloc * 10;
+    SwbDev& d = c->d;
+    const int colAlloc = (std::max(c->fastMaxCols[bucket], 8) + 7) & ~7;      // longest window among this bucket's pairs
+    const bool globalCols = colAlloc > SWB_FAST_SMEM_COLS;
+    const size_t per = (size_t)colAlloc * (globalCols ? 2 : 10);
+    // long windows: the global column-best scratch is bounded, the bucket is served in slices of the job list
+    int slicePairs = upperBoundPairs;
+    if (globalCols) {
+        const size_t budget = (size_t)4 << 30;
+        const size_t perPairPair = (size_t)2 * colAlloc * 4;
+        const size_t evenBudget = std::max<size_t>(2, 2 * (budget / perPairPair));      // pairs per slice (even: lane pairs stay intact)
+        slicePairs = (size_t)upperBoundPairs <= evenBudget ? upperBoundPairs : (int)evenBudget;
+        CUDA_TRY(c, c->b_fastcols.ensure((size_t)((slicePairs + 1) / 2) * perPairPair + 16));
+        d.fast_cols = (uint32_t*)c->b_fastcols.p;
+    } else d.fast_cols = nullptr;
     int groups = 128 / FAST_G;
     while (groups > 2 && groups * per > (size_t)c->smem_optin - 1024) groups /= 2;
     const int threads = groups * FAST_G;
-    const int ngroups = (upperBoundPairs + 1) / 2;
-    const int blocks = (ngroups + groups - 1) / groups;
     static bool attr_set[2][SWB_NBUCKETS] = {};
     if (!attr_set[DIR][bucket]) {
         cudaFuncSetAttribute(k_fast<R, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
         attr_set[DIR][bucket] = true;
     }
     const int slot = (DIR ? LIST_FAST_REV : LIST_FAST_FWD) + bucket;
-    k_fast<R, DIR><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc);
-    c->tm.n_launches++;
+    for (int off = 0; off < upperBoundPairs; off += slicePairs) {
+        const int n = std::min(slicePairs, upperBoundPairs - off);
+        const int ngroups = (n + 1) / 2;
+        const int blocks = (ngroups + groups - 1) / groups;
+        k_fast<R, DIR><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
+        c->tm.n_launches++;
+    }
     CUDA_TRY(c, cudaGetLastError());
     return stage_check(c, DIR ? "fast rev" : "fast fwd");
 }
@@ -441,15 +458,20 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
-        // the rare wide classes go to the side stream so their long, latency-bound threads overlap the bulk
-        const bool side = njobs[3] > 0 || njobs[4] > 0;
+        // the wider classes go to the side stream so their long, latency-bound threads overlap the bulk
+        const bool side = njobs[3] > 0 || njobs[4] > 0 || njobs[5] > 0;
         if (side) {
             CUDA_TRY(c, cudaEventRecord(c->ev_fork, s));
             CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-            if (njobs[4] > 0) { k_band<0, SWB_BAND_THREADS><<<(njobs[4] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, SWB_BAND_THREADS, 0, c->stream2>>>(d, cur, 4, 4); c->tm.n_launches++; }
+            if (njobs[5] > 0) { k_band<0, SWB_BAND_THREADS><<<(njobs[5] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, SWB_BAND_THREADS, 0, c->stream2>>>(d, cur, 5, 5, nxt); c->tm.n_launches++; }
+            if (njobs[4] > 0) {
+                k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS><<<(njobs[4] + SWB_BAND_WIDE_THREADS - 1) / SWB_BAND_WIDE_THREADS, SWB_BAND_WIDE_THREADS,
+                                                                    band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS), c->stream2>>>(d, cur, 4, 4, nxt);
+                c->tm.n_launches++;
+            }
             if (njobs[3] > 0) {
                 k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS><<<(njobs[3] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, SWB_BAND_MID_THREADS,
-                                                                  band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS), c->stream2>>>(d, cur, 3, 3);
+                                                                  band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS), c->stream2>>>(d, cur, 3, 3, nxt);
                 c->tm.n_launches++;
             }
             CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
@@ -457,7 +479,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         int blocks = 0;
         for (int k = 0; k < 3; ++k) blocks += (njobs[k] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
         if (blocks > 0) {
-            k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS><<<blocks, SWB_BAND_THREADS, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS), s>>>(d, cur, 0, 2);
+            k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS><<<blocks, SWB_BAND_THREADS, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS), s>>>(d, cur, 0, 2, nxt);
             c->tm.n_launches++;
         }
         if (side) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));
@@ -514,7 +536,7 @@ extern "C" int swb_compute(swb_ctx* c) {
     d.colmax_stride = (d.max_wlen + 7) & ~7;
     CUDA_TRY(c, c->b_colmax.ensure(np * (size_t)d.colmax_stride * 2 + 16)); d.colmax = (uint16_t*)c->b_colmax.p;
     // the fast path keeps 10 bytes per window column per lane-pair in shared memory
-    d.fast_max_cols = (c->smem_optin - 1024) / 2 / 10;
+    d.fast_max_cols = 16384;     // selectors (2 B/column/lane pair) must fit shared memory; column bests move to global memory beyond 1024 columns
     {
         // direction-byte scratch: enough for a typical band on every pair; pairs that do not fit are
         // deferred to the next round by the kernel itself
@@ -542,7 +564,7 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
     if (read_counters(c)) return -1;                        // bucket sizes for the fast path launches
     int fwdCounts[SWB_NBUCKETS]; int nFastTotal = 0;
-    for (int b = 0; b < SWB_NBUCKETS; ++b) { fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; nFastTotal += fwdCounts[b]; }
+    for (int b = 0; b < SWB_NBUCKETS; ++b) { fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; nFastTotal += fwdCounts[b]; c->fastMaxCols[b] = c->h_counters[CNT_FAST_MAXCOLS + b]; }
 
     // ---- forward (ssw.c:842-860) --------------------------------------------------------------------
     //   fast path: one 16-bit Gotoh sweep per pair (pairs it cannot decide are appended to the exact lists)

@@ -21,15 +21,17 @@
 
 // Instantiations: BW = largest half-width whose rolling rows fit the shared-memory layout (0 = rows in global
 // memory, any width), T = threads per block, RING = circular buffer of window bases per thread (>= band width).
-//   k_band<16, 128>  : classes 0-2 (the bulk)          k_band<112, 32> : class 3, bands up to 225 wide
-//   k_band<0, 128>   : anything wider (global rows; latency bound, rare)
+//   k_band<16, 128> : classes 0-2 (the bulk)      k_band<48, 64> : class 3      k_band<112, 32> : class 4
+//   k_band<0, 128>  : anything wider (global rows; latency bound, rare)
 #define SWB_BAND_LOCAL_BW 16
-#define SWB_BAND_MID_BW 112
+#define SWB_BAND_MID_BW 48
+#define SWB_BAND_WIDE_BW 112
 #define SWB_BAND_THREADS 128
-#define SWB_BAND_MID_THREADS 32
+#define SWB_BAND_MID_THREADS 64
+#define SWB_BAND_WIDE_THREADS 32
 #define SWB_BAND_MAX16 30000                          // largest score the 16-bit shared-memory rows may hold
 __host__ __device__ constexpr int band_rows_w(int BW) { return 2 * BW + 4; }
-__host__ __device__ constexpr int band_ring(int BW) { return BW <= 16 ? 64 : 256; }
+__host__ __device__ constexpr int band_ring(int BW) { return BW <= 16 ? 64 : (BW <= 48 ? 128 : 256); }
 __host__ __device__ constexpr int band_smem_bytes(int BW, int T) { return BW == 0 ? 0 : 3 * band_rows_w(BW) * T * 2 + band_ring(BW) * T; }
 
 __device__ __forceinline__ int band_x(int w, int i) { int x = i - w; return x > 0 ? x : 0; }
@@ -148,7 +150,7 @@ template <int T> struct BandRow<false, T> { int* p;   __device__ __forceinline__
 
 template <int BW, int T>
 __global__ void __launch_bounds__(T)
-k_band(SwbDev d, int listBase, int firstClass, int lastClass)
+k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
 {
     constexpr bool LOCAL = BW > 0;
     constexpr int ROWS_W = band_rows_w(BW);
@@ -209,8 +211,8 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass)
         if (LOCAL && (bw > BW || !fits16)) {
             // outgrew this instantiation's shared-memory rows: continue in the next wider one
             d.t_bw[p] = bw; d.t_best[p] = best;
-            const int c = (BW == SWB_BAND_LOCAL_BW && fits16) ? 3 : 4;
-            list_push(d.list[LIST_BAND_NEXT + c], d.counters + CNT_BAND_NEXT + c, p);
+            const int c = fits16 ? band_class(bw) : 5;             // the class whose instantiation holds this width (5: global rows)
+            list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
             warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
             return;
         }
@@ -224,8 +226,8 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass)
         if ((long long)off + need > d.band_cap) {      // out of scratch: retry in a later launch
             d.t_bw[p] = bw; d.t_best[p] = best;
             atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
-            const int c = BW == 0 ? 4 : (BW == SWB_BAND_MID_BW ? 3 : band_class(bw));
-            list_push(d.list[LIST_BAND_NEXT + c], d.counters + CNT_BAND_NEXT + c, p);
+            const int c = BW == 0 ? 5 : band_class(bw);
+            list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
             warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
             return;
         }

@@ -7,8 +7,8 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 40
-#define SWB_NCOUNTERS 64
+#define SWB_NLISTS 44
+#define SWB_NCOUNTERS 96
 
 // ---------------------------------------------------------------------------------------------
 // Device-resident batch ("workspace").  One per context, grown on demand.
@@ -59,18 +59,20 @@ struct SwbDev {
     int32_t ridx_base, widx_base;     // first read / window index present in the slice
     int32_t n_reads_total, n_windows_total;
     int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
+    uint32_t* fast_cols;   // global column-best storage of the fast path when windows are too long for shared memory (null otherwise)
     int32_t one;        // always 1, but opaque to the compiler: x * one + c compiles to a real IMAD (FMA pipe) instead of an ALU-pipe add
     int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
-#define SWB_NBANDCLASS 5         // band jobs are bucketed by half-width: 1 | 2-4 | 5-16 | 17-112 (32-thread blocks) | wider (global-memory rows)
+#define SWB_NBANDCLASS 6         // band jobs are bucketed by half-width: 1 | 2-4 | 5-16 | 17-48 (64-thread blocks) | 49-112 (32-thread blocks) | wider (global-memory rows)
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
-       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 29, LIST_BAND_FIRST = 34 };
+       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 30, LIST_BAND_FIRST = 36 };
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
-       CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 29,
-       CNT_CELLS_FWD = 40, CNT_CELLS_REV = 42, CNT_CELLS_BAND = 44, CNT_BAND_OVERFLOW = 46, CNT_CIGAR_OVERFLOW = 47,
-       CNT_FAST_DONE = 48, CNT_CERT_FAIL = 49, CNT_VERIFY_BYTE = 50, CNT_EXACT_JOBS = 51 };
+       CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 30,
+       CNT_CELLS_FWD = 48, CNT_CELLS_REV = 50, CNT_CELLS_BAND = 52, CNT_BAND_OVERFLOW = 54, CNT_CIGAR_OVERFLOW = 55,
+       CNT_FAST_DONE = 56, CNT_CERT_FAIL = 57, CNT_VERIFY_BYTE = 58, CNT_EXACT_JOBS = 59,
+       CNT_FAST_MAXCOLS = 64 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
 // p_state flags
 enum { PST_FAST = 1,        // forward result produced by the DPX fast path
        PST_NEED_CERT = 2,   // word-mode result accepted provisionally: the 8-bit pass still has to be shown to overflow
@@ -115,7 +117,7 @@ __device__ __forceinline__ void warp_count(int32_t* counter64, unsigned long lon
 }
 
 // band job class from the half-width (see SWB_NBANDCLASS)
-__host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : (bw <= 4 ? 1 : (bw <= 16 ? 2 : (bw <= 112 ? 3 : 4))); }
+__host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : (bw <= 4 ? 1 : (bw <= 16 ? 2 : (bw <= 48 ? 3 : (bw <= 112 ? 4 : 5)))); }
 
 // queue a pair for the banded traceback in the class of its initial band width |refLen - readLen| + 1 (ssw.c:899)
 __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_result& r) {

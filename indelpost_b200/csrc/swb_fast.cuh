@@ -52,7 +52,7 @@ struct FastLane {
 // job list entry j -> pairs (jobs[2j], jobs[2j+1]); an odd tail is paired with itself
 template <int R, int DIR>
 __global__ void __launch_bounds__(128)
-k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc)
+k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc, int pairOffset, int pairLimit)
 {
     constexpr int G = FAST_G;
     constexpr int BKT = R / 2 - 1;                               // read-length bucket this instantiation serves
@@ -60,7 +60,9 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_rowtab[SWB_MAX_N];
 
-    const int npairs = *njobs_ptr;
+    // this launch serves the slice [pairOffset, pairOffset + pairLimit) of the job list (pairOffset is even)
+    jobs += pairOffset;
+    const int npairs = min(max(*njobs_ptr - pairOffset, 0), pairLimit);
     const int ngroups = (npairs + 1) >> 1;
     const int groupsPerBlock = blockDim.x / G;
     if (blockIdx.x * groupsPerBlock >= ngroups) return;
@@ -103,10 +105,20 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     __syncthreads();
 
     // ---- shared memory: per group, per column: selector (u16), column best value (u32), its row (u32) ----
-    unsigned char* gbase = smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * 10);
-    uint32_t* colv = reinterpret_cast<uint32_t*>(gbase);
-    uint32_t* colr = colv + colAlloc;
-    uint16_t* selS = reinterpret_cast<uint16_t*>(colr + colAlloc);
+    // short windows: everything in shared memory (10 bytes per column).  Long windows: only the selectors stay in
+    // shared memory (2 bytes per column) and the column bests go to a global scratch (written once per step by the
+    // last thread, re-read by the post-sweep scans from L2), which keeps the occupancy register-limited.
+    uint32_t* colv; uint32_t* colr; uint16_t* selS;
+    if (d.fast_cols) {
+        selS = reinterpret_cast<uint16_t*>(smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * 2));
+        colv = d.fast_cols + (size_t)grp * 2 * colAlloc;
+        colr = colv + colAlloc;
+    } else {
+        unsigned char* gbase = smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * 10);
+        colv = reinterpret_cast<uint32_t*>(gbase);
+        colr = colv + colAlloc;
+        selS = reinterpret_cast<uint16_t*>(colr + colAlloc);
+    }
 
     const int maxcols = max(ln[0].ncols, ln[1].ncols);
     for (int c = g; c < maxcols; c += G) {

@@ -272,3 +272,27 @@ def test_gpu_flag_and_filter_variants(flag, filters, filterd):
     T.compare(rg, ag, ro, ao, what=f"flag={flag} filters={filters} filterd={filterd}")
     if flag in (2, 4, 6, 3):
         assert 0 < int((ro["cigar_len"] > 0).sum()) < b.n_pairs      # the filters really split the batch
+
+
+def test_gpu_mixed_window_lengths_long_windows_on_fast_path():
+    """windows longer than 1024 columns keep the fast path (column bests in global memory); one batch mixes them
+    with short windows and several read-length buckets"""
+    from gpuutil import gpu_align
+
+    parts = [T.make_pairs(300, 150, 400, seed=701), T.make_pairs(120, 250, (1500, 2600), seed=702, max_indel=60),
+             T.make_pairs(200, (40, 100), 300, seed=703), T.make_pairs(60, 150, (5000, 9000), seed=704)]
+    reads, wins, go, ge = [], [], [], []
+    for b in parts:
+        for p in range(b.n_pairs):
+            reads.append(b.reads[b.read_off[p]:b.read_off[p] + b.read_len[p]])
+            w = b.pair_win[p]
+            wins.append(b.windows[b.win_off[w]:b.win_off[w] + b.win_len[w]])
+            go.append(int(b.gap_open[p])); ge.append(int(b.gap_ext[p]))
+    idx = np.arange(len(reads), dtype=np.int32)
+    perm = np.random.default_rng(7).permutation(len(reads))
+    bb = T.batch_from_lists(reads, wins, idx[perm], idx[perm], np.array(go)[perm], np.array(ge)[perm])
+    bb.mat = T.dna_matrix(3, 2)
+    ro, ao = T.oracle_parallel(bb, threads=min(16, os.cpu_count() or 1))
+    rg, ag, tm = gpu_align(bb)
+    T.compare(rg, ag, ro, ao, what="mixed window lengths")
+    assert tm["n_fast"] > 0.8 * bb.n_pairs
