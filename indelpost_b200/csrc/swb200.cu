@@ -98,7 +98,7 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         d.p_mode[p] = wordSem ? 1 : 0;
         const int b = (lp16 + 31) / 32 - 1;
         list_push(d.list[LIST_FAST_FWD + b], d.counters + CNT_FAST_FWD + b, p);
-        atomicMax(d.counters + CNT_FAST_MAXCOLS + b, wl);
+        if (wl > *(volatile int32_t*)(d.counters + CNT_FAST_MAXCOLS + b)) atomicMax(d.counters + CNT_FAST_MAXCOLS + b, wl);   // test first: one hot address
     }
     else if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
     else list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
@@ -404,7 +404,8 @@ static int launch_fast_one(swb_ctx* c, int bucket, int upperBoundPairs) {
     const int threads = groups * FAST_G;
     static bool attr_set[2][SWB_NBUCKETS] = {};
     if (!attr_set[DIR][bucket]) {
-        cudaFuncSetAttribute(k_fast<R, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
+        cudaFuncSetAttribute(k_fast<R, DIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
+        cudaFuncSetAttribute(k_fast<R, DIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
         attr_set[DIR][bucket] = true;
     }
     const int slot = (DIR ? LIST_FAST_REV : LIST_FAST_FWD) + bucket;
@@ -412,7 +413,8 @@ static int launch_fast_one(swb_ctx* c, int bucket, int upperBoundPairs) {
         const int n = std::min(slicePairs, upperBoundPairs - off);
         const int ngroups = (n + 1) / 2;
         const int blocks = (ngroups + groups - 1) / groups;
-        k_fast<R, DIR><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
+        if (globalCols) k_fast<R, DIR, true><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
+        else k_fast<R, DIR, false><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
         c->tm.n_launches++;
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -50,7 +50,7 @@ struct FastLane {
 };
 
 // job list entry j -> pairs (jobs[2j], jobs[2j+1]); an odd tail is paired with itself
-template <int R, int DIR>
+template <int R, int DIR, bool GCOLS>
 __global__ void __launch_bounds__(128)
 k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc, int pairOffset, int pairLimit)
 {
@@ -108,8 +108,9 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     // short windows: everything in shared memory (10 bytes per column).  Long windows: only the selectors stay in
     // shared memory (2 bytes per column) and the column bests go to a global scratch (written once per step by the
     // last thread, re-read by the post-sweep scans from L2), which keeps the occupancy register-limited.
+    // (a template parameter, not a run-time pointer choice, so the shared-memory case keeps LDS/STS in the hot loop)
     uint32_t* colv; uint32_t* colr; uint16_t* selS;
-    if (d.fast_cols) {
+    if constexpr (GCOLS) {
         selS = reinterpret_cast<uint16_t*>(smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * 2));
         colv = d.fast_cols + (size_t)grp * 2 * colAlloc;
         colr = colv + colAlloc;
