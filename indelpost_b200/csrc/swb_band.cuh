@@ -211,7 +211,7 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
         if (LOCAL && (bw > BW || !fits16)) {
             // outgrew this instantiation's shared-memory rows: continue in the next wider one
             d.t_bw[p] = bw; d.t_best[p] = best;
-            const int c = fits16 ? band_class(bw) : 5;             // the class whose instantiation holds this width (5: global rows)
+            const int c = fits16 ? band_class(bw) : 7;             // the class whose instantiation holds this width (7: global rows)
             list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
             warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
             return;
@@ -226,7 +226,7 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
         if ((long long)off + need > d.band_cap) {      // out of scratch: retry in a later launch
             d.t_bw[p] = bw; d.t_best[p] = best;
             atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
-            const int c = BW == 0 ? 5 : band_class(bw);
+            const int c = BW == 0 ? 7 : band_class(bw);
             list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
             warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
             return;
@@ -261,6 +261,44 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
             const int rb = rbNext;
             rbNext = i + 1 < g.readLen ? read[i + 1] : 0;
             const unsigned long long rowTab = packRow ? s_rowTab[rb] : 0ull;
+            if constexpr (LOCAL) {
+                // Shared-memory rows: walk the slots with running pointers and carry the left (hCur[u-1]) and diagonal
+                // (hPrev[up-1] = the previous cell's upper neighbour) values in registers.  The rows start zeroed, so the
+                // reference's i == 0 special case (ssw.c:644-645) yields the same values and needs no branch.
+                const int up0 = beg - xp + 1;                          // set_u(e, w, i-1, beg); u starts at 1, lf at 0
+                const short* ph = hPrev.p + up0 * T;                   // hPrev[up]
+                short* peUp = ePrev.p + up0 * T;                       // ePrev[up] (read)
+                short* peU = ePrev.p + T;                              // ePrev[u]  (written)
+                short* pc = hCur.p + T;                                // hCur[u]
+                const unsigned char* pr = refRing;
+                int slot = beg & (RING - 1);
+                int hDiag = hPrev[up0 - 1], hLeft = 0;                 // hCur[0] = 0 (ssw.c:633)
+                for (int j = beg; j <= end; ++j) {
+                    const int hUp = *ph, eUp = *peUp;
+                    int a = hUp - go, b = eUp - ge;                    // ssw.c:644-648
+                    const int ev = a > b ? a : b;
+                    *peU = (short)ev;
+                    const int bitE = a > b ? 1 : 0;
+                    a = hLeft - go; b = f - ge;                        // ssw.c:650-653
+                    f = a > b ? a : b;
+                    const int bitF = a > b ? 1 : 0;
+                    const int e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;   // ssw.c:655-659
+                    const int gmax = e1 > f1 ? e1 : f1;
+                    const int rc = pr[slot * T];
+                    const int sc = packRow ? (int)(int8_t)(rowTab >> (8 * rc)) : (int)mat[rc * n + rb];
+                    const int m = hDiag + sc;
+                    const int h = gmax > m ? gmax : m;
+                    *pc = (short)h;
+                    if (h > best) best = h;                            // ssw.c:661
+                    const int sel = gmax <= m ? 0 : (e1 > f1 ? 1 : 2); // ssw.c:663-664
+                    const int x = j - xi;
+                    word |= (uint32_t)(bitE | (bitF << 1) | (sel << 2)) << (4 * (x & 7));
+                    if ((x & 7) == 7) { line[x >> 3] = word; word = 0; }
+                    hDiag = hUp; hLeft = h;
+                    ph += T; peUp += T; peU += T; pc += T; slot = (slot + 1) & (RING - 1);
+                }
+                u = end - xi + 1;
+            } else
             for (int j = beg; j <= end; ++j) {
                 u = j - xi + 1;                        // set_u(u, w, i, j)
                 const int up = j - xp + 1;             // set_u(e, w, i-1, j)

@@ -7,7 +7,7 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 44
+#define SWB_NLISTS 48
 #define SWB_NCOUNTERS 96
 
 // ---------------------------------------------------------------------------------------------
@@ -65,14 +65,15 @@ struct SwbDev {
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
-#define SWB_NBANDCLASS 6         // band jobs are bucketed by half-width: 1 | 2-4 | 5-16 | 17-48 (64-thread blocks) | 49-112 (32-thread blocks) | wider (global-memory rows)
+#define SWB_NBANDCLASS 8         // band jobs are bucketed by half-width: 1 | 2 | 3-4 | 5-8 | 9-16 | 17-48 (64-thread blocks) | 49-112 (32-thread blocks) | wider (global-memory rows)
+#define SWB_BAND_CLS_MID 5      // first class of k_band<48,64>; 6: k_band<112,32>; 7: k_band<0,128>
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
-       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 30, LIST_BAND_FIRST = 36 };
+       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40 };
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
-       CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 30,
-       CNT_CELLS_FWD = 48, CNT_CELLS_REV = 50, CNT_CELLS_BAND = 52, CNT_BAND_OVERFLOW = 54, CNT_CIGAR_OVERFLOW = 55,
-       CNT_FAST_DONE = 56, CNT_CERT_FAIL = 57, CNT_VERIFY_BYTE = 58, CNT_EXACT_JOBS = 59,
-       CNT_FAST_MAXCOLS = 64 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
+       CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
+       CNT_CELLS_FWD = 64, CNT_CELLS_REV = 66, CNT_CELLS_BAND = 68, CNT_BAND_OVERFLOW = 70, CNT_CIGAR_OVERFLOW = 71,
+       CNT_FAST_DONE = 72, CNT_CERT_FAIL = 73, CNT_VERIFY_BYTE = 74, CNT_EXACT_JOBS = 75,
+       CNT_FAST_MAXCOLS = 80 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
 // p_state flags
 enum { PST_FAST = 1,        // forward result produced by the DPX fast path
        PST_NEED_CERT = 2,   // word-mode result accepted provisionally: the 8-bit pass still has to be shown to overflow
@@ -117,7 +118,7 @@ __device__ __forceinline__ void warp_count(int32_t* counter64, unsigned long lon
 }
 
 // band job class from the half-width (see SWB_NBANDCLASS)
-__host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : (bw <= 4 ? 1 : (bw <= 16 ? 2 : (bw <= 48 ? 3 : (bw <= 112 ? 4 : 5)))); }
+__host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : bw <= 2 ? 1 : bw <= 4 ? 2 : bw <= 8 ? 3 : bw <= 16 ? 4 : bw <= 48 ? 5 : bw <= 112 ? 6 : 7; }
 
 // queue a pair for the banded traceback in the class of its initial band width |refLen - readLen| + 1 (ssw.c:899)
 __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_result& r) {
