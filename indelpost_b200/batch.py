@@ -90,7 +90,7 @@ class BatchAligner:
         b.n_windows = int(arrs["win_len"].shape[0])
         b.seq_encoding = int(seq_encoding)
         for k, a in arrs.items():
-            setattr(b, k, a.ctypes.data if a is not None and a.size else (a.ctypes.data if a is not None else None))
+            setattr(b, k, None if a is None else a.ctypes.data)
         b.n = int(n)
         b.score_size = int(score_size)
         b.flag = int(flag)

@@ -1,14 +1,18 @@
 // swb200.cu — libswb200: host pipeline + C ABI (include/swb200.h).
 //
-// One swb_ctx per GPU: a stream, timing events and grow-only device buffers.  A batch moves through
+// One swb_ctx per GPU: streams, timing events and grow-only device buffers.  A batch moves through
 //   upload  : one cudaMemcpyAsync per input array (tables + per-pair arrays)
-//   prepare : encode/validate sequences, derive per-pair pointers, seed the job lists
-//   forward : score / end position / sub-optimal score        (ssw.c:842-871)
-//   reverse : begin position                                   (ssw.c:875-891)
-//   band    : banded DP + traceback -> CIGAR, in doubling rounds (ssw.c:897-916)
+//   prepare : encode/validate sequences, derive per-pair pointers, route each pair to the DPX fast path
+//             (per read-length bucket) or to the exact striped emulation, seed the job lists
+//   forward : score / end position / sub-optimal score        (ssw.c:842-871)   k_fast<R,0>, k_exact2<.,0>
+//   reverse : begin position                                   (ssw.c:875-891)   k_fast<R,1>, k_exact2<.,1>
+//   band    : banded DP + traceback -> CIGAR                   (ssw.c:897-916)   k_band, in two phases so that the
+//             overflow certificate (swb_cert.cuh) of the pairs that can fail it and their exact 8-bit
+//             verification overlap the bulk of the traceback
 //   download: results + CIGAR arena
 // Stage-to-stage hand-over is through device-side job lists (append with warp-aggregated atomics), so
-// the host only synchronises to read the few counters that size the next launch.
+// the host only synchronises to read the few counters that size the next launch.  swb_align_batch additionally
+// pipelines large batches over two such contexts ("lanes") with chunk views of the caller's tables.
 // There is no CPU implementation behind any entry point: without a usable GPU every call fails.
 #include <cstdlib>
 #include <cstring>
@@ -445,7 +449,9 @@ static int launch_fast(swb_ctx* c, const int* counts) {
 
 // banded DP + traceback (ssw.c:897-916) over the four band-class lists; a launch round per class, repeated only
 // for pairs the kernel re-queued (scratch exhausted, or band outgrew the shared-memory rows)
-static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, int* firstJobs = nullptr) {
+// firstRoundOnly: launch the jobs of `firstBase` and leave what they re-queue in LIST_BAND_NEXT for a later call;
+// keepNext: LIST_BAND_NEXT already holds such re-queued jobs, append to them in the first round instead of clearing
+static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, int* firstJobs = nullptr, bool firstRoundOnly = false, bool keepNext = false) {
     SwbDev& d = c->d;
     cudaStream_t s = c->stream;
     if (read_counters(c)) return -1;
@@ -456,8 +462,8 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         int njobs[SWB_NBANDCLASS], total = 0;
         for (int k = 0; k < SWB_NBANDCLASS; ++k) { njobs[k] = c->h_counters[cur + k]; total += njobs[k]; }
         if (round == 0 && firstJobs) *firstJobs = total;
-        if (total <= 0) break;
-        CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
+        if (total <= 0 && !(round == 0 && keepNext)) break;
+        if (!(round == 0 && keepNext)) CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
         // the wider classes go to the side stream so their long, latency-bound threads overlap the bulk
@@ -488,8 +494,14 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "band")) return -1;
         if (record && round == 0) CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_R0], s));
+        if (firstRoundOnly) {
+            // no host round trip: whatever this round re-queued (band outgrown, scratch full) is picked up by the next call
+            CUDA_TRY(c, cudaMemsetAsync(d.counters + firstBase, 0, 4 * SWB_NBANDCLASS, s));
+            c->tm.band_rounds++;
+            return 0;
+        }
         if (read_counters(c)) return -1;
-        if (c->h_counters[CNT_BAND_OVERFLOW] >= total) {
+        if (total > 0 && c->h_counters[CNT_BAND_OVERFLOW] >= total) {
             // nothing fitted: the scratch is smaller than a single band; grow it
             if (++stalls > 8 || c->b_band.cap >= ((size_t)64 << 30)) { c->err = "banded traceback scratch exhausted"; return -1; }
             size_t want = c->b_band.cap * 4;
@@ -592,7 +604,7 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));      // consumed by the reverse stage; reused by the verification
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
     int nFirst = 0;
-    if (run_band_rounds(c, false, LIST_BAND_FIRST, &nFirst)) return -1;
+    if (run_band_rounds(c, false, LIST_BAND_FIRST, &nFirst, /*firstRoundOnly=*/true)) return -1;      // its re-queues join phase 2's rounds
     bool forked = false;
     if (certify && nFirst > 0) {
         k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, LIST_VERIFY);
@@ -604,7 +616,7 @@ extern "C" int swb_compute(swb_ctx* c) {
         CUDA_TRY(c, cudaEventRecord(c->ev_join2, c->stream3));
         forked = true;
     }
-    if (run_band_rounds(c, true, LIST_BAND)) return -1;
+    if (run_band_rounds(c, true, LIST_BAND, nullptr, false, /*keepNext=*/nFirst > 0)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_ALL], s));
     if (forked) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join2, 0));
 

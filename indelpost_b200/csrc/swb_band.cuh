@@ -10,11 +10,13 @@
 // Direction information (3 bytes per cell in the reference) is packed into 4 bits per cell, 8 cells per
 // 32-bit word, and kept in a global scratch arena (one word store per 8 cells instead of a 32-byte sector
 // per cell); each thread bump-allocates ceil((2w+1)/8)*4*readLen bytes.  The three rolling rows live in
-// shared memory laid out [slot][thread], which is bank-conflict free whatever slot each thread touches.  Band doubling
-// (ssw.c:668-669) happens inside the kernel with a fresh scratch allocation; a pair is only re-queued for a
-// later launch when the scratch arena is exhausted or its band outgrows the shared-memory rows.  Jobs are
-// bucketed by band-width class so the threads of a warp run bands of similar width.  The traceback is walked twice (count, then emit) so the CIGAR
-// can be written, already reversed, straight into the output arena.
+// shared memory laid out [slot][thread], which is bank-conflict free whatever slot each thread touches.
+// Band doubling (ssw.c:668-669) happens inside the kernel with a fresh scratch allocation; a pair is only
+// re-queued for a later launch when the scratch arena is exhausted or its band outgrows the shared-memory
+// rows of its instantiation.  Jobs are bucketed by band-width class and launched widest-first in one grid, so
+// the threads of a warp run bands of similar width and the short ones fill the tail.  The traceback is a single
+// walk with the band rows held / prefetched in registers; its ops are buffered in registers and written,
+// already reversed, into the output arena.
 #pragma once
 #include "swb_common.cuh"
 #include "swb_cert.cuh"
