@@ -447,11 +447,29 @@ static int launch_fast(swb_ctx* c, const int* counts) {
     return 0;
 }
 
+// certificate pass over the pairs whose traceback is done, then the exact 8-bit verification of those that failed it,
+// on the verification stream (no host round trip: the grid is sized by an upper bound, the kernel reads the real count)
+static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound) {
+    SwbDev& d = c->d;
+    cudaStream_t s = c->stream;
+    const size_t np = (size_t)d.n_pairs;
+    k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, verifyList);
+    c->tm.n_launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
+    if (launch_exact<0, 0>(c, verifyList, upperBound, c->stream3)) return -1;      // confirms the overflow, or produces the byte-mode result
+    CUDA_TRY(c, cudaEventRecord(c->ev_join2, c->stream3));
+    return 0;
+}
+static int certify_phase2_hook(swb_ctx* c, int total) { return total > 0 ? certify_and_verify_async(c, LIST_VERIFY2, total) : 0; }
+
 // banded DP + traceback (ssw.c:897-916) over the four band-class lists; a launch round per class, repeated only
 // for pairs the kernel re-queued (scratch exhausted, or band outgrew the shared-memory rows)
 // firstRoundOnly: launch the jobs of `firstBase` and leave what they re-queue in LIST_BAND_NEXT for a later call;
 // keepNext: LIST_BAND_NEXT already holds such re-queued jobs, append to them in the first round instead of clearing
-static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, int* firstJobs = nullptr, bool firstRoundOnly = false, bool keepNext = false) {
+static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, int* firstJobs = nullptr, bool firstRoundOnly = false, bool keepNext = false,
+                           int (*afterFirstRound)(swb_ctx*, int) = nullptr) {
     SwbDev& d = c->d;
     cudaStream_t s = c->stream;
     if (read_counters(c)) return -1;
@@ -494,6 +512,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "band")) return -1;
         if (record && round == 0) CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_R0], s));
+        if (round == 0 && afterFirstRound && afterFirstRound(c, total)) return -1;
         if (firstRoundOnly) {
             // no host round trip: whatever this round re-queued (band outgrown, scratch full) is picked up by the next call
             CUDA_TRY(c, cudaMemsetAsync(d.counters + firstBase, 0, 4 * SWB_NBANDCLASS, s));
@@ -603,34 +622,27 @@ extern "C" int swb_compute(swb_ctx* c) {
     const bool certify = nFastTotal > 0 && d.score_size == 2;
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));      // consumed by the reverse stage; reused by the verification
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_FWD, 0, 4, s));      // reused as the leftovers' verify list
     int nFirst = 0;
     if (run_band_rounds(c, false, LIST_BAND_FIRST, &nFirst, /*firstRoundOnly=*/true)) return -1;      // its re-queues join phase 2's rounds
-    bool forked = false;
-    if (certify && nFirst > 0) {
-        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, LIST_VERIFY);
-        tm.n_launches++;
-        CUDA_TRY(c, cudaGetLastError());
-        CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
-        CUDA_TRY(c, cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
-        if (launch_exact<0, 0>(c, LIST_VERIFY, nFirst, c->stream3)) return -1;     // confirms the overflow, or produces the byte-mode result
-        CUDA_TRY(c, cudaEventRecord(c->ev_join2, c->stream3));
-        forked = true;
-    }
-    if (run_band_rounds(c, true, LIST_BAND, nullptr, false, /*keepNext=*/nFirst > 0)) return -1;
+    if (certify && nFirst > 0 && certify_and_verify_async(c, LIST_VERIFY, nFirst)) return -1;
+    // phase 2; its first round is followed at once by the certificate + verification of its own pairs (hook), which
+    // then overlap the re-queue rounds
+    if (run_band_rounds(c, true, LIST_BAND, nullptr, false, /*keepNext=*/nFirst > 0, certify ? certify_phase2_hook : nullptr)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_ALL], s));
-    if (forked) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join2, 0));
+    if (certify) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join2, 0));      // both verifications done (no-op if none was launched)
 
-    // ---- leftovers: certificate for the pairs of phase 2 (rarely fails), byte-mode redo for verified pairs whose 8-bit
-    //      pass did not overflow (never observed in practice)
+    // ---- leftovers: certificate for the pairs finished in re-queue rounds (rarely fails), byte-mode redo for verified
+    //      pairs whose 8-bit pass did not overflow (never observed in practice)
     if (certify) {
-        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, LIST_VERIFY2);
+        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, LIST_BYTE_FWD);
         tm.n_launches++;
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "certify")) return -1;
         if (read_counters(c)) return -1;
-        const int nverify2 = c->h_counters[LIST_VERIFY2];
-        if (nverify2 > 0 && launch_exact<0, 0>(c, LIST_VERIFY2, nverify2)) return -1;
-        if (nverify2 > 0 && read_counters(c)) return -1;
+        const int nverify3 = c->h_counters[LIST_BYTE_FWD];
+        if (nverify3 > 0 && launch_exact<0, 0>(c, LIST_BYTE_FWD, nverify3)) return -1;
+        if (nverify3 > 0 && read_counters(c)) return -1;
         const int nbyte = c->h_counters[CNT_BYTE_REV];
         if (nbyte > 0) {
             if (launch_exact<0, 1>(c, LIST_BYTE_REV, nbyte)) return -1;
