@@ -30,6 +30,7 @@
 #include "swb_cert.cuh"
 #include "swb_band.cuh"
 #include "swb_fast.cuh"
+#include "swb_revband.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
 
@@ -447,6 +448,24 @@ static int launch_fast(swb_ctx* c, const int* counts) {
     return 0;
 }
 
+// banded reverse pass (swb_revband.cuh): one launch per band class, widest first; grids are sized by an upper bound
+// (the classes were filled by the forward sweep, no host round trip), blocks beyond the real count exit at once
+static int launch_rev_band(swb_ctx* c, int upperBoundPairs) {
+    if (upperBoundPairs <= 0 || (c->d.opt & 4)) return 0;
+    const SwbDev& d = c->d;
+    const int T = SWB_REVB_THREADS;
+    const int blocks = ((upperBoundPairs + 1) / 2 + T - 1) / T;
+    const int rows = std::min(d.max_rlen, 32 * SWB_NBUCKETS);
+#define SWB_REVB_LAUNCH(cls, WI, WD) { \
+        const int colAlloc = rows + WI + WD + 2; \
+        k_rev_band<WI, WD><<<blocks, T, (size_t)colAlloc * T * 2, c->stream>>>(d, d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, colAlloc); \
+        c->tm.n_launches++; }
+    SWB_REVB_LAUNCH(5, 13, 50) SWB_REVB_LAUNCH(4, 10, 37) SWB_REVB_LAUNCH(3, 6, 25) SWB_REVB_LAUNCH(2, 5, 18) SWB_REVB_LAUNCH(1, 3, 12) SWB_REVB_LAUNCH(0, 2, 5)
+#undef SWB_REVB_LAUNCH
+    CUDA_TRY(c, cudaGetLastError());
+    return stage_check(c, "rev band");
+}
+
 // certificate pass over the pairs whose traceback is done, then the exact 8-bit verification of those that failed it,
 // on the verification stream (no host round trip: the grid is sized by an upper bound, the kernel reads the real count)
 static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound) {
@@ -608,7 +627,8 @@ extern "C" int swb_compute(swb_ctx* c) {
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_FWD], s));
 
     // ---- reverse (ssw.c:875-891) ----------------------------------------------------------------
-    if (launch_fast<1>(c, fwdCounts)) return -1;            // rev bucket sizes are bounded by the fwd ones
+    if (launch_rev_band(c, nFastTotal)) return -1;          // the pairs the forward sweep put into a band class
+    if (launch_fast<1>(c, fwdCounts)) return -1;            // the rest; rev bucket sizes are bounded by the fwd ones
     if (launch_exact<0, 1>(c, LIST_BYTE_REV, (int)np)) return -1;
     if (launch_exact<1, 1>(c, LIST_WORD_REV, (int)np)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));

@@ -7,7 +7,7 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 48
+#define SWB_NLISTS 56
 #define SWB_NCOUNTERS 96
 
 // ---------------------------------------------------------------------------------------------
@@ -61,19 +61,28 @@ struct SwbDev {
     int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
     uint32_t* fast_cols;   // global column-best storage of the fast path when windows are too long for shared memory (null otherwise)
     int32_t one;        // always 1, but opaque to the compiler: x * one + c compiles to a real IMAD (FMA pipe) instead of an ALU-pipe add
-    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass
+    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
 #define SWB_NBANDCLASS 8         // band jobs are bucketed by half-width: 1 | 2 | 3-4 | 5-8 | 9-16 | 17-48 (64-thread blocks) | 49-112 (32-thread blocks) | wider (global-memory rows)
 #define SWB_BAND_CLS_MID 5      // first class of k_band<48,64>; 6: k_band<112,32>; 7: k_band<0,128>
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
-       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40 };
+       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48 };
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
        CNT_CELLS_FWD = 64, CNT_CELLS_REV = 66, CNT_CELLS_BAND = 68, CNT_BAND_OVERFLOW = 70, CNT_CIGAR_OVERFLOW = 71,
        CNT_FAST_DONE = 72, CNT_CERT_FAIL = 73, CNT_VERIFY_BYTE = 74, CNT_EXACT_JOBS = 75,
        CNT_FAST_MAXCOLS = 80 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
+// banded reverse pass (swb_revband.cuh): band classes as (rows below, columns right of) the main diagonal
+#define SWB_NREVB 6
+#define SWB_REVB_CLASSES(X) X(0, 2, 5) X(1, 3, 12) X(2, 5, 18) X(3, 6, 25) X(4, 10, 37) X(5, 13, 50)
+__host__ __device__ __forceinline__ int revb_class(int wi, int wd) {
+#define SWB_REVB_PICK(c, WI, WD) if (wi <= WI && wd <= WD) return c;
+    SWB_REVB_CLASSES(SWB_REVB_PICK)
+#undef SWB_REVB_PICK
+    return -1;
+}
 // p_state flags
 enum { PST_FAST = 1,        // forward result produced by the DPX fast path
        PST_NEED_CERT = 2,   // word-mode result accepted provisionally: the 8-bit pass still has to be shown to overflow

@@ -289,7 +289,19 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     d.p_state[p] = (wordSem && d.score_size == 2) ? (PST_FAST | PST_NEED_CERT) : PST_FAST;
                     { const unsigned am = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am) - 1) atomicAdd(d.counters + CNT_FAST_DONE, __popc(am)); }
                     const bool scoreOnly = d.flag == 0 || (d.flag == 2 && T < (int)d.filters);     // ssw.c:872
-                    if (!scoreOnly) list_push(d.list[LIST_FAST_REV + BKT], d.counters + CNT_FAST_REV + BKT, p);
+                    if (!scoreOnly) {
+                        // reverse pass: banded (swb_revband.cuh) when the score deficit B = mx*rows - T bounds the deviation
+                        // of every path scoring T from the main diagonal to one of the band classes, else the wavefront sweep
+                        int cls = -1;
+                        if (T > 0 && q.ge > 0 && !(d.opt & 4)) {
+                            const int B = d.max_score * (end_read + 1) - T;
+                            int wd = 0, wi = 0;
+                            if (B >= q.go) { wd = (B - q.go) / q.ge + 1; wi = (B - q.go + q.ge) / (d.max_score + q.ge); }
+                            cls = revb_class(wi, wd);
+                        }
+                        if (cls >= 0) list_push(d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, p);
+                        else list_push(d.list[LIST_FAST_REV + BKT], d.counters + CNT_FAST_REV + BKT, p);
+                    }
                     else d.p_state[p] |= PST_BAND_DONE;                            // no reverse pass / traceback will follow
                 }
             }
