@@ -133,6 +133,8 @@ struct swb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
+    cudaStream_t rev_stream[SWB_NREVB];                                     // banded reverse pass: one stream per band class
+    cudaEvent_t ev_rev_fork, ev_rev_join[SWB_NREVB];
     cudaEvent_t ev[EV_COUNT];
     std::string err;
     SwbDev d;
@@ -196,6 +198,8 @@ extern "C" swb_ctx* swb_create(int device) {
     cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_rev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamCreateWithFlags(&c->rev_stream[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&c->ev_rev_join[i], cudaEventDisableTiming); }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
     cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t));
     cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long));
@@ -224,6 +228,8 @@ extern "C" void swb_destroy(swb_ctx* c) {
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream3); cudaEventDestroy(c->ev_fork3);
+    cudaEventDestroy(c->ev_rev_fork);
+    for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamDestroy(c->rev_stream[i]); cudaEventDestroy(c->ev_rev_join[i]); }
     cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); cudaEventDestroy(c->ev_join2);
     delete c;
 }
@@ -448,21 +454,33 @@ static int launch_fast(swb_ctx* c, const int* counts) {
     return 0;
 }
 
-// banded reverse pass (swb_revband.cuh): one launch per band class, widest first; grids are sized by an upper bound
-// (the classes were filled by the forward sweep, no host round trip), blocks beyond the real count exit at once
+// banded reverse pass (swb_revband.cuh): one launch per band class, each on its own stream so that the classes
+// (a few thousand warps each) overlap; grids are sized by an upper bound (the classes were filled by the forward
+// sweep, no host round trip), blocks beyond the real count exit at once
 static int launch_rev_band(swb_ctx* c, int upperBoundPairs) {
     if (upperBoundPairs <= 0 || (c->d.opt & 4)) return 0;
     const SwbDev& d = c->d;
     const int T = SWB_REVB_THREADS;
     const int blocks = ((upperBoundPairs + 1) / 2 + T - 1) / T;
     const int rows = std::min(d.max_rlen, 32 * SWB_NBUCKETS);
+    CUDA_TRY(c, cudaEventRecord(c->ev_rev_fork, c->stream));
 #define SWB_REVB_LAUNCH(cls, WI, WD) { \
-        const int colAlloc = rows + WI + WD + 2; \
-        k_rev_band<WI, WD><<<blocks, T, (size_t)colAlloc * T * 2, c->stream>>>(d, d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, colAlloc); \
-        c->tm.n_launches++; }
-    SWB_REVB_LAUNCH(5, 13, 50) SWB_REVB_LAUNCH(4, 10, 37) SWB_REVB_LAUNCH(3, 6, 25) SWB_REVB_LAUNCH(2, 5, 18) SWB_REVB_LAUNCH(1, 3, 12) SWB_REVB_LAUNCH(0, 2, 5)
+        const size_t smem = (size_t)revb_stride_words(rows, WI + WD + 1) * 4 * T; \
+        static bool attr = false; \
+        if (!attr) { cudaFuncSetAttribute(k_rev_band<WI, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr = true; } \
+        CUDA_TRY(c, cudaStreamWaitEvent(c->rev_stream[cls], c->ev_rev_fork, 0)); \
+        k_rev_band<WI, WD><<<blocks, T, smem, c->rev_stream[cls]>>>(d, d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, rows); \
+        c->tm.n_launches++; \
+        CUDA_TRY(c, cudaEventRecord(c->ev_rev_join[cls], c->rev_stream[cls])); }
+    SWB_REVB_CLASSES(SWB_REVB_LAUNCH)
 #undef SWB_REVB_LAUNCH
     CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+// the main stream waits for the band classes (after it has queued the wavefront sweep of the remaining pairs)
+static int join_rev_band(swb_ctx* c, int upperBoundPairs) {
+    if (upperBoundPairs <= 0 || (c->d.opt & 4)) return 0;
+    for (int i = 0; i < SWB_NREVB; ++i) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_rev_join[i], 0));
     return stage_check(c, "rev band");
 }
 
@@ -629,6 +647,7 @@ extern "C" int swb_compute(swb_ctx* c) {
     // ---- reverse (ssw.c:875-891) ----------------------------------------------------------------
     if (launch_rev_band(c, nFastTotal)) return -1;          // the pairs the forward sweep put into a band class
     if (launch_fast<1>(c, fwdCounts)) return -1;            // the rest; rev bucket sizes are bounded by the fwd ones
+    if (join_rev_band(c, nFastTotal)) return -1;
     if (launch_exact<0, 1>(c, LIST_BYTE_REV, (int)np)) return -1;
     if (launch_exact<1, 1>(c, LIST_WORD_REV, (int)np)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));

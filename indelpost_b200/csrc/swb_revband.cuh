@@ -30,14 +30,23 @@
 
 #define SWB_REVB_THREADS 64
 
+struct RevbPar { const int8_t* readA; const int8_t* readB; const int8_t* refA; const int8_t* refB; int LA, LB, nA, nB; };
+
+// per-thread shared-memory region: [front pad + columns: u16 selectors][rows: u16 = codeA | codeB << 8], a whole number of
+// 32-bit words and an ODD number of them, so the threads of a warp (all on the same column / row) hit distinct banks
+__host__ __device__ __forceinline__ int revb_sel_cols(int rows, int M) { return ((M + 1) & ~1) + ((rows + M + 1) & ~1); }
+__host__ __device__ __forceinline__ int revb_stride_words(int rows, int M) { return ((revb_sel_cols(rows, M) + ((rows + 1) & ~1)) / 2) | 1; }
+
 template <int WI, int WD>
 __global__ void __launch_bounds__(SWB_REVB_THREADS)
-k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc)
+k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int rowsAlloc)
 {
     constexpr int M = WI + WD + 1;
     constexpr int T = SWB_REVB_THREADS;
+    constexpr int PF = (WI + 1) & ~1;                                    // even front pad: columns "left of 0" of the first rows
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_rowtab[SWB_MAX_N];
+    __shared__ RevbPar s_par[T];
     const int npairs = *njobs_ptr;
     const int ngroups = (npairs + 1) >> 1;
     if (blockIdx.x * T >= ngroups) return;
@@ -46,57 +55,96 @@ k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict
         for (int nt = 0; nt < 4; ++nt) t |= (uint32_t)(uint8_t)(int8_t)(FAST_SCALE * d.mat[nt * d.n + threadIdx.x]) << (8 * nt);
         s_rowtab[threadIdx.x] = t;
     }
-    __syncthreads();
     const int grp = blockIdx.x * T + threadIdx.x;
-    if (grp >= ngroups) return;
+    const bool valid = grp < ngroups;
 
     // ---- the two alignments of this thread ---------------------------------------------------------
-    int pA = jobs[2 * grp], pB = (2 * grp + 1 < npairs) ? jobs[2 * grp + 1] : -1;
-    const int qB = pB < 0 ? pA : pB;                                     // odd tail: lane B shadows lane A, its result is dropped
-    const swb_result rA = d.res[pA], rB = d.res[qB];
-    const int LA = rA.read_end1 + 1, LB = rB.read_end1 + 1;              // rows (ssw.c:875-877)
-    const int nA = rA.ref_end1 + 1, nB = rB.ref_end1 + 1;                // columns
-    const int8_t* readA = d.reads + d.p_roff[pA];
-    const int8_t* readB = d.reads + d.p_roff[qB];
-    const int8_t* refA = d.windows + d.p_woff[pA];
-    const int8_t* refB = d.windows + d.p_woff[qB];
+    int pA = -1, pB = -1, LA = 0, LB = 0, nA = 0, nB = 0;
+    uint32_t goP = 0, ngeP = 0, targetV = 0x7fff7fffu;
+    {
+        RevbPar q; q.readA = q.readB = q.refA = q.refB = nullptr; q.LA = q.LB = q.nA = q.nB = 0;
+        if (valid) {
+            pA = jobs[2 * grp]; pB = (2 * grp + 1 < npairs) ? jobs[2 * grp + 1] : -1;
+            const int qB = pB < 0 ? pA : pB;                             // odd tail: lane B shadows lane A, its result is dropped
+            const swb_result rA = d.res[pA], rB = d.res[qB];
+            LA = rA.read_end1 + 1; LB = rB.read_end1 + 1;                // rows (ssw.c:875-877)
+            nA = rA.ref_end1 + 1; nB = rB.ref_end1 + 1;                  // columns
+            q.readA = d.reads + d.p_roff[pA]; q.readB = d.reads + d.p_roff[qB];
+            q.refA = d.windows + d.p_woff[pA]; q.refB = d.windows + d.p_woff[qB];
+            q.LA = LA; q.LB = LB; q.nA = nA; q.nB = nB;
+            goP = pack2(FAST_SCALE * d.gap_open[pA], FAST_SCALE * d.gap_open[qB]);
+            ngeP = pack2(-FAST_SCALE * d.gap_ext[pA], -FAST_SCALE * d.gap_ext[qB]);
+            targetV = pack2(FAST_SCALE * rA.score1 + FAST_C, pB < 0 ? 0x7fff : FAST_SCALE * rB.score1 + FAST_C);
+        }
+        s_par[threadIdx.x] = q;
+    }
+    __syncthreads();
     const int Lmax = max(LA, LB);
 
-    // ---- selectors: column c of the reversed windows, shifted by WI so the first rows may index "column < 0" -------
-    uint16_t* selS = reinterpret_cast<uint16_t*>(smem_raw) + threadIdx.x;
-    const int ncolsBand = min(max(nA, nB), Lmax + WD);
-    for (int c = 0; c < WI; ++c) selS[c * T] = 0xC480u;
-#pragma unroll 4
-    for (int c = 0; c < ncolsBand; ++c) {
-        const int bA = c < nA ? refA[nA - 1 - c] : 0;
-        const int bB = c < nB ? refB[nB - 1 - c] : 0;
-        selS[(c + WI) * T] = (uint16_t)(0xC480u | (uint32_t)(bA & 3) * 0x11u | (uint32_t)(bB & 3) * 0x1100u);
+    // ---- staging: every warp fills the regions of its own 32 threads, one thread's sequences at a time, with the
+    //      lanes reading consecutive bytes (the per-thread byte streams of a one-thread-per-alignment loop would be a
+    //      dependent L2 round trip per row).  Selector of column c sits at index PF + c.
+    const int strideW = revb_stride_words(rowsAlloc, M);
+    const int selCols = revb_sel_cols(rowsAlloc, M);
+    uint32_t* const region0 = reinterpret_cast<uint32_t*>(smem_raw);
+    {
+        const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+        for (int src = 0; src < 32; ++src) {
+            const RevbPar q = s_par[wbase + src];
+            const int lm = max(q.LA, q.LB);
+            if (lm == 0) continue;
+            uint32_t* reg = region0 + (size_t)(wbase + src) * strideW;
+            if (lane < PF / 2) reg[lane] = 0xC480C480u;
+            const int ncols = min(lm + M + 1, selCols - PF);
+            for (int c0 = 2 * lane; c0 < ncols; c0 += 64) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c = c0 + u;
+                    const int bA = c < q.nA ? q.refA[q.nA - 1 - c] : 0;
+                    const int bB = c < q.nB ? q.refB[q.nB - 1 - c] : 0;
+                    w |= (0xC480u | (uint32_t)(bA & 3) * 0x11u | (uint32_t)(bB & 3) * 0x1100u) << (16 * u);
+                }
+                reg[(PF + c0) >> 1] = w;
+            }
+            uint32_t* rows = reg + selCols / 2;
+            for (int i0 = 2 * lane; i0 < lm; i0 += 64) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = i0 + u;
+                    const int cA = i < q.LA ? q.readA[q.LA - 1 - i] : 0;
+                    const int cB = i < q.LB ? q.readB[q.LB - 1 - i] : 0;
+                    w |= ((uint32_t)(cA & 0xff) | ((uint32_t)(cB & 0xff) << 8)) << (16 * u);
+                }
+                rows[i0 >> 1] = w;
+            }
+        }
+        __syncwarp();
     }
-    for (int c = ncolsBand + WI; c < min(colAlloc, Lmax + M); ++c) selS[c * T] = 0xC480u;
+    if (!valid) return;
+    const uint16_t* selT = reinterpret_cast<const uint16_t*>(region0 + (size_t)threadIdx.x * strideW) + (PF - WI);
+    const uint16_t* rowT = reinterpret_cast<const uint16_t*>(region0 + (size_t)threadIdx.x * strideW + selCols / 2);
 
     uint32_t H[M], V[M];
 #pragma unroll
     for (int k = 0; k < M; ++k) { H[k] = FAST_CPACK; V[k] = FAST_CPACK; }
-    uint32_t goP = pack2(FAST_SCALE * d.gap_open[pA], FAST_SCALE * d.gap_open[qB]);
-    uint32_t ngeP = pack2(-FAST_SCALE * d.gap_ext[pA], -FAST_SCALE * d.gap_ext[qB]);
-    const uint32_t targetV = pack2(FAST_SCALE * rA.score1 + FAST_C, pB < 0 ? 0x7fff : FAST_SCALE * rB.score1 + FAST_C);
     asm volatile("" : "+r"(goP), "+r"(ngeP));
 
     int bestColA = 0x7fffffff, bestRowA = 0, bestColB = 0x7fffffff, bestRowB = 0;
-    int cA = LA > 0 ? readA[LA - 1] : 0, cB = LB > 0 ? readB[LB - 1] : 0;      // software prefetch of the next row's read bases
+    uint32_t rw = rowT[0];                                              // software prefetch of the next row's read bases
 
     for (int i = 0; i < Lmax; ++i) {
-        const uint32_t tA = i < LA ? s_rowtab[cA] : 0u, tB = i < LB ? s_rowtab[cB] : 0u;
-        cA = (i + 1 < LA) ? readA[LA - 2 - i] : 0;
-        cB = (i + 1 < LB) ? readB[LB - 2 - i] : 0;
-        const uint16_t* sp = selS + (size_t)i * T;                       // selector of diagonal d: sp[d * T]
+        const uint32_t tA = s_rowtab[rw & 0xffu], tB = s_rowtab[rw >> 8];
+        rw = rowT[min(i + 1, Lmax - 1)];
+        const uint16_t* sp = selT + i;                                   // selector of diagonal k: sp[k]
         uint32_t G = FAST_CPACK, rm = 0;
         if (i < WI) {
             // first rows: diagonals left of column 0 do not exist; keep them at the zero level
 #pragma unroll
             for (int k = 0; k < M; ++k) {
                 const bool ok = k >= WI - i;
-                const uint32_t s = prmt(tA, tB, sp[k * T]);
+                const uint32_t s = prmt(tA, tB, sp[k]);
                 const uint32_t vin = k + 1 < M ? V[k + 1] : FAST_CPACK;
                 uint32_t h = __viaddmax_s16x2(H[k], s, vin);
                 h = __vimax3_s16x2(h, G, FAST_CPACK);
@@ -109,7 +157,7 @@ k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict
         } else {
 #pragma unroll
             for (int k = 0; k < M; ++k) {
-                const uint32_t s = prmt(tA, tB, sp[k * T]);
+                const uint32_t s = prmt(tA, tB, sp[k]);
                 const uint32_t vin = k + 1 < M ? V[k + 1] : FAST_CPACK;
                 uint32_t h = __viaddmax_s16x2(H[k], s, vin);                 // max(Hdiag + s, V)
                 h = __vimax3_s16x2(h, G, FAST_CPACK);                        // max(., G, 0)

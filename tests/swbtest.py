@@ -459,6 +459,47 @@ def make_pairs_fast(n_pairs: int, read_len: int = 150, win_len: int = 400, *, se
     )
 
 
+def make_window_edge_pairs(n_pairs: int, seed: int = 1) -> Batch:
+    """Reads anchored at the very start (or end) of their window with an indel close to the anchored end, mixed
+    gap penalties with gap_extension > 0: the reverse rectangle (ssw.c:875-886) then has fewer columns than rows
+    and the optimal start lies off the main diagonal -- the geometry the banded reverse pass (swb_revband.cuh)
+    must get right (band columns beyond the rectangle, first rows of the band, competing equal-score starts)."""
+    rng = np.random.default_rng(seed)
+    grid = [(3, 1), (5, 1), (4, 1), (6, 2), (2, 1), (7, 3)]
+    wins, reads, go, ge = [], [], [], []
+    for p in range(n_pairs):
+        wl = int(rng.integers(120, 420))
+        W = rng.integers(0, 4, size=wl, dtype=np.int8)
+        L = int(rng.integers(40, min(160, wl - 30)))
+        ev = int(rng.integers(1, 14))
+        kind = int(rng.integers(0, 3))
+        at_end = rng.random() < 0.3
+        if kind == 0:      # insertion near the anchored end
+            span = L - ev
+            start = int(rng.integers(0, 5)) if not at_end else wl - span - int(rng.integers(0, 5))
+            cut = int(rng.integers(1, max(2, min(24, span - 1)))) if not at_end else span - int(rng.integers(1, max(2, min(24, span - 1))))
+            ins = rng.integers(0, 4, size=ev, dtype=np.int8) if rng.random() < 0.6 else W[max(0, start + cut - ev) : start + cut][:ev].copy()
+            r = np.concatenate([W[start : start + cut], ins, W[start + cut : start + span]])
+        elif kind == 1:    # deletion near the anchored end
+            span = L + ev
+            start = int(rng.integers(0, 5)) if not at_end else wl - span - int(rng.integers(0, 5))
+            cut = int(rng.integers(1, 24)) if not at_end else L - int(rng.integers(1, 24))
+            r = np.concatenate([W[start : start + cut], W[start + cut + ev : start + span]])
+        else:              # both, a few bases apart
+            ev2 = int(rng.integers(1, 8))
+            span = L - ev + ev2
+            start = int(rng.integers(0, 5)) if not at_end else wl - span - int(rng.integers(0, 5))
+            cut = int(rng.integers(2, 16))
+            cut2 = cut + int(rng.integers(3, 12))
+            r = np.concatenate([W[start : start + cut], rng.integers(0, 4, size=ev, dtype=np.int8), W[start + cut : start + cut2], W[start + cut2 + ev2 : start + span]])
+        r = r.astype(np.int8)
+        m = rng.random(r.shape[0]) < 0.015
+        r[m] = (r[m] + rng.integers(1, 4, size=int(m.sum()), dtype=np.int8)) % 4
+        g = grid[int(rng.integers(0, len(grid)))]
+        wins.append(W); reads.append(r); go.append(g[0]); ge.append(g[1])
+    return batch_from_lists(reads, wins, np.arange(n_pairs), np.arange(n_pairs), np.array(go), np.array(ge))
+
+
 def make_overflow_zone_pairs(n_pairs: int, seed: int = 1) -> Batch:
     """Targeted stress for the 8-bit/16-bit escalation decision (ssw.c:842-847): reads whose best
     alignment needs an insertion placed where the running score is around 128 (the zone in which the

@@ -167,6 +167,18 @@ def test_gpu_overflow_decision_stress(seed):
     assert tm["n_fast"] > 0
 
 
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_gpu_reverse_band_window_edges(seed):
+    """banded reverse pass (swb_revband.cuh): alignments anchored at a window edge with indels next to it"""
+    from gpuutil import gpu_align
+
+    b = T.make_window_edge_pairs(6000, seed=seed)
+    ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+    rg, ag, tm = gpu_align(b)
+    T.compare(rg, ag, ro, ao, what=f"window-edge reverse stress seed={seed}")
+    assert tm["n_fast"] > 0
+
+
 def test_gpu_pipelined_batch_equals_single_pass(monkeypatch):
     """large batches go through the two-lane chunked pipeline of swb_align_batch (table slices, index rebasing,
     CIGAR arena stitched from chunks): results must equal the single-pass path and the oracle"""
