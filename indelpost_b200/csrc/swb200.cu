@@ -31,6 +31,7 @@
 #include "swb_band.cuh"
 #include "swb_fast.cuh"
 #include "swb_revband.cuh"
+#include "swb_bandreg.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
 
@@ -135,6 +136,7 @@ struct swb_ctx {
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
     cudaStream_t rev_stream[SWB_NREVB];                                     // banded reverse pass: one stream per band class
     cudaEvent_t ev_rev_fork, ev_rev_join[SWB_NREVB];
+    unsigned bandreg_used = 0; int bandreg_base = 0;                       // side streams the register-band kernels of the current round run on
     cudaEvent_t ev[EV_COUNT];
     std::string err;
     SwbDev d;
@@ -501,6 +503,55 @@ static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound) 
 }
 static int certify_phase2_hook(swb_ctx* c, int total) { return total > 0 ? certify_and_verify_async(c, LIST_VERIFY2, total) : 0; }
 
+// register-band kernels (swb_bandreg.cuh): one launch per exact half-width, spread over the side streams
+template <int W>
+static int launch_band_reg_one(swb_ctx* c, int listSlot, int njobs, int nextBase, cudaStream_t st) {
+    const SwbDev& d = c->d;
+    const int rows = std::min(d.max_rlen, SWB_BANDREG_MAXROWS);
+    const size_t smem = (size_t)bandreg_stride_words(rows) * 4 * SWB_BANDREG_THREADS;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_band_reg<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr = true; }
+    k_band_reg<W><<<(njobs + SWB_BANDREG_THREADS - 1) / SWB_BANDREG_THREADS, SWB_BANDREG_THREADS, smem, st>>>(d, d.list[listSlot], njobs, nextBase, rows);
+    c->tm.n_launches++;
+    return 0;
+}
+static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBase) {
+    int any = 0;
+    for (int w = 1; w <= SWB_BANDW_MAX; ++w) any += njobsW[w - 1];
+    if (!any) return 0;
+    CUDA_TRY(c, cudaEventRecord(c->ev_rev_fork, c->stream));
+    bool used[SWB_NREVB] = {};
+    for (int w = SWB_BANDW_MAX; w >= 1; --w) {              // widest (longest threads) first
+        const int n = njobsW[w - 1];
+        if (n <= 0) continue;
+        const int si = w % SWB_NREVB;
+        cudaStream_t st = c->rev_stream[si];
+        if (!used[si]) { CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_rev_fork, 0)); used[si] = true; }
+        switch (w) {
+#define SWB_BR_CASE(W) case W: launch_band_reg_one<W>(c, baseW + W - 1, n, nextBase, st); break;
+            SWB_BR_CASE(1) SWB_BR_CASE(2) SWB_BR_CASE(3) SWB_BR_CASE(4) SWB_BR_CASE(5) SWB_BR_CASE(6) SWB_BR_CASE(7) SWB_BR_CASE(8)
+            SWB_BR_CASE(9) SWB_BR_CASE(10) SWB_BR_CASE(11) SWB_BR_CASE(12) SWB_BR_CASE(13) SWB_BR_CASE(14) SWB_BR_CASE(15) SWB_BR_CASE(16)
+#undef SWB_BR_CASE
+        }
+    }
+    c->bandreg_used = 0;
+    for (int i = 0; i < SWB_NREVB; ++i) if (used[i]) {
+        CUDA_TRY(c, cudaEventRecord(c->ev_rev_join[i], c->rev_stream[i]));
+        c->bandreg_used |= 1u << i;
+    }
+    c->bandreg_base = baseW;
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+// the main stream waits for the register-band kernels (after it has queued the literal kernel for the other jobs)
+static int join_band_reg(swb_ctx* c) {
+    if (!c->bandreg_used) return 0;
+    for (int i = 0; i < SWB_NREVB; ++i) if (c->bandreg_used & (1u << i)) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_rev_join[i], 0));
+    CUDA_TRY(c, cudaMemsetAsync(c->d.counters + c->bandreg_base, 0, 4 * SWB_BANDW_MAX, c->stream));      // lists consumed
+    c->bandreg_used = 0;
+    return 0;
+}
+
 // banded DP + traceback (ssw.c:897-916) over the four band-class lists; a launch round per class, repeated only
 // for pairs the kernel re-queued (scratch exhausted, or band outgrew the shared-memory rows)
 // firstRoundOnly: launch the jobs of `firstBase` and leave what they re-queue in LIST_BAND_NEXT for a later call;
@@ -516,6 +567,10 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
     for (;;) {
         int njobs[SWB_NBANDCLASS], total = 0;
         for (int k = 0; k < SWB_NBANDCLASS; ++k) { njobs[k] = c->h_counters[cur + k]; total += njobs[k]; }
+        // round 0 also serves the register-band lists that belong to this phase (their re-queues land in `nxt`)
+        int njobsW[SWB_BANDW_MAX] = {};
+        const int baseW = firstBase == LIST_BAND_FIRST ? LIST_BANDW_FIRST : LIST_BANDW;
+        if (round == 0) for (int k = 0; k < SWB_BANDW_MAX; ++k) { njobsW[k] = c->h_counters[baseW + k]; total += njobsW[k]; }
         if (round == 0 && firstJobs) *firstJobs = total;
         if (total <= 0 && !(round == 0 && keepNext)) break;
         if (!(round == 0 && keepNext)) CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
@@ -539,6 +594,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
             }
             CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
         }
+        if (round == 0 && launch_band_reg(c, baseW, njobsW, nxt)) return -1;
         int blocks = 0;
         for (int k = 0; k < SWB_BAND_CLS_MID; ++k) blocks += (njobs[k] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
         if (blocks > 0) {
@@ -546,6 +602,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
             c->tm.n_launches++;
         }
         if (side) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));
+        if (join_band_reg(c)) return -1;
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "band")) return -1;
         if (record && round == 0) CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_R0], s));

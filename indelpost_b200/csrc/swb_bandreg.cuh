@@ -1,0 +1,223 @@
+// swb_bandreg.cuh — banded_sw (ssw.c:588-772) with the rolling band rows in REGISTERS, for the first band width of
+// the "regular" jobs: half-width W = |refLen - readLen| + 1 <= SWB_BANDW_MAX known at compile time, refLen >= 2W + 2
+// (the band is narrower than the matrix, so none of the reference's buffer-reuse quirks is reachable, see below),
+// matrix edge n <= 8.  Everything else — wider or irregular bands, band doubling (ssw.c:668-669) — goes to the literal
+// kernel k_band (swb_band.cuh), which also provides the traceback walk used here.
+//
+// Slot algebra (ssw.c:92-95, set_u): cell (i, j) of row i lives in slot u = j - max(0, i - W) + 1 of the rolling
+// buffers; x = u - 1 below.
+//   rows i <= W      : x = j.            upper neighbour (i-1, j) = slot x, diagonal neighbour = slot x-1 (0 for x = 0)
+//   rows i >= W + 1  : x = j - (i - W).  upper neighbour = slot x+1, diagonal neighbour = slot x
+// so the band is a fixed array of 2W+1 registers per buffer updated in place, and the position of a cell's direction
+// nibble inside its row (set_d) is x in both regimes.  Slots the reference clears at a row start (ssw.c:633: 0 and
+// `edge` = the slot right of the row's last cell) are exactly the out-of-band neighbours: constants 0 here.  With
+// refLen >= 2W+2 a row is clipped by the matrix edge only for i >= W+1, its `edge` slot (2W+2) is then not read, and
+// the slots a later row reads are always ones the copy loop ssw.c:666 refreshed; cells right of the matrix edge are
+// computed (nothing valid depends on them) but excluded from the running maximum.
+// One thread per alignment; jobs are listed per exact W so a warp runs one instantiation.  Substitution scores:
+// one PRMT per cell from the read base's 8-byte score row and a per-column selector kept in shared memory
+// ([thread][column], odd word stride = conflict free), staged by the warp with coalesced loads.
+#pragma once
+#include "swb_common.cuh"
+#include "swb_band.cuh"
+#include "swb_fast.cuh"
+
+#define SWB_BANDREG_THREADS 64
+
+struct BandRegPar { const int8_t* read; const int8_t* ref; int readLen, refLen; };
+
+// per-thread shared-memory region: [columns: u16 selectors][rows: u8 read codes], odd number of 32-bit words
+__host__ __device__ __forceinline__ int bandreg_sel_cols(int rows) { return (rows + SWB_BANDW_MAX + 2 * SWB_BANDW_MAX + 4) & ~1; }
+__host__ __device__ __forceinline__ int bandreg_stride_words(int rows) { return ((bandreg_sel_cols(rows) * 2 + ((rows + 3) & ~3)) / 4) | 1; }
+
+// one DP cell (ssw.c:637-664).  hUp/eUp: upper neighbour, hDiag: diagonal neighbour, hLeft/f: left neighbour state.
+// Returns H; writes E back through eOut; ORs the 4-bit direction code (bit0: E opened from H, bit1: F opened from H,
+// bits 2-3: 0 diagonal / 1 E / 2 F) into `word` at nibble NIB (a constant after unrolling).
+__device__ __forceinline__ int bandreg_cell(const int NIB, int hUp, int eUp, int hDiag, int hLeft, int& f, int& eOut, int sc, int go, int ge, uint32_t& word)
+{
+    int a = hUp - go, b = eUp - ge;                       // ssw.c:644-648
+    const int ev = a > b ? a : b;
+    uint32_t bits = a > b ? (1u << (4 * NIB)) : 0u;
+    eOut = ev;
+    a = hLeft - go; b = f - ge;                           // ssw.c:650-653
+    f = a > b ? a : b;
+    bits |= a > b ? (2u << (4 * NIB)) : 0u;
+    const int e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;   // ssw.c:655-659
+    const int gmax = e1 > f1 ? e1 : f1;
+    const int m = hDiag + sc;
+    const int h = gmax > m ? gmax : m;
+    const uint32_t selv = gmax <= m ? 0u : (e1 > f1 ? (4u << (4 * NIB)) : (8u << (4 * NIB)));   // ssw.c:663-664
+    word |= bits | selv;
+    return h;
+}
+
+template <int W>
+__global__ void __launch_bounds__(SWB_BANDREG_THREADS)
+k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, int rowsAlloc)
+{
+    constexpr int NX = 2 * W + 1;
+    constexpr int NW = (NX + 7) / 8;                      // direction words per row
+    constexpr int T = SWB_BANDREG_THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long s_rowTab[8];            // per read base: its scores against every window base, 8 x int8
+    __shared__ BandRegPar s_par[T];
+    if (threadIdx.x < 8) {
+        unsigned long long tab = 0;
+        if ((int)threadIdx.x < d.n) for (int nt = 0; nt < d.n; ++nt) tab |= (unsigned long long)(uint8_t)d.mat[nt * d.n + threadIdx.x] << (8 * nt);
+        s_rowTab[threadIdx.x] = tab;
+    }
+    const int t = blockIdx.x * T + threadIdx.x;
+    const bool valid = t < njobs;
+    int p = -1;
+    BandGeom g; g.w = W; g.width_d = NX; g.strideW = NW; g.refLen = 0; g.readLen = 0;
+    {
+        BandRegPar q; q.read = q.ref = nullptr; q.readLen = q.refLen = 0;
+        if (valid) {
+            p = jobs[t];
+            const swb_result& r = d.res[p];
+            g.refLen = r.ref_end1 - r.ref_begin1 + 1;     // ssw.c:897-899
+            g.readLen = r.read_end1 - r.read_begin1 + 1;
+            q.ref = d.windows + d.p_woff[p] + r.ref_begin1;
+            q.read = d.reads + d.p_roff[p] + r.read_begin1;
+            q.readLen = g.readLen; q.refLen = g.refLen;
+        }
+        s_par[threadIdx.x] = q;
+    }
+    __syncthreads();
+
+    // ---- staging (one thread's sequences at a time, lanes on consecutive bytes) --------------------------------
+    const int strideW = bandreg_stride_words(rowsAlloc);
+    const int selCols = bandreg_sel_cols(rowsAlloc);
+    uint32_t* const region0 = reinterpret_cast<uint32_t*>(smem_raw);
+    {
+        const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+        for (int src = 0; src < 32; ++src) {
+            const BandRegPar q = s_par[wbase + src];
+            if (q.readLen == 0) continue;
+            uint32_t* reg = region0 + (size_t)(wbase + src) * strideW;
+            const int ncols = min(q.refLen + NX + 1, selCols);
+            for (int c0 = 2 * lane; c0 < ncols; c0 += 64) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c = c0 + u;
+                    const uint32_t rc = c < q.refLen ? (uint32_t)(q.ref[c] & 7) : 0u;
+                    w |= (rc * 0x1111u | 0x8880u) << (16 * u);          // PRMT selector: byte rc, sign-extended to 32 bits
+                }
+                reg[c0 >> 1] = w;
+            }
+            uint32_t* rows = reg + selCols / 2;
+            for (int i0 = 4 * lane; i0 < q.readLen; i0 += 128) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u;
+                    const uint32_t cb = i < q.readLen ? (uint32_t)(q.read[i] & 7) : 0u;
+                    w |= cb << (8 * u);
+                }
+                rows[i0 >> 2] = w;
+            }
+        }
+        __syncwarp();
+    }
+    if (!valid) return;
+    const uint16_t* selT = reinterpret_cast<const uint16_t*>(region0 + (size_t)threadIdx.x * strideW);
+    const uint8_t* rowT = reinterpret_cast<const uint8_t*>(region0 + (size_t)threadIdx.x * strideW + selCols / 2);
+
+    swb_result& r = d.res[p];
+    const int score = r.score1;
+    const int go = d.gap_open[p], ge = d.gap_ext[p];
+    const int len = g.refLen > g.readLen ? g.refLen : g.readLen;
+
+    // ---- scratch for the packed direction words -----------------------------------------------------------------
+    const long long need = (long long)NW * 4 * g.readLen;
+    const unsigned long long off = warp_bump(&d.bump[0], (unsigned long long)need);
+    if ((long long)off + need > d.band_cap) {               // out of scratch: the literal kernel retries in a later round
+        d.t_bw[p] = W; d.t_best[p] = 0;
+        atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
+        const int c = band_class(W);
+        list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
+        return;
+    }
+    uint32_t* dir = reinterpret_cast<uint32_t*>(d.band + off);
+
+    int Hs[NX], Es[NX];
+#pragma unroll
+    for (int x = 0; x < NX; ++x) { Hs[x] = 0; Es[x] = 0; }
+    int best = 0;
+    long long cells = 0;
+
+    // ---- rows 0 .. W: slot x = column x, cells x <= i + W ---------------------------------------------------------
+    const int rowsA = min(W + 1, g.readLen);
+    for (int i = 0; i < rowsA; ++i) {
+        const unsigned long long tab = s_rowTab[rowT[i]];
+        const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
+        uint32_t words[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) words[k] = 0;
+        int f = 0, hLeft = 0, hDiag = 0;
+        const int lim = i + W;                              // regular jobs: lim <= 2W <= refLen - 2, no clipping here
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+            if (x <= lim) {
+                const int hUp = Hs[x], eUp = Es[x];
+                const int sc = (int)prmt(tabLo, tabHi, selT[x]);
+                const int h = bandreg_cell(x & 7, hUp, eUp, hDiag, hLeft, f, Es[x], sc, go, ge, words[x >> 3]);
+                Hs[x] = h;
+                best = max(best, h);                        // ssw.c:661
+                hDiag = hUp; hLeft = h;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k) dir[(size_t)i * NW + k] = words[k];
+        cells += lim + 1;
+    }
+
+    // ---- rows W+1 .. readLen-1: slot x = column x + i - W --------------------------------------------------------
+    for (int i = W + 1; i < g.readLen; ++i) {
+        const unsigned long long tab = s_rowTab[rowT[i]];
+        const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
+        const uint16_t* sp = selT + (i - W);
+        uint32_t words[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) words[k] = 0;
+        int f = 0, hLeft = 0;
+        const int xmax = g.refLen - 1 - (i - W);            // last slot inside the matrix (>= 2W: row not clipped)
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+            const int hUp = x + 1 < NX ? Hs[x + 1] : 0, eUp = x + 1 < NX ? Es[x + 1] : 0;
+            const int sc = (int)prmt(tabLo, tabHi, sp[x]);
+            const int h = bandreg_cell(x & 7, hUp, eUp, Hs[x], hLeft, f, Es[x], sc, go, ge, words[x >> 3]);
+            Hs[x] = h;
+            if (x <= xmax) best = max(best, h);
+            hLeft = h;
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k) dir[(size_t)i * NW + k] = words[k];
+        cells += min(xmax, 2 * W) + 1;
+    }
+    warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
+
+    if (best < score && W * 2 <= len) {                     // ssw.c:668-669: widen and redo (literal kernel)
+        d.t_bw[p] = 2 * W; d.t_best[p] = best;
+        const int c = band_class(2 * W);
+        list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
+        return;
+    }
+
+    // ---- traceback: one walk (ops buffered in registers), allocate, emit reversed ---------------------------------
+    BandOps ops;
+    constexpr bool regRows = NW <= BAND_ROWWORDS;
+    const int l = band_traceback<regRows>(dir, g, ops, nullptr, 0);
+    if (l < 0) { r.flag = 1; r.cigar_len = 0; r.cigar_off = 0; d.p_state[p] |= PST_BAND_DONE; return; }      // ssw.c:911
+    const unsigned long long coff = warp_bump(&d.bump[1], (unsigned long long)l);
+    r.cigar_len = l; r.cigar_off = (int64_t)coff;
+    if ((long long)coff + l > d.cigar_cap) { atomicAdd(d.counters + CNT_CIGAR_OVERFLOW, 1); return; }
+    if (l <= BAND_OPBUF) {
+#pragma unroll
+        for (int q = 0; q < BAND_OPBUF; ++q) if (q < l) d.cigar[coff + (l - 1 - q)] = ops.op[q];   // reverse (ssw.c:753-762)
+    } else {
+        band_traceback<regRows>(dir, g, ops, d.cigar + coff, l);
+    }
+    d.p_state[p] |= PST_BAND_DONE;
+}

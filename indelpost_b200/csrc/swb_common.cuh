@@ -7,8 +7,8 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 56
-#define SWB_NCOUNTERS 96
+#define SWB_NLISTS 88
+#define SWB_NCOUNTERS 128
 
 // ---------------------------------------------------------------------------------------------
 // Device-resident batch ("workspace").  One per context, grown on demand.
@@ -61,19 +61,22 @@ struct SwbDev {
     int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
     uint32_t* fast_cols;   // global column-best storage of the fast path when windows are too long for shared memory (null otherwise)
     int32_t one;        // always 1, but opaque to the compiler: x * one + c compiles to a real IMAD (FMA pipe) instead of an ALU-pipe add
-    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass
+    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass, bit4 = no register-band kernel
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
 #define SWB_NBANDCLASS 8         // band jobs are bucketed by half-width: 1 | 2 | 3-4 | 5-8 | 9-16 | 17-48 (64-thread blocks) | 49-112 (32-thread blocks) | wider (global-memory rows)
 #define SWB_BAND_CLS_MID 5      // first class of k_band<48,64>; 6: k_band<112,32>; 7: k_band<0,128>
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
-       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48 };
+       LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
+       LIST_BANDW = 56, LIST_BANDW_FIRST = 72 };   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh)
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
-       CNT_CELLS_FWD = 64, CNT_CELLS_REV = 66, CNT_CELLS_BAND = 68, CNT_BAND_OVERFLOW = 70, CNT_CIGAR_OVERFLOW = 71,
-       CNT_FAST_DONE = 72, CNT_CERT_FAIL = 73, CNT_VERIFY_BYTE = 74, CNT_EXACT_JOBS = 75,
-       CNT_FAST_MAXCOLS = 80 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
+       CNT_CELLS_FWD = 96, CNT_CELLS_REV = 98, CNT_CELLS_BAND = 100, CNT_BAND_OVERFLOW = 102, CNT_CIGAR_OVERFLOW = 103,
+       CNT_FAST_DONE = 104, CNT_CERT_FAIL = 105, CNT_VERIFY_BYTE = 106, CNT_EXACT_JOBS = 107,
+       CNT_FAST_MAXCOLS = 112 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
+#define SWB_BANDW_MAX 16           // widest half-width the register-band kernel is instantiated for
+#define SWB_BANDREG_MAXROWS 320    // longest read segment it stages in shared memory
 // banded reverse pass (swb_revband.cuh): band classes as (rows below, columns right of) the main diagonal
 #define SWB_NREVB 6
 #define SWB_REVB_CLASSES(X) X(0, 2, 5) X(1, 3, 12) X(2, 5, 18) X(3, 6, 25) X(4, 10, 37) X(5, 13, 50)
@@ -131,12 +134,20 @@ __host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 
 
 // queue a pair for the banded traceback in the class of its initial band width |refLen - readLen| + 1 (ssw.c:899)
 __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_result& r) {
-    int dl = (r.ref_end1 - r.ref_begin1) - (r.read_end1 - r.read_begin1);
+    const int refLen = r.ref_end1 - r.ref_begin1 + 1, readLen = r.read_end1 - r.read_begin1 + 1;
+    const int dl = refLen - readLen;
     const int bw = (dl < 0 ? -dl : dl) + 1;
-    const int c = band_class(bw);
     // provisional 16-bit results whose alignment has a net insertion are the only ones that can fail the overflow
     // certificate (swb_cert.cuh): they are traced back first so their verification overlaps the rest of the stage
-    const int base = ((d.p_state[p] & PST_NEED_CERT) && dl < 0) ? LIST_BAND_FIRST : LIST_BAND;
+    const bool first = (d.p_state[p] & PST_NEED_CERT) && dl < 0;
+    // regular jobs (band narrower than the matrix, see swb_bandreg.cuh) go to the register-band kernel of their exact width
+    if (bw <= SWB_BANDW_MAX && refLen >= 2 * bw + 2 && readLen <= SWB_BANDREG_MAXROWS && d.n <= 8 && r.ref_begin1 >= 0 && r.read_begin1 >= 0 && !(d.opt & 16)) {
+        const int slot = (first ? LIST_BANDW_FIRST : LIST_BANDW) + bw - 1;
+        list_push(d.list[slot], d.counters + slot, p);
+        return;
+    }
+    const int c = band_class(bw);
+    const int base = first ? LIST_BAND_FIRST : LIST_BAND;
     list_push(d.list[base + c], d.counters + base + c, p);
 }
 
