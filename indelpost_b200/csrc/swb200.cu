@@ -133,6 +133,9 @@ enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0
 struct swb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
+    cudaStream_t bulk_stream = nullptr;                                     // lowest priority: the forward DPX sweep (yields SM slots to the short, latency-bound kernels of the other lane)
+    cudaStream_t bulk_stream2 = nullptr;                                    // second one: consecutive forward slices of the streamed one-shot path overlap their tails
+    cudaEvent_t ev_bulk_fork, ev_bulk_join, ev_bulk_join2, ev_piece;
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
     cudaStream_t rev_stream[SWB_NREVB];                                     // banded reverse pass: one stream per band class
     cudaEvent_t ev_rev_fork, ev_rev_join[SWB_NREVB];
@@ -148,15 +151,23 @@ struct swb_ctx {
     DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe, b_fastcols;
     int fastMaxCols[SWB_NBUCKETS] = {};
     int32_t* h_counters = nullptr;              // pinned mirror of counters
+    int32_t* h_snap[2] = {nullptr, nullptr};    // streamed path: counter snapshots of the piece in flight and the one before
+    cudaEvent_t ev_snap[2];
     unsigned long long* h_bump = nullptr;       // pinned mirror of bump
     swb_timing tm;
     int smem_optin = 0;
     int n_sm = 0;
     int64_t chunk_pairs = 0;
+    std::vector<std::pair<const char*, double>> trace;
     swb_ctx* sibling = nullptr;                 // second lane, created on demand by the pipelined swb_align_batch
     bool pipelined_last = false;
 };
 
+// SWB200_TRACE=1: host wall-clock marks (after the host-side synchronisation points) dumped to stderr per swb_align_batch call
+#include <chrono>
+static const bool g_trace = getenv("SWB200_TRACE") != nullptr;
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TR(ctx, name) do { if (g_trace) (ctx)->trace.push_back(std::make_pair((const char*)(name), now_ms())); } while (0)
 static std::string g_create_err;
 static std::mutex g_mu;
 
@@ -192,18 +203,29 @@ extern "C" swb_ctx* swb_create(int device) {
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     memset(&c->d, 0, sizeof c->d);
     memset(&c->tm, 0, sizeof c->tm);
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // stream priorities: the long forward sweep runs at the lowest priority, the per-class side streams in the middle and
+    // everything on the critical path (small launches between host round trips) at the highest, so that with two pipeline
+    // lanes one lane's short kernels are not queued behind the other lane's thousands of sweep blocks
+    int prLeast = 0, prGreatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
+    const int prMid = (prLeast + prGreatest) / 2;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) {
         g_create_err = std::string("cannot create stream: ") + cudaGetErrorString(cudaGetLastError());
         delete c; return nullptr;
     }
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
-    cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking);
+    cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prGreatest);
+    cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prGreatest);
+    cudaStreamCreateWithPriority(&c->bulk_stream, cudaStreamNonBlocking, prLeast);
+    cudaStreamCreateWithPriority(&c->bulk_stream2, cudaStreamNonBlocking, prLeast);
+    cudaEventCreateWithFlags(&c->ev_bulk_join2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_piece, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_bulk_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bulk_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_rev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamCreateWithFlags(&c->rev_stream[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&c->ev_rev_join[i], cudaEventDisableTiming); }
+    for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamCreateWithPriority(&c->rev_stream[i], cudaStreamNonBlocking, prMid); cudaEventCreateWithFlags(&c->ev_rev_join[i], cudaEventDisableTiming); }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
     cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t));
+    for (int i = 0; i < 2; ++i) { cudaMallocHost((void**)&c->h_snap[i], SWB_NCOUNTERS * sizeof(int32_t)); cudaEventCreateWithFlags(&c->ev_snap[i], cudaEventDisableTiming); }
     cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long));
     // opt in to large dynamic shared memory for the exact kernels
     cudaFuncSetAttribute(k_exact<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
@@ -228,8 +250,11 @@ extern "C" void swb_destroy(swb_ctx* c) {
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(c->h_snap[i]); cudaEventDestroy(c->ev_snap[i]); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream3); cudaEventDestroy(c->ev_fork3);
+    cudaStreamDestroy(c->bulk_stream); cudaEventDestroy(c->ev_bulk_fork); cudaEventDestroy(c->ev_bulk_join);
+    cudaStreamDestroy(c->bulk_stream2); cudaEventDestroy(c->ev_bulk_join2); cudaEventDestroy(c->ev_piece);
     cudaEventDestroy(c->ev_rev_fork);
     for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamDestroy(c->rev_stream[i]); cudaEventDestroy(c->ev_rev_join[i]); }
     cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); cudaEventDestroy(c->ev_join2);
@@ -277,6 +302,26 @@ extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
     return upload_view(c, b, v);
 }
 
+// batch-level scalars of SwbDev (everything but the device pointers)
+static void set_batch_scalars(swb_ctx* c, const swb_batch* b, const ChunkView& v, int32_t max_rl, int32_t max_wl) {
+    SwbDev& d = c->d;
+    d.n_pairs = b->n_pairs; d.n_reads = b->n_reads; d.n_windows = b->n_windows;
+    d.ridx_base = v.ridx_base; d.widx_base = v.widx_base; d.n_reads_total = v.n_reads_total; d.n_windows_total = v.n_windows_total;
+    d.rbyte_base = v.rbyte_base; d.wbyte_base = v.wbyte_base;
+    d.n = b->n; d.score_size = b->score_size; d.flag = b->flag; d.filters = b->filters; d.filterd = b->filterd;
+    d.seq_encoding = b->seq_encoding;
+    d.max_rlen = max_rl; d.max_wlen = max_wl;
+    int bias = 0;
+    for (int i = 0; i < b->n * b->n; ++i) if (b->mat[i] < bias) bias = b->mat[i];       // ssw.c:795-797
+    d.bias = (b->score_size == 0 || b->score_size == 2) ? std::abs(bias) : 0;
+    int mx = 0; bool small = true;
+    for (int i = 0; i < b->n * b->n; ++i) { mx = std::max<int>(mx, b->mat[i]); if (b->mat[i] > 7 || b->mat[i] < -7) small = false; }
+    d.max_score = mx;
+    { const char* o = getenv("SWB200_OPT"); d.opt = o ? atoi(o) : 0; }
+    d.one = 1;
+    d.fast_ok = (small && b->n >= 4 && mx > 0 && (b->score_size == 1 || b->score_size == 2) && !getenv("SWB200_NO_FAST")) ? 1 : 0;
+}
+
 static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v) {
     if (!c) return -1;
     c->err.clear();
@@ -318,21 +363,7 @@ static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v) {
     if (up(c, c->b_mat, b->mat, (size_t)b->n * b->n, &d.mat)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], c->stream));
 
-    d.n_pairs = b->n_pairs; d.n_reads = b->n_reads; d.n_windows = b->n_windows;
-    d.ridx_base = v.ridx_base; d.widx_base = v.widx_base; d.n_reads_total = v.n_reads_total; d.n_windows_total = v.n_windows_total;
-    d.rbyte_base = v.rbyte_base; d.wbyte_base = v.wbyte_base;
-    d.n = b->n; d.score_size = b->score_size; d.flag = b->flag; d.filters = b->filters; d.filterd = b->filterd;
-    d.seq_encoding = b->seq_encoding;
-    d.max_rlen = max_rl; d.max_wlen = max_wl;
-    int bias = 0;
-    for (int i = 0; i < b->n * b->n; ++i) if (b->mat[i] < bias) bias = b->mat[i];       // ssw.c:795-797
-    d.bias = (b->score_size == 0 || b->score_size == 2) ? std::abs(bias) : 0;
-    int mx = 0; bool small = true;
-    for (int i = 0; i < b->n * b->n; ++i) { mx = std::max<int>(mx, b->mat[i]); if (b->mat[i] > 7 || b->mat[i] < -7) small = false; }
-    d.max_score = mx;
-    { const char* o = getenv("SWB200_OPT"); d.opt = o ? atoi(o) : 0; }
-    d.one = 1;
-    d.fast_ok = (small && b->n >= 4 && mx > 0 && (b->score_size == 1 || b->score_size == 2) && !getenv("SWB200_NO_FAST")) ? 1 : 0;
+    set_batch_scalars(c, b, v, max_rl, max_wl);
     c->have_batch = true;
     return 0;
 }
@@ -355,6 +386,7 @@ static int read_counters(swb_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->d.counters, SWB_NCOUNTERS * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_bump, c->d.bump, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    TR(c, "counters");
     return 0;
 }
 
@@ -397,18 +429,18 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t s
 #define SWB_FAST_SMEM_COLS 1024     // windows longer than this keep their column bests in global memory
 
 template <int R, int DIR>
-static int launch_fast_one(swb_ctx* c, int bucket, int upperBoundPairs) {
+static int launch_fast_one(swb_ctx* c, int bucket, int firstPair, int upperBoundPairs, cudaStream_t st) {
     SwbDev& d = c->d;
     const int colAlloc = (std::max(c->fastMaxCols[bucket], 8) + 7) & ~7;      // longest window among this bucket's pairs
     const bool globalCols = colAlloc > SWB_FAST_SMEM_COLS;
     const size_t per = (size_t)colAlloc * (globalCols ? 2 : 10);
     // long windows: the global column-best scratch is bounded, the bucket is served in slices of the job list
-    int slicePairs = upperBoundPairs;
+    int slicePairs = upperBoundPairs - firstPair;
     if (globalCols) {
         const size_t budget = (size_t)4 << 30;
         const size_t perPairPair = (size_t)2 * colAlloc * 4;
         const size_t evenBudget = std::max<size_t>(2, 2 * (budget / perPairPair));      // pairs per slice (even: lane pairs stay intact)
-        slicePairs = (size_t)upperBoundPairs <= evenBudget ? upperBoundPairs : (int)evenBudget;
+        slicePairs = (size_t)slicePairs <= evenBudget ? slicePairs : (int)evenBudget;
         CUDA_TRY(c, c->b_fastcols.ensure((size_t)((slicePairs + 1) / 2) * perPairPair + 16));
         d.fast_cols = (uint32_t*)c->b_fastcols.p;
     } else d.fast_cols = nullptr;
@@ -422,38 +454,48 @@ static int launch_fast_one(swb_ctx* c, int bucket, int upperBoundPairs) {
         attr_set[DIR][bucket] = true;
     }
     const int slot = (DIR ? LIST_FAST_REV : LIST_FAST_FWD) + bucket;
-    for (int off = 0; off < upperBoundPairs; off += slicePairs) {
+    for (int off = firstPair; off < upperBoundPairs; off += slicePairs) {
         const int n = std::min(slicePairs, upperBoundPairs - off);
         const int ngroups = (n + 1) / 2;
         const int blocks = (ngroups + groups - 1) / groups;
-        if (globalCols) k_fast<R, DIR, true><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
-        else k_fast<R, DIR, false><<<blocks, threads, groups * per, c->stream>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
+        if (globalCols) k_fast<R, DIR, true><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
+        else k_fast<R, DIR, false><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
         c->tm.n_launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
-    return stage_check(c, DIR ? "fast rev" : "fast fwd");
+    return 0;
 }
 
+// one launch per non-empty read-length bucket (R = 2*(bucket+1) rows per thread) over the list ranges [first[b], counts[b])
 template <int DIR>
-static int launch_fast(swb_ctx* c, const int* counts) {
-    // one launch per non-empty read-length bucket (R = 2*(bucket+1) rows per thread)
+static int launch_fast_range(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) {
     for (int b = 0; b < SWB_NBUCKETS; ++b) {
-        const int n = counts[b];
-        if (n <= 0) continue;
+        const int n = counts[b], f = first ? first[b] : 0;
+        if (n <= f) continue;
         int rc = 0;
         switch (b) {
-            case 0: rc = launch_fast_one<2, DIR>(c, b, n); break;
-            case 1: rc = launch_fast_one<4, DIR>(c, b, n); break;
-            case 2: rc = launch_fast_one<6, DIR>(c, b, n); break;
-            case 3: rc = launch_fast_one<8, DIR>(c, b, n); break;
-            case 4: rc = launch_fast_one<10, DIR>(c, b, n); break;
-            case 5: rc = launch_fast_one<12, DIR>(c, b, n); break;
-            case 6: rc = launch_fast_one<14, DIR>(c, b, n); break;
-            case 7: rc = launch_fast_one<16, DIR>(c, b, n); break;
+            case 0: rc = launch_fast_one<2, DIR>(c, b, f, n, st); break;
+            case 1: rc = launch_fast_one<4, DIR>(c, b, f, n, st); break;
+            case 2: rc = launch_fast_one<6, DIR>(c, b, f, n, st); break;
+            case 3: rc = launch_fast_one<8, DIR>(c, b, f, n, st); break;
+            case 4: rc = launch_fast_one<10, DIR>(c, b, f, n, st); break;
+            case 5: rc = launch_fast_one<12, DIR>(c, b, f, n, st); break;
+            case 6: rc = launch_fast_one<14, DIR>(c, b, f, n, st); break;
+            case 7: rc = launch_fast_one<16, DIR>(c, b, f, n, st); break;
         }
         if (rc) return rc;
     }
     return 0;
+}
+
+template <int DIR>
+static int launch_fast(swb_ctx* c, const int* counts) {
+    // the forward sweeps go to the low-priority stream (see swb_create), the reverse ones stay on the main stream
+    if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_fork, c->stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_fork, 0)); }
+    const int rc = launch_fast_range<DIR>(c, nullptr, counts, DIR == 0 ? c->bulk_stream : c->stream);
+    if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join, c->bulk_stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_bulk_join, 0)); }
+    if (rc) return rc;
+    return stage_check(c, DIR ? "fast rev" : "fast fwd");
 }
 
 // banded reverse pass (swb_revband.cuh): one launch per band class, each on its own stream so that the classes
@@ -632,9 +674,8 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
     return 0;
 }
 
-extern "C" int swb_compute(swb_ctx* c) {
-    if (!c) return -1;
-    if (!c->have_batch) { c->err = "swb_compute: no batch uploaded"; return -1; }
+// workspace for the batch described by c->d (grow-only buffers), counters cleared, start event recorded
+static int compute_setup(swb_ctx* c) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     SwbDev& d = c->d;
     const size_t np = (size_t)d.n_pairs;
@@ -677,26 +718,21 @@ extern "C" int swb_compute(swb_ctx* c) {
     }
 
     cudaStream_t s = c->stream;
+    TR(c, "compute_begin");
     CUDA_TRY(c, cudaMemsetAsync(d.counters, 0, SWB_NCOUNTERS * 4, s));
     CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 16, s));
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_START], s));
+    return 0;
+}
 
-    // ---- prepare ------------------------------------------------------------------------------
-    if (d.n_reads) { k_encode_validate<<<(d.n_reads + 3) / 4, 128, 0, s>>>(d.reads, d.read_off, d.read_len, d.n_reads, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p, d.rbyte_base); tm.n_launches++; }
-    if (d.n_windows) { k_encode_validate<<<(d.n_windows + 3) / 4, 128, 0, s>>>(d.windows, d.win_off, d.win_len, d.n_windows, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p, d.wbyte_base); tm.n_launches++; }
-    d.seq_encoding = SWB_SEQ_CODES;                         // tables are codes from now on (repeat computes must not re-encode)
-    if (np) { k_prepare<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, 0, (int32_t)np); tm.n_launches++; }
-    CUDA_TRY(c, cudaGetLastError());
-    if (stage_check(c, "prepare")) return -1;
-    CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
-    if (read_counters(c)) return -1;                        // bucket sizes for the fast path launches
-    int fwdCounts[SWB_NBUCKETS]; int nFastTotal = 0;
-    for (int b = 0; b < SWB_NBUCKETS; ++b) { fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; nFastTotal += fwdCounts[b]; c->fastMaxCols[b] = c->h_counters[CNT_FAST_MAXCOLS + b]; }
+static int swb_compute_impl(swb_ctx* c);
 
-    // ---- forward (ssw.c:842-860) --------------------------------------------------------------------
-    //   fast path: one 16-bit Gotoh sweep per pair (pairs it cannot decide are appended to the exact lists)
-    //   exact path: 8-bit pass, then 16-bit pass for the pairs that overflowed
-    if (launch_fast<0>(c, fwdCounts)) return -1;
+// everything after the fast-path forward sweeps: exact forward passes, reverse, banded traceback, certificate, timings
+static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
+    SwbDev& d = c->d;
+    const size_t np = (size_t)d.n_pairs;
+    swb_timing& tm = c->tm;
+    cudaStream_t s = c->stream;
     if (launch_exact<0, 0>(c, LIST_BYTE_FWD, (int)np)) return -1;
     if (launch_exact<1, 0>(c, LIST_WORD_FWD, (int)np)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_FWD], s));
@@ -708,6 +744,7 @@ extern "C" int swb_compute(swb_ctx* c) {
     if (launch_exact<0, 1>(c, LIST_BYTE_REV, (int)np)) return -1;
     if (launch_exact<1, 1>(c, LIST_WORD_REV, (int)np)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));
+    TR(c, "fwd_rev_enqueued");
 
     // ---- banded DP + traceback (ssw.c:897-916), overlapped with the overflow verification -----------------------
     // phase 1: the pairs that can fail the certificate (provisional 16-bit result + net insertion), then the certificate
@@ -751,7 +788,7 @@ extern "C" int swb_compute(swb_ctx* c) {
         // device arena too small: grow to the exact requirement and redo (rare; the default is 16 ops/pair)
         size_t need = (size_t)c->h_bump[1] + 1024;
         CUDA_TRY(c, c->b_cigar.ensure(need * 4));
-        return swb_compute(c);
+        return swb_compute_impl(c);
     }
     cudaEventElapsedTime(&tm.ms_prepare, c->ev[EV_START], c->ev[EV_PREP]);
     cudaEventElapsedTime(&tm.ms_forward, c->ev[EV_PREP], c->ev[EV_FWD]);
@@ -767,7 +804,39 @@ extern "C" int swb_compute(swb_ctx* c) {
     tm.n_fast = c->h_counters[CNT_FAST_DONE] - c->h_counters[CNT_VERIFY_BYTE];
     tm.n_exact = c->h_counters[CNT_EXACT_JOBS];
     c->computed = true;
+    TR(c, "compute_end");
     return 0;
+}
+
+static int swb_compute_impl(swb_ctx* c) {
+    if (compute_setup(c)) return -1;
+    SwbDev& d = c->d;
+    const size_t np = (size_t)d.n_pairs;
+    swb_timing& tm = c->tm;
+    cudaStream_t s = c->stream;
+    // ---- prepare ------------------------------------------------------------------------------
+    if (d.n_reads) { k_encode_validate<<<(d.n_reads + 3) / 4, 128, 0, s>>>(d.reads, d.read_off, d.read_len, d.n_reads, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p, d.rbyte_base); tm.n_launches++; }
+    if (d.n_windows) { k_encode_validate<<<(d.n_windows + 3) / 4, 128, 0, s>>>(d.windows, d.win_off, d.win_len, d.n_windows, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p, d.wbyte_base); tm.n_launches++; }
+    d.seq_encoding = SWB_SEQ_CODES;                         // tables are codes from now on (repeat computes must not re-encode)
+    if (np) { k_prepare<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, 0, (int32_t)np); tm.n_launches++; }
+    CUDA_TRY(c, cudaGetLastError());
+    if (stage_check(c, "prepare")) return -1;
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
+    if (read_counters(c)) return -1;                        // bucket sizes for the fast path launches
+    int fwdCounts[SWB_NBUCKETS]; int nFastTotal = 0;
+    for (int b = 0; b < SWB_NBUCKETS; ++b) { fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; nFastTotal += fwdCounts[b]; c->fastMaxCols[b] = c->h_counters[CNT_FAST_MAXCOLS + b]; }
+
+    // ---- forward (ssw.c:842-860) --------------------------------------------------------------------
+    //   fast path: one 16-bit Gotoh sweep per pair (pairs it cannot decide are appended to the exact lists)
+    //   exact path: 8-bit pass, then 16-bit pass for the pairs that overflowed
+    if (launch_fast<0>(c, fwdCounts)) return -1;
+    return compute_tail(c, fwdCounts, nFastTotal);
+}
+
+extern "C" int swb_compute(swb_ctx* c) {
+    if (!c) return -1;
+    if (!c->have_batch) { c->err = "swb_compute: no batch uploaded"; return -1; }
+    return swb_compute_impl(c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -791,6 +860,209 @@ extern "C" int swb_download(swb_ctx* c, swb_result* results, uint32_t* cigar_are
     cudaEventElapsedTime(&c->tm.ms_d2h, c->ev[EV_D2H0], c->ev[EV_D2H1]);
     cudaEventElapsedTime(&c->tm.ms_h2d, c->ev[EV_H2D0], c->ev[EV_H2D1]);
     return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// streamed one-shot path: ONE pass over the batch, but the host->device copies are cut into pieces of
+// consecutive pairs and the fast-path forward sweep of a piece is queued as soon as its sequences are on the
+// device, so PCIe runs underneath the forward stage (which is longer than the whole upload) instead of in front
+// of it.  Reverse, traceback and certificate then run once over the whole batch.
+// ------------------------------------------------------------------------------------------------
+
+// byte extent and longest entry of a sequence table; false on a negative offset / length
+static bool scan_table_range(const int64_t* off, const int32_t* len, int32_t i0, int32_t i1, int64_t& extent, int32_t& maxlen) {
+    int64_t ext = 0, minoff = 0; int32_t ml = 0, minlen = 0;
+    for (int32_t i = i0; i < i1; ++i) {
+        const int64_t o = off[i]; const int32_t l = len[i];
+        ext = std::max<int64_t>(ext, o + l); ml = std::max(ml, l); minoff = std::min(minoff, o); minlen = std::min(minlen, l);
+    }
+    extent = ext; maxlen = ml;
+    return minoff >= 0 && minlen >= 0;
+}
+// both tables, split over a few host threads when they are large (two million entries take ~3 ms on one core)
+static bool scan_tables(const swb_batch* b, int64_t& reads_bytes, int32_t& max_rl, int64_t& win_bytes, int32_t& max_wl) {
+    const int NT = ((int64_t)b->n_reads + b->n_windows >= 400000) ? 6 : 1;      // 3 slices per table
+    struct Part { int64_t ext = 0; int32_t ml = 0; bool ok = true; };
+    Part pr[3], pw[3];
+    auto work = [&](int k) {
+        const int which = k / 3, sl = k % 3;
+        const int32_t n = which ? b->n_windows : b->n_reads;
+        const int32_t i0 = (int32_t)((int64_t)n * sl / 3), i1 = (int32_t)((int64_t)n * (sl + 1) / 3);
+        Part& q = which ? pw[sl] : pr[sl];
+        q.ok = which ? scan_table_range(b->win_off, b->win_len, i0, i1, q.ext, q.ml) : scan_table_range(b->read_off, b->read_len, i0, i1, q.ext, q.ml);
+    };
+    if (NT == 1) { for (int k = 0; k < 6; ++k) work(k); }
+    else {
+        std::thread th[5];
+        for (int k = 1; k < 6; ++k) th[k - 1] = std::thread(work, k);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    reads_bytes = 0; win_bytes = 0; max_rl = 0; max_wl = 0; bool ok = true;
+    for (int k = 0; k < 3; ++k) {
+        reads_bytes = std::max(reads_bytes, pr[k].ext); max_rl = std::max(max_rl, pr[k].ml); ok = ok && pr[k].ok;
+        win_bytes = std::max(win_bytes, pw[k].ext); max_wl = std::max(max_wl, pw[k].ml); ok = ok && pw[k].ok;
+    }
+    return ok;
+}
+
+struct TableStream {                 // upload frontier of one sequence table
+    const int8_t* blob; const int64_t* off; const int32_t* len; int32_t n;
+    int8_t* d_blob; int64_t* d_off; int32_t* d_len; uint8_t* d_bad;
+    int32_t front = 0;               // entries [0, front) are on the device
+    int64_t ulo = 0, uhi = 0;        // blob bytes [ulo, uhi) are on the device
+};
+
+// make entries [front, upto] resident: their table rows, the blob bytes they cover (the resident byte interval stays
+// contiguous), then encode / validate them
+static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, int ascii) {
+    if (upto < t.front) return 0;
+    const int32_t i0 = t.front, n = upto - t.front + 1;
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int32_t i = i0; i <= upto; ++i) { lo = std::min<int64_t>(lo, t.off[i]); hi = std::max<int64_t>(hi, t.off[i] + t.len[i]); }
+    cudaStream_t s = c->stream;
+    auto copy = [&](int64_t a, int64_t b2) -> int {
+        if (b2 <= a) return 0;
+        CUDA_TRY(c, cudaMemcpyAsync(t.d_blob + a, t.blob + a, (size_t)(b2 - a), cudaMemcpyHostToDevice, s));
+        c->tm.h2d_bytes += b2 - a;
+        return 0;
+    };
+    if (hi > lo) {
+        if (t.uhi == t.ulo) { if (copy(lo, hi)) return -1; t.ulo = lo; t.uhi = hi; }
+        else {
+            if (lo < t.ulo) { if (copy(lo, t.ulo)) return -1; t.ulo = lo; }
+            if (hi > t.uhi) { if (copy(t.uhi, hi)) return -1; t.uhi = hi; }
+        }
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(t.d_off + i0, t.off + i0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(t.d_len + i0, t.len + i0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    c->tm.h2d_bytes += (int64_t)n * 12;
+    k_encode_validate<<<(n + 3) / 4, 128, 0, s>>>(t.d_blob, t.d_off + i0, t.d_len + i0, n, c->d.n, ascii, t.d_bad + i0, 0);
+    c->tm.n_launches++;
+    t.front = upto + 1;
+    return 0;
+}
+
+static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used) {
+    c->err.clear();
+    c->have_batch = false; c->computed = false; c->pipelined_last = false;
+    if (b->n < 1 || b->n > SWB_MAX_N || !b->mat) { c->err = "substitution matrix edge n must be in [1, 32]"; return -1; }
+    if (!b->pair_read || !b->pair_win || !b->gap_open || !b->gap_ext) { c->err = "missing per-pair arrays"; return -1; }
+    if (!b->reads || !b->read_off || !b->read_len || !b->windows || !b->win_off || !b->win_len) { c->err = "missing sequence tables"; return -1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    SwbDev& d = c->d;
+    memset(&c->tm, 0, sizeof c->tm);
+    TR(c, "stream_begin");
+    int64_t reads_bytes = 0, win_bytes = 0; int32_t max_rl = 0, max_wl = 0;
+    if (!scan_tables(b, reads_bytes, max_rl, win_bytes, max_wl)) { c->err = "negative sequence offset/length"; return -1; }
+    TR(c, "tables_scanned");
+    const size_t np = (size_t)b->n_pairs, nr = (size_t)b->n_reads, nw = (size_t)b->n_windows;
+
+    // device input buffers (filled piece by piece below)
+    CUDA_TRY(c, c->b_reads.ensure((size_t)reads_bytes + 16));   d.reads = (int8_t*)c->b_reads.p;
+    CUDA_TRY(c, c->b_read_off.ensure(nr * 8 + 16));             d.read_off = (int64_t*)c->b_read_off.p;
+    CUDA_TRY(c, c->b_read_len.ensure(nr * 4 + 16));             d.read_len = (int32_t*)c->b_read_len.p;
+    CUDA_TRY(c, c->b_windows.ensure((size_t)win_bytes + 16));   d.windows = (int8_t*)c->b_windows.p;
+    CUDA_TRY(c, c->b_win_off.ensure(nw * 8 + 16));              d.win_off = (int64_t*)c->b_win_off.p;
+    CUDA_TRY(c, c->b_win_len.ensure(nw * 4 + 16));              d.win_len = (int32_t*)c->b_win_len.p;
+    CUDA_TRY(c, c->b_pair_read.ensure(np * 4 + 16));            d.pair_read = (int32_t*)c->b_pair_read.p;
+    CUDA_TRY(c, c->b_pair_win.ensure(np * 4 + 16));             d.pair_win = (int32_t*)c->b_pair_win.p;
+    d.ref_beg = nullptr; d.ref_len = nullptr; d.mask_len = nullptr;
+    if (b->ref_beg) { CUDA_TRY(c, c->b_ref_beg.ensure(np * 4 + 16)); d.ref_beg = (int32_t*)c->b_ref_beg.p; }
+    if (b->ref_len) { CUDA_TRY(c, c->b_ref_len.ensure(np * 4 + 16)); d.ref_len = (int32_t*)c->b_ref_len.p; }
+    if (b->mask_len) { CUDA_TRY(c, c->b_mask.ensure(np * 4 + 16)); d.mask_len = (int32_t*)c->b_mask.p; }
+    CUDA_TRY(c, c->b_go.ensure(np + 16));                       d.gap_open = (uint8_t*)c->b_go.p;
+    CUDA_TRY(c, c->b_ge.ensure(np + 16));                       d.gap_ext = (uint8_t*)c->b_ge.p;
+    ChunkView v; v.n_reads_total = b->n_reads; v.n_windows_total = b->n_windows;
+    set_batch_scalars(c, b, v, max_rl, max_wl);
+    const int ascii = b->seq_encoding == SWB_SEQ_ASCII;
+    cudaStream_t s = c->stream;
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D0], s));
+    if (up(c, c->b_mat, b->mat, (size_t)b->n * b->n, &d.mat)) return -1;
+    if (compute_setup(c)) return -1;
+    swb_timing& tm = c->tm;
+
+    TableStream tr, tw;
+    tr.blob = b->reads; tr.off = b->read_off; tr.len = b->read_len; tr.n = b->n_reads;
+    tr.d_blob = d.reads; tr.d_off = d.read_off; tr.d_len = d.read_len; tr.d_bad = (uint8_t*)c->b_rbad.p;
+    tw.blob = b->windows; tw.off = b->win_off; tw.len = b->win_len; tw.n = b->n_windows;
+    tw.d_blob = d.windows; tw.d_off = d.win_off; tw.d_len = d.win_len; tw.d_bad = (uint8_t*)c->b_wbad.p;
+
+    // piece boundaries: small first pieces (the sweep starts early), growing by 1.3x -- slower than the ratio of the
+    // sweep's to the copy's throughput, so the copies stay ahead -- up to an eighth of the batch
+    std::vector<int64_t> bounds(1, 0);
+    { double sz = std::max<double>(16384.0, (double)np / 48.0); const double cap = std::max<double>(32768.0, (double)np / 8.0);
+      while (bounds.back() < (int64_t)np) { int64_t nx = bounds.back() + ((int64_t)sz & ~(int64_t)1); if ((int64_t)np - nx < (int64_t)sz / 2) nx = (int64_t)np; bounds.push_back(std::min<int64_t>(nx, (int64_t)np)); sz = std::min(cap, sz * 1.3); } }
+    const int npieces = (int)bounds.size() - 1;
+
+    int done[SWB_NBUCKETS] = {};
+    bool used2 = false, used1 = false;
+    // The host runs one piece ahead: piece k+1's copies and prepare kernel are queued before it waits for piece k's
+    // fast-list lengths, so PCIe never idles during a host round trip.
+    auto enqueue_piece = [&](int k) -> int {
+        const int32_t p0 = (int32_t)bounds[k], p1 = (int32_t)bounds[k + 1];
+        int32_t rmax = -1, wmax = -1;
+        for (int32_t p = p0; p < p1; ++p) {
+            const int32_t r = b->pair_read[p], w = b->pair_win[p];
+            if ((uint32_t)r < (uint32_t)b->n_reads) rmax = std::max(rmax, r);
+            if ((uint32_t)w < (uint32_t)b->n_windows) wmax = std::max(wmax, w);
+        }
+        if (table_advance(c, tr, rmax, ascii) || table_advance(c, tw, wmax, ascii)) return -1;
+        const size_t n = (size_t)(p1 - p0);
+        CUDA_TRY(c, cudaMemcpyAsync(d.pair_read + p0, b->pair_read + p0, n * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(d.pair_win + p0, b->pair_win + p0, n * 4, cudaMemcpyHostToDevice, s));
+        if (b->ref_beg) CUDA_TRY(c, cudaMemcpyAsync(d.ref_beg + p0, b->ref_beg + p0, n * 4, cudaMemcpyHostToDevice, s));
+        if (b->ref_len) CUDA_TRY(c, cudaMemcpyAsync(d.ref_len + p0, b->ref_len + p0, n * 4, cudaMemcpyHostToDevice, s));
+        if (b->mask_len) CUDA_TRY(c, cudaMemcpyAsync(d.mask_len + p0, b->mask_len + p0, n * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(d.gap_open + p0, b->gap_open + p0, n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(d.gap_ext + p0, b->gap_ext + p0, n, cudaMemcpyHostToDevice, s));
+        tm.h2d_bytes += (int64_t)n * (10 + (b->ref_beg ? 4 : 0) + (b->ref_len ? 4 : 0) + (b->mask_len ? 4 : 0));
+        k_prepare<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, p0, p1);
+        tm.n_launches++;
+        CUDA_TRY(c, cudaGetLastError());
+        if (k + 1 == npieces) { CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], s)); CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s)); }
+        // fast-list lengths after this piece, into the snapshot buffer of its parity; the sweep streams wait on the same event
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_snap[k & 1], d.counters, SWB_NCOUNTERS * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaEventRecord(c->ev_snap[k & 1], s));
+        return 0;
+    };
+    if (npieces > 0 && enqueue_piece(0)) return -1;
+    for (int k = 0; k < npieces; ++k) {
+        const bool last = k + 1 == npieces;
+        if (!last && enqueue_piece(k + 1)) return -1;
+        CUDA_TRY(c, cudaEventSynchronize(c->ev_snap[k & 1]));
+        TR(c, "piece_ready");
+        const int32_t* hc = c->h_snap[k & 1];
+        int upper[SWB_NBUCKETS]; bool any = false, global = false;
+        for (int q = 0; q < SWB_NBUCKETS; ++q) {
+            const int cnt = hc[CNT_FAST_FWD + q];
+            upper[q] = last ? cnt : (cnt & ~1);                  // lane pairs stay intact: an odd leftover waits for the next piece
+            c->fastMaxCols[q] = hc[CNT_FAST_MAXCOLS + q];
+            if (upper[q] > done[q]) any = true;
+            if (c->fastMaxCols[q] > SWB_FAST_SMEM_COLS) global = true;   // shared column scratch: slices must not overlap
+        }
+        if (any) {
+            const bool second = (k & 1) && !global;
+            cudaStream_t st = second ? c->bulk_stream2 : c->bulk_stream;
+            CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_snap[k & 1], 0));
+            if (launch_fast_range<0>(c, done, upper, st)) return -1;
+            (second ? used2 : used1) = true;
+            for (int q = 0; q < SWB_NBUCKETS; ++q) done[q] = upper[q];
+        }
+    }
+    if (npieces == 0) { CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], s)); CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s)); }
+    if (used1) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join, c->bulk_stream)); CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_bulk_join, 0)); }
+    if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_bulk_join2, 0)); }
+    // only the table entries some pair refers to are resident: a later swb_compute on this context must not touch the rest
+    d.n_reads = tr.front; d.n_windows = tw.front;
+    d.seq_encoding = SWB_SEQ_CODES;
+    c->have_batch = true;
+    int nFastTotal = 0;
+    for (int q = 0; q < SWB_NBUCKETS; ++q) nFastTotal += done[q];
+    TR(c, "pieces_enqueued");
+    if (compute_tail(c, done, nFastTotal)) return -1;
+    return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -821,9 +1093,21 @@ static bool plan_chunks(const swb_batch* b, std::vector<ChunkPlan>& plans)
     const int64_t np = b->n_pairs;
     const bool off = getenv("SWB200_NO_PIPELINE") != nullptr;
     if (off || np < 524288 || b->n_reads <= 0 || b->n_windows <= 0) return false;
-    int64_t chunkPairs = 524288;          // per-chunk fixed latencies (host round trips, tail rounds) favour large chunks
-    if (const char* e = getenv("SWB200_CHUNK_PAIRS")) chunkPairs = std::max<int64_t>(16384, atoll(e));
-    const int nchunks = (int)std::max<int64_t>(2, (np + chunkPairs - 1) / chunkPairs);
+    // Chunk sizes: a small first chunk so that the kernels start while most of the batch is still crossing PCIe, then
+    // growing ones (per-chunk fixed latencies -- host round trips, tail rounds -- favour few, large chunks).
+    // SWB200_CHUNK_PLAN overrides the relative sizes ("1,2,3"), SWB200_CHUNK_PAIRS forces equal chunks of that many pairs.
+    std::vector<double> weights;
+    if (const char* e = getenv("SWB200_CHUNK_PAIRS")) {
+        const int64_t chunkPairs = std::max<int64_t>(16384, atoll(e));
+        weights.assign((size_t)std::max<int64_t>(2, (np + chunkPairs - 1) / chunkPairs), 1.0);
+    } else if (const char* e2 = getenv("SWB200_CHUNK_PLAN")) {
+        for (const char* q = e2; *q; ) { char* end = nullptr; const double w = strtod(q, &end); if (end == q) break; if (w > 0) weights.push_back(w); q = *end ? end + 1 : end; }
+    }
+    if (weights.size() < 2) weights = {1, 2, 3, 3, 3.5, 3.5};
+    const int nchunks = (int)weights.size();
+    std::vector<int64_t> bounds(nchunks + 1, 0);
+    { double tot = 0, acc = 0; for (double w : weights) tot += w;
+      for (int k = 0; k < nchunks; ++k) { acc += weights[k]; bounds[k + 1] = k + 1 == nchunks ? np : (int64_t)((double)np * acc / tot) & ~(int64_t)1; } }
     int64_t total_r = 0, total_w = 0;
     for (int32_t i = 0; i < b->n_reads; ++i) total_r = std::max<int64_t>(total_r, b->read_off[i] + std::max(b->read_len[i], 0));
     for (int32_t i = 0; i < b->n_windows; ++i) total_w = std::max<int64_t>(total_w, b->win_off[i] + std::max(b->win_len[i], 0));
@@ -831,7 +1115,7 @@ static bool plan_chunks(const swb_batch* b, std::vector<ChunkPlan>& plans)
     plans.assign(nchunks, ChunkPlan());
     for (int k = 0; k < nchunks; ++k) {
         ChunkPlan& pl = plans[k];
-        pl.p0 = (int32_t)(np * k / nchunks); pl.p1 = (int32_t)(np * (k + 1) / nchunks);
+        pl.p0 = (int32_t)bounds[k]; pl.p1 = (int32_t)bounds[k + 1];
         int32_t rlo = INT32_MAX, rhi = -1, wlo = INT32_MAX, whi = -1;
         for (int32_t p = pl.p0; p < pl.p1; ++p) {
             const int32_t r = b->pair_read[p], w = b->pair_win[p];
@@ -865,6 +1149,17 @@ static bool plan_chunks(const swb_batch* b, std::vector<ChunkPlan>& plans)
 extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used) {
     if (!c) return -1;
     std::vector<ChunkPlan> plans;
+    const double t_call = now_ms();
+    // SWB200_PIPELINE = stream (default: streamed single pass) | lanes (two-lane chunk pipeline) | off
+    const char* mode = getenv("SWB200_PIPELINE");
+    const bool lanes = (mode && !strcmp(mode, "lanes")) || getenv("SWB200_CHUNK_PAIRS") || getenv("SWB200_CHUNK_PLAN");
+    const bool off = (mode && !strcmp(mode, "off")) || getenv("SWB200_NO_PIPELINE");
+    if (b && !off && !lanes && b->n_pairs >= 262144 && b->n_reads > 0 && b->n_windows > 0) {
+        if (g_trace) c->trace.clear();
+        const int rc = align_batch_streamed(c, b, results, cigar_arena, cigar_cap, cigar_used);
+        if (g_trace) { fprintf(stderr, "TRACE streamed:"); for (auto& e : c->trace) fprintf(stderr, " %s@%.2f", e.first, e.second - t_call); fprintf(stderr, " end@%.2f\n", now_ms() - t_call); }
+        return rc;
+    }
     if (!b || !plan_chunks(b, plans)) {
         int rc = swb_upload(c, b);
         if (rc) return rc;
@@ -888,6 +1183,7 @@ extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* resul
         for (size_t k = (size_t)li; k < plans.size(); k += 2) {
             if (failed.load()) return;
             const ChunkPlan& pl = plans[k];
+            TR(L, "chunk_begin");
             if (upload_view(L, &pl.b, pl.v) || swb_compute(L)) { failed = 1; errs[li] = L->err; return; }
             const int32_t n = pl.p1 - pl.p0;
             const long long used = (long long)L->h_bump[1];
@@ -902,15 +1198,26 @@ extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* resul
             ok = ok && cudaEventRecord(L->ev[EV_D2H1], s) == cudaSuccess;
             ok = ok && cudaStreamSynchronize(s) == cudaSuccess;
             if (!ok) { failed = 1; errs[li] = std::string("download: ") + cudaGetErrorString(cudaGetLastError()); return; }
+            TR(L, "download_done");
             L->tm.d2h_bytes = (int64_t)n * (int64_t)sizeof(swb_result) + used * 4;
             cudaEventElapsedTime(&L->tm.ms_d2h, L->ev[EV_D2H0], L->ev[EV_D2H1]);
             cudaEventElapsedTime(&L->tm.ms_h2d, L->ev[EV_H2D0], L->ev[EV_H2D1]);
             add_timing(acc[li], L->tm);
         }
     };
+    const double t_begin = now_ms();
+    if (g_trace) { c->trace.clear(); c->sibling->trace.clear(); fprintf(stderr, "TRACE plan %.2f ms, %d chunks\n", t_begin - t_call, (int)plans.size()); }
     std::thread t1(worker, 1);
     worker(0);
     t1.join();
+    if (g_trace) {
+        for (int li = 0; li < 2; ++li) {
+            swb_ctx* L = li ? c->sibling : c;
+            fprintf(stderr, "TRACE lane%d:", li);
+            for (auto& e : L->trace) fprintf(stderr, " %s@%.2f", e.first, e.second - t_begin);
+            fprintf(stderr, "\n");
+        }
+    }
     cudaSetDevice(c->device);
     if (failed.load()) { c->err = !errs[0].empty() ? errs[0] : errs[1]; c->computed = false; return -1; }
     memset(&c->tm, 0, sizeof c->tm);

@@ -180,11 +180,11 @@ def test_gpu_reverse_band_window_edges(seed):
 
 
 def test_gpu_pipelined_batch_equals_single_pass(monkeypatch):
-    """large batches go through the two-lane chunked pipeline of swb_align_batch (table slices, index rebasing,
-    CIGAR arena stitched from chunks): results must equal the single-pass path and the oracle"""
+    """large batches go through the streamed one-shot path of swb_align_batch (copies cut into pieces, forward sweeps
+    queued per piece) or, on request, through the two-lane chunked pipeline (table slices, index rebasing, CIGAR arena
+    stitched from chunks): both must equal the single-pass path and the oracle"""
     from gpuutil import gpu_align
 
-    monkeypatch.setenv("SWB200_CHUNK_PAIRS", "70000")          # force several chunks on a test-sized batch
     b = T.make_pairs_fast(600000, 100, 260, seed=9, reads_per_window=40)
     # shuffle penalties a bit and add bad indices at chunk edges
     b.gap_open[::7] = 5
@@ -192,15 +192,38 @@ def test_gpu_pipelined_batch_equals_single_pass(monkeypatch):
     b.pair_read[12345] = -1
     b.pair_win[250000] = b.n_windows + 3
     assert b.n_pairs >= 524288
+    r2, a2, tm2 = gpu_align(b)                                   # default: streamed
+    monkeypatch.setenv("SWB200_CHUNK_PAIRS", "70000")          # two-lane pipeline, several chunks on a test-sized batch
     r1, a1, tm1 = gpu_align(b)
+    monkeypatch.delenv("SWB200_CHUNK_PAIRS")
     monkeypatch.setenv("SWB200_NO_PIPELINE", "1")
     r0, a0, tm0 = gpu_align(b)
-    T.compare(r1, a1, r0, a0, what="pipelined vs single pass")
+    T.compare(r1, a1, r0, a0, what="two-lane pipeline vs single pass")
+    T.compare(r2, a2, r0, a0, what="streamed vs single pass")
     assert r1["status"][12345] == 2 and r1["status"][250000] == 2
+    assert r2["status"][12345] == 2 and r2["status"][250000] == 2
     sub = np.arange(0, b.n_pairs, 97)
     sub = sub[(sub != 12345) & (sub != 250000)]
     ro, ao = T.oracle_parallel(b.subset(sub), threads=min(16, os.cpu_count() or 1))
-    T.compare(r1[sub].copy(), a1, ro, ao, what="pipelined vs oracle")
+    T.compare(r2[sub].copy(), a2, ro, ao, what="streamed vs oracle")
+
+
+def test_gpu_streamed_batch_unordered_tables(monkeypatch):
+    """streamed path with pairs that refer to the sequence tables in random order (the upload frontier jumps to the
+    end with the first piece) and ASCII input"""
+    from gpuutil import gpu_align
+
+    b = T.make_pairs_fast(300000, 80, 200, seed=11, reads_per_window=25)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(b.n_pairs)
+    b = b.subset(perm)
+    r2, a2, _ = gpu_align(b)
+    monkeypatch.setenv("SWB200_NO_PIPELINE", "1")
+    r0, a0, _ = gpu_align(b)
+    T.compare(r2, a2, r0, a0, what="streamed (shuffled pairs) vs single pass")
+    sub = np.arange(0, b.n_pairs, 211)
+    ro, ao = T.oracle_parallel(b.subset(sub), threads=min(16, os.cpu_count() or 1))
+    T.compare(r2[sub].copy(), a2, ro, ao, what="streamed (shuffled pairs) vs oracle")
 
 
 def test_multi_gpu_aligner_shards_and_stitches():
