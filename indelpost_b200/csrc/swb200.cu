@@ -133,6 +133,7 @@ enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0
 struct swb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
+    cudaStream_t stream4 = nullptr; cudaEvent_t ev_join3; unsigned verify_pending = 0;   // second verification stream
     cudaStream_t bulk_stream = nullptr;                                     // lowest priority: the forward DPX sweep (yields SM slots to the short, latency-bound kernels of the other lane)
     cudaStream_t bulk_stream2 = nullptr;                                    // second one: consecutive forward slices of the streamed one-shot path overlap their tails
     cudaEvent_t ev_bulk_fork, ev_bulk_join, ev_bulk_join2, ev_piece;
@@ -216,6 +217,7 @@ extern "C" swb_ctx* swb_create(int device) {
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
     cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prGreatest);
     cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prGreatest);
+    cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prGreatest); cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming);
     cudaStreamCreateWithPriority(&c->bulk_stream, cudaStreamNonBlocking, prLeast);
     cudaStreamCreateWithPriority(&c->bulk_stream2, cudaStreamNonBlocking, prLeast);
     cudaEventCreateWithFlags(&c->ev_bulk_join2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_piece, cudaEventDisableTiming);
@@ -253,6 +255,7 @@ extern "C" void swb_destroy(swb_ctx* c) {
     for (int i = 0; i < 2; ++i) { cudaFreeHost(c->h_snap[i]); cudaEventDestroy(c->ev_snap[i]); }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->stream3); cudaEventDestroy(c->ev_fork3);
+    cudaStreamDestroy(c->stream4); cudaEventDestroy(c->ev_join3);
     cudaStreamDestroy(c->bulk_stream); cudaEventDestroy(c->ev_bulk_fork); cudaEventDestroy(c->ev_bulk_join);
     cudaStreamDestroy(c->bulk_stream2); cudaEventDestroy(c->ev_bulk_join2); cudaEventDestroy(c->ev_piece);
     cudaEventDestroy(c->ev_rev_fork);
@@ -530,20 +533,22 @@ static int join_rev_band(swb_ctx* c, int upperBoundPairs) {
 
 // certificate pass over the pairs whose traceback is done, then the exact 8-bit verification of those that failed it,
 // on the verification stream (no host round trip: the grid is sized by an upper bound, the kernel reads the real count)
-static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound) {
+static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound, int which = 0) {
     SwbDev& d = c->d;
     cudaStream_t s = c->stream;
+    cudaStream_t vs = which ? c->stream4 : c->stream3;       // the two verifications of a compute run side by side (each is a long, serial kernel over a handful of pairs)
     const size_t np = (size_t)d.n_pairs;
     k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, verifyList);
     c->tm.n_launches++;
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
-    CUDA_TRY(c, cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
-    if (launch_exact<0, 0>(c, verifyList, upperBound, c->stream3)) return -1;      // confirms the overflow, or produces the byte-mode result
-    CUDA_TRY(c, cudaEventRecord(c->ev_join2, c->stream3));
+    CUDA_TRY(c, cudaStreamWaitEvent(vs, c->ev_fork3, 0));
+    if (launch_exact<0, 0>(c, verifyList, upperBound, vs)) return -1;      // confirms the overflow, or produces the byte-mode result
+    CUDA_TRY(c, cudaEventRecord(which ? c->ev_join3 : c->ev_join2, vs));
+    c->verify_pending |= 1u << which;
     return 0;
 }
-static int certify_phase2_hook(swb_ctx* c, int total) { return total > 0 ? certify_and_verify_async(c, LIST_VERIFY2, total) : 0; }
+static int certify_phase2_hook(swb_ctx* c, int total) { return total > 0 ? certify_and_verify_async(c, LIST_VERIFY2, total, 1) : 0; }
 
 // register-band kernels (swb_bandreg.cuh): one launch per exact half-width, spread over the side streams
 template <int W>
@@ -752,6 +757,7 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     //          bound, the kernel reads the real count) while
     // phase 2: the bulk of the traceback runs on the main stream.
     tm.band_rounds = 0;
+    c->verify_pending = 0;
     const bool certify = nFastTotal > 0 && d.score_size == 2;
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));      // consumed by the reverse stage; reused by the verification
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
@@ -763,7 +769,9 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     // then overlap the re-queue rounds
     if (run_band_rounds(c, true, LIST_BAND, nullptr, false, /*keepNext=*/nFirst > 0, certify ? certify_phase2_hook : nullptr)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_ALL], s));
-    if (certify) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join2, 0));      // both verifications done (no-op if none was launched)
+    if (c->verify_pending & 1) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join2, 0));      // both verifications done
+    if (c->verify_pending & 2) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join3, 0));
+    c->verify_pending = 0;
 
     // ---- leftovers: certificate for the pairs finished in re-queue rounds (rarely fails), byte-mode redo for verified
     //      pairs whose 8-bit pass did not overflow (never observed in practice)

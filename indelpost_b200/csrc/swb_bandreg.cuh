@@ -60,69 +60,37 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     constexpr int T = SWB_BANDREG_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_rowTab[8];            // per read base: its scores against every window base, 8 x int8
-    __shared__ BandRegPar s_par[T];
     if (threadIdx.x < 8) {
         unsigned long long tab = 0;
         if ((int)threadIdx.x < d.n) for (int nt = 0; nt < d.n; ++nt) tab |= (unsigned long long)(uint8_t)d.mat[nt * d.n + threadIdx.x] << (8 * nt);
         s_rowTab[threadIdx.x] = tab;
     }
-    const int t = blockIdx.x * T + threadIdx.x;
-    const bool valid = t < njobs;
-    int p = -1;
-    BandGeom g; g.w = W; g.width_d = NX; g.strideW = NW; g.refLen = 0; g.readLen = 0;
-    {
-        BandRegPar q; q.read = q.ref = nullptr; q.readLen = q.refLen = 0;
-        if (valid) {
-            p = jobs[t];
-            const swb_result& r = d.res[p];
-            g.refLen = r.ref_end1 - r.ref_begin1 + 1;     // ssw.c:897-899
-            g.readLen = r.read_end1 - r.read_begin1 + 1;
-            q.ref = d.windows + d.p_woff[p] + r.ref_begin1;
-            q.read = d.reads + d.p_roff[p] + r.read_begin1;
-            q.readLen = g.readLen; q.refLen = g.refLen;
-        }
-        s_par[threadIdx.x] = q;
-    }
     __syncthreads();
+    const int t = blockIdx.x * T + threadIdx.x;
+    if (t >= njobs) return;
+    const int p = jobs[t];
+    BandGeom g; g.w = W; g.width_d = NX; g.strideW = NW;
+    {
+        const swb_result& r0 = d.res[p];
+        g.refLen = r0.ref_end1 - r0.ref_begin1 + 1;       // ssw.c:897-899
+        g.readLen = r0.read_end1 - r0.read_begin1 + 1;
+    }
 
-    // ---- staging (one thread's sequences at a time, lanes on consecutive bytes) --------------------------------
+    // ---- staging: every thread copies its own window / read segment into its shared-memory region ------------------
     const int strideW = bandreg_stride_words(rowsAlloc);
     const int selCols = bandreg_sel_cols(rowsAlloc);
-    uint32_t* const region0 = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* const region = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)threadIdx.x * strideW;
+    uint16_t* selW = reinterpret_cast<uint16_t*>(region);
+    uint8_t* rowW = reinterpret_cast<uint8_t*>(region + selCols / 2);
     {
-        const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-        for (int src = 0; src < 32; ++src) {
-            const BandRegPar q = s_par[wbase + src];
-            if (q.readLen == 0) continue;
-            uint32_t* reg = region0 + (size_t)(wbase + src) * strideW;
-            const int ncols = min(q.refLen + NX + 1, selCols);
-            for (int c0 = 2 * lane; c0 < ncols; c0 += 64) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int c = c0 + u;
-                    const uint32_t rc = c < q.refLen ? (uint32_t)(q.ref[c] & 7) : 0u;
-                    w |= (rc * 0x1111u | 0x8880u) << (16 * u);          // PRMT selector: byte rc, sign-extended to 32 bits
-                }
-                reg[c0 >> 1] = w;
-            }
-            uint32_t* rows = reg + selCols / 2;
-            for (int i0 = 4 * lane; i0 < q.readLen; i0 += 128) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u;
-                    const uint32_t cb = i < q.readLen ? (uint32_t)(q.read[i] & 7) : 0u;
-                    w |= cb << (8 * u);
-                }
-                rows[i0 >> 2] = w;
-            }
-        }
-        __syncwarp();
+        const swb_result& r0 = d.res[p];
+        for_each_byte16(d.windows + d.p_woff[p] + r0.ref_begin1, g.refLen, [&](int c, uint32_t v) { selW[c] = (uint16_t)((v & 7u) * 0x1111u | 0x8880u); });   // PRMT selector: byte rc, sign-extended
+        const int ncols = min(g.refLen + NX + 1, selCols);
+        for (int c = g.refLen; c < ncols; ++c) selW[c] = 0x8880u;
+        for_each_byte16(d.reads + d.p_roff[p] + r0.read_begin1, g.readLen, [&](int i, uint32_t v) { rowW[i] = (uint8_t)(v & 7u); });
     }
-    if (!valid) return;
-    const uint16_t* selT = reinterpret_cast<const uint16_t*>(region0 + (size_t)threadIdx.x * strideW);
-    const uint8_t* rowT = reinterpret_cast<const uint8_t*>(region0 + (size_t)threadIdx.x * strideW + selCols / 2);
+    const uint16_t* selT = selW;
+    const uint8_t* rowT = rowW;
 
     swb_result& r = d.res[p];
     const int score = r.score1;

@@ -129,6 +129,30 @@ __device__ __forceinline__ void warp_count(int32_t* counter64, unsigned long lon
     if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(reinterpret_cast<unsigned long long*>(counter64), tot);
 }
 
+// f(idx, byte) for every byte of the sequence [ptr, ptr + len), read as aligned 16-byte chunks (one thread walks its own
+// sequence: a dozen independent vector loads instead of a dependent byte stream).  Reads up to 15 bytes before / after
+// the sequence: every sequence blob is a cudaMalloc allocation (256-byte aligned) with 16 bytes of slack at its end.
+template <typename F>
+__device__ __forceinline__ void for_each_byte16(const int8_t* ptr, int len, F f) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+    const int mis = (int)(a & 15);
+    const uint4* base = reinterpret_cast<const uint4*>(a - mis);
+    const int nch = (mis + len + 15) >> 4;
+#pragma unroll 2
+    for (int ch = 0; ch < nch; ++ch) {
+        const uint4 v = __ldg(base + ch);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int i0 = ch * 16 - mis;
+        if (i0 >= 0 && i0 + 16 <= len) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) if ((unsigned)(i0 + q) < (unsigned)len) f(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+        }
+    }
+}
+
 // band job class from the half-width (see SWB_NBANDCLASS)
 __host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : bw <= 2 ? 1 : bw <= 4 ? 2 : bw <= 8 ? 3 : bw <= 16 ? 4 : bw <= 48 ? 5 : bw <= 112 ? 6 : 7; }
 

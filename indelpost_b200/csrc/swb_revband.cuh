@@ -46,7 +46,6 @@ k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict
     constexpr int PF = (WI + 1) & ~1;                                    // even front pad: columns "left of 0" of the first rows
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_rowtab[SWB_MAX_N];
-    __shared__ RevbPar s_par[T];
     const int npairs = *njobs_ptr;
     const int ngroups = (npairs + 1) >> 1;
     if (blockIdx.x * T >= ngroups) return;
@@ -55,76 +54,40 @@ k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict
         for (int nt = 0; nt < 4; ++nt) t |= (uint32_t)(uint8_t)(int8_t)(FAST_SCALE * d.mat[nt * d.n + threadIdx.x]) << (8 * nt);
         s_rowtab[threadIdx.x] = t;
     }
+    __syncthreads();
     const int grp = blockIdx.x * T + threadIdx.x;
-    const bool valid = grp < ngroups;
+    if (grp >= ngroups) return;
 
     // ---- the two alignments of this thread ---------------------------------------------------------
-    int pA = -1, pB = -1, LA = 0, LB = 0, nA = 0, nB = 0;
-    uint32_t goP = 0, ngeP = 0, targetV = 0x7fff7fffu;
-    {
-        RevbPar q; q.readA = q.readB = q.refA = q.refB = nullptr; q.LA = q.LB = q.nA = q.nB = 0;
-        if (valid) {
-            pA = jobs[2 * grp]; pB = (2 * grp + 1 < npairs) ? jobs[2 * grp + 1] : -1;
-            const int qB = pB < 0 ? pA : pB;                             // odd tail: lane B shadows lane A, its result is dropped
-            const swb_result rA = d.res[pA], rB = d.res[qB];
-            LA = rA.read_end1 + 1; LB = rB.read_end1 + 1;                // rows (ssw.c:875-877)
-            nA = rA.ref_end1 + 1; nB = rB.ref_end1 + 1;                  // columns
-            q.readA = d.reads + d.p_roff[pA]; q.readB = d.reads + d.p_roff[qB];
-            q.refA = d.windows + d.p_woff[pA]; q.refB = d.windows + d.p_woff[qB];
-            q.LA = LA; q.LB = LB; q.nA = nA; q.nB = nB;
-            goP = pack2(FAST_SCALE * d.gap_open[pA], FAST_SCALE * d.gap_open[qB]);
-            ngeP = pack2(-FAST_SCALE * d.gap_ext[pA], -FAST_SCALE * d.gap_ext[qB]);
-            targetV = pack2(FAST_SCALE * rA.score1 + FAST_C, pB < 0 ? 0x7fff : FAST_SCALE * rB.score1 + FAST_C);
-        }
-        s_par[threadIdx.x] = q;
-    }
-    __syncthreads();
+    const int pA = jobs[2 * grp], pB = (2 * grp + 1 < npairs) ? jobs[2 * grp + 1] : -1;
+    const int qB = pB < 0 ? pA : pB;                                     // odd tail: lane B shadows lane A, its result is dropped
+    const swb_result rA = d.res[pA], rB = d.res[qB];
+    const int LA = rA.read_end1 + 1, LB = rB.read_end1 + 1;              // rows (ssw.c:875-877)
+    const int nA = rA.ref_end1 + 1, nB = rB.ref_end1 + 1;                // columns
+    uint32_t goP = pack2(FAST_SCALE * d.gap_open[pA], FAST_SCALE * d.gap_open[qB]);
+    uint32_t ngeP = pack2(-FAST_SCALE * d.gap_ext[pA], -FAST_SCALE * d.gap_ext[qB]);
+    const uint32_t targetV = pack2(FAST_SCALE * rA.score1 + FAST_C, pB < 0 ? 0x7fff : FAST_SCALE * rB.score1 + FAST_C);
     const int Lmax = max(LA, LB);
 
-    // ---- staging: every warp fills the regions of its own 32 threads, one thread's sequences at a time, with the
-    //      lanes reading consecutive bytes (the per-thread byte streams of a one-thread-per-alignment loop would be a
-    //      dependent L2 round trip per row).  Selector of column c sits at index PF + c.
+    // ---- staging: every thread copies what its band can touch of its two (reversed) windows and reads into its own
+    //      shared-memory region.  Selector of column c sits at index PF + c.
     const int strideW = revb_stride_words(rowsAlloc, M);
     const int selCols = revb_sel_cols(rowsAlloc, M);
-    uint32_t* const region0 = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* const region = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)threadIdx.x * strideW;
     {
-        const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-        for (int src = 0; src < 32; ++src) {
-            const RevbPar q = s_par[wbase + src];
-            const int lm = max(q.LA, q.LB);
-            if (lm == 0) continue;
-            uint32_t* reg = region0 + (size_t)(wbase + src) * strideW;
-            if (lane < PF / 2) reg[lane] = 0xC480C480u;
-            const int ncols = min(lm + M + 1, selCols - PF);
-            for (int c0 = 2 * lane; c0 < ncols; c0 += 64) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int c = c0 + u;
-                    const int bA = c < q.nA ? q.refA[q.nA - 1 - c] : 0;
-                    const int bB = c < q.nB ? q.refB[q.nB - 1 - c] : 0;
-                    w |= (0xC480u | (uint32_t)(bA & 3) * 0x11u | (uint32_t)(bB & 3) * 0x1100u) << (16 * u);
-                }
-                reg[(PF + c0) >> 1] = w;
-            }
-            uint32_t* rows = reg + selCols / 2;
-            for (int i0 = 2 * lane; i0 < lm; i0 += 64) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int i = i0 + u;
-                    const int cA = i < q.LA ? q.readA[q.LA - 1 - i] : 0;
-                    const int cB = i < q.LB ? q.readB[q.LB - 1 - i] : 0;
-                    w |= ((uint32_t)(cA & 0xff) | ((uint32_t)(cB & 0xff) << 8)) << (16 * u);
-                }
-                rows[i0 >> 1] = w;
-            }
-        }
-        __syncwarp();
+        uint16_t* selW = reinterpret_cast<uint16_t*>(region);
+        uint16_t* rowW = reinterpret_cast<uint16_t*>(region + selCols / 2);
+        const int ncols = min(Lmax + M + 1, selCols - PF);               // columns the band can reach
+        for (int c = 0; c < PF + ncols; ++c) selW[c] = 0xC480u;          // base A / A: columns left of 0 and right of the windows
+        const int kA = min(nA, ncols), kB = min(nB, ncols);              // reversed column c = window position n - 1 - c
+        for_each_byte16(d.windows + d.p_woff[pA] + (nA - kA), kA, [&](int i, uint32_t v) { selW[PF + kA - 1 - i] |= (uint16_t)((v & 3u) * 0x11u); });
+        for_each_byte16(d.windows + d.p_woff[qB] + (nB - kB), kB, [&](int i, uint32_t v) { selW[PF + kB - 1 - i] |= (uint16_t)((v & 3u) * 0x1100u); });
+        for (int i = 0; i < Lmax; ++i) rowW[i] = 0;
+        for_each_byte16(d.reads + d.p_roff[pA], LA, [&](int i, uint32_t v) { rowW[LA - 1 - i] |= (uint16_t)(v & 0xffu); });
+        for_each_byte16(d.reads + d.p_roff[qB], LB, [&](int i, uint32_t v) { rowW[LB - 1 - i] |= (uint16_t)((v & 0xffu) << 8); });
     }
-    if (!valid) return;
-    const uint16_t* selT = reinterpret_cast<const uint16_t*>(region0 + (size_t)threadIdx.x * strideW) + (PF - WI);
-    const uint16_t* rowT = reinterpret_cast<const uint16_t*>(region0 + (size_t)threadIdx.x * strideW + selCols / 2);
+    const uint16_t* selT = reinterpret_cast<const uint16_t*>(region) + (PF - WI);
+    const uint16_t* rowT = reinterpret_cast<const uint16_t*>(region + selCols / 2);
 
     uint32_t H[M], V[M];
 #pragma unroll
