@@ -140,6 +140,7 @@ struct swb_ctx {
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
     cudaStream_t rev_stream[SWB_NREVB];                                     // banded reverse pass: one stream per band class
     cudaEvent_t ev_rev_fork, ev_rev_join[SWB_NREVB];
+    cudaStream_t bandw_stream[SWB_BANDW_MAX]; cudaEvent_t ev_bandw_join[SWB_BANDW_MAX];   // register-band kernels: one stream per half-width
     unsigned bandreg_used = 0; int bandreg_base = 0;                       // side streams the register-band kernels of the current round run on
     cudaEvent_t ev[EV_COUNT];
     std::string err;
@@ -224,6 +225,7 @@ extern "C" swb_ctx* swb_create(int device) {
     cudaEventCreateWithFlags(&c->ev_bulk_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bulk_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_rev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < SWB_BANDW_MAX; ++i) { cudaStreamCreateWithPriority(&c->bandw_stream[i], cudaStreamNonBlocking, prMid); cudaEventCreateWithFlags(&c->ev_bandw_join[i], cudaEventDisableTiming); }
     for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamCreateWithPriority(&c->rev_stream[i], cudaStreamNonBlocking, prMid); cudaEventCreateWithFlags(&c->ev_rev_join[i], cudaEventDisableTiming); }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
     cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t));
@@ -260,6 +262,7 @@ extern "C" void swb_destroy(swb_ctx* c) {
     cudaStreamDestroy(c->bulk_stream2); cudaEventDestroy(c->ev_bulk_join2); cudaEventDestroy(c->ev_piece);
     cudaEventDestroy(c->ev_rev_fork);
     for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamDestroy(c->rev_stream[i]); cudaEventDestroy(c->ev_rev_join[i]); }
+    for (int i = 0; i < SWB_BANDW_MAX; ++i) { cudaStreamDestroy(c->bandw_stream[i]); cudaEventDestroy(c->ev_bandw_join[i]); }
     cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); cudaEventDestroy(c->ev_join2);
     delete c;
 }
@@ -567,24 +570,20 @@ static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBas
     for (int w = 1; w <= SWB_BANDW_MAX; ++w) any += njobsW[w - 1];
     if (!any) return 0;
     CUDA_TRY(c, cudaEventRecord(c->ev_rev_fork, c->stream));
-    bool used[SWB_NREVB] = {};
+    c->bandreg_used = 0;
     for (int w = SWB_BANDW_MAX; w >= 1; --w) {              // widest (longest threads) first
         const int n = njobsW[w - 1];
         if (n <= 0) continue;
-        const int si = w % SWB_NREVB;
-        cudaStream_t st = c->rev_stream[si];
-        if (!used[si]) { CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_rev_fork, 0)); used[si] = true; }
+        cudaStream_t st = c->bandw_stream[w - 1];
+        CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_rev_fork, 0));
         switch (w) {
 #define SWB_BR_CASE(W) case W: launch_band_reg_one<W>(c, baseW + W - 1, n, nextBase, st); break;
             SWB_BR_CASE(1) SWB_BR_CASE(2) SWB_BR_CASE(3) SWB_BR_CASE(4) SWB_BR_CASE(5) SWB_BR_CASE(6) SWB_BR_CASE(7) SWB_BR_CASE(8)
             SWB_BR_CASE(9) SWB_BR_CASE(10) SWB_BR_CASE(11) SWB_BR_CASE(12) SWB_BR_CASE(13) SWB_BR_CASE(14) SWB_BR_CASE(15) SWB_BR_CASE(16)
 #undef SWB_BR_CASE
         }
-    }
-    c->bandreg_used = 0;
-    for (int i = 0; i < SWB_NREVB; ++i) if (used[i]) {
-        CUDA_TRY(c, cudaEventRecord(c->ev_rev_join[i], c->rev_stream[i]));
-        c->bandreg_used |= 1u << i;
+        CUDA_TRY(c, cudaEventRecord(c->ev_bandw_join[w - 1], st));
+        c->bandreg_used |= 1u << (w - 1);
     }
     c->bandreg_base = baseW;
     CUDA_TRY(c, cudaGetLastError());
@@ -593,7 +592,7 @@ static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBas
 // the main stream waits for the register-band kernels (after it has queued the literal kernel for the other jobs)
 static int join_band_reg(swb_ctx* c) {
     if (!c->bandreg_used) return 0;
-    for (int i = 0; i < SWB_NREVB; ++i) if (c->bandreg_used & (1u << i)) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_rev_join[i], 0));
+    for (int i = 0; i < SWB_BANDW_MAX; ++i) if (c->bandreg_used & (1u << i)) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_bandw_join[i], 0));
     CUDA_TRY(c, cudaMemsetAsync(c->d.counters + c->bandreg_base, 0, 4 * SWB_BANDW_MAX, c->stream));      // lists consumed
     c->bandreg_used = 0;
     return 0;
@@ -653,6 +652,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "band")) return -1;
         if (record && round == 0) CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_R0], s));
+        TR(c, "band_round_enqueued");
         if (round == 0 && afterFirstRound && afterFirstRound(c, total)) return -1;
         if (firstRoundOnly) {
             // no host round trip: whatever this round re-queued (band outgrown, scratch full) is picked up by the next call
@@ -844,7 +844,11 @@ static int swb_compute_impl(swb_ctx* c) {
 extern "C" int swb_compute(swb_ctx* c) {
     if (!c) return -1;
     if (!c->have_batch) { c->err = "swb_compute: no batch uploaded"; return -1; }
-    return swb_compute_impl(c);
+    if (g_trace) c->trace.clear();
+    const double t0 = now_ms();
+    const int rc = swb_compute_impl(c);
+    if (g_trace) { fprintf(stderr, "TRACE compute:"); for (auto& e : c->trace) fprintf(stderr, " %s@%.2f", e.first, e.second - t0); fprintf(stderr, "\n"); }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

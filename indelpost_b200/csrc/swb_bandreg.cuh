@@ -51,6 +51,57 @@ __device__ __forceinline__ int bandreg_cell(const int NIB, int hUp, int eUp, int
     return h;
 }
 
+// Traceback walk (ssw.c:672-751) for the regular in-band case, reading the packed direction rows through a window of
+// the thread's shared-memory region (the selectors are dead by now): the window is refilled with independent loads
+// whenever the walk climbs above it, so the walk pays one L2 round trip per WROWS rows instead of one per row.
+// Returns the op count, -1 for the reference's "Trace back error", -2 if the walk leaves the cells this kernel
+// computed (the caller then repeats it with the literal index arithmetic of band_traceback).
+template <int NW>
+__device__ __forceinline__ int bandreg_traceback(const uint32_t* __restrict__ dir, const BandGeom& g, uint32_t* win, const int wrows,
+                                                 BandOps& ops, uint32_t* out, int total)
+{
+    int i = g.readLen - 1, j = g.refLen - 1;
+    int e = 0, state = 2;
+    int op = 0, prev_op = 0;                           // 0 M, 1 I, 2 D  (BAM op codes)
+    ops.n = 0;
+    int winBase = 0x7fffffff;                          // first row held in the window
+    while (i >= 0 && j > 0) {                          // ssw.c:679
+        const int x = j - band_x(g.w, i);
+        if (x < 0 || x >= g.width_d || j > g.end(i)) return -2;
+        if (i < winBase) {
+            winBase = max(0, i - (wrows - 1));
+            const int nwords = (i - winBase + 1) * NW;
+            const uint32_t* src = dir + (size_t)winBase * NW;
+#pragma unroll 8
+            for (int k = 0; k < nwords; ++k) win[k] = src[k];
+        }
+        const uint32_t w = win[(i - winBase) * NW + (NW > 1 ? (x >> 3) : 0)];
+        const int b = (int)((w >> (4 * (x & 7))) & 15u);
+        const int de = 2 + (b & 1), df = 4 + ((b >> 1) & 1);
+        const int sel = (b >> 2) & 3;
+        const int dv = state == 0 ? de : (state == 1 ? df : (sel == 0 ? 1 : (sel == 1 ? de : df)));
+        switch (dv) {
+            case 1: --i; --j; state = 2; op = 0; break;
+            case 2: --i;      state = 0; op = 1; break;
+            case 3: --i;      state = 2; op = 1; break;
+            case 4: --j;      state = 1; op = 2; break;
+            default: --j;     state = 2; op = 2; break;     // 5 (every cell of a regular band row was written: no other value occurs)
+        }
+        if (op == prev_op) ++e;
+        else {
+            band_push(ops, ((uint32_t)e << 4) | (uint32_t)prev_op, out, total);
+            prev_op = op; e = 1;
+        }
+    }
+    if (op == 0) {                                     // ssw.c:734-751
+        band_push(ops, ((uint32_t)(e + 1) << 4) | 0u, out, total);
+    } else {
+        band_push(ops, ((uint32_t)e << 4) | (uint32_t)op, out, total);
+        band_push(ops, (1u << 4) | 0u, out, total);
+    }
+    return ops.n;
+}
+
 template <int W>
 __global__ void __launch_bounds__(SWB_BANDREG_THREADS)
 k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, int rowsAlloc)
@@ -176,7 +227,11 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     // ---- traceback: one walk (ops buffered in registers), allocate, emit reversed ---------------------------------
     BandOps ops;
     constexpr bool regRows = NW <= BAND_ROWWORDS;
-    const int l = band_traceback<regRows>(dir, g, ops, nullptr, 0);
+    __syncwarp();                                           // the region is reused as the traceback window: all lanes are done with their selectors
+    const int wrows = min(32, (strideW - 1) / NW);
+    int l = bandreg_traceback<NW>(dir, g, region, wrows, ops, nullptr, 0);
+    const bool literal = l == -2;
+    if (literal) l = band_traceback<regRows>(dir, g, ops, nullptr, 0);
     if (l < 0) { r.flag = 1; r.cigar_len = 0; r.cigar_off = 0; d.p_state[p] |= PST_BAND_DONE; return; }      // ssw.c:911
     const unsigned long long coff = warp_bump(&d.bump[1], (unsigned long long)l);
     r.cigar_len = l; r.cigar_off = (int64_t)coff;
@@ -184,8 +239,10 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     if (l <= BAND_OPBUF) {
 #pragma unroll
         for (int q = 0; q < BAND_OPBUF; ++q) if (q < l) d.cigar[coff + (l - 1 - q)] = ops.op[q];   // reverse (ssw.c:753-762)
-    } else {
+    } else if (literal) {
         band_traceback<regRows>(dir, g, ops, d.cigar + coff, l);
+    } else {
+        bandreg_traceback<NW>(dir, g, region, wrows, ops, d.cigar + coff, l);
     }
     d.p_state[p] |= PST_BAND_DONE;
 }
