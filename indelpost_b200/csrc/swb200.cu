@@ -396,8 +396,10 @@ static int read_counters(swb_ctx* c) {
     return 0;
 }
 
+// fewJobsLikely: the list is expected to hold a handful of jobs (overflow verification) but its length is only known on the
+// device: launch the dense and the one-job-per-warp schedule of k_exact2 side by side, the kernels pick by the real count
 template <int MODE, int DIR>
-static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t st = nullptr) {
+static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t st = nullptr, bool fewJobsLikely = false) {
     if (upperBound <= 0) return 0;
     if (!st) st = c->stream;
     const SwbDev& d = c->d;
@@ -417,8 +419,13 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t s
         if ((size_t)g2 * per2 <= (size_t)c->smem_optin) {
             static bool attr2[2][2] = {};
             if (!attr2[MODE][DIR]) { cudaFuncSetAttribute(k_exact2<MODE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr2[MODE][DIR] = true; }
-            k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2);
+            k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2, fewJobsLikely ? 1 : 0);
             c->tm.n_launches++;
+            if (fewJobsLikely) {
+                const int warps = g2 * T2 / 32;
+                k_exact2<MODE, DIR><<<(SWB_EXACT_SPARSE_MAX + warps - 1) / warps, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2, 2);
+                c->tm.n_launches++;
+            }
             CUDA_TRY(c, cudaGetLastError());
             return stage_check(c, MODE ? (DIR ? "exact2 word rev" : "exact2 word fwd") : (DIR ? "exact2 byte rev" : "exact2 byte fwd"));
         }
@@ -546,7 +553,7 @@ static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound, 
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
     CUDA_TRY(c, cudaStreamWaitEvent(vs, c->ev_fork3, 0));
-    if (launch_exact<0, 0>(c, verifyList, upperBound, vs)) return -1;      // confirms the overflow, or produces the byte-mode result
+    if (launch_exact<0, 0>(c, verifyList, upperBound, vs, /*fewJobsLikely=*/true)) return -1;      // confirms the overflow, or produces the byte-mode result
     CUDA_TRY(c, cudaEventRecord(which ? c->ev_join3 : c->ev_join2, vs));
     c->verify_pending |= 1u << which;
     return 0;
@@ -782,7 +789,7 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
         if (stage_check(c, "certify")) return -1;
         if (read_counters(c)) return -1;
         const int nverify3 = c->h_counters[LIST_BYTE_FWD];
-        if (nverify3 > 0 && launch_exact<0, 0>(c, LIST_BYTE_FWD, nverify3)) return -1;
+        if (nverify3 > 0 && launch_exact<0, 0>(c, LIST_BYTE_FWD, nverify3, nullptr, /*fewJobsLikely=*/true)) return -1;
         if (nverify3 > 0 && read_counters(c)) return -1;
         const int nbyte = c->h_counters[CNT_BYTE_REV];
         if (nbyte > 0) {

@@ -17,6 +17,8 @@ __device__ __forceinline__ uint32_t x2_max_s(uint32_t a, uint32_t b) { uint32_t 
 __device__ __forceinline__ uint32_t x2_max_u(uint32_t a, uint32_t b) { uint32_t d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 __device__ __forceinline__ uint32_t x2_pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
+#define SWB_EXACT_SPARSE_MAX 64     // most jobs the one-job-per-warp schedule of k_exact2 serves
+
 __host__ __device__ inline int exact2_smem_per_group(int mode, int n, int max_rlen) {
     const int W = mode ? 8 : 16;
     const int seg = (max_rlen + W - 1) / W;
@@ -25,8 +27,13 @@ __host__ __device__ inline int exact2_smem_per_group(int mode, int n, int max_rl
 
 template <int MODE, int DIR>
 __global__ void __launch_bounds__(128)
-k_exact2(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int segAlloc, int smemPerGroup)
+k_exact2(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int segAlloc, int smemPerGroup, int sched)
 {
+    // sched 0: one group per job, the groups of a warp in lock step (throughput).
+    // The groups of a warp advance column by column together, and a column costs every group as much as the slowest one
+    // (the lazy-F loop runs 16*segLen steps once scores pass 128): a handful of jobs is served much faster one per WARP.
+    // sched 1 / 2 are the two halves of a launch pair that picks by the job count on the device (no host round trip):
+    //   1 = as 0 but only if there are more than SWB_EXACT_SPARSE_MAX jobs,  2 = one job per warp, only if there are at most that many.
     constexpr int W = MODE ? 8 : 16;                  // SSE2 lanes per alignment
     constexpr int T = W / 2;                          // threads per alignment
     constexpr unsigned FULL = 0xffffffffu;
@@ -38,9 +45,11 @@ k_exact2(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__
     const int gt = lane % T;                          // thread inside the group: SSE2 lanes 2*gt and 2*gt+1
     const int gw = lane / T;                          // group inside the warp
     const int groupInBlock = threadIdx.x / T;
-    const int job = blockIdx.x * (blockDim.x / T) + groupInBlock;
-    if (blockIdx.x * (blockDim.x / T) >= njobs) return;
-    const bool valid = job < njobs;
+    if (sched == 1 && njobs <= SWB_EXACT_SPARSE_MAX) return;
+    if (sched == 2 && njobs > SWB_EXACT_SPARSE_MAX) return;
+    const int job = sched == 2 ? (int)(blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) : (int)(blockIdx.x * (blockDim.x / T) + groupInBlock);
+    if ((sched == 2 ? blockIdx.x * (blockDim.x / 32) : blockIdx.x * (blockDim.x / T)) >= (unsigned)njobs) return;
+    const bool valid = job < njobs && (sched != 2 || gw == 0);
     const int p = valid ? jobs[job] : -1;
 
     int rl = 0, cols = 0, go = 0, ge = 0, maskLen = 0, terminate = 0;
