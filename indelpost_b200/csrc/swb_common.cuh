@@ -61,7 +61,7 @@ struct SwbDev {
     int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
     uint32_t* fast_cols;   // global column-best storage of the fast path when windows are too long for shared memory (null otherwise)
     int32_t one;        // always 1, but opaque to the compiler: x * one + c compiles to a real IMAD (FMA pipe) instead of an ALU-pipe add
-    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass, bit4 = no register-band kernel
+    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass, bit4 = no register-band kernel, bit5 = single traceback phase
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
@@ -163,7 +163,7 @@ __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_resu
     const int bw = (dl < 0 ? -dl : dl) + 1;
     // provisional 16-bit results whose alignment has a net insertion are the only ones that can fail the overflow
     // certificate (swb_cert.cuh): they are traced back first so their verification overlaps the rest of the stage
-    const bool first = (d.p_state[p] & PST_NEED_CERT) && dl < 0;
+    const bool first = (d.p_state[p] & PST_NEED_CERT) && dl < 0 && !(d.opt & 32);
     // regular jobs (band narrower than the matrix, see swb_bandreg.cuh) go to the register-band kernel of their exact width
     if (bw <= SWB_BANDW_MAX && refLen >= 2 * bw + 2 && readLen <= SWB_BANDREG_MAXROWS && d.n <= 8 && r.ref_begin1 >= 0 && r.read_begin1 >= 0 && !(d.opt & 16)) {
         const int slot = (first ? LIST_BANDW_FIRST : LIST_BANDW) + bw - 1;
