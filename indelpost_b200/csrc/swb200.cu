@@ -587,6 +587,7 @@ static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBas
 #define SWB_BR_CASE(W) case W: launch_band_reg_one<W>(c, baseW + W - 1, n, nextBase, st); break;
             SWB_BR_CASE(1) SWB_BR_CASE(2) SWB_BR_CASE(3) SWB_BR_CASE(4) SWB_BR_CASE(5) SWB_BR_CASE(6) SWB_BR_CASE(7) SWB_BR_CASE(8)
             SWB_BR_CASE(9) SWB_BR_CASE(10) SWB_BR_CASE(11) SWB_BR_CASE(12) SWB_BR_CASE(13) SWB_BR_CASE(14) SWB_BR_CASE(15) SWB_BR_CASE(16)
+            SWB_BR_CASE(17) SWB_BR_CASE(18) SWB_BR_CASE(19) SWB_BR_CASE(20) SWB_BR_CASE(21) SWB_BR_CASE(22) SWB_BR_CASE(23) SWB_BR_CASE(24)
 #undef SWB_BR_CASE
         }
         CUDA_TRY(c, cudaEventRecord(c->ev_bandw_join[w - 1], st));
