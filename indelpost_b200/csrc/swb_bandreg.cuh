@@ -26,9 +26,15 @@
 
 struct BandRegPar { const int8_t* read; const int8_t* ref; int readLen, refLen; };
 
-// per-thread shared-memory region: [columns: u16 selectors][rows: u8 read codes], odd number of 32-bit words
-__host__ __device__ __forceinline__ int bandreg_sel_cols(int rows) { return (rows + SWB_BANDW_MAX + 2 * SWB_BANDW_MAX + 4) & ~1; }
-__host__ __device__ __forceinline__ int bandreg_stride_words(int rows) { return ((bandreg_sel_cols(rows) * 2 + ((rows + 3) & ~3)) / 4) | 1; }
+// per-thread shared-memory region: [columns: u8 window codes][rows: u8 read codes], odd number of 32-bit words (the PRMT
+// selector of a column is rebuilt from its code with one IMAD on the FMA pipe: half the bytes of a u16 selector array, and
+// shared memory is what limits the occupancy of this kernel)
+__host__ __device__ __forceinline__ int bandreg_sel_cols(int rows) { return (rows + SWB_BANDW_MAX + 2 * SWB_BANDW_MAX + 4 + 3) & ~3; }
+__host__ __device__ __forceinline__ int bandreg_stride_words(int rows) { return ((bandreg_sel_cols(rows) + ((rows + 3) & ~3)) / 4) | 1; }
+
+// PRMT selector of a window code: byte rc of the score row, sign-extended to 32 bits (`one` is 1 but opaque to the
+// compiler, so this stays a real IMAD on the FMA pipe)
+__device__ __forceinline__ uint32_t bandreg_sel(uint32_t rc, int one) { return rc * (uint32_t)(0x1111 * one) + 0x8880u; }
 
 // one DP cell (ssw.c:637-664).  hUp/eUp: upper neighbour, hDiag: diagonal neighbour, hLeft/f: left neighbour state.
 // Returns H; writes E back through eOut; ORs the 4-bit direction code (bit0: E opened from H, bit1: F opened from H,
@@ -131,16 +137,16 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     const int strideW = bandreg_stride_words(rowsAlloc);
     const int selCols = bandreg_sel_cols(rowsAlloc);
     uint32_t* const region = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)threadIdx.x * strideW;
-    uint16_t* selW = reinterpret_cast<uint16_t*>(region);
-    uint8_t* rowW = reinterpret_cast<uint8_t*>(region + selCols / 2);
+    uint8_t* selW = reinterpret_cast<uint8_t*>(region);
+    uint8_t* rowW = reinterpret_cast<uint8_t*>(region + selCols / 4);
     {
         const swb_result& r0 = d.res[p];
-        for_each_byte16(d.windows + d.p_woff[p] + r0.ref_begin1, g.refLen, [&](int c, uint32_t v) { selW[c] = (uint16_t)((v & 7u) * 0x1111u | 0x8880u); });   // PRMT selector: byte rc, sign-extended
+        for_each_byte16(d.windows + d.p_woff[p] + r0.ref_begin1, g.refLen, [&](int c, uint32_t v) { selW[c] = (uint8_t)(v & 7u); });
         const int ncols = min(g.refLen + NX + 1, selCols);
-        for (int c = g.refLen; c < ncols; ++c) selW[c] = 0x8880u;
+        for (int c = g.refLen; c < ncols; ++c) selW[c] = 0;
         for_each_byte16(d.reads + d.p_roff[p] + r0.read_begin1, g.readLen, [&](int i, uint32_t v) { rowW[i] = (uint8_t)(v & 7u); });
     }
-    const uint16_t* selT = selW;
+    const uint8_t* selT = selW;
     const uint8_t* rowT = rowW;
 
     swb_result& r = d.res[p];
@@ -180,7 +186,7 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
         for (int x = 0; x < NX; ++x) {
             if (x <= lim) {
                 const int hUp = Hs[x], eUp = Es[x];
-                const int sc = (int)prmt(tabLo, tabHi, selT[x]);
+                const int sc = (int)prmt(tabLo, tabHi, bandreg_sel(selT[x], d.one));
                 const int h = bandreg_cell(x & 7, hUp, eUp, hDiag, hLeft, f, Es[x], sc, go, ge, words[x >> 3]);
                 Hs[x] = h;
                 best = max(best, h);                        // ssw.c:661
@@ -196,7 +202,7 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     for (int i = W + 1; i < g.readLen; ++i) {
         const unsigned long long tab = s_rowTab[rowT[i]];
         const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
-        const uint16_t* sp = selT + (i - W);
+        const uint8_t* sp = selT + (i - W);
         uint32_t words[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) words[k] = 0;
@@ -205,7 +211,7 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
 #pragma unroll
         for (int x = 0; x < NX; ++x) {
             const int hUp = x + 1 < NX ? Hs[x + 1] : 0, eUp = x + 1 < NX ? Es[x + 1] : 0;
-            const int sc = (int)prmt(tabLo, tabHi, sp[x]);
+            const int sc = (int)prmt(tabLo, tabHi, bandreg_sel(sp[x], d.one));
             const int h = bandreg_cell(x & 7, hUp, eUp, Hs[x], hLeft, f, Es[x], sc, go, ge, words[x >> 3]);
             Hs[x] = h;
             if (x <= xmax) best = max(best, h);
