@@ -181,6 +181,34 @@ int swb_download(swb_ctx* ctx, swb_result* results, uint32_t* cigar_arena,
 
 int swb_get_timing(const swb_ctx* ctx, swb_timing* out);
 
+/* ------------------------------------------------------------------ */
+/* 3. CIGAR -> indel records                     */
+/* ------------------------------------------------------------------ */
+/* One record per I / D token of the alignment's CIGAR after indelPost's make_insertion_first reordering
+ * (utilities.pyx:360-401): the integer core of findall_indels (localn.pyx:542-621).  The strings the
+ * reference puts into its dicts are slices at these indices: lt_ref = ref[:ref_idx], lt_flank = read[:read_idx],
+ * indel_seq = read[read_idx : read_idx+len] (I), del_seq = ref[ref_idx : ref_idx+len] (D), pos = genome_aln_pos + pos_off. */
+typedef struct {
+    int32_t  pair;       /* index of the alignment                                  */
+    uint32_t cigar_op;   /* len << 4 | op (1 = I, 2 = D), BAM packing               */
+    int32_t  ref_idx;    /* reference index of the event (relative like ref_begin1) */
+    int32_t  read_idx;   /* read index of the event                                 */
+    int32_t  pos_off;    /* pos - genome_aln_pos (starts at -1, localn.pyx:544)     */
+} swb_indel;
+
+/* Indels of the alignments the context holds after swb_compute() / swb_align_batch().  indel_off / indel_cnt /
+ * read_end have n_pairs entries: the records of pair p are indels[indel_off[p] .. +indel_cnt[p]) in CIGAR order,
+ * read_end[p] is the read index after the last token (start of rt_clipped, localn.pyx:615).  Returns -2 with
+ * *used = required capacity when `cap` records are not enough. */
+int swb_indels(swb_ctx* ctx, int64_t* indel_off, int32_t* indel_cnt, int32_t* read_end,
+               swb_indel* indels, int64_t cap, int64_t* used);
+/* The same for caller-supplied alignments: n CIGARs in BAM packing inside `cigar_arena` (arena_len uint32s). */
+int swb_indels_from_cigars(swb_ctx* ctx, int32_t n, const uint32_t* cigar_arena, int64_t arena_len,
+                           const int64_t* cigar_off, const int32_t* cigar_len,
+                           const int32_t* ref_start, const int32_t* read_start,
+                           int64_t* indel_off, int32_t* indel_cnt, int32_t* read_end,
+                           swb_indel* indels, int64_t cap, int64_t* used);
+
 /* pinned host memory helpers for the staging buffers */
 void* swb_host_alloc(int64_t bytes);
 void  swb_host_free(void* p);

@@ -27,6 +27,10 @@ RESULT_DTYPE = np.dtype(
 )
 assert RESULT_DTYPE.itemsize == 40
 
+# swb_indel (20 bytes): one I / D token of an alignment (include/swb200.h, section 3)
+INDEL_DTYPE = np.dtype([("pair", "<i4"), ("cigar_op", "<u4"), ("ref_idx", "<i4"), ("read_idx", "<i4"), ("pos_off", "<i4")])
+assert INDEL_DTYPE.itemsize == 20
+
 
 class SwbBatch(C.Structure):
     _fields_ = [
@@ -68,6 +72,7 @@ EXPORTS = (
     "swb_device_count", "swb_create", "swb_destroy", "swb_last_error",
     "swb_align_batch", "swb_upload", "swb_compute", "swb_download", "swb_get_timing",
     "swb_host_alloc", "swb_host_free", "swb_encode_dna", "swb_version",
+    "swb_indels", "swb_indels_from_cigars",
 )
 
 _lib = None
@@ -101,6 +106,11 @@ def load():
     lib.swb_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.swb_get_timing.restype = C.c_int
     lib.swb_get_timing.argtypes = [C.c_void_p, C.POINTER(SwbTiming)]
+    lib.swb_indels.restype = C.c_int
+    lib.swb_indels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.swb_indels_from_cigars.restype = C.c_int
+    lib.swb_indels_from_cigars.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.swb_host_alloc.restype = C.c_void_p
     lib.swb_host_alloc.argtypes = [C.c_int64]
     lib.swb_host_free.argtypes = [C.c_void_p]

@@ -148,6 +148,42 @@ class BatchAligner:
                 raise L.SwbError(self._err())
             return res, arena[: used.value]
 
+    # ------------------------------------------------------------------
+    # CIGAR -> indel records (include/swb200.h section 3; reference localn.pyx:542-621 + utilities.pyx:360-401)
+    def _indel_call(self, n, fn):
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        cnt = np.zeros(max(n, 1), dtype=np.int32)
+        rend = np.zeros(max(n, 1), dtype=np.int32)
+        cap = max(64, 2 * n)
+        used = C.c_int64(0)
+        while True:
+            recs = np.zeros(cap, dtype=L.INDEL_DTYPE)
+            rc = fn(off, cnt, rend, recs, cap, used)
+            if rc == -2:
+                cap = int(used.value) + 16
+                continue
+            if rc != 0:
+                raise L.SwbError(self._err())
+            return off[:n], cnt[:n], rend[:n], recs[: used.value]
+
+    def indels(self, n_pairs: int):
+        """indel records of the alignments this aligner holds on the device (after compute() or a streamed / single-pass
+        align()): (indel_off, indel_cnt, read_end, records) -- the records of pair p are records[off[p] : off[p] + cnt[p]]"""
+        return self._indel_call(n_pairs, lambda off, cnt, rend, recs, cap, used: self.lib.swb_indels(
+            self.ctx, off.ctypes.data, cnt.ctypes.data, rend.ctypes.data, recs.ctypes.data, cap, C.byref(used)))
+
+    def indels_from_cigars(self, cigar_arena, cigar_off, cigar_len, ref_start, read_start):
+        """the same for caller-supplied alignments (BAM-packed CIGARs in an arena)"""
+        arena = np.ascontiguousarray(cigar_arena, dtype=np.uint32)
+        coff = np.ascontiguousarray(cigar_off, dtype=np.int64)
+        clen = np.ascontiguousarray(cigar_len, dtype=np.int32)
+        rs = np.ascontiguousarray(ref_start, dtype=np.int32)
+        qs = np.ascontiguousarray(read_start, dtype=np.int32)
+        n = int(coff.shape[0])
+        return self._indel_call(n, lambda off, cnt, rend, recs, cap, used: self.lib.swb_indels_from_cigars(
+            self.ctx, n, arena.ctypes.data, int(arena.shape[0]), coff.ctypes.data, clen.ctypes.data, rs.ctypes.data, qs.ctypes.data,
+            off.ctypes.data, cnt.ctypes.data, rend.ctypes.data, recs.ctypes.data, cap, C.byref(used)))
+
     def timing(self) -> dict:
         t = L.SwbTiming()
         self.lib.swb_get_timing(self.ctx, C.byref(t))

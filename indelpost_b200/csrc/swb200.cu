@@ -32,6 +32,7 @@
 #include "swb_fast.cuh"
 #include "swb_revband.cuh"
 #include "swb_bandreg.cuh"
+#include "swb_indels.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
 
@@ -151,6 +152,7 @@ struct swb_ctx {
     DevBuf b_pair_read, b_pair_win, b_ref_beg, b_ref_len, b_go, b_ge, b_mask, b_mat;
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
     DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe, b_fastcols;
+    DevBuf b_ind_off, b_ind_cnt, b_ind_rend, b_ind_recs, b_ind_misc, b_ind_cig, b_ind_coff, b_ind_clen, b_ind_rs, b_ind_qs;   // indel extraction
     int fastMaxCols[SWB_NBUCKETS] = {};
     int32_t* h_counters = nullptr;              // pinned mirror of counters
     int32_t* h_snap[2] = {nullptr, nullptr};    // streamed path: counter snapshots of the piece in flight and the one before
@@ -250,7 +252,8 @@ extern "C" void swb_destroy(swb_ctx* c) {
     DevBuf* all[] = { &c->b_reads, &c->b_read_off, &c->b_read_len, &c->b_windows, &c->b_win_off, &c->b_win_len, &c->b_pair_read, &c->b_pair_win,
                       &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
                       &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
-                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe, &c->b_fastcols };
+                      &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe, &c->b_fastcols,
+                      &c->b_ind_off, &c->b_ind_cnt, &c->b_ind_rend, &c->b_ind_recs, &c->b_ind_misc, &c->b_ind_cig, &c->b_ind_coff, &c->b_ind_clen, &c->b_ind_rs, &c->b_ind_qs };
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
@@ -1247,6 +1250,78 @@ extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* resul
     if (cigar_used) *cigar_used = used;
     if (used > cigar_cap || (used > 0 && !cigar_arena)) { c->err = "cigar arena too small"; return -2; }
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CIGAR -> indel records (swb_indels.cuh)
+// ------------------------------------------------------------------------------------------------
+static int run_indels(swb_ctx* c, bool aos, const uint32_t* d_cigar, const int64_t* d_coff, const int32_t* d_clen, const int32_t* d_rs, const int32_t* d_qs, int32_t n,
+                      int64_t* indel_off, int32_t* indel_cnt, int32_t* read_end, swb_indel* indels, int64_t cap, int64_t* used) {
+    cudaStream_t s = c->stream;
+    const size_t np = (size_t)std::max(n, 0);
+    CUDA_TRY(c, c->b_ind_off.ensure(np * 8 + 16));
+    CUDA_TRY(c, c->b_ind_cnt.ensure(np * 4 + 16));
+    CUDA_TRY(c, c->b_ind_rend.ensure(np * 4 + 16));
+    CUDA_TRY(c, c->b_ind_misc.ensure(16));
+    const int64_t devCap = std::max<int64_t>(cap, 1);
+    CUDA_TRY(c, c->b_ind_recs.ensure((size_t)devCap * sizeof(swb_indel) + 16));
+    CUDA_TRY(c, cudaMemsetAsync(c->b_ind_misc.p, 0, 16, s));
+    unsigned long long* bump = (unsigned long long*)c->b_ind_misc.p;
+    int32_t* overflow = (int32_t*)((char*)c->b_ind_misc.p + 8);
+    if (n > 0) {
+        const unsigned blocks = (unsigned)((np + 127) / 128);
+        if (aos) k_indels<true><<<blocks, 128, 0, s>>>(c->d.res, d_cigar, nullptr, nullptr, nullptr, nullptr, n, (int64_t*)c->b_ind_off.p, (int32_t*)c->b_ind_cnt.p, (int32_t*)c->b_ind_rend.p, (swb_indel*)c->b_ind_recs.p, devCap, bump, overflow);
+        else k_indels<false><<<blocks, 128, 0, s>>>(nullptr, d_cigar, d_coff, d_clen, d_rs, d_qs, n, (int64_t*)c->b_ind_off.p, (int32_t*)c->b_ind_cnt.p, (int32_t*)c->b_ind_rend.p, (swb_indel*)c->b_ind_recs.p, devCap, bump, overflow);
+        CUDA_TRY(c, cudaGetLastError());
+    }
+    unsigned long long h_misc[2] = {0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(h_misc, c->b_ind_misc.p, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    const int64_t need = (int64_t)h_misc[0];
+    if (used) *used = need;
+    if (need > cap || (need > 0 && !indels)) { c->err = "indel arena too small"; return -2; }
+    if (n > 0) {
+        CUDA_TRY(c, cudaMemcpyAsync(indel_off, c->b_ind_off.p, np * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaMemcpyAsync(indel_cnt, c->b_ind_cnt.p, np * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaMemcpyAsync(read_end, c->b_ind_rend.p, np * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (need > 0) CUDA_TRY(c, cudaMemcpyAsync(indels, c->b_ind_recs.p, (size_t)need * sizeof(swb_indel), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int swb_indels(swb_ctx* c, int64_t* indel_off, int32_t* indel_cnt, int32_t* read_end, swb_indel* indels, int64_t cap, int64_t* used) {
+    if (!c) return -1;
+    if (!c->computed) { c->err = "swb_indels: nothing computed on this context (after a two-lane pipelined swb_align_batch the results are not resident: use swb_indels_from_cigars)"; return -1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->d.n_pairs && (!indel_off || !indel_cnt || !read_end)) { c->err = "swb_indels: missing output arrays"; return -1; }
+    return run_indels(c, true, c->d.cigar, nullptr, nullptr, nullptr, nullptr, c->d.n_pairs, indel_off, indel_cnt, read_end, indels, cap, used);
+}
+
+extern "C" int swb_indels_from_cigars(swb_ctx* c, int32_t n, const uint32_t* cigar_arena, int64_t arena_len, const int64_t* cigar_off, const int32_t* cigar_len,
+                                      const int32_t* ref_start, const int32_t* read_start, int64_t* indel_off, int32_t* indel_cnt, int32_t* read_end,
+                                      swb_indel* indels, int64_t cap, int64_t* used) {
+    if (!c) return -1;
+    if (n < 0 || arena_len < 0 || (n > 0 && (!cigar_off || !cigar_len || !ref_start || !read_start || !indel_off || !indel_cnt || !read_end)) || (arena_len > 0 && !cigar_arena)) { c->err = "swb_indels_from_cigars: bad arguments"; return -1; }
+    for (int32_t i = 0; i < n; ++i)
+        if (cigar_len[i] < 0 || cigar_off[i] < 0 || cigar_off[i] + cigar_len[i] > arena_len) { c->err = "swb_indels_from_cigars: CIGAR outside the arena"; return -1; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t np = (size_t)n;
+    CUDA_TRY(c, c->b_ind_cig.ensure((size_t)arena_len * 4 + 16));
+    CUDA_TRY(c, c->b_ind_coff.ensure(np * 8 + 16));
+    CUDA_TRY(c, c->b_ind_clen.ensure(np * 4 + 16));
+    CUDA_TRY(c, c->b_ind_rs.ensure(np * 4 + 16));
+    CUDA_TRY(c, c->b_ind_qs.ensure(np * 4 + 16));
+    if (arena_len) CUDA_TRY(c, cudaMemcpyAsync(c->b_ind_cig.p, cigar_arena, (size_t)arena_len * 4, cudaMemcpyHostToDevice, s));
+    if (n) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->b_ind_coff.p, cigar_off, np * 8, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(c->b_ind_clen.p, cigar_len, np * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(c->b_ind_rs.p, ref_start, np * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(c->b_ind_qs.p, read_start, np * 4, cudaMemcpyHostToDevice, s));
+    }
+    return run_indels(c, false, (const uint32_t*)c->b_ind_cig.p, (const int64_t*)c->b_ind_coff.p, (const int32_t*)c->b_ind_clen.p, (const int32_t*)c->b_ind_rs.p,
+                      (const int32_t*)c->b_ind_qs.p, n, indel_off, indel_cnt, read_end, indels, cap, used);
 }
 
 extern "C" int swb_get_timing(const swb_ctx* c, swb_timing* out) {

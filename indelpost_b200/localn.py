@@ -2,7 +2,14 @@
 indelpost/localn.pyx:464-472), plus its batched counterpart."""
 from __future__ import annotations
 
-from .sswpy import SSW, align_batch
+import re
+
+import numpy as np
+
+from .sswpy import SSW, align_batch, _aligner
+
+cigar_ptrn = re.compile(r"[0-9]+[MIDNSHPX=]")  # localn.pyx:12
+_OPS = "MIDNSHP=X"
 
 
 def make_aligner(ref_seq, match_score, mismatch_penalty):  # localn.pyx:464-467
@@ -21,3 +28,78 @@ def align_many(ref_seqs, read_seqs, pair_read, pair_ref, gap_open_penalty, gap_e
     `align(make_aligner(ref), read, go, ge)` returns for each pair, as a list in pair order."""
     return align_batch(read_seqs, ref_seqs, pair_read, pair_ref, gap_open_penalty, gap_extension_penalty,
                        match_score=match_score, mismatch_penalty=mismatch_penalty, device=device)
+
+
+def _pack_cigar(cigarstring):
+    """'37M1D113M' -> BAM-packed uint32 ops (len << 4 | op, ssw.h:171-190)"""
+    toks = cigar_ptrn.findall(cigarstring or "")
+    return np.array([(int(t[:-1]) << 4) | _OPS.index(t[-1]) for t in toks], dtype=np.uint32)
+
+
+def findall_indels_many(alignments, genome_aln_positions, ref_seqs, read_seqs, report_snvs=False, basequals=None, device=0):
+    """findall_indels (localn.pyx:542-621) for many alignments at once: the CIGAR walk with indelPost's
+    make_insertion_first reordering (utilities.pyx:360-401) runs on the GPU (k_indels), the dicts -- same keys and
+    values as the reference's -- are sliced out of the sequences at the indices it returns."""
+    n = len(alignments)
+    packed = [_pack_cigar(a.CIGAR) for a in alignments]
+    clen = np.array([p.shape[0] for p in packed], dtype=np.int32)
+    coff = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        coff[1:] = np.cumsum(clen[:-1], dtype=np.int64)
+    arena = np.concatenate(packed) if n and int(clen.sum()) else np.zeros(0, dtype=np.uint32)
+    rs = np.array([a.reference_start for a in alignments], dtype=np.int32)
+    qs = np.array([a.read_start for a in alignments], dtype=np.int32)
+    off, cnt, rend, recs = _aligner(device).indels_from_cigars(arena, coff, clen, rs, qs)
+    out = []
+    for k in range(n):
+        ref_seq, read_seq, gpos = ref_seqs[k], read_seqs[k], genome_aln_positions[k]
+        quals = basequals[k] if basequals is not None else None
+        lt_clipped = read_seq[: alignments[k].read_start]
+        rt_clipped = read_seq[int(rend[k]):]
+        indels = []
+        for r in recs[int(off[k]): int(off[k]) + int(cnt[k])]:
+            ln, op = int(r["cigar_op"]) >> 4, int(r["cigar_op"]) & 15
+            ref_idx, read_idx = int(r["ref_idx"]), int(r["read_idx"])
+            d = {"pos": gpos + int(r["pos_off"]), "lt_ref": ref_seq[:ref_idx], "lt_flank": read_seq[:read_idx]}
+            if quals:
+                d["lt_qual"] = quals[:read_idx]
+            if op == 1:
+                d.update(indel_type="I", indel_seq=read_seq[read_idx: read_idx + ln], rt_ref=ref_seq[ref_idx:], rt_flank=read_seq[read_idx + ln:],
+                         ref_idx=ref_idx, read_idx=read_idx)
+                if quals:
+                    d["rt_qual"] = quals[read_idx + ln:]
+            else:
+                d.update(indel_type="D", indel_seq="", del_seq=ref_seq[ref_idx: ref_idx + ln], rt_ref=ref_seq[ref_idx + ln:], rt_flank=read_seq[read_idx:],
+                         ref_idx=ref_idx, read_idx=read_idx)
+                if quals:
+                    d["rt_qual"] = quals[read_idx:]
+            d["lt_clipped"] = lt_clipped
+            d["rt_clipped"] = rt_clipped
+            indels.append(d)
+        if not report_snvs:
+            out.append(indels)
+            continue
+        # localn.pyx:594-606: mismatches inside the M tokens, walked between the events the device reported
+        snvs = []
+        pos = gpos - 1
+        ref_idx, read_idx = alignments[k].reference_start, alignments[k].read_start
+        events = [(int(r["ref_idx"]), int(r["read_idx"]), int(r["cigar_op"]) >> 4, int(r["cigar_op"]) & 15) for r in recs[int(off[k]): int(off[k]) + int(cnt[k])]]
+        events.append((None, int(rend[k]), 0, 0))
+        for e_ref, e_read, ln, op in events:
+            m = e_read - read_idx                            # matched run up to the next event (or the end of the alignment)
+            for i in range(m):
+                a, b = ref_seq[ref_idx + i: ref_idx + i + 1], read_seq[read_idx + i: read_idx + i + 1]
+                if a != b:
+                    snvs.append({"pos": pos + i + 1, "ref": a, "alt": b})
+            ref_idx += m; read_idx += m; pos += m
+            if op == 1:
+                read_idx += ln
+            elif op == 2:
+                ref_idx += ln; pos += ln
+        out.append((indels, snvs))
+    return out
+
+
+def findall_indels(ref_aln, genome_aln_pos, ref_seq, read_seq, report_snvs=False, basequals=None):  # localn.pyx:542
+    return findall_indels_many([ref_aln], [genome_aln_pos], [ref_seq], [read_seq], report_snvs=report_snvs,
+                               basequals=None if basequals is None else [basequals])[0]

@@ -3,6 +3,7 @@ reproduce bit-for-bit (a) every committed golden vector generated from the refer
 (b) the CPU oracle on fresh seeded inputs, for every s_align field and every CIGAR op."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -331,3 +332,90 @@ def test_gpu_mixed_window_lengths_long_windows_on_fast_path():
     rg, ag, tm = gpu_align(bb)
     T.compare(rg, ag, ro, ao, what="mixed window lengths")
     assert tm["n_fast"] > 0.8 * bb.n_pairs
+
+
+# ---------------------------------------------------------------------------------------------
+# CIGAR -> indel records on the device (include/swb200.h section 3, swb_indels.cuh)
+# ---------------------------------------------------------------------------------------------
+
+def _oracle_records(cigar, rs, qs):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import indels_oracle as O
+
+    recs, rend = O.indel_records(cigar, rs, qs)
+    return [((n << 4) | (1 if op == "I" else 2), ri, qi, po) for op, n, ri, qi, po in recs], rend
+
+
+def test_gpu_indels_reproduce_reference_golden():
+    """findall_indels through the device kernel equals the dicts the unmodified reference produced"""
+    from collections import namedtuple
+
+    from indelpost_b200 import localn
+
+    Aln = namedtuple("Aln", "CIGAR reference_start read_start")
+    with open(os.path.join(GOLDEN_DIR, "indels.json")) as fh:
+        cases = json.load(fh)["cases"]
+    for snv in (False, True):
+        sel = [c for c in cases if c["report_snvs"] == snv]
+        outs = localn.findall_indels_many([Aln(c["cigar"], c["reference_start"], c["read_start"]) for c in sel], [c["genome_aln_pos"] for c in sel],
+                                          [c["ref_seq"] for c in sel], [c["read_seq"] for c in sel], report_snvs=snv)
+        for c, out in zip(sel, outs):
+            indels, snvs = out if snv else (out, None)
+            assert indels == c["indels"], c["cigar"]
+            assert snvs == c["snvs"], c["cigar"]
+    c = cases[0]
+    one = localn.findall_indels(Aln(c["cigar"], c["reference_start"], c["read_start"]), c["genome_aln_pos"], c["ref_seq"], c["read_seq"], report_snvs=c["report_snvs"])
+    assert (one[0] if c["report_snvs"] else one) == c["indels"]
+
+
+def test_gpu_indels_fuzz_against_oracle():
+    """random op strings (adjacent gap runs in every order, gaps at both ends, empty CIGARs) through swb_indels_from_cigars"""
+    from gpuutil import aligner
+    from indelpost_b200 import localn
+
+    rng = np.random.default_rng(77)
+    cigars, rs, qs = [], [], []
+    for k in range(20000):
+        n = int(rng.integers(0, 9))
+        toks = []
+        for _ in range(n):
+            op = "MID"[int(rng.choice(3, p=[0.4, 0.3, 0.3]))]
+            if toks and toks[-1][-1] == op == "M":
+                continue
+            toks.append(f"{int(rng.integers(1, 40))}{op}")
+        cigars.append("".join(toks))
+        rs.append(int(rng.integers(0, 50)))
+        qs.append(int(rng.integers(0, 20)))
+    packed = [localn._pack_cigar(c) for c in cigars]
+    clen = np.array([p.shape[0] for p in packed], dtype=np.int32)
+    coff = np.zeros(len(cigars), dtype=np.int64)
+    coff[1:] = np.cumsum(clen[:-1])
+    off, cnt, rend, recs = aligner().indels_from_cigars(np.concatenate(packed), coff, clen, rs, qs)
+    assert int(cnt.sum()) == recs.shape[0]
+    for k, c in enumerate(cigars):
+        want, want_end = _oracle_records(c, rs[k], qs[k])
+        got = [(int(r["cigar_op"]), int(r["ref_idx"]), int(r["read_idx"]), int(r["pos_off"])) for r in recs[int(off[k]): int(off[k]) + int(cnt[k])]]
+        assert got == want, (c, got, want)
+        assert int(rend[k]) == want_end, c
+        assert all(int(r["pair"]) == k for r in recs[int(off[k]): int(off[k]) + int(cnt[k])])
+
+
+def test_gpu_indels_of_resident_alignments():
+    """swb_indels on the alignments a compute just produced equals the oracle walk over the downloaded CIGARs"""
+    from gpuutil import aligner
+
+    b = T.make_pairs(5000, (60, 150), 400, seed=91, grid=True, max_indel=12)
+    a = aligner()
+    n = a.upload(b.reads, b.read_off, b.read_len, b.windows, b.win_off, b.win_len, b.pair_read, b.pair_win, b.gap_open, b.gap_ext, mat=b.mat, n=5, score_size=2, flag=1)
+    a.compute()
+    res, arena = a.download(n)
+    off, cnt, rend, recs = a.indels(n)
+    n_events = 0
+    for p in range(n):
+        cg = T.cigar_string(arena, int(res["cigar_off"][p]), int(res["cigar_len"][p])) if res["cigar_len"][p] > 0 else ""
+        want, want_end = _oracle_records(cg, int(res["ref_begin1"][p]), int(res["read_begin1"][p]))
+        got = [(int(r["cigar_op"]), int(r["ref_idx"]), int(r["read_idx"]), int(r["pos_off"])) for r in recs[int(off[p]): int(off[p]) + int(cnt[p])]]
+        assert got == want, (p, cg)
+        assert int(rend[p]) == want_end
+        n_events += len(want)
+    assert n_events > 1000
