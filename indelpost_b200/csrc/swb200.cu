@@ -327,6 +327,9 @@ static void set_batch_scalars(swb_ctx* c, const swb_batch* b, const ChunkView& v
     for (int i = 0; i < b->n * b->n; ++i) { mx = std::max<int>(mx, b->mat[i]); if (b->mat[i] > 7 || b->mat[i] < -7) small = false; }
     d.max_score = mx;
     { const char* o = getenv("SWB200_OPT"); d.opt = o ? atoi(o) : 0; }
+    // small batches are latency bound: one traceback phase (the two-phase split only pays once the traceback of the bulk is
+    // long enough to hide the overflow verification of the pairs traced back first; measured crossover ~200 k pairs)
+    if (b->n_pairs < 200000) d.opt |= 32;
     d.one = 1;
     d.fast_ok = (small && b->n >= 4 && mx > 0 && (b->score_size == 1 || b->score_size == 2) && !getenv("SWB200_NO_FAST")) ? 1 : 0;
 }
@@ -565,17 +568,17 @@ static int certify_phase2_hook(swb_ctx* c, int total) { return total > 0 ? certi
 
 // register-band kernels (swb_bandreg.cuh): one launch per exact half-width, spread over the side streams
 template <int W>
-static int launch_band_reg_one(swb_ctx* c, int listSlot, int njobs, int nextBase, cudaStream_t st) {
+static int launch_band_reg_one(swb_ctx* c, int listSlot, int njobs, int nextBase, int nextBaseW, int resume, cudaStream_t st) {
     const SwbDev& d = c->d;
     const int rows = std::min(d.max_rlen, SWB_BANDREG_MAXROWS);
     const size_t smem = (size_t)bandreg_stride_words(rows) * 4 * SWB_BANDREG_THREADS;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_band_reg<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr = true; }
-    k_band_reg<W><<<(njobs + SWB_BANDREG_THREADS - 1) / SWB_BANDREG_THREADS, SWB_BANDREG_THREADS, smem, st>>>(d, d.list[listSlot], njobs, nextBase, rows);
+    k_band_reg<W><<<(njobs + SWB_BANDREG_THREADS - 1) / SWB_BANDREG_THREADS, SWB_BANDREG_THREADS, smem, st>>>(d, d.list[listSlot], njobs, nextBase, nextBaseW, resume, rows);
     c->tm.n_launches++;
     return 0;
 }
-static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBase) {
+static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBase, int nextBaseW, int resume) {
     int any = 0;
     for (int w = 1; w <= SWB_BANDW_MAX; ++w) any += njobsW[w - 1];
     if (!any) return 0;
@@ -587,7 +590,7 @@ static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBas
         cudaStream_t st = c->bandw_stream[w - 1];
         CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_rev_fork, 0));
         switch (w) {
-#define SWB_BR_CASE(W) case W: launch_band_reg_one<W>(c, baseW + W - 1, n, nextBase, st); break;
+#define SWB_BR_CASE(W) case W: launch_band_reg_one<W>(c, baseW + W - 1, n, nextBase, nextBaseW, resume, st); break;
             SWB_BR_CASE(1) SWB_BR_CASE(2) SWB_BR_CASE(3) SWB_BR_CASE(4) SWB_BR_CASE(5) SWB_BR_CASE(6) SWB_BR_CASE(7) SWB_BR_CASE(8)
             SWB_BR_CASE(9) SWB_BR_CASE(10) SWB_BR_CASE(11) SWB_BR_CASE(12) SWB_BR_CASE(13) SWB_BR_CASE(14) SWB_BR_CASE(15) SWB_BR_CASE(16)
             SWB_BR_CASE(17) SWB_BR_CASE(18) SWB_BR_CASE(19) SWB_BR_CASE(20) SWB_BR_CASE(21) SWB_BR_CASE(22) SWB_BR_CASE(23) SWB_BR_CASE(24)
@@ -625,10 +628,12 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         int njobs[SWB_NBANDCLASS], total = 0;
         for (int k = 0; k < SWB_NBANDCLASS; ++k) { njobs[k] = c->h_counters[cur + k]; total += njobs[k]; }
         // round 0 also serves the register-band lists that belong to this phase (their re-queues land in `nxt`)
+        // later rounds: the jobs a register-band kernel widened once and that are still regular (LIST_BANDW_NEXT)
         int njobsW[SWB_BANDW_MAX] = {};
-        const int baseW = firstBase == LIST_BAND_FIRST ? LIST_BANDW_FIRST : LIST_BANDW;
-        if (round == 0) for (int k = 0; k < SWB_BANDW_MAX; ++k) { njobsW[k] = c->h_counters[baseW + k]; total += njobsW[k]; }
+        const int baseW = round == 0 ? (firstBase == LIST_BAND_FIRST ? LIST_BANDW_FIRST : LIST_BANDW) : LIST_BANDW_NEXT;
+        if (round == 0 || !firstRoundOnly) for (int k = 0; k < SWB_BANDW_MAX; ++k) { njobsW[k] = c->h_counters[baseW + k]; total += njobsW[k]; }
         if (round == 0 && firstJobs) *firstJobs = total;
+        if (g_trace) { fprintf(stderr, "TRACE band round %d base %d: classes", round, cur); for (int k = 0; k < SWB_NBANDCLASS; ++k) fprintf(stderr, " %d", njobs[k]); fprintf(stderr, " | reg"); for (int k = 0; k < SWB_BANDW_MAX; ++k) fprintf(stderr, " %d", njobsW[k]); fprintf(stderr, "\n"); }
         if (total <= 0 && !(round == 0 && keepNext)) break;
         if (!(round == 0 && keepNext)) CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
@@ -651,7 +656,10 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
             }
             CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
         }
-        if (round == 0 && launch_band_reg(c, baseW, njobsW, nxt)) return -1;
+        // widened jobs: small batches are latency bound and re-run them with the (faster) register-band kernel of the doubled
+        // width; large ones hand them to the literal kernel, which keeps doubling in place and so never needs a third round
+        const int regNext = (round == 0 && d.n_pairs < 200000) ? LIST_BANDW_NEXT : -1;
+        if (launch_band_reg(c, baseW, njobsW, nxt, regNext, round == 0 ? 0 : 1)) return -1;
         int blocks = 0;
         for (int k = 0; k < SWB_BAND_CLS_MID; ++k) blocks += (njobs[k] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
         if (blocks > 0) {

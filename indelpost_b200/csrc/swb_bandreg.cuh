@@ -110,7 +110,7 @@ __device__ __forceinline__ int bandreg_traceback(const uint32_t* __restrict__ di
 
 template <int W>
 __global__ void __launch_bounds__(SWB_BANDREG_THREADS)
-k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, int rowsAlloc)
+k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, int nextBaseW, int resume, int rowsAlloc)
 {
     constexpr int NX = 2 * W + 1;
     constexpr int NW = (NX + 7) / 8;                      // direction words per row
@@ -169,7 +169,7 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     int Hs[NX], Es[NX];
 #pragma unroll
     for (int x = 0; x < NX; ++x) { Hs[x] = 0; Es[x] = 0; }
-    int best = 0;
+    int best = resume ? d.t_best[p] : 0;                   // a widened job carries its running maximum along (ssw.c:661 is not reset)
     long long cells = 0;
 
     // ---- rows 0 .. W: slot x = column x, cells x <= i + W ---------------------------------------------------------
@@ -223,10 +223,14 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     }
     warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
 
-    if (best < score && W * 2 <= len) {                     // ssw.c:668-669: widen and redo (literal kernel)
+    if (best < score && W * 2 <= len) {                     // ssw.c:668-669: widen and redo in the next round
         d.t_bw[p] = 2 * W; d.t_best[p] = best;
-        const int c = band_class(2 * W);
-        list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
+        if (nextBaseW >= 0 && 2 * W <= SWB_BANDW_MAX && g.refLen >= 4 * W + 2) {
+            list_push(d.list[nextBaseW + 2 * W - 1], d.counters + nextBaseW + 2 * W - 1, p);      // still regular: this kernel's 2W instantiation
+        } else {
+            const int c = band_class(2 * W);
+            list_push(d.list[nextBase + c], d.counters + nextBase + c, p);                           // literal kernel
+        }
         return;
     }
 

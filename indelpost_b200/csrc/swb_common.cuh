@@ -7,8 +7,8 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 104
-#define SWB_NCOUNTERS 144
+#define SWB_NLISTS 128
+#define SWB_NCOUNTERS 168
 
 // ---------------------------------------------------------------------------------------------
 // Device-resident batch ("workspace").  One per context, grown on demand.
@@ -69,12 +69,12 @@ struct SwbDev {
 #define SWB_BAND_CLS_MID 5      // first class of k_band<48,64>; 6: k_band<112,32>; 7: k_band<0,128>
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
        LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
-       LIST_BANDW = 56, LIST_BANDW_FIRST = 80 };   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh)
+       LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104 };   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _NEXT: jobs it widened once
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
-       CNT_CELLS_FWD = 112, CNT_CELLS_REV = 114, CNT_CELLS_BAND = 116, CNT_BAND_OVERFLOW = 118, CNT_CIGAR_OVERFLOW = 119,
-       CNT_FAST_DONE = 120, CNT_CERT_FAIL = 121, CNT_VERIFY_BYTE = 122, CNT_EXACT_JOBS = 123,
-       CNT_FAST_MAXCOLS = 128 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
+       CNT_CELLS_FWD = 136, CNT_CELLS_REV = 138, CNT_CELLS_BAND = 140, CNT_BAND_OVERFLOW = 142, CNT_CIGAR_OVERFLOW = 143,
+       CNT_FAST_DONE = 144, CNT_CERT_FAIL = 145, CNT_VERIFY_BYTE = 146, CNT_EXACT_JOBS = 147,
+       CNT_FAST_MAXCOLS = 152 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
 #define SWB_BANDW_MAX 24           // widest half-width the register-band kernel is instantiated for
 #define SWB_BANDREG_MAXROWS 320    // longest read segment it stages in shared memory
 // banded reverse pass (swb_revband.cuh): band classes as (rows below, columns right of) the main diagonal
