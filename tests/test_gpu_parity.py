@@ -227,6 +227,29 @@ def test_gpu_streamed_batch_unordered_tables(monkeypatch):
     T.compare(r2[sub].copy(), a2, ro, ao, what="streamed (shuffled pairs) vs oracle")
 
 
+def test_gpu_streamed_batch_ascii_subranges_and_masks(monkeypatch):
+    """streamed path with every optional input: ASCII sequences (encoded piece by piece on the device), per-pair
+    ref_beg / ref_len sub-ranges and explicit mask lengths"""
+    from gpuutil import gpu_align
+
+    b = T.make_pairs_fast(280000, 90, 240, seed=21, reads_per_window=30)
+    rng = np.random.default_rng(3)
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    b.reads = lut[b.reads].view(np.int8)
+    b.windows = lut[b.windows].view(np.int8)
+    b.seq_encoding = 1
+    b.ref_beg = rng.integers(0, 30, size=b.n_pairs).astype(np.int32)
+    b.ref_len = (240 - b.ref_beg - rng.integers(0, 30, size=b.n_pairs)).astype(np.int32)
+    b.mask_len = rng.integers(10, 60, size=b.n_pairs).astype(np.int32)
+    r2, a2, _ = gpu_align(b)
+    monkeypatch.setenv("SWB200_NO_PIPELINE", "1")
+    r0, a0, _ = gpu_align(b)
+    T.compare(r2, a2, r0, a0, what="streamed (ASCII, sub-ranges, masks) vs single pass")
+    sub = np.arange(0, b.n_pairs, 173)
+    ro, ao = T.oracle_parallel(b.subset(sub), threads=min(16, os.cpu_count() or 1))
+    T.compare(r2[sub].copy(), a2, ro, ao, what="streamed (ASCII, sub-ranges, masks) vs oracle")
+
+
 def test_multi_gpu_aligner_shards_and_stitches():
     """host-side sharding over several contexts (here: two contexts on the available device(s))"""
     import torch
