@@ -72,6 +72,9 @@ class SSW:
         self._profile = None
         self.read_length = 0
         self.ref_length = 0
+        # results of this aligner's recent calls: indelPost repeats alignments with identical inputs (update_read_info,
+        # pileup.pyx:849, re-runs what retarget computed at pileup.pyx:647 -- SURVEY.md 8f item 1); a hit skips the GPU round trip
+        self._memo = {}
 
     def __del__(self):  # __dealloc__, sswpy.pyx:135-147
         try:
@@ -97,6 +100,7 @@ class SSW:
         self._ref_arr = np.ascontiguousarray(_LUT[np.frombuffer(raw, dtype=np.uint8)])
         self.reference = reference
         self.ref_length = len(raw)
+        self._memo.clear()
 
     def align(self, gap_open: int = 3, gap_extension: int = 1, start_idx: int = 0, end_idx: int = 0) -> Alignment:
         """sswpy.pyx:227-304 (same checks, same order, same messages)"""
@@ -116,6 +120,10 @@ class SSW:
             raise ValueError("call setReference first")
         if not self._profile:
             raise ValueError("Must set profile first")
+        key = (self._read_arr.tobytes(), gap_open & 0xFF, gap_extension & 0xFF, start_idx, search_length)
+        hit = self._memo.get(key)
+        if hit is not None:
+            return hit
         mask_len = self.read_length // 2  # align_c, sswpy.pyx:209-211
         mask_len = 15 if mask_len < 15 else mask_len
         ref_ptr = self._ref_arr.ctypes.data + start_idx
@@ -130,6 +138,9 @@ class SSW:
             cigar = cigar_to_string(ops)
         out = Alignment(cigar, r.score1, r.score2, r.ref_begin1, r.ref_end1, r.read_begin1, r.read_end1)
         self._lib.align_destroy(res)
+        if len(self._memo) >= 256:
+            self._memo.clear()
+        self._memo[key] = out
         return out
 
 

@@ -97,6 +97,31 @@ def test_sswpy_api_matches_reference_golden():
     assert [list(o) for o in outs] == wants
 
 
+def test_sswpy_memo_returns_identical_results():
+    """repeated SSW.align calls with identical inputs are served from the aligner's memo (update_read_info
+    repeats retarget's alignment); a new reference or different penalties must not hit it"""
+    from indelpost_b200 import SSW
+
+    rng = np.random.default_rng(4)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 300))
+    read = ref[60:130] + "GG" + ref[130:200]
+    a = SSW(3, 2)
+    a.setReference(ref)
+    a.setRead(read)
+    first = a.align(3, 1)
+    assert a.align(3, 1) is first                      # memo hit: the very same tuple
+    other = a.align(5, 0)
+    assert other is not first
+    a.setRead(read[:100])
+    shorter = a.align(3, 1)
+    assert shorter != first
+    a.setRead(read)
+    assert a.align(3, 1) == first
+    a.setReference(ref[10:])
+    moved = a.align(3, 1)
+    assert moved.reference_start == first.reference_start - 10 and moved.CIGAR == first.CIGAR
+
+
 def test_c_abi_single_pair_entry_points():
     """ssw_init / ssw_align / align_destroy / init_destroy exactly as sswpy.pyx's extern block binds them"""
     import ctypes as C
