@@ -149,7 +149,7 @@ def run_reference(args):
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     cores = host_cores()
     sample_pairs = max(cores * 250, min(args.pairs, cores * 1500))
     b = T.make_pairs_fast(sample_pairs, READ_LEN, WIN_LEN, seed=1234)
@@ -172,7 +172,7 @@ def run_reference(args):
         "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
 
 
 # ----------------------------------------------------------------------------------------------
@@ -197,6 +197,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    result_line = None
     if world > 1:
         torch.cuda.set_device(local)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line there
@@ -337,10 +338,11 @@ def run_ours(args):
             "cpu_baseline": {"value": sb.cells() / cdt / 1e9, "unit": UNIT, "cores": cores, "kind": kind, "reads_per_s": sample_pairs / cdt,
                              "sample": f"{sample_pairs} pairs of the same workload, split evenly over {cores} threads"},
         }
-        print(json.dumps(line))
+        result_line = line
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return result_line
 
 
 def main():
@@ -351,10 +353,19 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line (rank 0): while the benchmark runs, file descriptor 1 points at stderr, so that
+    # banners printed by native libraries (NCCL's version line, the reference's warnings) cannot land in front of it
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
