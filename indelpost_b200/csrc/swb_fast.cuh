@@ -28,6 +28,7 @@
 // best column (ssw.c:325-333 / 530-534), mask rule and the reverse pass' "first column whose maximum
 // equals score1" (ssw.c:337/539) are resolved by a short scan after the sweep.
 #pragma once
+#include <type_traits>
 #include "swb_common.cuh"
 
 #define FAST_C      0x4000            // lane bias
@@ -161,14 +162,23 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     const uint32_t targetV = pack2(ln[0].target >= 0 ? FAST_SCALE * ln[0].target + FAST_C : 0x7fff, ln[1].target >= 0 ? FAST_SCALE * ln[1].target + FAST_C : 0x7fff);
     bool done = false;                                         // reverse pass: both lanes have hit their target
 
-    for (int t = 0; t < nsteps; ++t) {
+    // boundary of the first thread of a group as masks (loop invariants kept in registers: no per-step predicate set-up)
+    uint32_t m0 = g == 0 ? 0u : 0xffffffffu, c0 = g == 0 ? FAST_CPACK : 0u;
+    asm volatile("" : "+r"(m0), "+r"(c0));
+    // steps in which every thread of the warp is on a valid column need no range check: [G-1, smallest maxcols of the warp's groups)
+    int steadyEnd = valid ? maxcols : 0;
+    steadyEnd = min(steadyEnd, __shfl_xor_sync(FULL, steadyEnd, 16));
+    if (DIR == 1) steadyEnd = 0;                                // the reverse sweep stops early: keep it checked
+
+    auto step = [&](const int t, auto checkedTag) {
+        constexpr bool CHECKED = decltype(checkedTag)::value;
         uint32_t inH = __shfl_up_sync(FULL, outH, 1, G);
         uint32_t inF = __shfl_up_sync(FULL, outF, 1, G);
         uint32_t inV = __shfl_up_sync(FULL, outV, 1, G);
         uint32_t inRow = __shfl_up_sync(FULL, outRow, 1, G);
-        if (g == 0) { inH = FAST_CPACK; inF = FAST_CPACK; inV = 0; inRow = 0; }
+        inH = (inH & m0) | c0; inF = (inF & m0) | c0; inV &= m0; inRow &= m0;
         const int c = t - g;
-        if (c >= 0 && c < maxcols && !done) {
+        if (!CHECKED || (c >= 0 && c < maxcols && !done)) {
             const uint32_t sel = selS[c];
             uint32_t F = inF, hd = prevInH, cm = 0;
             prevInH = inH;
@@ -199,6 +209,13 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             outRow = (inRow & keep) | (lrow & ~keep);
             if (g == G - 1) { colv[c] = outV; colr[c] = outRow; }
         }
+    };
+
+    int t = 0;
+    for (; t < min(G - 1, nsteps); ++t) step(t, std::true_type{});
+    for (; t < steadyEnd; ++t) step(t, std::false_type{});
+    for (; t < nsteps; ++t) {
+        step(t, std::true_type{});
         if (DIR == 1 && (t & 31) == 31) {
             // every 32 steps: have both lanes of this group seen a column whose maximum equals score1?
             __syncwarp();
