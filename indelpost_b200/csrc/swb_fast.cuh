@@ -197,7 +197,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     E[kk] = __viaddmax_s16x2(E[kk], ngeP, hg);                   // max(E - ge, H - go)
                     F = __viaddmax_s16x2(F, ngeP, hg);                           // max(F - ge, H - go)
                 }
-                cm = __vimax3_s16x2(cm, key[0], key[1]);                         // column best over keys, two rows per ALU instruction
+                cm = k == 0 ? vmax2(key[0], key[1]) : __vimax3_s16x2(cm, key[0], key[1]);   // column best over keys, two rows per ALU instruction
             }
             outH = H[R - 1]; outF = F;
             // local column best -> (value, absolute row); merge with the rows above (they win ties)
@@ -213,6 +213,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
 
     int t = 0;
     for (; t < min(G - 1, nsteps); ++t) step(t, std::true_type{});
+#pragma unroll 4
     for (; t < steadyEnd; ++t) step(t, std::false_type{});
     for (; t < nsteps; ++t) {
         step(t, std::true_type{});
