@@ -65,6 +65,7 @@ class SSW:
     def __init__(self, match_score: int = 2, mismatch_penalty: int = 2):
         self._lib = L.load()
         self.score_matrix = dna_score_matrix(_c_int(match_score), _c_int(mismatch_penalty))  # buildDNAScoreMatrix
+        self._mkey = self.score_matrix.tobytes()
         self.read = None
         self.reference = None
         self._read_arr = None
@@ -98,6 +99,7 @@ class SSW:
     def setReference(self, reference: STR_T):  # sswpy.pyx:180-197
         raw = _to_bytes(reference)
         self._ref_arr = np.ascontiguousarray(_LUT[np.frombuffer(raw, dtype=np.uint8)])
+        self._ref_key = self._ref_arr.tobytes()
         self.reference = reference
         self.ref_length = len(raw)
         self._memo.clear()
@@ -122,6 +124,8 @@ class SSW:
             raise ValueError("Must set profile first")
         key = (self._read_arr.tobytes(), gap_open & 0xFF, gap_extension & 0xFF, start_idx, search_length)
         hit = self._memo.get(key)
+        if hit is None and _PREFETCHED:
+            hit = _PREFETCHED.get((self._mkey, self._ref_key) + key)          # filled by prefetch_alignments()
         if hit is not None:
             return hit
         mask_len = self.read_length // 2  # align_c, sswpy.pyx:209-211
@@ -239,6 +243,61 @@ def align_batch(
         r = res[k]
         out.append(Alignment(cg, int(r["score1"]), int(r["score2"]), int(r["ref_begin1"]), int(r["ref_end1"]), int(r["read_begin1"]), int(r["read_end1"])))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# prefetch: batch now, answer the per-call API from memory later
+# ---------------------------------------------------------------------------------------------
+# indelPost's control flow asks for one alignment at a time (retarget / grid_search / is_target_by_ssw), but what it
+# can ask for is known as soon as a locus' pileup is built: its reads x its windows (reference window, contig) x the
+# gap-penalty grid (varaln.pyx:1127-1143).  prefetch_alignments() computes that whole set in ONE GPU batch and
+# SSW.align() answers from it, so the unmodified per-call code runs at batch throughput.  Results are the same
+# tuples align() would compute; nothing is approximated.
+
+INDELPOST_GRID = ((3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0))          # varaln.pyx:1127-1143
+_PREFETCHED: dict = {}
+_PREFETCH_LIMIT = 4_000_000
+
+
+def clear_prefetched():
+    _PREFETCHED.clear()
+
+
+def prefetch_alignments(reads: Sequence[STR_T], references: Sequence[STR_T], pair_read=None, pair_ref=None, grid=INDELPOST_GRID,
+                        match_score: int = 3, mismatch_penalty: int = 2, device: int = 0) -> int:
+    """Align every (read, reference) pair -- all combinations if ``pair_read`` / ``pair_ref`` are None -- under every
+    (gap_open, gap_extension) of ``grid`` in one GPU batch and keep the results for ``SSW.align``.  A grid entry whose
+    gap_open is the string ``"len"`` stands for ``gap_open = len(read)`` (localn.pyx:253-255).  Returns the number of
+    alignments computed."""
+    if pair_read is None or pair_ref is None:
+        pair_read = np.repeat(np.arange(len(reads), dtype=np.int32), len(references))
+        pair_ref = np.tile(np.arange(len(references), dtype=np.int32), len(reads))
+    pr = np.asarray(pair_read, dtype=np.int32)
+    pw = np.asarray(pair_ref, dtype=np.int32)
+    n, g = pr.shape[0], len(grid)
+    if n == 0 or g == 0:
+        return 0
+    raws_r = [_to_bytes(s) for s in reads]
+    rlen = np.fromiter((len(r) for r in raws_r), dtype=np.int64, count=len(raws_r))
+    go = np.empty((g, n), dtype=np.int64)
+    ge = np.empty((g, n), dtype=np.int64)
+    for k, (o, e) in enumerate(grid):
+        go[k] = rlen[pr] if o == "len" else int(o)
+        ge[k] = rlen[pr] if e == "len" else int(e)
+    alns = align_batch(reads, references, np.tile(pr, g), np.tile(pw, g), go.reshape(-1), ge.reshape(-1),
+                       match_score=match_score, mismatch_penalty=mismatch_penalty, device=device)
+    if len(_PREFETCHED) + len(alns) > _PREFETCH_LIMIT:
+        _PREFETCHED.clear()
+    mkey = dna_score_matrix(_c_int(match_score), _c_int(mismatch_penalty)).tobytes()
+    ref_keys = [_LUT[np.frombuffer(_to_bytes(s), dtype=np.uint8)].tobytes() for s in references]
+    read_keys = [_LUT[np.frombuffer(r, dtype=np.uint8)].tobytes() for r in raws_r]
+    ref_len = [len(k) for k in ref_keys]
+    gof, gef = go.reshape(-1), ge.reshape(-1)
+    for k, a in enumerate(alns):
+        p = k % n
+        r, w = int(pr[p]), int(pw[p])
+        _PREFETCHED[(mkey, ref_keys[w], read_keys[r], int(gof[k]) & 0xFF, int(gef[k]) & 0xFF, 0, ref_len[w])] = a
+    return len(alns)
 
 
 # ---------------------------------------------------------------------------------------------

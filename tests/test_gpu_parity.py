@@ -122,6 +122,42 @@ def test_sswpy_memo_returns_identical_results():
     assert moved.reference_start == first.reference_start - 10 and moved.CIGAR == first.CIGAR
 
 
+def test_prefetch_serves_the_per_call_api():
+    """prefetch_alignments computes reads x windows x gap grid in one batch; the unmodified per-call API (make_aligner /
+    align, localn.pyx:464-472) then answers from it with exactly the tuples it would have computed"""
+    import indelpost_b200 as ip
+    from indelpost_b200 import localn, sswpy
+
+    rng = np.random.default_rng(8)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 320))
+    contig = ref[:150] + "TTGCA" + ref[150:]
+    reads = []
+    for k in range(24):
+        s0 = int(rng.integers(0, 150))
+        src = contig if k % 2 else ref
+        reads.append(src[s0: s0 + 120])
+    ip.clear_prefetched()
+    direct = {}
+    for w, win in enumerate((ref, contig)):
+        al = localn.make_aligner(win, 3, 2)
+        for r, rd in enumerate(reads[:6]):
+            for go, ge in ((3, 1), (4, 0), (len(rd), 1)):
+                direct[(w, r, go, ge)] = localn.align(al, rd, go, ge)
+    grid = sswpy.INDELPOST_GRID + (("len", 1),)
+    n = ip.prefetch_alignments(reads, [ref, contig], grid=grid, match_score=3, mismatch_penalty=2)
+    assert n == len(reads) * 2 * len(grid)
+    for w, win in enumerate((ref, contig)):
+        al = localn.make_aligner(win, 3, 2)                # a fresh aligner: its own memo is empty
+        for r, rd in enumerate(reads):
+            for go, ge in ((3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0), (len(rd), 1)):
+                got = localn.align(al, rd, go, ge)
+                key = (sswpy.dna_score_matrix(3, 2).tobytes(), al._ref_key, al._read_arr.tobytes(), go & 0xFF, ge & 0xFF, 0, len(win))
+                assert sswpy._PREFETCHED[key] is got         # served from the prefetched set
+                if (w, r, go, ge) in direct:
+                    assert got == direct[(w, r, go, ge)]
+    ip.clear_prefetched()
+
+
 def test_c_abi_single_pair_entry_points():
     """ssw_init / ssw_align / align_destroy / init_destroy exactly as sswpy.pyx's extern block binds them"""
     import ctypes as C
