@@ -234,14 +234,13 @@ def align_batch(
     )
     if n and (res["status"] != 0).any():
         raise ValueError("Problem Running alignment, see stdout")
-    out = []
-    offs = res["cigar_off"]
-    lens = res["cigar_len"]
-    for k in range(n):
-        ln = int(lens[k])
-        cg = cigar_to_string(arena[int(offs[k]) : int(offs[k]) + ln]) if ln > 0 else None
-        r = res[k]
-        out.append(Alignment(cg, int(r["score1"]), int(r["score2"]), int(r["ref_begin1"]), int(r["ref_end1"]), int(r["read_begin1"]), int(r["read_end1"])))
+    # Alignment tuples exactly like sswpy.pyx:283-298; the CIGAR tokens of the whole batch are formatted in one vectorised pass
+    # ("%d%s" per op, MAPSTR "MIDNSHP=X", ssw.h:171-190: op codes above 8 print as 'M')
+    ops_chars = np.array(list(_OPS + "M" * 7))
+    tok = np.char.add((arena >> 4).astype("U"), ops_chars[arena & 15]).tolist() if arena.shape[0] else []
+    out = [Alignment("".join(tok[o : o + l]) if l > 0 else None, a, b, c, d, e, f)
+           for o, l, a, b, c, d, e, f in zip(res["cigar_off"].tolist(), res["cigar_len"].tolist(), res["score1"].tolist(), res["score2"].tolist(),
+                                             res["ref_begin1"].tolist(), res["ref_end1"].tolist(), res["read_begin1"].tolist(), res["read_end1"].tolist())]
     return out
 
 
