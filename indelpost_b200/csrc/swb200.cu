@@ -35,6 +35,7 @@
 #include "swb_indels.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
+#define SWB_MAX_DEVICES 64
 
 // ------------------------------------------------------------------------------------------------
 // small kernels
@@ -423,8 +424,8 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t s
         int g2 = 128 / T2;
         while (g2 > 32 / T2 && (size_t)g2 * per2 > (size_t)c->smem_optin) g2 /= 2;
         if ((size_t)g2 * per2 <= (size_t)c->smem_optin) {
-            static bool attr2[2][2] = {};
-            if (!attr2[MODE][DIR]) { cudaFuncSetAttribute(k_exact2<MODE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr2[MODE][DIR] = true; }
+            static bool attr2[SWB_MAX_DEVICES] = {};          // function attributes are per device: one flag per device, not one per process
+            if (!attr2[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_exact2<MODE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr2[c->device % SWB_MAX_DEVICES] = true; }
             k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2, fewJobsLikely ? 1 : 0);
             c->tm.n_launches++;
             if (fewJobsLikely) {
@@ -466,11 +467,11 @@ static int launch_fast_one(swb_ctx* c, int bucket, int firstPair, int upperBound
     int groups = 128 / FAST_G;
     while (groups > 2 && groups * per > (size_t)c->smem_optin - 1024) groups /= 2;
     const int threads = groups * FAST_G;
-    static bool attr_set[2][SWB_NBUCKETS] = {};
-    if (!attr_set[DIR][bucket]) {
+    static bool attr_set[SWB_MAX_DEVICES] = {};               // per template instantiation and device
+    if (!attr_set[c->device % SWB_MAX_DEVICES]) {
         cudaFuncSetAttribute(k_fast<R, DIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
         cudaFuncSetAttribute(k_fast<R, DIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
-        attr_set[DIR][bucket] = true;
+        attr_set[c->device % SWB_MAX_DEVICES] = true;
     }
     const int slot = (DIR ? LIST_FAST_REV : LIST_FAST_FWD) + bucket;
     for (int off = firstPair; off < upperBoundPairs; off += slicePairs) {
@@ -529,8 +530,8 @@ static int launch_rev_band(swb_ctx* c, int upperBoundPairs) {
     CUDA_TRY(c, cudaEventRecord(c->ev_rev_fork, c->stream));
 #define SWB_REVB_LAUNCH(cls, WI, WD) { \
         const size_t smem = (size_t)revb_stride_words(rows, WI + WD + 1) * 4 * T; \
-        static bool attr = false; \
-        if (!attr) { cudaFuncSetAttribute(k_rev_band<WI, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr = true; } \
+        static bool attr[SWB_MAX_DEVICES] = {}; \
+        if (!attr[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_rev_band<WI, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr[c->device % SWB_MAX_DEVICES] = true; } \
         CUDA_TRY(c, cudaStreamWaitEvent(c->rev_stream[cls], c->ev_rev_fork, 0)); \
         k_rev_band<WI, WD><<<blocks, T, smem, c->rev_stream[cls]>>>(d, d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, rows); \
         c->tm.n_launches++; \
@@ -572,8 +573,8 @@ static int launch_band_reg_one(swb_ctx* c, int listSlot, int njobs, int nextBase
     const SwbDev& d = c->d;
     const int rows = std::min(d.max_rlen, SWB_BANDREG_MAXROWS);
     const size_t smem = (size_t)bandreg_stride_words(rows) * 4 * SWB_BANDREG_THREADS;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_band_reg<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr = true; }
+    static bool attr[SWB_MAX_DEVICES] = {};
+    if (!attr[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_band_reg<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr[c->device % SWB_MAX_DEVICES] = true; }
     k_band_reg<W><<<(njobs + SWB_BANDREG_THREADS - 1) / SWB_BANDREG_THREADS, SWB_BANDREG_THREADS, smem, st>>>(d, d.list[listSlot], njobs, nextBase, nextBaseW, resume, rows);
     c->tm.n_launches++;
     return 0;

@@ -319,7 +319,9 @@ def test_multi_gpu_aligner_shards_and_stitches():
 
     ndev = max(1, torch.cuda.device_count())
     devs = [0, 1 % ndev, 0][: 3 if ndev == 1 else 2]
-    b = T.make_pairs(3000, (40, 150), (100, 400), seed=81, reads_per_window=30, grid=True, n_rate=0.003)
+    # windows up to 1000 columns and bands up to the widest class: every kernel family needs its opt-in shared-memory size on
+    # EVERY device of the process (function attributes are per device)
+    b = T.make_pairs(3000, (40, 150), (100, 1000), seed=81, reads_per_window=30, grid=True, n_rate=0.003, max_indel=25)
     m = MultiGpuAligner(devs)
     try:
         r, a = m.align(b.reads, b.read_off, b.read_len, b.windows, b.win_off, b.win_len, b.pair_read, b.pair_win, b.gap_open, b.gap_ext,
