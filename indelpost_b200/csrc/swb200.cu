@@ -137,6 +137,7 @@ struct swb_ctx {
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
     cudaStream_t stream4 = nullptr; cudaEvent_t ev_join3; unsigned verify_pending = 0;   // second verification stream
     cudaStream_t bulk_stream = nullptr;                                     // lowest priority: the forward DPX sweep (yields SM slots to the short, latency-bound kernels of the other lane)
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy;              // streamed path: host->device copies back to back on their own stream
     cudaStream_t bulk_stream2 = nullptr;                                    // second one: consecutive forward slices of the streamed one-shot path overlap their tails
     cudaEvent_t ev_bulk_fork, ev_bulk_join, ev_bulk_join2, ev_piece;
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
@@ -224,6 +225,7 @@ extern "C" swb_ctx* swb_create(int device) {
     cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prGreatest); cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming);
     cudaStreamCreateWithPriority(&c->bulk_stream, cudaStreamNonBlocking, prLeast);
     cudaStreamCreateWithPriority(&c->bulk_stream2, cudaStreamNonBlocking, prLeast);
+    cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prGreatest); cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_bulk_join2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_piece, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_bulk_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bulk_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming);
@@ -264,6 +266,7 @@ extern "C" void swb_destroy(swb_ctx* c) {
     cudaStreamDestroy(c->stream4); cudaEventDestroy(c->ev_join3);
     cudaStreamDestroy(c->bulk_stream); cudaEventDestroy(c->ev_bulk_fork); cudaEventDestroy(c->ev_bulk_join);
     cudaStreamDestroy(c->bulk_stream2); cudaEventDestroy(c->ev_bulk_join2); cudaEventDestroy(c->ev_piece);
+    cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_copy);
     cudaEventDestroy(c->ev_rev_fork);
     for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamDestroy(c->rev_stream[i]); cudaEventDestroy(c->ev_rev_join[i]); }
     for (int i = 0; i < SWB_BANDW_MAX; ++i) { cudaStreamDestroy(c->bandw_stream[i]); cudaEventDestroy(c->ev_bandw_join[i]); }
@@ -948,12 +951,16 @@ struct TableStream {                 // upload frontier of one sequence table
 
 // make entries [front, upto] resident: their table rows, the blob bytes they cover (the resident byte interval stays
 // contiguous), then encode / validate them
-static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, int ascii) {
+// copies on the copy stream; the encode / validate kernel of the new entries is queued by the caller on the main stream
+// (after it waits for the copies) through table_encode()
+struct TableStep { int32_t i0 = 0, n = 0; };
+static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, TableStep& st) {
+    st.i0 = t.front; st.n = 0;
     if (upto < t.front) return 0;
     const int32_t i0 = t.front, n = upto - t.front + 1;
     int64_t lo = INT64_MAX, hi = 0;
     for (int32_t i = i0; i <= upto; ++i) { lo = std::min<int64_t>(lo, t.off[i]); hi = std::max<int64_t>(hi, t.off[i] + t.len[i]); }
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->copy_stream;
     auto copy = [&](int64_t a, int64_t b2) -> int {
         if (b2 <= a) return 0;
         CUDA_TRY(c, cudaMemcpyAsync(t.d_blob + a, t.blob + a, (size_t)(b2 - a), cudaMemcpyHostToDevice, s));
@@ -970,9 +977,14 @@ static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, int ascii) {
     CUDA_TRY(c, cudaMemcpyAsync(t.d_off + i0, t.off + i0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(c, cudaMemcpyAsync(t.d_len + i0, t.len + i0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     c->tm.h2d_bytes += (int64_t)n * 12;
-    k_encode_validate<<<(n + 3) / 4, 128, 0, s>>>(t.d_blob, t.d_off + i0, t.d_len + i0, n, c->d.n, ascii, t.d_bad + i0, 0);
-    c->tm.n_launches++;
+    st.n = n;
     t.front = upto + 1;
+    return 0;
+}
+static int table_encode(swb_ctx* c, TableStream& t, const TableStep& st, int ascii) {
+    if (st.n <= 0) return 0;
+    k_encode_validate<<<(st.n + 3) / 4, 128, 0, c->stream>>>(t.d_blob, t.d_off + st.i0, t.d_len + st.i0, st.n, c->d.n, ascii, t.d_bad + st.i0, 0);
+    c->tm.n_launches++;
     return 0;
 }
 
@@ -1010,9 +1022,12 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     set_batch_scalars(c, b, v, max_rl, max_wl);
     const int ascii = b->seq_encoding == SWB_SEQ_ASCII;
     cudaStream_t s = c->stream;
-    CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D0], s));
     if (up(c, c->b_mat, b->mat, (size_t)b->n * b->n, &d.mat)) return -1;
     if (compute_setup(c)) return -1;
+    // the copy stream starts after whatever the main stream still had queued on these buffers
+    CUDA_TRY(c, cudaEventRecord(c->ev_copy, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D0], c->copy_stream));
     swb_timing& tm = c->tm;
 
     TableStream tr, tw;
@@ -1021,11 +1036,29 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     tw.blob = b->windows; tw.off = b->win_off; tw.len = b->win_len; tw.n = b->n_windows;
     tw.d_blob = d.windows; tw.d_off = d.win_off; tw.d_len = d.win_len; tw.d_bad = (uint8_t*)c->b_wbad.p;
 
-    // piece boundaries: small first pieces (the sweep starts early), growing by 1.3x -- slower than the ratio of the
-    // sweep's to the copy's throughput, so the copies stay ahead -- up to an eighth of the batch
+    // piece boundaries: small first pieces (the sweep starts early), growing by 1.3x -- slower than the ratio of the sweep's to
+    // the copy's throughput, so the copies stay ahead -- up to an eighth of the batch, and shrinking again at the end: the sweep
+    // of the last piece cannot start before the last byte has arrived, so that piece should be short
     std::vector<int64_t> bounds(1, 0);
-    { double sz = std::max<double>(16384.0, (double)np / 48.0); const double cap = std::max<double>(32768.0, (double)np / 8.0);
-      while (bounds.back() < (int64_t)np) { int64_t nx = bounds.back() + ((int64_t)sz & ~(int64_t)1); if ((int64_t)np - nx < (int64_t)sz / 2) nx = (int64_t)np; bounds.push_back(std::min<int64_t>(nx, (int64_t)np)); sz = std::min(cap, sz * 1.3); } }
+    {
+        const double lo = std::max<double>(16384.0, (double)np / 48.0), cap = std::max<double>(32768.0, (double)np / 8.0);
+        std::vector<int64_t> ramp;
+        int64_t rampSum = 0;
+        for (double sz = lo; sz < cap; sz *= 1.3) { ramp.push_back((int64_t)sz & ~(int64_t)1); rampSum += ramp.back(); }
+        std::vector<int64_t> sizes;
+        if (2 * rampSum >= (int64_t)np) {                      // small batch: a single ramp up
+            int64_t left = (int64_t)np;
+            for (size_t k = 0; left > 0; ++k) { int64_t szk = k < ramp.size() ? ramp[k] : (int64_t)cap; if (left - szk < szk / 2) szk = left; sizes.push_back(szk); left -= szk; }
+        } else {
+            sizes = ramp;
+            int64_t mid = (int64_t)np - 2 * rampSum;
+            const int nmid = (int)std::max<int64_t>(1, (mid + (int64_t)cap - 1) / (int64_t)cap);
+            for (int k = 0; k < nmid; ++k) { const int64_t szk = k + 1 == nmid ? mid : ((mid / (nmid - k)) & ~(int64_t)1); sizes.push_back(szk); mid -= szk; }
+            for (size_t k = ramp.size(); k-- > 0; ) sizes.push_back(ramp[k]);
+        }
+        for (int64_t szk : sizes) if (szk > 0) bounds.push_back(std::min<int64_t>(bounds.back() + szk, (int64_t)np));
+        bounds.back() = (int64_t)np;
+    }
     const int npieces = (int)bounds.size() - 1;
 
     int done[SWB_NBUCKETS] = {};
@@ -1040,20 +1073,27 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
             if ((uint32_t)r < (uint32_t)b->n_reads) rmax = std::max(rmax, r);
             if ((uint32_t)w < (uint32_t)b->n_windows) wmax = std::max(wmax, w);
         }
-        if (table_advance(c, tr, rmax, ascii) || table_advance(c, tw, wmax, ascii)) return -1;
+        TableStep sr, sw;
+        if (table_advance(c, tr, rmax, sr) || table_advance(c, tw, wmax, sw)) return -1;
         const size_t n = (size_t)(p1 - p0);
-        CUDA_TRY(c, cudaMemcpyAsync(d.pair_read + p0, b->pair_read + p0, n * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(d.pair_win + p0, b->pair_win + p0, n * 4, cudaMemcpyHostToDevice, s));
-        if (b->ref_beg) CUDA_TRY(c, cudaMemcpyAsync(d.ref_beg + p0, b->ref_beg + p0, n * 4, cudaMemcpyHostToDevice, s));
-        if (b->ref_len) CUDA_TRY(c, cudaMemcpyAsync(d.ref_len + p0, b->ref_len + p0, n * 4, cudaMemcpyHostToDevice, s));
-        if (b->mask_len) CUDA_TRY(c, cudaMemcpyAsync(d.mask_len + p0, b->mask_len + p0, n * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(d.gap_open + p0, b->gap_open + p0, n, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(d.gap_ext + p0, b->gap_ext + p0, n, cudaMemcpyHostToDevice, s));
+        cudaStream_t cs = c->copy_stream;
+        CUDA_TRY(c, cudaMemcpyAsync(d.pair_read + p0, b->pair_read + p0, n * 4, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(c, cudaMemcpyAsync(d.pair_win + p0, b->pair_win + p0, n * 4, cudaMemcpyHostToDevice, cs));
+        if (b->ref_beg) CUDA_TRY(c, cudaMemcpyAsync(d.ref_beg + p0, b->ref_beg + p0, n * 4, cudaMemcpyHostToDevice, cs));
+        if (b->ref_len) CUDA_TRY(c, cudaMemcpyAsync(d.ref_len + p0, b->ref_len + p0, n * 4, cudaMemcpyHostToDevice, cs));
+        if (b->mask_len) CUDA_TRY(c, cudaMemcpyAsync(d.mask_len + p0, b->mask_len + p0, n * 4, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(c, cudaMemcpyAsync(d.gap_open + p0, b->gap_open + p0, n, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(c, cudaMemcpyAsync(d.gap_ext + p0, b->gap_ext + p0, n, cudaMemcpyHostToDevice, cs));
         tm.h2d_bytes += (int64_t)n * (10 + (b->ref_beg ? 4 : 0) + (b->ref_len ? 4 : 0) + (b->mask_len ? 4 : 0));
+        if (k + 1 == npieces) CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], cs));
+        // the piece's kernels wait for its copies; the copy stream itself runs on to the next piece
+        CUDA_TRY(c, cudaEventRecord(c->ev_copy, cs));
+        CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_copy, 0));
+        if (table_encode(c, tr, sr, ascii) || table_encode(c, tw, sw, ascii)) return -1;
         k_prepare<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, p0, p1);
         tm.n_launches++;
         CUDA_TRY(c, cudaGetLastError());
-        if (k + 1 == npieces) { CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], s)); CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s)); }
+        if (k + 1 == npieces) CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
         // fast-list lengths after this piece, into the snapshot buffer of its parity; the sweep streams wait on the same event
         CUDA_TRY(c, cudaMemcpyAsync(c->h_snap[k & 1], d.counters, SWB_NCOUNTERS * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(c, cudaEventRecord(c->ev_snap[k & 1], s));
