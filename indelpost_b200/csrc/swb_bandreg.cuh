@@ -39,21 +39,28 @@ __device__ __forceinline__ uint32_t bandreg_sel(uint32_t rc, int one) { return r
 // one DP cell (ssw.c:637-664).  hUp/eUp: upper neighbour, hDiag: diagonal neighbour, hLeft/f: left neighbour state.
 // Returns H; writes E back through eOut; ORs the 4-bit direction code (bit0: E opened from H, bit1: F opened from H,
 // bits 2-3: 0 diagonal / 1 E / 2 F) into `word` at nibble NIB (a constant after unrolling).
-__device__ __forceinline__ int bandreg_cell(const int NIB, int hUp, int eUp, int hDiag, int hLeft, int& f, int& eOut, int sc, int go, int ge, uint32_t& word)
+// CHAIN: gap_open >= gap_extension, the usual case: the F value handed to the next cell, max(f - ge, h - go), then equals
+// max(f - ge, max(e1, m) - go) -- h - go adds only f1 - go <= max(f - ge, -go) and max(e1, m) >= 0 -- so the row's serial
+// dependency is ONE add-max per cell and everything else (H, the direction bits) hangs off it.  fNext carries that value; the
+// F of THIS cell (f) is still formed exactly as the reference does, from hLeft and the previous f, for the direction bit.
+template <bool CHAIN>
+__device__ __forceinline__ int bandreg_cell(const int NIB, int hUp, int eUp, int hDiag, int hLeft, int& f, int& fNext, int& eOut, int sc, int go, int ge, uint32_t& word)
 {
     int a = hUp - go, b = eUp - ge;                       // ssw.c:644-648
     const int ev = a > b ? a : b;
     uint32_t bits = a > b ? (1u << (4 * NIB)) : 0u;
     eOut = ev;
     a = hLeft - go; b = f - ge;                           // ssw.c:650-653
-    f = a > b ? a : b;
+    const int fv = CHAIN ? fNext : (a > b ? a : b);
     bits |= a > b ? (2u << (4 * NIB)) : 0u;
-    const int e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;   // ssw.c:655-659
+    const int e1 = ev > 0 ? ev : 0, f1 = fv > 0 ? fv : 0; // ssw.c:655-659
     const int gmax = e1 > f1 ? e1 : f1;
     const int m = hDiag + sc;
     const int h = gmax > m ? gmax : m;
     const uint32_t selv = gmax <= m ? 0u : (e1 > f1 ? (4u << (4 * NIB)) : (8u << (4 * NIB)));   // ssw.c:663-664
     word |= bits | selv;
+    if (CHAIN) { const int w = (e1 > m ? e1 : m) - go; const int x = fv - ge; fNext = x > w ? x : w; }
+    f = fv;
     return h;
 }
 
@@ -106,6 +113,70 @@ __device__ __forceinline__ int bandreg_traceback(const uint32_t* __restrict__ di
         band_push(ops, (1u << 4) | 0u, out, total);
     }
     return ops.n;
+}
+
+// The DP of one band width (ssw.c:612-667) over the staged sequences; returns the running maximum, writes the packed
+// direction rows to `dir`.  CHAIN: see bandreg_cell.
+template <int W, bool CHAIN>
+__device__ __forceinline__ int bandreg_dp(const BandGeom& g, const uint8_t* selT, const uint8_t* rowT, const unsigned long long* s_rowTab,
+                                          const int go, const int ge, const int one, uint32_t* __restrict__ dir, int best, long long& cells)
+{
+    constexpr int NX = 2 * W + 1;
+    constexpr int NW = (NX + 7) / 8;                      // direction words per row
+    int Hs[NX], Es[NX];
+#pragma unroll
+    for (int x = 0; x < NX; ++x) { Hs[x] = 0; Es[x] = 0; }
+
+    // ---- rows 0 .. W: slot x = column x, cells x <= i + W ---------------------------------------------------------
+    const int rowsA = min(W + 1, g.readLen);
+    for (int i = 0; i < rowsA; ++i) {
+        const unsigned long long tab = s_rowTab[rowT[i]];
+        const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
+        uint32_t words[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) words[k] = 0;
+        int f = 0, fNext = CHAIN ? -ge : 0, hLeft = 0, hDiag = 0;     // ssw.c:633: f = h_c[0] = 0, so the first cell's F is max(-go, -ge)
+        const int lim = i + W;                              // regular jobs: lim <= 2W <= refLen - 2, no clipping here
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+            if (x <= lim) {
+                const int hUp = Hs[x], eUp = Es[x];
+                const int sc = (int)prmt(tabLo, tabHi, bandreg_sel(selT[x], one));
+                const int h = bandreg_cell<CHAIN>(x & 7, hUp, eUp, hDiag, hLeft, f, fNext, Es[x], sc, go, ge, words[x >> 3]);
+                Hs[x] = h;
+                best = max(best, h);                        // ssw.c:661
+                hDiag = hUp; hLeft = h;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k) dir[(size_t)i * NW + k] = words[k];
+        cells += lim + 1;
+    }
+
+    // ---- rows W+1 .. readLen-1: slot x = column x + i - W --------------------------------------------------------
+    for (int i = W + 1; i < g.readLen; ++i) {
+        const unsigned long long tab = s_rowTab[rowT[i]];
+        const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
+        const uint8_t* sp = selT + (i - W);
+        uint32_t words[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) words[k] = 0;
+        int f = 0, fNext = CHAIN ? -ge : 0, hLeft = 0;
+        const int xmax = g.refLen - 1 - (i - W);            // last slot inside the matrix (>= 2W: row not clipped)
+#pragma unroll
+        for (int x = 0; x < NX; ++x) {
+            const int hUp = x + 1 < NX ? Hs[x + 1] : 0, eUp = x + 1 < NX ? Es[x + 1] : 0;
+            const int sc = (int)prmt(tabLo, tabHi, bandreg_sel(sp[x], one));
+            const int h = bandreg_cell<CHAIN>(x & 7, hUp, eUp, Hs[x], hLeft, f, fNext, Es[x], sc, go, ge, words[x >> 3]);
+            Hs[x] = h;
+            if (x <= xmax) best = max(best, h);
+            hLeft = h;
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k) dir[(size_t)i * NW + k] = words[k];
+        cells += min(xmax, 2 * W) + 1;
+    }
+    return best;
 }
 
 template <int W>
@@ -166,61 +237,11 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     }
     uint32_t* dir = reinterpret_cast<uint32_t*>(d.band + off);
 
-    int Hs[NX], Es[NX];
-#pragma unroll
-    for (int x = 0; x < NX; ++x) { Hs[x] = 0; Es[x] = 0; }
-    int best = resume ? d.t_best[p] : 0;                   // a widened job carries its running maximum along (ssw.c:661 is not reset)
     long long cells = 0;
-
-    // ---- rows 0 .. W: slot x = column x, cells x <= i + W ---------------------------------------------------------
-    const int rowsA = min(W + 1, g.readLen);
-    for (int i = 0; i < rowsA; ++i) {
-        const unsigned long long tab = s_rowTab[rowT[i]];
-        const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
-        uint32_t words[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) words[k] = 0;
-        int f = 0, hLeft = 0, hDiag = 0;
-        const int lim = i + W;                              // regular jobs: lim <= 2W <= refLen - 2, no clipping here
-#pragma unroll
-        for (int x = 0; x < NX; ++x) {
-            if (x <= lim) {
-                const int hUp = Hs[x], eUp = Es[x];
-                const int sc = (int)prmt(tabLo, tabHi, bandreg_sel(selT[x], d.one));
-                const int h = bandreg_cell(x & 7, hUp, eUp, hDiag, hLeft, f, Es[x], sc, go, ge, words[x >> 3]);
-                Hs[x] = h;
-                best = max(best, h);                        // ssw.c:661
-                hDiag = hUp; hLeft = h;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NW; ++k) dir[(size_t)i * NW + k] = words[k];
-        cells += lim + 1;
-    }
-
-    // ---- rows W+1 .. readLen-1: slot x = column x + i - W --------------------------------------------------------
-    for (int i = W + 1; i < g.readLen; ++i) {
-        const unsigned long long tab = s_rowTab[rowT[i]];
-        const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
-        const uint8_t* sp = selT + (i - W);
-        uint32_t words[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) words[k] = 0;
-        int f = 0, hLeft = 0;
-        const int xmax = g.refLen - 1 - (i - W);            // last slot inside the matrix (>= 2W: row not clipped)
-#pragma unroll
-        for (int x = 0; x < NX; ++x) {
-            const int hUp = x + 1 < NX ? Hs[x + 1] : 0, eUp = x + 1 < NX ? Es[x + 1] : 0;
-            const int sc = (int)prmt(tabLo, tabHi, bandreg_sel(sp[x], d.one));
-            const int h = bandreg_cell(x & 7, hUp, eUp, Hs[x], hLeft, f, Es[x], sc, go, ge, words[x >> 3]);
-            Hs[x] = h;
-            if (x <= xmax) best = max(best, h);
-            hLeft = h;
-        }
-#pragma unroll
-        for (int k = 0; k < NW; ++k) dir[(size_t)i * NW + k] = words[k];
-        cells += min(xmax, 2 * W) + 1;
-    }
+    // a widened job carries its running maximum along (ssw.c:661 is not reset)
+    const int best0 = resume ? d.t_best[p] : 0;
+    const int best = go >= ge ? bandreg_dp<W, true>(g, selT, rowT, s_rowTab, go, ge, d.one, dir, best0, cells)
+                              : bandreg_dp<W, false>(g, selT, rowT, s_rowTab, go, ge, d.one, dir, best0, cells);
     warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
 
     if (best < score && W * 2 <= len) {                     // ssw.c:668-669: widen and redo in the next round

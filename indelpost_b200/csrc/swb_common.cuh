@@ -138,17 +138,23 @@ __device__ __forceinline__ void for_each_byte16(const int8_t* ptr, int len, F f)
     const int mis = (int)(a & 15);
     const uint4* base = reinterpret_cast<const uint4*>(a - mis);
     const int nch = (mis + len + 15) >> 4;
-#pragma unroll 2
-    for (int ch = 0; ch < nch; ++ch) {
-        const uint4 v = __ldg(base + ch);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        const int i0 = ch * 16 - mis;
-        if (i0 >= 0 && i0 + 16 <= len) {
+    // four chunks in flight: the thread-per-alignment kernels run at low occupancy, so the staging is as long as its loads' latency
+    for (int ch0 = 0; ch0 < nch; ch0 += 4) {
+        uint4 v[4];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) f(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
-        } else {
+        for (int u = 0; u < 4; ++u) if (ch0 + u < nch) v[u] = __ldg(base + ch0 + u);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) if ((unsigned)(i0 + q) < (unsigned)len) f(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+        for (int u = 0; u < 4; ++u) {
+            if (ch0 + u >= nch) break;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            const int i0 = (ch0 + u) * 16 - mis;
+            if (i0 >= 0 && i0 + 16 <= len) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) f(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) if ((unsigned)(i0 + q) < (unsigned)len) f(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            }
         }
     }
 }

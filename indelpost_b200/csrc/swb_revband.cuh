@@ -122,12 +122,14 @@ k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict
             for (int k = 0; k < M; ++k) {
                 const uint32_t s = prmt(tA, tB, sp[k]);
                 const uint32_t vin = k + 1 < M ? V[k + 1] : FAST_CPACK;
-                uint32_t h = __viaddmax_s16x2(H[k], s, vin);                 // max(Hdiag + s, V)
-                h = __vimax3_s16x2(h, G, FAST_CPACK);                        // max(., G, 0)
+                const uint32_t t = __viaddmax_s16x2(H[k], s, vin);           // max(Hdiag + s, V)
+                const uint32_t h = __vimax3_s16x2(t, G, FAST_CPACK);         // max(., G, 0)
                 H[k] = h;
                 const uint32_t hg = h - goP;                                 // no lane borrow: h >= 0x4000 > 16*go
                 V[k] = __viaddmax_s16x2(vin, ngeP, hg);                      // vertical-gap state of the cell below
-                G = __viaddmax_s16x2(G, ngeP, hg);                           // horizontal-gap state of the cell to the right
+                // horizontal-gap state of the cell to the right: max(G - ge, h - go) = max(G - ge, max(t, 0) - go) because
+                // G - go <= G - ge (go > ge on the fast path): the row's serial chain is ONE instruction per cell, h is off it
+                G = __viaddmax_s16x2(G, ngeP, vmax2(t, FAST_CPACK) - goP);
                 rm = vmax2(rm, h);
             }
         }
