@@ -702,6 +702,30 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
     return 0;
 }
 
+// the part of the workspace whose size depends on the longest read / window of the batch (only the stages after the forward
+// sweeps use it, so the streamed path can size it once it has seen every table entry)
+static int compute_setup_lens(swb_ctx* c) {
+    SwbDev& d = c->d;
+    const size_t np = (size_t)d.n_pairs;
+    d.colmax_stride = (d.max_wlen + 7) & ~7;
+    CUDA_TRY(c, c->b_colmax.ensure(np * (size_t)d.colmax_stride * 2 + 16)); d.colmax = (uint16_t*)c->b_colmax.p;
+    // the fast path keeps 10 bytes per window column per lane-pair in shared memory
+    d.fast_max_cols = 16384;     // selectors (2 B/column/lane pair) must fit shared memory; column bests move to global memory beyond 1024 columns
+    {
+        // direction-byte scratch: enough for a typical band on every pair; pairs that do not fit are
+        // deferred to the next round by the kernel itself
+        size_t want = std::max<size_t>((size_t)64 << 20, np * (size_t)(d.max_rlen + 8) * 12);
+        want = std::min<size_t>(want, (size_t)8 << 30);
+        if (c->b_band.cap < want) CUDA_TRY(c, c->b_band.ensure(want));
+        d.band = (uint8_t*)c->b_band.p; d.band_cap = (int64_t)c->b_band.cap;
+        size_t cw = std::max<size_t>(4096, np * 16);
+        if (c->b_cigar.cap < cw * 4) CUDA_TRY(c, c->b_cigar.ensure(cw * 4));
+        d.cigar = (uint32_t*)c->b_cigar.p; d.cigar_cap = (int64_t)(c->b_cigar.cap / 4);
+    }
+
+    return 0;
+}
+
 // workspace for the batch described by c->d (grow-only buffers), counters cleared, start event recorded
 static int compute_setup(swb_ctx* c) {
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -729,21 +753,7 @@ static int compute_setup(swb_ctx* c) {
     CUDA_TRY(c, c->b_tbest.ensure(np * 4 + 16));  d.t_best = (int32_t*)c->b_tbest.p;
     CUDA_TRY(c, c->b_rbad.ensure((size_t)d.n_reads + 16));
     CUDA_TRY(c, c->b_wbad.ensure((size_t)d.n_windows + 16));
-    d.colmax_stride = (d.max_wlen + 7) & ~7;
-    CUDA_TRY(c, c->b_colmax.ensure(np * (size_t)d.colmax_stride * 2 + 16)); d.colmax = (uint16_t*)c->b_colmax.p;
-    // the fast path keeps 10 bytes per window column per lane-pair in shared memory
-    d.fast_max_cols = 16384;     // selectors (2 B/column/lane pair) must fit shared memory; column bests move to global memory beyond 1024 columns
-    {
-        // direction-byte scratch: enough for a typical band on every pair; pairs that do not fit are
-        // deferred to the next round by the kernel itself
-        size_t want = std::max<size_t>((size_t)64 << 20, np * (size_t)(d.max_rlen + 8) * 12);
-        want = std::min<size_t>(want, (size_t)8 << 30);
-        if (c->b_band.cap < want) CUDA_TRY(c, c->b_band.ensure(want));
-        d.band = (uint8_t*)c->b_band.p; d.band_cap = (int64_t)c->b_band.cap;
-        size_t cw = std::max<size_t>(4096, np * 16);
-        if (c->b_cigar.cap < cw * 4) CUDA_TRY(c, c->b_cigar.ensure(cw * 4));
-        d.cigar = (uint32_t*)c->b_cigar.p; d.cigar_cap = (int64_t)(c->b_cigar.cap / 4);
-    }
+    if (compute_setup_lens(c)) return -1;
 
     cudaStream_t s = c->stream;
     TR(c, "compute_begin");
@@ -945,6 +955,8 @@ static bool scan_tables(const swb_batch* b, int64_t& reads_bytes, int32_t& max_r
 struct TableStream {                 // upload frontier of one sequence table
     const int8_t* blob; const int64_t* off; const int32_t* len; int32_t n;
     int8_t* d_blob; int64_t* d_off; int32_t* d_len; uint8_t* d_bad;
+    int64_t cap = 0;                 // bytes the device blob can hold
+    int32_t maxlen = 0;              // longest entry seen so far
     int32_t front = 0;               // entries [0, front) are on the device
     int64_t ulo = 0, uhi = 0;        // blob bytes [ulo, uhi) are on the device
 };
@@ -959,7 +971,14 @@ static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, TableStep& st
     if (upto < t.front) return 0;
     const int32_t i0 = t.front, n = upto - t.front + 1;
     int64_t lo = INT64_MAX, hi = 0;
-    for (int32_t i = i0; i <= upto; ++i) { lo = std::min<int64_t>(lo, t.off[i]); hi = std::max<int64_t>(hi, t.off[i] + t.len[i]); }
+    int64_t minoff = 0; int32_t minlen = 0, ml = t.maxlen;
+    for (int32_t i = i0; i <= upto; ++i) {
+        const int64_t o = t.off[i]; const int32_t l = t.len[i];
+        lo = std::min<int64_t>(lo, o); hi = std::max<int64_t>(hi, o + l); minoff = std::min(minoff, o); minlen = std::min(minlen, l); ml = std::max(ml, l);
+    }
+    if (minoff < 0 || minlen < 0) { c->err = "negative sequence offset/length"; return -1; }
+    t.maxlen = ml;
+    if (hi > t.cap) return -3;                              // the blob outgrew the buffer sized from the previous call: the caller restarts with a full scan
     cudaStream_t s = c->copy_stream;
     auto copy = [&](int64_t a, int64_t b2) -> int {
         if (b2 <= a) return 0;
@@ -988,7 +1007,9 @@ static int table_encode(swb_ctx* c, TableStream& t, const TableStep& st, int asc
     return 0;
 }
 
-static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used) {
+// forceScan = false: trust the buffer capacities left by the previous call (steady state: the same kind of batch again) and
+// check every piece against them; returns -3 if a blob does not fit, the caller then repeats the call with forceScan = true
+static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used, bool forceScan) {
     c->err.clear();
     c->have_batch = false; c->computed = false; c->pipelined_last = false;
     if (b->n < 1 || b->n > SWB_MAX_N || !b->mat) { c->err = "substitution matrix edge n must be in [1, 32]"; return -1; }
@@ -999,7 +1020,12 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     memset(&c->tm, 0, sizeof c->tm);
     TR(c, "stream_begin");
     int64_t reads_bytes = 0, win_bytes = 0; int32_t max_rl = 0, max_wl = 0;
-    if (!scan_tables(b, reads_bytes, max_rl, win_bytes, max_wl)) { c->err = "negative sequence offset/length"; return -1; }
+    const bool scan = forceScan || c->b_reads.cap < 64 || c->b_windows.cap < 64;
+    if (scan) {
+        if (!scan_tables(b, reads_bytes, max_rl, win_bytes, max_wl)) { c->err = "negative sequence offset/length"; return -1; }
+    } else {
+        reads_bytes = (int64_t)c->b_reads.cap - 16; win_bytes = (int64_t)c->b_windows.cap - 16;      // what is already there; lengths follow from the pieces
+    }
     TR(c, "tables_scanned");
     const size_t np = (size_t)b->n_pairs, nr = (size_t)b->n_reads, nw = (size_t)b->n_windows;
 
@@ -1035,6 +1061,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     tr.d_blob = d.reads; tr.d_off = d.read_off; tr.d_len = d.read_len; tr.d_bad = (uint8_t*)c->b_rbad.p;
     tw.blob = b->windows; tw.off = b->win_off; tw.len = b->win_len; tw.n = b->n_windows;
     tw.d_blob = d.windows; tw.d_off = d.win_off; tw.d_len = d.win_len; tw.d_bad = (uint8_t*)c->b_wbad.p;
+    tr.cap = reads_bytes; tw.cap = win_bytes;
 
     // piece boundaries: small first pieces (the sweep starts early), growing by 1.3x -- slower than the ratio of the sweep's to
     // the copy's throughput, so the copies stay ahead -- up to an eighth of the batch, and shrinking again at the end: the sweep
@@ -1074,7 +1101,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
             if ((uint32_t)w < (uint32_t)b->n_windows) wmax = std::max(wmax, w);
         }
         TableStep sr, sw;
-        if (table_advance(c, tr, rmax, sr) || table_advance(c, tw, wmax, sw)) return -1;
+        { const int e1 = table_advance(c, tr, rmax, sr); if (e1) return e1; const int e2 = table_advance(c, tw, wmax, sw); if (e2) return e2; }
         const size_t n = (size_t)(p1 - p0);
         cudaStream_t cs = c->copy_stream;
         CUDA_TRY(c, cudaMemcpyAsync(d.pair_read + p0, b->pair_read + p0, n * 4, cudaMemcpyHostToDevice, cs));
@@ -1099,10 +1126,10 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
         CUDA_TRY(c, cudaEventRecord(c->ev_snap[k & 1], s));
         return 0;
     };
-    if (npieces > 0 && enqueue_piece(0)) return -1;
+    if (npieces > 0) { const int e0 = enqueue_piece(0); if (e0) return e0; }
     for (int k = 0; k < npieces; ++k) {
         const bool last = k + 1 == npieces;
-        if (!last && enqueue_piece(k + 1)) return -1;
+        if (!last) { const int e1 = enqueue_piece(k + 1); if (e1) return e1; }
         CUDA_TRY(c, cudaEventSynchronize(c->ev_snap[k & 1]));
         TR(c, "piece_ready");
         const int32_t* hc = c->h_snap[k & 1];
@@ -1128,6 +1155,10 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_bulk_join2, 0)); }
     // only the table entries some pair refers to are resident: a later swb_compute on this context must not touch the rest
     d.n_reads = tr.front; d.n_windows = tw.front;
+    if (!scan) {                                            // lengths as seen by the pieces (every entry a pair refers to)
+        d.max_rlen = tr.maxlen; d.max_wlen = tw.maxlen;
+        if (compute_setup_lens(c)) return -1;
+    }
     d.seq_encoding = SWB_SEQ_CODES;
     c->have_batch = true;
     int nFastTotal = 0;
@@ -1228,7 +1259,12 @@ extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* resul
     const bool off = (mode && !strcmp(mode, "off")) || getenv("SWB200_NO_PIPELINE");
     if (b && !off && !lanes && b->n_pairs >= 262144 && b->n_reads > 0 && b->n_windows > 0) {
         if (g_trace) c->trace.clear();
-        const int rc = align_batch_streamed(c, b, results, cigar_arena, cigar_cap, cigar_used);
+        int rc = align_batch_streamed(c, b, results, cigar_arena, cigar_cap, cigar_used, getenv("SWB200_ALWAYS_SCAN") != nullptr);
+        if (rc == -3) {
+            // a sequence blob larger than the buffers of the previous call: let everything queued so far drain, then size exactly
+            cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->bulk_stream); cudaStreamSynchronize(c->bulk_stream2);
+            rc = align_batch_streamed(c, b, results, cigar_arena, cigar_cap, cigar_used, true);
+        }
         if (g_trace) { fprintf(stderr, "TRACE streamed:"); for (auto& e : c->trace) fprintf(stderr, " %s@%.2f", e.first, e.second - t_call); fprintf(stderr, " end@%.2f\n", now_ms() - t_call); }
         return rc;
     }
