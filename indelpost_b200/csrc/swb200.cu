@@ -62,6 +62,43 @@ __global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_
     if (lane == 0) bad[w] = (b ? 1 : 0) | (hi ? 2 : 0);
 }
 
+// codes-only variant of k_encode_validate (nothing to rewrite): 8 lanes per sequence, aligned 16-byte loads, byte-parallel
+// range tests.  bad[s] as above.
+__global__ void k_validate_codes(const int8_t* __restrict__ blob, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int32_t nseq, int n, uint8_t* bad, int64_t byte_base)
+{
+    const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);
+    bool b = false, hi = false;
+    if (sidx < nseq) {
+        const int8_t* s = blob + (off[sidx] - byte_base);
+        const int L = len[sidx];
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        const int mis = (int)(a & 15);
+        const uint4* base = reinterpret_cast<const uint4*>(a - mis);
+        const int nch = (mis + L + 15) >> 4;
+        const uint32_t nn = (uint32_t)n * 0x01010101u;
+        for (int ch = sub; ch < nch; ch += 8) {
+            const uint4 v = __ldg(base + ch);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const int i0 = ch * 16 - mis;                   // sequence index of this chunk's first byte
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                // keep only the bytes that belong to the sequence (the others read as code 0)
+                uint32_t keep = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if ((unsigned)(i0 + 4 * q + k) < (unsigned)L) keep |= 0xffu << (8 * k);
+                const uint32_t x = w[q] & keep;
+                if (__vcmpgeu4(x, nn)) b = true;            // unsigned compare: negative codes are >= 128
+                if (__vcmpgeu4(x, 0x04040404u)) hi = true;
+            }
+        }
+    }
+    b = (__ballot_sync(0xffffffffu, b) & gm) != 0;
+    hi = (__ballot_sync(0xffffffffu, hi) & gm) != 0;
+    if (sidx < nseq && sub == 0) bad[sidx] = (b ? 1 : 0) | (hi ? 2 : 0);
+}
+
 __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_bad, int32_t p0, int32_t p1)
 {
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,6 +440,16 @@ static int read_counters(swb_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->h_bump, c->d.bump, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     TR(c, "counters");
+    return 0;
+}
+
+// sequence table -> codes in place (ASCII input) + per-sequence validity flags
+static int launch_validate(swb_ctx* c, int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int ascii, uint8_t* bad, int64_t byte_base, cudaStream_t st) {
+    if (nseq <= 0) return 0;
+    if (ascii) k_encode_validate<<<(nseq + 3) / 4, 128, 0, st>>>(blob, off, len, nseq, c->d.n, 1, bad, byte_base);
+    else k_validate_codes<<<(nseq + 15) / 16, 128, 0, st>>>(blob, off, len, nseq, c->d.n, bad, byte_base);
+    c->tm.n_launches++;
+    CUDA_TRY(c, cudaGetLastError());
     return 0;
 }
 
@@ -856,8 +903,8 @@ static int swb_compute_impl(swb_ctx* c) {
     swb_timing& tm = c->tm;
     cudaStream_t s = c->stream;
     // ---- prepare ------------------------------------------------------------------------------
-    if (d.n_reads) { k_encode_validate<<<(d.n_reads + 3) / 4, 128, 0, s>>>(d.reads, d.read_off, d.read_len, d.n_reads, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p, d.rbyte_base); tm.n_launches++; }
-    if (d.n_windows) { k_encode_validate<<<(d.n_windows + 3) / 4, 128, 0, s>>>(d.windows, d.win_off, d.win_len, d.n_windows, d.n, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p, d.wbyte_base); tm.n_launches++; }
+    if (launch_validate(c, d.reads, d.read_off, d.read_len, d.n_reads, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p, d.rbyte_base, s)) return -1;
+    if (launch_validate(c, d.windows, d.win_off, d.win_len, d.n_windows, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p, d.wbyte_base, s)) return -1;
     d.seq_encoding = SWB_SEQ_CODES;                         // tables are codes from now on (repeat computes must not re-encode)
     if (np) { k_prepare<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, 0, (int32_t)np); tm.n_launches++; }
     CUDA_TRY(c, cudaGetLastError());
@@ -1002,9 +1049,7 @@ static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, TableStep& st
 }
 static int table_encode(swb_ctx* c, TableStream& t, const TableStep& st, int ascii) {
     if (st.n <= 0) return 0;
-    k_encode_validate<<<(st.n + 3) / 4, 128, 0, c->stream>>>(t.d_blob, t.d_off + st.i0, t.d_len + st.i0, st.n, c->d.n, ascii, t.d_bad + st.i0, 0);
-    c->tm.n_launches++;
-    return 0;
+    return launch_validate(c, t.d_blob, t.d_off + st.i0, t.d_len + st.i0, st.n, ascii, t.d_bad + st.i0, 0, c->stream);
 }
 
 // forceScan = false: trust the buffer capacities left by the previous call (steady state: the same kind of batch again) and
