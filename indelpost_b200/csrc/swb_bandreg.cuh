@@ -212,10 +212,10 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     uint8_t* rowW = reinterpret_cast<uint8_t*>(region + selCols / 4);
     {
         const swb_result& r0 = d.res[p];
-        for_each_byte16(d.windows + d.p_woff[p] + r0.ref_begin1, g.refLen, [&](int c, uint32_t v) { selW[c] = (uint8_t)(v & 7u); });
+        for_each_byte16_pair(d.windows + d.p_woff[p] + r0.ref_begin1, g.refLen, [&](int c, uint32_t v) { selW[c] = (uint8_t)(v & 7u); },
+                             d.reads + d.p_roff[p] + r0.read_begin1, g.readLen, [&](int i, uint32_t v) { rowW[i] = (uint8_t)(v & 7u); });
         const int ncols = min(g.refLen + NX + 1, selCols);
         for (int c = g.refLen; c < ncols; ++c) selW[c] = 0;
-        for_each_byte16(d.reads + d.p_roff[p] + r0.read_begin1, g.readLen, [&](int i, uint32_t v) { rowW[i] = (uint8_t)(v & 7u); });
     }
     const uint8_t* selT = selW;
     const uint8_t* rowT = rowW;

@@ -159,6 +159,37 @@ __device__ __forceinline__ void for_each_byte16(const int8_t* ptr, int len, F f)
     }
 }
 
+// two sequences at once: the loads of both are issued before either is consumed (eight 16-byte loads in flight)
+template <typename FA, typename FB>
+__device__ __forceinline__ void for_each_byte16_pair(const int8_t* pa, int la, FA fa, const int8_t* pb, int lb, FB fb) {
+    const uintptr_t aa = reinterpret_cast<uintptr_t>(pa), ab = reinterpret_cast<uintptr_t>(pb);
+    const int ma = (int)(aa & 15), mb = (int)(ab & 15);
+    const uint4* ba = reinterpret_cast<const uint4*>(aa - ma);
+    const uint4* bb = reinterpret_cast<const uint4*>(ab - mb);
+    const int na = (ma + la + 15) >> 4, nb = (mb + lb + 15) >> 4;
+    const int nmax = na > nb ? na : nb;
+    for (int ch0 = 0; ch0 < nmax; ch0 += 4) {
+        uint4 va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { if (ch0 + u < na) va[u] = __ldg(ba + ch0 + u); if (ch0 + u < nb) vb[u] = __ldg(bb + ch0 + u); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ch0 + u < na) {
+                const uint32_t w[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
+                const int i0 = (ch0 + u) * 16 - ma;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) if ((unsigned)(i0 + q) < (unsigned)la) fa(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            }
+            if (ch0 + u < nb) {
+                const uint32_t w[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+                const int i0 = (ch0 + u) * 16 - mb;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) if ((unsigned)(i0 + q) < (unsigned)lb) fb(i0 + q, (w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+            }
+        }
+    }
+}
+
 // band job class from the half-width (see SWB_NBANDCLASS)
 __host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : bw <= 2 ? 1 : bw <= 4 ? 2 : bw <= 8 ? 3 : bw <= 16 ? 4 : bw <= 48 ? 5 : bw <= 112 ? 6 : 7; }
 

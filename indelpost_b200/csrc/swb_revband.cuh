@@ -80,11 +80,11 @@ k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict
         const int ncols = min(Lmax + M + 1, selCols - PF);               // columns the band can reach
         for (int c = 0; c < PF + ncols; ++c) selW[c] = 0xC480u;          // base A / A: columns left of 0 and right of the windows
         const int kA = min(nA, ncols), kB = min(nB, ncols);              // reversed column c = window position n - 1 - c
-        for_each_byte16(d.windows + d.p_woff[pA] + (nA - kA), kA, [&](int i, uint32_t v) { selW[PF + kA - 1 - i] |= (uint16_t)((v & 3u) * 0x11u); });
-        for_each_byte16(d.windows + d.p_woff[qB] + (nB - kB), kB, [&](int i, uint32_t v) { selW[PF + kB - 1 - i] |= (uint16_t)((v & 3u) * 0x1100u); });
+        for_each_byte16_pair(d.windows + d.p_woff[pA] + (nA - kA), kA, [&](int i, uint32_t v) { selW[PF + kA - 1 - i] |= (uint16_t)((v & 3u) * 0x11u); },
+                             d.windows + d.p_woff[qB] + (nB - kB), kB, [&](int i, uint32_t v) { selW[PF + kB - 1 - i] |= (uint16_t)((v & 3u) * 0x1100u); });
         for (int i = 0; i < Lmax; ++i) rowW[i] = 0;
-        for_each_byte16(d.reads + d.p_roff[pA], LA, [&](int i, uint32_t v) { rowW[LA - 1 - i] |= (uint16_t)(v & 0xffu); });
-        for_each_byte16(d.reads + d.p_roff[qB], LB, [&](int i, uint32_t v) { rowW[LB - 1 - i] |= (uint16_t)((v & 0xffu) << 8); });
+        for_each_byte16_pair(d.reads + d.p_roff[pA], LA, [&](int i, uint32_t v) { rowW[LA - 1 - i] |= (uint16_t)(v & 0xffu); },
+                             d.reads + d.p_roff[qB], LB, [&](int i, uint32_t v) { rowW[LB - 1 - i] |= (uint16_t)((v & 0xffu) << 8); });
     }
     const uint16_t* selT = reinterpret_cast<const uint16_t*>(region) + (PF - WI);
     const uint16_t* rowT = reinterpret_cast<const uint16_t*>(region + selCols / 2);
