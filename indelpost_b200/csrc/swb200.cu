@@ -281,6 +281,7 @@ extern "C" swb_ctx* swb_create(int device) {
     cudaFuncSetAttribute(k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS));
     cudaFuncSetAttribute(k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS));
     cudaFuncSetAttribute(k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS));
+    cudaFuncSetAttribute(k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS));
     return c;
 }
 
@@ -690,19 +691,24 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
         // the wider classes go to the side stream so their long, latency-bound threads overlap the bulk
-        const bool side = njobs[5] > 0 || njobs[6] > 0 || njobs[7] > 0;
+        const bool side = njobs[4] > 0 || njobs[5] > 0 || njobs[6] > 0 || njobs[7] > 0;
         if (side) {
             CUDA_TRY(c, cudaEventRecord(c->ev_fork, s));
             CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             if (njobs[7] > 0) { k_band<0, SWB_BAND_THREADS><<<(njobs[7] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, SWB_BAND_THREADS, 0, c->stream2>>>(d, cur, 7, 7, nxt); c->tm.n_launches++; }
             if (njobs[6] > 0) {
-                k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS><<<(njobs[6] + SWB_BAND_WIDE_THREADS - 1) / SWB_BAND_WIDE_THREADS, SWB_BAND_WIDE_THREADS,
-                                                                    band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS), c->stream2>>>(d, cur, 6, 6, nxt);
+                k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS><<<(njobs[6] + SWB_BAND_HUGE_THREADS - 1) / SWB_BAND_HUGE_THREADS, SWB_BAND_HUGE_THREADS,
+                                                                    band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS), c->stream2>>>(d, cur, 6, 6, nxt);
                 c->tm.n_launches++;
             }
             if (njobs[5] > 0) {
-                k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS><<<(njobs[5] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, SWB_BAND_MID_THREADS,
-                                                                  band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS), c->stream2>>>(d, cur, 5, 5, nxt);
+                k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS><<<(njobs[5] + SWB_BAND_WIDE_THREADS - 1) / SWB_BAND_WIDE_THREADS, SWB_BAND_WIDE_THREADS,
+                                                                    band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS), c->stream2>>>(d, cur, 5, 5, nxt);
+                c->tm.n_launches++;
+            }
+            if (njobs[4] > 0) {
+                k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS><<<(njobs[4] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, SWB_BAND_MID_THREADS,
+                                                                  band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS), c->stream2>>>(d, cur, 4, 4, nxt);
                 c->tm.n_launches++;
             }
             CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));

@@ -23,17 +23,19 @@
 
 // Instantiations: BW = largest half-width whose rolling rows fit the shared-memory layout (0 = rows in global
 // memory, any width), T = threads per block, RING = circular buffer of window bases per thread (>= band width).
-//   k_band<16, 128> : classes 0-2 (the bulk)      k_band<48, 64> : class 3      k_band<112, 32> : class 4
-//   k_band<0, 128>  : anything wider (global rows; latency bound, rare)
+//   k_band<16, 128> : classes 0-3 (the bulk)   k_band<48, 64> : class 4   k_band<112, 32> : class 5   k_band<254, 32> : class 6
+//   k_band<0, 128>  : anything needing more than 512 slots, or scores beyond 16 bits (global rows; latency bound, rare)
 #define SWB_BAND_LOCAL_BW 16
 #define SWB_BAND_MID_BW 48
 #define SWB_BAND_WIDE_BW 112
+#define SWB_BAND_HUGE_BW 254                           // 512 slots: every band over a window of up to 509 columns
 #define SWB_BAND_THREADS 128
 #define SWB_BAND_MID_THREADS 64
 #define SWB_BAND_WIDE_THREADS 32
+#define SWB_BAND_HUGE_THREADS 32
 #define SWB_BAND_MAX16 30000                          // largest score the 16-bit shared-memory rows may hold
 __host__ __device__ constexpr int band_rows_w(int BW) { return 2 * BW + 4; }
-__host__ __device__ constexpr int band_ring(int BW) { return BW <= 16 ? 64 : (BW <= 48 ? 128 : 256); }
+__host__ __device__ constexpr int band_ring(int BW) { return BW <= 16 ? 64 : (BW <= 48 ? 128 : (BW <= 112 ? 256 : 512)); }
 __host__ __device__ constexpr int band_smem_bytes(int BW, int T) { return BW == 0 ? 0 : 3 * band_rows_w(BW) * T * 2 + band_ring(BW) * T; }
 
 __device__ __forceinline__ int band_x(int w, int i) { int x = i - w; return x > 0 ? x : 0; }
@@ -210,10 +212,10 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
     long long cells = 0;
 
     for (;;) {                                         // band widening loop, ssw.c:612-669
-        if (LOCAL && (bw > BW || !fits16)) {
+        if (LOCAL && (band_rows_needed(bw, g.refLen) > ROWS_W || !fits16)) {
             // outgrew this instantiation's shared-memory rows: continue in the next wider one
             d.t_bw[p] = bw; d.t_best[p] = best;
-            const int c = fits16 ? band_class(bw) : 7;             // the class whose instantiation holds this width (7: global rows)
+            const int c = band_class(bw, g.refLen, fits16);        // the class whose instantiation holds these rows (7: global rows)
             list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
             warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
             return;
@@ -228,7 +230,7 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
         if ((long long)off + need > d.band_cap) {      // out of scratch: retry in a later launch
             d.t_bw[p] = bw; d.t_best[p] = best;
             atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
-            const int c = BW == 0 ? 7 : band_class(bw);
+            const int c = BW == 0 ? 7 : band_class(bw, g.refLen, fits16);
             list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
             warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
             return;
@@ -240,7 +242,11 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
         }
         // the reference's buffers are realloc'ed across widenings and not cleared; every slot it reads is
         // written first within an iteration except where it reads uninitialised memory -- start from zeros
-        for (int j = 0; j <= width; ++j) { hPrev[j] = 0; ePrev[j] = 0; hCur[j] = 0; }
+        {
+            // (only slots 0 .. refLen+1 are ever touched, see band_class)
+            const int zmax = LOCAL ? min(width, ROWS_W - 1) : width;
+            for (int j = 0; j <= zmax; ++j) { hPrev[j] = 0; ePrev[j] = 0; hCur[j] = 0; }
+        }
 
         int ringHi = -1;                               // last window column already in refRing
         int rbNext = g.readLen > 0 ? read[0] : 0;      // software prefetch: next row's read base and the next window base

@@ -231,7 +231,7 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     if ((long long)off + need > d.band_cap) {               // out of scratch: the literal kernel retries in a later round
         d.t_bw[p] = W; d.t_best[p] = 0;
         atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
-        const int c = band_class(W);
+        const int c = band_class(W, g.refLen);
         list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
         return;
     }
@@ -249,7 +249,7 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
         if (nextBaseW >= 0 && 2 * W <= SWB_BANDW_MAX && g.refLen >= 4 * W + 2) {
             list_push(d.list[nextBaseW + 2 * W - 1], d.counters + nextBaseW + 2 * W - 1, p);      // still regular: this kernel's 2W instantiation
         } else {
-            const int c = band_class(2 * W);
+            const int c = band_class(2 * W, g.refLen);
             list_push(d.list[nextBase + c], d.counters + nextBase + c, p);                           // literal kernel
         }
         return;

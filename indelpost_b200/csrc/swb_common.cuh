@@ -65,8 +65,8 @@ struct SwbDev {
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
-#define SWB_NBANDCLASS 8         // band jobs are bucketed by half-width: 1 | 2 | 3-4 | 5-8 | 9-16 | 17-48 (64-thread blocks) | 49-112 (32-thread blocks) | wider (global-memory rows)
-#define SWB_BAND_CLS_MID 5      // first class of k_band<48,64>; 6: k_band<112,32>; 7: k_band<0,128>
+#define SWB_NBANDCLASS 8         // band jobs are bucketed by the rolling-buffer slots they need, see band_class()
+#define SWB_BAND_CLS_MID 4      // first class of k_band<48,64>; 5: k_band<112,32>; 6: k_band<254,32>; 7: k_band<0,128> (see band_class)
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
        LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
        LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104 };   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _NEXT: jobs it widened once
@@ -191,7 +191,18 @@ __device__ __forceinline__ void for_each_byte16_pair(const int8_t* pa, int la, F
 }
 
 // band job class from the half-width (see SWB_NBANDCLASS)
-__host__ __device__ __forceinline__ int band_class(int bw) { return bw <= 1 ? 0 : bw <= 2 ? 1 : bw <= 4 ? 2 : bw <= 8 ? 3 : bw <= 16 ? 4 : bw <= 48 ? 5 : bw <= 112 ? 6 : 7; }
+// The rolling buffers of banded_sw are 2*bw+3 slots wide, but no slot beyond refLen+1 is ever read (set_u gives u <= j+1 <= refLen and
+// the upper neighbour is u or u+1): a job needs min(2*bw+4, refLen+3) slots, which decides the instantiation of k_band that can
+// keep its rows in shared memory -- also for the very wide bands a free gap extension produces (bw > refLen).
+//   classes 0-3: rows <= 36  (k_band<16,128>; bucketed by width 1-2 | 3-4 | 5-8 | wider so a warp runs similar bands)
+//   class 4: rows <= 100 (k_band<48,64>)   5: <= 228 (k_band<112,32>)   6: <= 512 (k_band<254,32>)   7: global-memory rows
+__host__ __device__ __forceinline__ int band_rows_needed(int bw, int refLen) { const int a = 2 * bw + 4, b = refLen + 3; return a < b ? a : b; }
+__host__ __device__ __forceinline__ int band_class(int bw, int refLen, bool fits16 = true) {
+    if (!fits16) return 7;
+    const int need = band_rows_needed(bw, refLen);
+    if (need <= 36) return bw <= 2 ? 0 : bw <= 4 ? 1 : bw <= 8 ? 2 : 3;
+    return need <= 100 ? 4 : need <= 228 ? 5 : need <= 512 ? 6 : 7;
+}
 
 // queue a pair for the banded traceback in the class of its initial band width |refLen - readLen| + 1 (ssw.c:899)
 __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_result& r) {
@@ -207,7 +218,7 @@ __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_resu
         list_push(d.list[slot], d.counters + slot, p);
         return;
     }
-    const int c = band_class(bw);
+    const int c = band_class(bw, refLen, (long long)d.max_score * (readLen > 0 ? readLen : 1) <= 30000);
     const int base = first ? LIST_BAND_FIRST : LIST_BAND;
     list_push(d.list[base + c], d.counters + base + c, p);
 }
