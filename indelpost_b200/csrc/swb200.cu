@@ -32,6 +32,7 @@
 #include "swb_fast.cuh"
 #include "swb_revband.cuh"
 #include "swb_bandreg.cuh"
+#include "swb_bandwarp.cuh"
 #include "swb_indels.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
@@ -684,6 +685,10 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         int njobsW[SWB_BANDW_MAX] = {};
         const int baseW = round == 0 ? (firstBase == LIST_BAND_FIRST ? LIST_BANDW_FIRST : LIST_BANDW) : LIST_BANDW_NEXT;
         if (round == 0 || !firstRoundOnly) for (int k = 0; k < SWB_BANDW_MAX; ++k) { njobsW[k] = c->h_counters[baseW + k]; total += njobsW[k]; }
+        // round 0: the wide regular bands of this phase (one warp per alignment, swb_bandwarp.cuh)
+        const int baseWarp = firstBase == LIST_BAND_FIRST ? LIST_BANDWARP_FIRST : LIST_BANDWARP;
+        const int nWarp = round == 0 ? c->h_counters[baseWarp] : 0;
+        total += nWarp;
         if (round == 0 && firstJobs) *firstJobs = total;
         if (g_trace) { fprintf(stderr, "TRACE band round %d base %d: classes", round, cur); for (int k = 0; k < SWB_NBANDCLASS; ++k) fprintf(stderr, " %d", njobs[k]); fprintf(stderr, " | reg"); for (int k = 0; k < SWB_BANDW_MAX; ++k) fprintf(stderr, " %d", njobsW[k]); fprintf(stderr, "\n"); }
         if (total <= 0 && !(round == 0 && keepNext)) break;
@@ -691,10 +696,15 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
         // the wider classes go to the side stream so their long, latency-bound threads overlap the bulk
-        const bool side = njobs[4] > 0 || njobs[5] > 0 || njobs[6] > 0 || njobs[7] > 0;
+        const bool side = njobs[4] > 0 || njobs[5] > 0 || njobs[6] > 0 || njobs[7] > 0 || nWarp > 0;
         if (side) {
             CUDA_TRY(c, cudaEventRecord(c->ev_fork, s));
             CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            if (nWarp > 0) {
+                k_band_warp<<<(nWarp + SWB_BANDWARP_WARPS - 1) / SWB_BANDWARP_WARPS, 32 * SWB_BANDWARP_WARPS, 0, c->stream2>>>(d, d.list[baseWarp], nWarp, nxt);
+                c->tm.n_launches++;
+                CUDA_TRY(c, cudaMemsetAsync(d.counters + baseWarp, 0, 4, c->stream2));      // list consumed
+            }
             if (njobs[7] > 0) { k_band<0, SWB_BAND_THREADS><<<(njobs[7] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, SWB_BAND_THREADS, 0, c->stream2>>>(d, cur, 7, 7, nxt); c->tm.n_launches++; }
             if (njobs[6] > 0) {
                 k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS><<<(njobs[6] + SWB_BAND_HUGE_THREADS - 1) / SWB_BAND_HUGE_THREADS, SWB_BAND_HUGE_THREADS,

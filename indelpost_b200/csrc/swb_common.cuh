@@ -7,7 +7,7 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 128
+#define SWB_NLISTS 130
 #define SWB_NCOUNTERS 168
 
 // ---------------------------------------------------------------------------------------------
@@ -61,7 +61,7 @@ struct SwbDev {
     int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
     uint32_t* fast_cols;   // global column-best storage of the fast path when windows are too long for shared memory (null otherwise)
     int32_t one;        // always 1, but opaque to the compiler: x * one + c compiles to a real IMAD (FMA pipe) instead of an ALU-pipe add
-    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass, bit4 = no register-band kernel, bit5 = single traceback phase
+    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass, bit4 = no register-band kernel, bit5 = single traceback phase, bit6 = no warp-per-alignment band kernel
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
@@ -69,7 +69,8 @@ struct SwbDev {
 #define SWB_BAND_CLS_MID 4      // first class of k_band<48,64>; 5: k_band<112,32>; 6: k_band<254,32>; 7: k_band<0,128> (see band_class)
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
        LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
-       LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104 };   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _NEXT: jobs it widened once
+       LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104,
+       LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129 };   // wide regular bands: one warp per alignment (swb_bandwarp.cuh)   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _NEXT: jobs it widened once
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
        CNT_CELLS_FWD = 136, CNT_CELLS_REV = 138, CNT_CELLS_BAND = 140, CNT_BAND_OVERFLOW = 142, CNT_CIGAR_OVERFLOW = 143,
@@ -215,6 +216,13 @@ __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_resu
     // regular jobs (band narrower than the matrix, see swb_bandreg.cuh) go to the register-band kernel of their exact width
     if (bw <= SWB_BANDW_MAX && refLen >= 2 * bw + 2 && readLen <= SWB_BANDREG_MAXROWS && d.n <= 8 && r.ref_begin1 >= 0 && r.read_begin1 >= 0 && !(d.opt & 16)) {
         const int slot = (first ? LIST_BANDW_FIRST : LIST_BANDW) + bw - 1;
+        list_push(d.list[slot], d.counters + slot, p);
+        return;
+    }
+    // wide regular bands (what a free gap extension produces): one warp per alignment
+    if (bw > SWB_BANDW_MAX && (refLen >= 2 * bw + 2 || bw >= readLen - 1) && refLen <= 512 && readLen <= SWB_BANDREG_MAXROWS && d.n <= 8 &&
+        r.ref_begin1 >= 0 && r.read_begin1 >= 0 && !(d.opt & 64)) {
+        const int slot = first ? LIST_BANDWARP_FIRST : LIST_BANDWARP;
         list_push(d.list[slot], d.counters + slot, p);
         return;
     }
