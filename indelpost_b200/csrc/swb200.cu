@@ -246,6 +246,7 @@ extern "C" swb_ctx* swb_create(int device) {
     c->n_sm = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     memset(&c->d, 0, sizeof c->d);
+    c->d.warp_next = -1;
     memset(&c->tm, 0, sizeof c->tm);
     // stream priorities: the long forward sweep runs at the lowest priority, the per-class side streams in the middle and
     // everything on the critical path (small launches between host round trips) at the highest, so that with two pipeline
@@ -686,13 +687,19 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         const int baseW = round == 0 ? (firstBase == LIST_BAND_FIRST ? LIST_BANDW_FIRST : LIST_BANDW) : LIST_BANDW_NEXT;
         if (round == 0 || !firstRoundOnly) for (int k = 0; k < SWB_BANDW_MAX; ++k) { njobsW[k] = c->h_counters[baseW + k]; total += njobsW[k]; }
         // round 0: the wide regular bands of this phase (one warp per alignment, swb_bandwarp.cuh)
-        const int baseWarp = firstBase == LIST_BAND_FIRST ? LIST_BANDWARP_FIRST : LIST_BANDWARP;
-        const int nWarp = round == 0 ? c->h_counters[baseWarp] : 0;
+        // later rounds: the widened jobs that fit it (LIST_BANDWARP_NEXT, two lists alternating like cur / nxt)
+        const int baseWarp = round == 0 ? (firstBase == LIST_BAND_FIRST ? LIST_BANDWARP_FIRST : LIST_BANDWARP) : LIST_BANDWARP_NEXT + ((round - 1) & 1);
+        const int warpNxt = LIST_BANDWARP_NEXT + (round & 1);
+        const int nWarp = c->h_counters[baseWarp];
         total += nWarp;
         if (round == 0 && firstJobs) *firstJobs = total;
         if (g_trace) { fprintf(stderr, "TRACE band round %d base %d: classes", round, cur); for (int k = 0; k < SWB_NBANDCLASS; ++k) fprintf(stderr, " %d", njobs[k]); fprintf(stderr, " | reg"); for (int k = 0; k < SWB_BANDW_MAX; ++k) fprintf(stderr, " %d", njobsW[k]); fprintf(stderr, "\n"); }
         if (total <= 0 && !(round == 0 && keepNext)) break;
-        if (!(round == 0 && keepNext)) CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
+        if (!(round == 0 && keepNext)) {
+            CUDA_TRY(c, cudaMemsetAsync(d.counters + nxt, 0, 4 * SWB_NBANDCLASS, s));
+            CUDA_TRY(c, cudaMemsetAsync(d.counters + warpNxt, 0, 4, s));
+        }
+        d.warp_next = warpNxt;
         CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BAND_OVERFLOW, 0, 4, s));
         CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 8, s));
         // the wider classes go to the side stream so their long, latency-bound threads overlap the bulk
@@ -762,6 +769,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
     // leave the list sets this call used empty for a later phase
     CUDA_TRY(c, cudaMemsetAsync(d.counters + firstBase, 0, 4 * SWB_NBANDCLASS, s));
     CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BAND_NEXT, 0, 4 * SWB_NBANDCLASS, s));
+    CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BANDWARP_NEXT, 0, 8, s));
     return 0;
 }
 

@@ -215,8 +215,9 @@ k_band(SwbDev d, int listBase, int firstClass, int lastClass, int nextBase)
         if (LOCAL && (band_rows_needed(bw, g.refLen) > ROWS_W || !fits16)) {
             // outgrew this instantiation's shared-memory rows: continue in the next wider one
             d.t_bw[p] = bw; d.t_best[p] = best;
-            const int c = band_class(bw, g.refLen, fits16);        // the class whose instantiation holds these rows (7: global rows)
-            list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
+            // the class whose instantiation holds these rows (7: global rows), or the warp-per-alignment kernel
+            if (ubRef || r.read_begin1 < 0) { const int c = band_class(bw, g.refLen, fits16); list_push(d.list[nextBase + c], d.counters + nextBase + c, p); }
+            else requeue_band(d, nextBase, p, bw, g.refLen, g.readLen, r, fits16);
             warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
             return;
         }

@@ -249,8 +249,7 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
         if (nextBaseW >= 0 && 2 * W <= SWB_BANDW_MAX && g.refLen >= 4 * W + 2) {
             list_push(d.list[nextBaseW + 2 * W - 1], d.counters + nextBaseW + 2 * W - 1, p);      // still regular: this kernel's 2W instantiation
         } else {
-            const int c = band_class(2 * W, g.refLen);
-            list_push(d.list[nextBase + c], d.counters + nextBase + c, p);                           // literal kernel
+            requeue_band(d, nextBase, p, 2 * W, g.refLen, g.readLen, r);                            // warp-per-alignment or literal kernel
         }
         return;
     }

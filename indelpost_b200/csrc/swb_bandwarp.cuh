@@ -46,7 +46,9 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
     const int refLen = r.ref_end1 - r.ref_begin1 + 1;      // ssw.c:897-899
     const int readLen = r.read_end1 - r.read_begin1 + 1;
     const int dl = refLen - readLen;
-    const int W = (dl < 0 ? -dl : dl) + 1;
+    int W = (dl < 0 ? -dl : dl) + 1;
+    int best = 0;
+    if (d.t_bw[p] != 0) { W = d.t_bw[p]; best = d.t_best[p]; }      // re-queued by another kernel: its width and running maximum
     const int score = r.score1;
     const int go = d.gap_open[p], ge = d.gap_ext[p];
     const int len = refLen > readLen ? refLen : readLen;
@@ -62,8 +64,6 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
     for (int k = lane; k < readLen; k += 32) s_read[threadIdx.x >> 5][k] = (uint8_t)(read[k] & 7);
     __syncwarp();
     const uint8_t* rd = s_read[threadIdx.x >> 5];
-    // a band that never slides and is wider than the matrix: the last column loses its upper neighbour (see above)
-    const bool cutLast = refLen < 2 * W + 2;
 
     // scratch for the direction words (column layout)
     unsigned long long off = 0;
@@ -88,10 +88,14 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
         codes[q] = w;
     }
 
+    int bestIn;                                            // running maximum before the current width's pass
+    for (;;) {                                             // band doubling, ssw.c:612-669 (the direction words do not depend on W)
+    bestIn = best;
+    // a band that never slides and is wider than the matrix: the last column loses its upper neighbour (see above)
+    const bool cutLast = refLen < 2 * W + 2;
     int Hp[C], Ev[C];                                      // H of the previous row / vertical-gap state, per own column
 #pragma unroll
     for (int k = 0; k < C; ++k) { Hp[k] = 0; Ev[k] = 0; }
-    int best = 0;
     int outH = 0, outF = 0, outDiag = 0;                   // what lane+1 receives at the next step
     const int nsteps = readLen + 31;
     for (int s = 0; s < nsteps; ++s) {
@@ -134,14 +138,16 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
     __syncwarp();
-    if (lane != 0) return;
-
     {
         long long cells = 0;                               // statistics: cells of the band inside the matrix
-        for (int i = 0; i < readLen; ++i) cells += min(i + W, refLen - 1) - max(i - W, 0) + 1;
-        atomicAdd(reinterpret_cast<unsigned long long*>(d.counters + CNT_CELLS_BAND), (unsigned long long)cells);
+        for (int i = lane; i < readLen; i += 32) cells += min(i + W, refLen - 1) - max(i - W, 0) + 1;
+        warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
     }
-    if (best < score && W * 2 <= len) { to_literal(2 * W, best); return; }      // ssw.c:668-669: widen and redo (literal kernel)
+    if (!(best < score && W * 2 <= len)) break;            // ssw.c:668-669
+    W *= 2;                                                // widen and redo: here while the band is still one of the two kinds
+    if (!(refLen >= 2 * W + 2 || W >= readLen - 1)) { if (lane == 0) to_literal(W, best); return; }
+    }
+    if (lane != 0) return;
 
     // ---- traceback (ssw.c:672-751), lane 0, column layout; the word of the row above is fetched one step ahead ------------
     __threadfence_block();
@@ -169,7 +175,7 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
             if (op == prev_op) ++e;
             else { band_push(ops, ((uint32_t)e << 4) | (uint32_t)prev_op, out, total); prev_op = op; e = 1; }
         }
-        if (leftBand) { to_literal(W, 0); return; }         // the reference's index arithmetic takes over (literal kernel, from scratch)
+        if (leftBand) { to_literal(W, bestIn); return; }         // the reference's index arithmetic takes over (literal kernel, from scratch)
         if (op == 0) band_push(ops, ((uint32_t)(e + 1) << 4) | 0u, out, total);     // ssw.c:734-751
         else { band_push(ops, ((uint32_t)e << 4) | (uint32_t)op, out, total); band_push(ops, (1u << 4) | 0u, out, total); }
         if (pass == 1) break;

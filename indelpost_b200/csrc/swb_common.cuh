@@ -7,7 +7,7 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 130
+#define SWB_NLISTS 132
 #define SWB_NCOUNTERS 168
 
 // ---------------------------------------------------------------------------------------------
@@ -45,6 +45,7 @@ struct SwbDev {
     unsigned long long* bump;   // [0]: band scratch bump pointer, [1]: cigar arena bump pointer
     int32_t*  t_bw;     // current band width per pair (banded rounds)
     int32_t*  t_best;   // running DP maximum per pair (not reset between widenings, ssw.c:600,661)
+    int32_t   warp_next;   // list that takes the re-queued jobs fit for the warp-per-alignment kernel this round (-1: none)
 
     int32_t n_pairs, n_reads, n_windows;
     int32_t n;          // matrix edge
@@ -70,7 +71,7 @@ struct SwbDev {
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
        LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
        LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104,
-       LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129 };   // wide regular bands: one warp per alignment (swb_bandwarp.cuh)   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _NEXT: jobs it widened once
+       LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129, LIST_BANDWARP_NEXT = 130 /* two, alternating by round */ };   // wide regular bands: one warp per alignment (swb_bandwarp.cuh)   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _NEXT: jobs it widened once
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
        CNT_CELLS_FWD = 136, CNT_CELLS_REV = 138, CNT_CELLS_BAND = 140, CNT_BAND_OVERFLOW = 142, CNT_CIGAR_OVERFLOW = 143,
@@ -205,6 +206,20 @@ __host__ __device__ __forceinline__ int band_class(int bw, int refLen, bool fits
     return need <= 100 ? 4 : need <= 228 ? 5 : need <= 512 ? 6 : 7;
 }
 
+// bands the warp-per-alignment kernel (swb_bandwarp.cuh) takes: wider than the register-band kernel's, and either narrower than the
+// matrix (regular) or never sliding
+__device__ __forceinline__ bool bandwarp_ok(const SwbDev& d, int bw, int refLen, int readLen, const swb_result& r) {
+    return bw > SWB_BANDW_MAX && (refLen >= 2 * bw + 2 || bw >= readLen - 1) && refLen <= 512 && readLen <= SWB_BANDREG_MAXROWS && d.n <= 8 &&
+           r.ref_begin1 >= 0 && r.read_begin1 >= 0 && !(d.opt & 64);
+}
+
+// re-queue a job whose band has grown to bw (t_bw / t_best already stored) for the next round
+__device__ __forceinline__ void requeue_band(const SwbDev& d, int nextBase, int p, int bw, int refLen, int readLen, const swb_result& r, bool fits16 = true) {
+    if (d.warp_next >= 0 && bandwarp_ok(d, bw, refLen, readLen, r)) { list_push(d.list[d.warp_next], d.counters + d.warp_next, p); return; }
+    const int c = band_class(bw, refLen, fits16);
+    list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
+}
+
 // queue a pair for the banded traceback in the class of its initial band width |refLen - readLen| + 1 (ssw.c:899)
 __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_result& r) {
     const int refLen = r.ref_end1 - r.ref_begin1 + 1, readLen = r.read_end1 - r.read_begin1 + 1;
@@ -220,8 +235,7 @@ __device__ __forceinline__ void push_band(const SwbDev& d, int p, const swb_resu
         return;
     }
     // wide regular bands (what a free gap extension produces): one warp per alignment
-    if (bw > SWB_BANDW_MAX && (refLen >= 2 * bw + 2 || bw >= readLen - 1) && refLen <= 512 && readLen <= SWB_BANDREG_MAXROWS && d.n <= 8 &&
-        r.ref_begin1 >= 0 && r.read_begin1 >= 0 && !(d.opt & 64)) {
+    if (bandwarp_ok(d, bw, refLen, readLen, r)) {
         const int slot = first ? LIST_BANDWARP_FIRST : LIST_BANDWARP;
         list_push(d.list[slot], d.counters + slot, p);
         return;
