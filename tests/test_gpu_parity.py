@@ -37,6 +37,10 @@ FUZZ = [
     dict(n_pairs=2000, read_len=(40, 200), win_len=(100, 500), seed=211, go=0, ge=0),
     dict(n_pairs=2000, read_len=(40, 200), win_len=(100, 500), seed=212, go=6, ge=2, match=1, mismatch=4),
     dict(n_pairs=1000, read_len=(200, 600), win_len=(300, 900), seed=213, grid=True, max_indel=60),
+    # free gap extension + long deletions: wide bands (swb_bandwarp.cuh), regular and wider than the matrix, doubled ones
+    dict(n_pairs=4000, read_len=(60, 150), win_len=(250, 500), seed=214, go=3, ge=0, max_indel=120),
+    dict(n_pairs=4000, read_len=(30, 120), win_len=(200, 512), seed=215, go=5, ge=0, max_indel=200, junk_tail=0.2, low_complexity=0.1),
+    dict(n_pairs=3000, read_len=(100, 300), win_len=(300, 700), seed=216, go=4, ge=0, max_indel=150, sub_rate=0.03),
 ]
 
 
