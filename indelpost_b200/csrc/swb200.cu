@@ -671,10 +671,10 @@ static int join_band_reg(swb_ctx* c) {
 // firstRoundOnly: launch the jobs of `firstBase` and leave what they re-queue in LIST_BAND_NEXT for a later call;
 // keepNext: LIST_BAND_NEXT already holds such re-queued jobs, append to them in the first round instead of clearing
 static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, int* firstJobs = nullptr, bool firstRoundOnly = false, bool keepNext = false,
-                           int (*afterFirstRound)(swb_ctx*, int) = nullptr) {
+                           int (*afterFirstRound)(swb_ctx*, int) = nullptr, bool haveCounters = false) {
     SwbDev& d = c->d;
     cudaStream_t s = c->stream;
-    if (read_counters(c)) return -1;
+    if (!haveCounters && read_counters(c)) return -1;       // haveCounters: the host copy already holds this phase's list sizes
     int cur = firstBase, nxt = LIST_BAND_NEXT;
     int round = 0, stalls = 0;
     if (firstJobs) *firstJobs = 0;
@@ -871,7 +871,8 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     if (certify && nFirst > 0 && certify_and_verify_async(c, LIST_VERIFY, nFirst)) return -1;
     // phase 2; its first round is followed at once by the certificate + verification of its own pairs (hook), which
     // then overlap the re-queue rounds
-    if (run_band_rounds(c, true, LIST_BAND, nullptr, false, /*keepNext=*/nFirst > 0, certify ? certify_phase2_hook : nullptr)) return -1;
+    //          (its lists were complete when phase 1 read the counters: no host round trip between the phases)
+    if (run_band_rounds(c, true, LIST_BAND, nullptr, false, /*keepNext=*/nFirst > 0, certify ? certify_phase2_hook : nullptr, /*haveCounters=*/true)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_BAND_ALL], s));
     if (c->verify_pending & 1) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join2, 0));      // both verifications done
     if (c->verify_pending & 2) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join3, 0));

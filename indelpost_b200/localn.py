@@ -6,7 +6,7 @@ import re
 
 import numpy as np
 
-from .sswpy import SSW, align_batch, _aligner
+from .sswpy import SSW, align_batch, prefetch_alignments, _aligner
 
 cigar_ptrn = re.compile(r"[0-9]+[MIDNSHPX=]")  # localn.pyx:12
 _OPS = "MIDNSHP=X"
@@ -28,6 +28,32 @@ def align_many(ref_seqs, read_seqs, pair_read, pair_ref, gap_open_penalty, gap_e
     `align(make_aligner(ref), read, go, ge)` returns for each pair, as a list in pair order."""
     return align_batch(read_seqs, ref_seqs, pair_read, pair_ref, gap_open_penalty, gap_extension_penalty,
                        match_score=match_score, mismatch_penalty=mismatch_penalty, device=device)
+
+
+def generate_grid(auto_adjust_extension_penalty, gap_open_penalty, gap_extension_penalty, target):
+    """The (gap_open, gap_extension) points `grid_search` walks for a target indel (reference
+    indelpost/varaln.pyx:1122-1146): the user's pair first when it is not (3, 1); (3, 0) moves ahead of (3, 1) for
+    indels of 20 bases or more; a single point when auto-adjustment is off.  `target` needs `.indel_seq` only."""
+    if not auto_adjust_extension_penalty:
+        return [(gap_open_penalty, gap_extension_penalty)]
+    head = [(3, 1), (3, 0)] if len(target.indel_seq) < 20 else [(3, 0), (3, 1)]
+    grid = head + [(5, 1), (5, 0), (4, 1), (4, 0)]
+    if (gap_open_penalty, gap_extension_penalty) != (3, 1):
+        grid.insert(0, (gap_open_penalty, gap_extension_penalty))
+    return grid
+
+
+def prefetch_grid_search(target, read_seqs, ref_seqs, auto_adjust_extension_penalty=True, gap_open_penalty=3, gap_extension_penalty=1,
+                         match_score=3, mismatch_penalty=2, with_perfect_match=True, device=0):
+    """One GPU batch holding every alignment `grid_search` -> `retarget` -> `update_read_info` (varaln.pyx:1164-1243,
+    pileup.pyx:639-648, 849) can ask for at one locus: reads x windows x generate_grid(...), plus the `gap_open = len(read)`
+    calls of `is_target_by_ssw` (localn.pyx:253-255) and `gap_open = gap_extension = len(read)` of `is_perfect_match`
+    (varaln.pyx:1228-1234).  The unmodified per-call code then finds its results in the prefetched set (sswpy.SSW.align).
+    Returns the number of alignments computed."""
+    grid = list(dict.fromkeys(generate_grid(auto_adjust_extension_penalty, gap_open_penalty, gap_extension_penalty, target)))
+    if with_perfect_match:
+        grid += [("len", gap_extension_penalty), ("len", "len")]
+    return prefetch_alignments(read_seqs, ref_seqs, grid=tuple(grid), match_score=match_score, mismatch_penalty=mismatch_penalty, device=device)
 
 
 def _pack_cigar(cigarstring):

@@ -162,6 +162,40 @@ def test_prefetch_serves_the_per_call_api():
     ip.clear_prefetched()
 
 
+def test_prefetch_grid_search_covers_the_locus_calls():
+    """localn.prefetch_grid_search: reads x windows x generate_grid (+ the len(read) penalties of is_target_by_ssw and
+    is_perfect_match) in one batch; every per-call alignment of the locus is then a prefetched tuple equal to a direct call"""
+    import indelpost_b200 as ip
+    from indelpost_b200 import localn, sswpy
+
+    class Target:
+        indel_seq = "TTGCA"
+
+    rng = np.random.default_rng(18)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, 300))
+    contig = ref[:140] + "TTGCA" + ref[140:]
+    reads = [(contig if k % 2 else ref)[s0: s0 + 100] for k, s0 in enumerate(rng.integers(0, 190, 16))]
+    ip.clear_prefetched()
+    direct = {}
+    for w, win in enumerate((ref, contig)):
+        al = localn.make_aligner(win, 3, 2)
+        for r in (0, 5, 11):
+            for go, ge in ((5, 0), (len(reads[r]), 1), (len(reads[r]), len(reads[r]))):
+                direct[(w, r, go, ge)] = localn.align(al, reads[r], go, ge)
+    n = localn.prefetch_grid_search(Target(), reads, [ref, contig], True, 3, 1, 3, 2)
+    assert n == len(reads) * 2 * 8
+    for w, win in enumerate((ref, contig)):
+        al = localn.make_aligner(win, 3, 2)
+        for r, rd in enumerate(reads):
+            for go, ge in localn.generate_grid(True, 3, 1, Target()) + [(len(rd), 1), (len(rd), len(rd))]:
+                got = localn.align(al, rd, go, ge)
+                key = (sswpy.dna_score_matrix(3, 2).tobytes(), al._ref_key, al._read_arr.tobytes(), go & 0xFF, ge & 0xFF, 0, len(win))
+                assert sswpy._PREFETCHED[key] is got
+                if (w, r, go, ge) in direct:
+                    assert got == direct[(w, r, go, ge)]
+    ip.clear_prefetched()
+
+
 def test_c_abi_single_pair_entry_points():
     """ssw_init / ssw_align / align_destroy / init_destroy exactly as sswpy.pyx's extern block binds them"""
     import ctypes as C

@@ -106,3 +106,37 @@ def test_gpu_sswpy_layer_reproduces_pipeline_calls():
             continue
         got = align(make_aligner(seqs[c["ref"]], 3, 2), seqs[c["read"]], c["go"], c["ge"])
         assert tuple(got) == tuple(c["out"])
+
+
+class _Target:
+    def __init__(self, indel_seq):
+        self.indel_seq = indel_seq
+
+
+def test_generate_grid_follows_the_reference_order():
+    """varaln.pyx:1122-1146, case by case"""
+    from indelpost_b200.localn import generate_grid
+
+    short, long_ = _Target("ACG"), _Target("A" * 20)
+    assert generate_grid(True, 3, 1, short) == [(3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0)]
+    assert generate_grid(True, 3, 1, long_) == [(3, 0), (3, 1), (5, 1), (5, 0), (4, 1), (4, 0)]
+    assert generate_grid(True, 6, 2, short) == [(6, 2), (3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0)]
+    assert generate_grid(True, 5, 1, long_) == [(5, 1), (3, 0), (3, 1), (5, 1), (5, 0), (4, 1), (4, 0)]
+    assert generate_grid(False, 6, 2, short) == [(6, 2)]
+    assert generate_grid(False, 3, 1, long_) == [(3, 1)]
+
+
+def test_prefetch_grid_covers_every_recorded_call():
+    """the penalty pairs prefetch_grid_search() submits for a locus are a superset of what the reference pipeline asked for"""
+    from indelpost_b200.localn import generate_grid
+
+    doc = _load()
+    grid = set(generate_grid(True, 3, 1, _Target("A")))
+    missing = Counter()
+    for c in doc["calls"]:
+        L = len(doc["seqs"][c["read"]])
+        go, ge = c["go"], c["ge"]
+        if (go, ge) in grid or (go, ge) in ((L, 1), (L, L)) or (go, ge) in ((L & 0xFF, 1), (L & 0xFF, L & 0xFF)):
+            continue
+        missing[(go, ge)] += 1
+    assert not missing, missing
