@@ -63,7 +63,52 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
+    def _nvml_start(self):
+        # in-process NVML polling (every ~4 ms): a 100 ms timed region still gets tens of samples
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = None
+        if h is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [x for x in vis.split(",") if x.strip().isdigit()]
+            h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)          # fail here, not in the thread
+        self.nv, self.h, self.samples, self.stop_flag = nv, h, [], False
+        self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+
+        def poll():
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                try:
+                    self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+                except Exception:
+                    pass
+                time.sleep(0.004)
+        self.t = threading.Thread(target=poll, daemon=True)
+        self.t.start()
+
+    def _nvml_stop(self, t0, t1):
+        self.stop_flag = True
+        self.t.join(timeout=1.0)
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}   # nvml.h nvmlClocksEventReason*
+        sm = [c for ts, c, r in self.samples if t0 <= ts <= t1]
+        reasons = sorted({name for ts, c, r in self.samples if t0 <= ts <= t1 for name, b in bits.items() if r & b})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm), "source": "nvml"}
+
     def start(self):
+        self.nvml = False
+        try:
+            self._nvml_start()
+            self.nvml = True
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
@@ -78,6 +123,8 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml:
+            return self._nvml_stop(t0, t1)
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

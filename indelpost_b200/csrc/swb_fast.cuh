@@ -163,8 +163,10 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     bool done = false;                                         // reverse pass: both lanes have hit their target
 
     // boundary of the first thread of a group as masks (loop invariants kept in registers: no per-step predicate set-up)
-    uint32_t m0 = g == 0 ? 0u : 0xffffffffu, c0 = g == 0 ? FAST_CPACK : 0u;
-    asm volatile("" : "+r"(m0), "+r"(c0));
+    // boundary lane (g == 0): inputs become the constants of row -1.  Done as x * m1 + c0 with an opaque m1 in {0, 1}: a true
+    // IMAD (FMA pipe) instead of a LOP3 on the ALU pipe that bounds this loop
+    uint32_t m1 = g == 0 ? 0u : 1u, c0 = g == 0 ? FAST_CPACK : 0u;
+    asm volatile("" : "+r"(m1), "+r"(c0));
     // steps in which every thread of the warp is on a valid column need no range check: [G-1, smallest maxcols of the warp's groups)
     int steadyEnd = valid ? maxcols : 0;
     steadyEnd = min(steadyEnd, __shfl_xor_sync(FULL, steadyEnd, 16));
@@ -176,7 +178,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         uint32_t inF = __shfl_up_sync(FULL, outF, 1, G);
         uint32_t inV = __shfl_up_sync(FULL, outV, 1, G);
         uint32_t inRow = __shfl_up_sync(FULL, outRow, 1, G);
-        inH = (inH & m0) | c0; inF = (inF & m0) | c0; inV &= m0; inRow &= m0;
+        inH = inH * m1 + c0; inF = inF * m1 + c0; inV *= m1; inRow *= m1;
         const int c = t - g;
         if (!CHECKED || (c >= 0 && c < maxcols && !done)) {
             const uint32_t sel = selS[c];
@@ -203,7 +205,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             // local column best -> (value, absolute row); merge with the rows above (they win ties)
             const uint32_t lv = (cm + 0x000F000Fu) & 0xFFF0FFF0u;
             const uint32_t lrow = lv - cm + rowBase;
-            const uint32_t x = (inV | 0x80008000u) - lv;                     // lane bit15 set <=> inV >= lv
+            const uint32_t x = inV + 0x80008000u - lv;                       // lane bit15 set <=> inV >= lv (inV lanes are < 0x8000)
             const uint32_t keep = prmt(x, 0u, 0xBB99u);                 // 0xFFFF in lanes where the upstream value stays
             outV = vmax2(inV, lv);
             outRow = (inRow & keep) | (lrow & ~keep);
