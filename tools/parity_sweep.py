@@ -21,6 +21,10 @@ cfgs = [
     dict(read_len=(100, 150), win_len=(260, 420), seed=1008, go=6, ge=2, match=2, mismatch=3, max_indel=15),
     dict(read_len=(120, 150), win_len=400, seed=1009, go=2, ge=1, match=1, mismatch=1, max_indel=10),
     dict(read_len=150, win_len=400, seed=1010, go=3, ge=1, reads_per_window=50, max_indel=10, sub_rate=0.05),
+    # free gap extension + long deletions: wide bands (regular, wider than the matrix, doubled)
+    dict(read_len=(60, 150), win_len=(250, 500), seed=1011, go=3, ge=0, max_indel=120),
+    dict(read_len=(30, 120), win_len=(200, 512), seed=1012, go=5, ge=0, max_indel=200, junk_tail=0.2, low_complexity=0.1),
+    dict(read_len=(100, 300), win_len=(300, 700), seed=1013, go=4, ge=0, max_indel=150, sub_rate=0.03),
 ]
 bad = 0
 for cfg in cfgs:
