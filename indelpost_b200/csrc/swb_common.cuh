@@ -68,10 +68,13 @@ struct SwbDev {
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
 #define SWB_NBANDCLASS 8         // band jobs are bucketed by the rolling-buffer slots they need, see band_class()
 #define SWB_BAND_CLS_MID 4      // first class of k_band<48,64>; 5: k_band<112,32>; 6: k_band<254,32>; 7: k_band<0,128> (see band_class)
+// LIST_BANDW*: register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _FIRST: the traceback phase that is
+// certified first; _NEXT: jobs that kernel widened once.  LIST_BANDWARP*: wide bands, one warp per alignment (swb_bandwarp.cuh);
+// _NEXT is two lists used alternately by the re-queue rounds.
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
        LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
        LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104,
-       LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129, LIST_BANDWARP_NEXT = 130 /* two, alternating by round */ };   // wide regular bands: one warp per alignment (swb_bandwarp.cuh)   // register-band jobs per exact half-width 1..SWB_BANDW_MAX (swb_bandreg.cuh); _NEXT: jobs it widened once
+       LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129, LIST_BANDWARP_NEXT = 130 };
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
        CNT_CELLS_FWD = 136, CNT_CELLS_REV = 138, CNT_CELLS_BAND = 140, CNT_BAND_OVERFLOW = 142, CNT_CIGAR_OVERFLOW = 143,
