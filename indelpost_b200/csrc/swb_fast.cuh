@@ -215,7 +215,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
 
     int t = 0;
     for (; t < min(G - 1, nsteps); ++t) step(t, std::true_type{});
-#pragma unroll 4
+#pragma unroll (R == 10 ? 8 : 4)
     for (; t < steadyEnd; ++t) step(t, std::false_type{});
     for (; t < nsteps; ++t) {
         step(t, std::true_type{});
