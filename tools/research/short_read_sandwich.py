@@ -37,32 +37,40 @@ def sweep(read, ref, mat, go, ge, hot=None):
 
 
 def sweep_tight(read, ref, mat, go, ge):
-    """L_tight: Gotoh in which a vertical-gap CONTINUATION is dropped whenever its value lies in W = [128, 127 + go - ge], the only
-    values the signed exit test of the 8-bit lazy-F loop (ssw.c:309-311) can mis-read as 'no lane needs F any more'; a chain whose
-    value is outside W is always seen correctly, opens (H - go) are applied unconditionally (main loop / first lazy iteration).
-    E opens from H without F (ssw.c computes E before the lazy correction).  L_tight <= H(8-bit) <= Gotoh, no column flags needed."""
+    """L_tight, computed side by side with Gotoh (U): a vertical-gap CONTINUATION is dropped whenever the chain's value in the 8-bit
+    pass -- which lies between L's and U's value of that chain -- can be in W = [128, 127 + go - ge], the only values the signed exit
+    test of the 8-bit lazy-F loop (ssw.c:309-311) can mis-read as 'no lane needs F any more'.  A chain whose value is outside W is
+    always seen correctly, and opens (H - go) are applied unconditionally (main loop / first lazy iteration).  E opens from H without F
+    (ssw.c computes E before the lazy correction).  By induction over the cells L <= H(8-bit) <= U; no column flags needed."""
     m = len(read)
-    H = [0] * m; E = [0] * m
+    HL = [0] * m; EL = [0] * m; HU = [0] * m; EU = [0] * m
     colmax = np.zeros(len(ref), dtype=np.int64); brow = np.zeros(len(ref), dtype=np.int64)
     sc = mat[:, read]
     lo, hi = 128, 127 + go - ge
     NEG = -10**9
     for c, rb in enumerate(ref):
         srow = sc[rb]
-        hd = 0; f = NEG; hprev = None
+        hdL = hdU = 0; fL = fU = NEG; hpL = hpU = 0
         best = -1; bi = 0
         for i in range(m):
-            hnf = max(hd + int(srow[i]), E[i], 0)
+            s_ = int(srow[i])
+            hnfL = max(hdL + s_, EL[i], 0)
+            hU = max(hdU + s_, EU[i], 0)
             if i > 0:
-                cont = f - ge
-                if lo <= cont <= hi:
-                    cont = NEG
-                f = max(cont, hprev - go)
-            h = max(hnf, f) if i > 0 else hnf
-            hd = H[i]; H[i] = h; hprev = h
-            E[i] = max(E[i] - ge, hnf - go)
-            if h > best:
-                best = h; bi = i
+                contL = fL - ge; contU = fU - ge
+                if contL <= hi and contU >= lo:            # [contL, contU] meets W
+                    contL = NEG
+                fL = max(contL, hpL - go)
+                fU = max(contU, hpU - go)
+                hL = max(hnfL, fL); hU = max(hU, fU)
+            else:
+                hL = hnfL
+            hdL = HL[i]; HL[i] = hL; hpL = hL
+            hdU = HU[i]; HU[i] = hU; hpU = hU
+            EL[i] = max(EL[i] - ge, hnfL - go)
+            EU[i] = max(EU[i] - ge, hU - go)
+            if hL > best:
+                best = hL; bi = i
         colmax[c] = best; brow[c] = bi
     return colmax, brow
 
