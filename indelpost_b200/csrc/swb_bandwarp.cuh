@@ -1,4 +1,4 @@
-// swb_bandwarp.cuh — banded_sw (ssw.c:588-772) for WIDE regular bands, one WARP per alignment.
+// swb_bandwarp.cuh — banded_sw (ssw.c:588-772) for WIDE bands, one WARP per alignment.
 //
 // A free gap extension (indelPost's grid has gap_extension = 0 in 40 % of its calls) lets alignments span deletions of tens
 // to hundreds of bases, so |refLen - readLen| + 1 = W reaches 25-150.  One thread per alignment then walks (2W+1) x readLen cells
@@ -13,8 +13,10 @@
 // literally): there the only thing that differs from the plain recurrence is ssw.c:633 -- `edge` = min(end + 1, 2W + 2) is the
 // slot of the LAST column once the band has reached it (end = refLen - 1 < 2W + 2), so from that row on the last column reads
 // 0 for its upper neighbour's H and E.  Direction nibbles are stored by COLUMN (word j >> 3 of a 64-word row; a lane owns whole words),
-// the traceback is walked by lane 0.  Anything unusual -- the walk leaving the band, a band that has to be doubled, scratch
-// exhausted -- hands the job to the literal kernel, which starts it over.
+// the traceback is walked by lane 0.  The band is doubled in place (ssw.c:668-669; the layout does not depend on W) while the
+// doubled band is still one of the two kinds, and jobs the other band kernels widened into this kernel's range arrive with their
+// width and running maximum in t_bw / t_best.  Anything else -- the walk leaving the band, a doubled band that slides and is wider
+// than the matrix, scratch exhausted -- hands the job to the literal kernel with the state it needs to carry on exactly.
 #pragma once
 #include "swb_common.cuh"
 #include "swb_band.cuh"
