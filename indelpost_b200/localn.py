@@ -52,7 +52,8 @@ def prefetch_grid_search(target, read_seqs, ref_seqs, auto_adjust_extension_pena
     Returns the number of alignments computed."""
     grid = list(dict.fromkeys(generate_grid(auto_adjust_extension_penalty, gap_open_penalty, gap_extension_penalty, target)))
     if with_perfect_match:
-        grid += [("len", gap_extension_penalty), ("len", "len")]
+        # is_target_by_ssw runs with the gap_extension of the grid point that WON the search (varaln.pyx:421, localn.pyx:255)
+        grid += [("len", e) for e in dict.fromkeys([gap_extension_penalty] + [e for _, e in grid])] + [("len", "len")]
     return prefetch_alignments(read_seqs, ref_seqs, grid=tuple(grid), match_score=match_score, mismatch_penalty=mismatch_penalty, device=device)
 
 

@@ -1,0 +1,6 @@
+cdef class VariantRecord:
+    pass
+cdef class VariantRecordFilter:
+    pass
+cdef class VariantFile:
+    pass
