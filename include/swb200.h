@@ -87,7 +87,12 @@ uint32_t swb_to_cigar_int(uint32_t length, char op_letter);
 
 /* Input: de-duplicated read table and window table + per-pair indices.
  * All pointers are host pointers (pinned memory gives the best transfer
- * rate but is not required).  Offsets are in bytes from the blob start. */
+ * rate but is not required).  Offsets are in bytes from the blob start.
+ * SWB_SEQ_CODES tables may place entries anywhere in the blob (entries may
+ * even share bytes).  SWB_SEQ_ASCII tables are encoded in place on the
+ * device, so their entries must be in ascending offset order and must not
+ * overlap (off[i] >= off[i-1] + len[i-1]); a table that breaks the rule
+ * fails the call with -1. */
 typedef struct {
     int32_t        n_pairs;
     int32_t        n_reads;

@@ -31,6 +31,50 @@ def _c(a, dtype):
     return a
 
 
+class _OutLease:
+    """a (results, cigar arena) pair of pinned buffers on loan from a BatchAligner's pool"""
+
+    def __init__(self, owner, n, cap):
+        self.owner = owner
+        need_r, need_a = max(1, n) * L.RESULT_DTYPE.itemsize, max(64, cap) * 4
+        pool = owner._out_pool
+        pick = None
+        for i, (r, a) in enumerate(pool):
+            if r.nbytes >= need_r and a.nbytes >= need_a:
+                pick = i
+                break
+        if pick is not None:
+            self.res, self.arena = pool.pop(pick)
+        else:
+            if len(pool) >= 4:                      # keep the pool bounded: drop the smallest idle pair
+                j = min(range(len(pool)), key=lambda q: pool[q][0].nbytes + pool[q][1].nbytes)
+                for b in pool.pop(j):
+                    b.close()
+            self.res = L.PinnedBuffer(need_r + need_r // 8)
+            self.arena = L.PinnedBuffer(need_a + need_a // 8)
+
+    def views(self, n):
+        return self.res.view(L.RESULT_DTYPE, n), self.arena.view(np.uint32, self.arena.nbytes // 4)
+
+    def grow_arena(self, cap):
+        self.arena.close()
+        self.arena = L.PinnedBuffer(cap * 4 + cap // 2)
+
+    def release(self):
+        if self.res is not None:
+            if getattr(self.owner, "ctx", None):
+                self.owner._out_pool.append((self.res, self.arena))
+            else:
+                self.res.close(); self.arena.close()
+            self.res = self.arena = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class BatchAligner:
     def __init__(self, device: int = 0):
         self.lib = L.load()
@@ -41,6 +85,7 @@ class BatchAligner:
         self._keep = None
         self._res_pin = None      # pinned output staging, grown on demand and reused across calls
         self._arena_pin = None
+        self._out_pool = []       # pinned (results, arena) buffer pairs handed out by align_leased() and returned by their lease
 
     def _out_buffers(self, n: int, cap: int):
         """pinned (cudaMallocHost) result / CIGAR buffers: D2H into pageable numpy memory would be staged and
@@ -65,6 +110,9 @@ class BatchAligner:
             if getattr(self, b, None) is not None:
                 getattr(self, b).close()
                 setattr(self, b, None)
+        for r, a in getattr(self, "_out_pool", []):
+            r.close(); a.close()
+        self._out_pool = []
 
     def __del__(self):
         try:
@@ -88,6 +136,14 @@ class BatchAligner:
         b.n_pairs = int(arrs["pair_read"].shape[0])
         b.n_reads = int(arrs["read_len"].shape[0])
         b.n_windows = int(arrs["win_len"].shape[0])
+        # the C ABI trusts these sizes: a short array would be read past its end
+        for k in ("pair_win", "gap_open", "gap_ext", "ref_beg", "ref_len", "mask_len"):
+            if arrs[k] is not None and arrs[k].shape != (b.n_pairs,):
+                raise ValueError(f"{k} must have one entry per pair ({b.n_pairs}), got shape {arrs[k].shape}")
+        if arrs["read_off"].shape != (b.n_reads,) or arrs["win_off"].shape != (b.n_windows,):
+            raise ValueError("read_off / read_len and win_off / win_len must have equal sizes")
+        if arrs["mat"].size != int(n) * int(n):
+            raise ValueError(f"mat must hold n*n = {int(n) * int(n)} entries")
         b.seq_encoding = int(seq_encoding)
         for k, a in arrs.items():
             setattr(b, k, None if a is None else a.ctypes.data)
@@ -121,6 +177,25 @@ class BatchAligner:
                 raise L.SwbError(self._err())
             a = arena[: used.value]
             return (res.copy(), a.copy()) if copy else (res, a)
+
+    def align_leased(self, *args, cigar_cap: int | None = None, **kw):
+        """like align(), but the outputs land in pinned buffers taken from a pool and stay valid for as long as the returned
+        lease object lives (the buffers go back to the pool when it is released) -- no copy of the records"""
+        b, keep = self._make_batch(*args, **kw)
+        n = b.n_pairs
+        cap = int(cigar_cap if cigar_cap is not None else max(64, 8 * n))
+        used = C.c_int64(0)
+        lease = _OutLease(self, n, cap)
+        while True:
+            res, arena = lease.views(n)
+            rc = self.lib.swb_align_batch(self.ctx, C.byref(b), res.ctypes.data, arena.ctypes.data, arena.shape[0], C.byref(used))
+            if rc == -2:
+                lease.grow_arena(int(used.value) + 64)
+                continue
+            if rc != 0:
+                lease.release()
+                raise L.SwbError(self._err())
+            return res, arena[: used.value], lease
 
     # split form (device-resident timing)
     def upload(self, *args, **kw):

@@ -214,6 +214,7 @@ static inline double now_ms() { return std::chrono::duration<double, std::milli>
 #define TR(ctx, name) do { if (g_trace) (ctx)->trace.push_back(std::make_pair((const char*)(name), now_ms())); } while (0)
 static std::string g_create_err;
 static std::mutex g_mu;
+static void destroy_ctx(swb_ctx* c);
 
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 
@@ -251,67 +252,94 @@ extern "C" swb_ctx* swb_create(int device) {
     // stream priorities: the long forward sweep runs at the lowest priority, the per-class side streams in the middle and
     // everything on the critical path (small launches between host round trips) at the highest, so that with two pipeline
     // lanes one lane's short kernels are not queued behind the other lane's thousands of sweep blocks
+    int prevDevice = -1;
+    cudaGetDevice(&prevDevice);
     int prLeast = 0, prGreatest = 0;
-    cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
-    const int prMid = (prLeast + prGreatest) / 2;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess) {
-        g_create_err = std::string("cannot create stream: ") + cudaGetErrorString(cudaGetLastError());
+    if (cudaSetDevice(device) != cudaSuccess) {
+        g_create_err = std::string("cannot select device: ") + cudaGetErrorString(cudaGetLastError());
         delete c; return nullptr;
     }
-    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
-    cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prGreatest);
-    cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prGreatest);
-    cudaStreamCreateWithPriority(&c->stream4, cudaStreamNonBlocking, prGreatest); cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming);
-    cudaStreamCreateWithPriority(&c->bulk_stream, cudaStreamNonBlocking, prLeast);
-    cudaStreamCreateWithPriority(&c->bulk_stream2, cudaStreamNonBlocking, prLeast);
-    cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prGreatest); cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_bulk_join2, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_piece, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_bulk_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_bulk_join, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_rev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < SWB_BANDW_MAX; ++i) { cudaStreamCreateWithPriority(&c->bandw_stream[i], cudaStreamNonBlocking, prMid); cudaEventCreateWithFlags(&c->ev_bandw_join[i], cudaEventDisableTiming); }
-    for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamCreateWithPriority(&c->rev_stream[i], cudaStreamNonBlocking, prMid); cudaEventCreateWithFlags(&c->ev_rev_join[i], cudaEventDisableTiming); }
-    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
-    cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t));
-    for (int i = 0; i < 2; ++i) { cudaMallocHost((void**)&c->h_snap[i], SWB_NCOUNTERS * sizeof(int32_t)); cudaEventCreateWithFlags(&c->ev_snap[i], cudaEventDisableTiming); }
-    cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long));
+    cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
+    const int prMid = (prLeast + prGreatest) / 2;
+    // every creation / allocation is checked: a context with a missing stream or a null pinned mirror must not be handed out
+    cudaError_t bad = cudaSuccess; const char* what = "";
+    auto chk = [&](cudaError_t e2, const char* w) { if (e2 != cudaSuccess && bad == cudaSuccess) { bad = e2; what = w; } };
+    auto mkStream = [&](cudaStream_t* st, int prio) { chk(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio), "cudaStreamCreateWithPriority"); };
+    auto mkEvent = [&](cudaEvent_t* ev) { chk(cudaEventCreateWithFlags(ev, cudaEventDisableTiming), "cudaEventCreateWithFlags"); };
+    mkStream(&c->stream, prGreatest);
+    for (int i = 0; i < EV_COUNT; ++i) chk(cudaEventCreate(&c->ev[i]), "cudaEventCreate");
+    mkStream(&c->stream2, prGreatest);
+    mkStream(&c->stream3, prGreatest);
+    mkStream(&c->stream4, prGreatest); mkEvent(&c->ev_join3);
+    mkStream(&c->bulk_stream, prLeast);
+    mkStream(&c->bulk_stream2, prLeast);
+    mkStream(&c->copy_stream, prGreatest); mkEvent(&c->ev_copy);
+    mkEvent(&c->ev_bulk_join2); mkEvent(&c->ev_piece);
+    mkEvent(&c->ev_bulk_fork); mkEvent(&c->ev_bulk_join);
+    mkEvent(&c->ev_fork3);
+    mkEvent(&c->ev_rev_fork);
+    for (int i = 0; i < SWB_BANDW_MAX; ++i) { mkStream(&c->bandw_stream[i], prMid); mkEvent(&c->ev_bandw_join[i]); }
+    for (int i = 0; i < SWB_NREVB; ++i) { mkStream(&c->rev_stream[i], prMid); mkEvent(&c->ev_rev_join[i]); }
+    mkEvent(&c->ev_fork); mkEvent(&c->ev_join); mkEvent(&c->ev_join2);
+    chk(cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t)), "cudaMallocHost");
+    for (int i = 0; i < 2; ++i) { chk(cudaMallocHost((void**)&c->h_snap[i], SWB_NCOUNTERS * sizeof(int32_t)), "cudaMallocHost"); mkEvent(&c->ev_snap[i]); }
+    chk(cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long)), "cudaMallocHost");
     // opt in to large dynamic shared memory for the exact kernels
-    cudaFuncSetAttribute(k_exact<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-    cudaFuncSetAttribute(k_exact<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-    cudaFuncSetAttribute(k_exact<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-    cudaFuncSetAttribute(k_exact<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-    cudaFuncSetAttribute(k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS));
-    cudaFuncSetAttribute(k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS));
-    cudaFuncSetAttribute(k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS));
-    cudaFuncSetAttribute(k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS));
+    chk(cudaFuncSetAttribute(k_exact<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
+    chk(cudaFuncSetAttribute(k_exact<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
+    chk(cudaFuncSetAttribute(k_exact<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
+    chk(cudaFuncSetAttribute(k_exact<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
+    chk(cudaFuncSetAttribute(k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS)), "cudaFuncSetAttribute");
+    chk(cudaFuncSetAttribute(k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS)), "cudaFuncSetAttribute");
+    chk(cudaFuncSetAttribute(k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS)), "cudaFuncSetAttribute");
+    chk(cudaFuncSetAttribute(k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS)), "cudaFuncSetAttribute");
+    if (prevDevice >= 0 && prevDevice != device) cudaSetDevice(prevDevice);      // leave the caller's current device as it was
+    if (bad != cudaSuccess) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(bad);
+        cudaGetLastError();
+        destroy_ctx(c);
+        return nullptr;
+    }
     return c;
 }
 
-extern "C" void swb_destroy(swb_ctx* c) {
+static void destroy_ctx(swb_ctx* c) {
     if (!c) return;
-    if (c->sibling) { swb_destroy(c->sibling); c->sibling = nullptr; }
+    if (c->sibling) { destroy_ctx(c->sibling); c->sibling = nullptr; }
+    int prevDevice = -1;
+    cudaGetDevice(&prevDevice);
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* all[] = { &c->b_reads, &c->b_read_off, &c->b_read_len, &c->b_windows, &c->b_win_off, &c->b_win_len, &c->b_pair_read, &c->b_pair_win,
                       &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
                       &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
                       &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe, &c->b_fastcols,
                       &c->b_ind_off, &c->b_ind_cnt, &c->b_ind_rend, &c->b_ind_recs, &c->b_ind_misc, &c->b_ind_cig, &c->b_ind_coff, &c->b_ind_clen, &c->b_ind_rs, &c->b_ind_qs };
     for (DevBuf* b : all) b->release();
-    for (int i = 0; i < EV_COUNT; ++i) cudaEventDestroy(c->ev[i]);
-    cudaFreeHost(c->h_counters); cudaFreeHost(c->h_bump);
-    for (int i = 0; i < 2; ++i) { cudaFreeHost(c->h_snap[i]); cudaEventDestroy(c->ev_snap[i]); }
-    cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->stream3); cudaEventDestroy(c->ev_fork3);
-    cudaStreamDestroy(c->stream4); cudaEventDestroy(c->ev_join3);
-    cudaStreamDestroy(c->bulk_stream); cudaEventDestroy(c->ev_bulk_fork); cudaEventDestroy(c->ev_bulk_join);
-    cudaStreamDestroy(c->bulk_stream2); cudaEventDestroy(c->ev_bulk_join2); cudaEventDestroy(c->ev_piece);
-    cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_copy);
-    cudaEventDestroy(c->ev_rev_fork);
-    for (int i = 0; i < SWB_NREVB; ++i) { cudaStreamDestroy(c->rev_stream[i]); cudaEventDestroy(c->ev_rev_join[i]); }
-    for (int i = 0; i < SWB_BANDW_MAX; ++i) { cudaStreamDestroy(c->bandw_stream[i]); cudaEventDestroy(c->ev_bandw_join[i]); }
-    cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); cudaEventDestroy(c->ev_join2);
+    auto dS = [](cudaStream_t st) { if (st) cudaStreamDestroy(st); };
+    auto dE = [](cudaEvent_t ev) { if (ev) cudaEventDestroy(ev); };
+    for (int i = 0; i < EV_COUNT; ++i) dE(c->ev[i]);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_bump) cudaFreeHost(c->h_bump);
+    for (int i = 0; i < 2; ++i) { if (c->h_snap[i]) cudaFreeHost(c->h_snap[i]); dE(c->ev_snap[i]); }
+    dS(c->stream);
+    dS(c->stream3); dE(c->ev_fork3);
+    dS(c->stream4); dE(c->ev_join3);
+    dS(c->bulk_stream); dE(c->ev_bulk_fork); dE(c->ev_bulk_join);
+    dS(c->bulk_stream2); dE(c->ev_bulk_join2); dE(c->ev_piece);
+    dS(c->copy_stream); dE(c->ev_copy);
+    dE(c->ev_rev_fork);
+    for (int i = 0; i < SWB_NREVB; ++i) { dS(c->rev_stream[i]); dE(c->ev_rev_join[i]); }
+    for (int i = 0; i < SWB_BANDW_MAX; ++i) { dS(c->bandw_stream[i]); dE(c->ev_bandw_join[i]); }
+    dS(c->stream2); dE(c->ev_fork); dE(c->ev_join); dE(c->ev_join2);
+    cudaGetLastError();
+    if (prevDevice >= 0 && prevDevice != c->device) cudaSetDevice(prevDevice);
     delete c;
+}
+
+extern "C" void swb_destroy(swb_ctx* c) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    destroy_ctx(c);
 }
 
 extern "C" const char* swb_last_error(const swb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
@@ -392,12 +420,17 @@ static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v) {
 
     // table extents (host scan of the small length arrays; also the max lengths that size shared memory)
     int64_t reads_bytes = 0, win_bytes = 0; int32_t max_rl = 0, max_wl = 0;
+    // ASCII tables are encoded IN PLACE on the device and DNA_BASE_LUT is not idempotent ('A' -> 0 -> 4): entries that share
+    // blob bytes would be encoded twice.  ASCII entries must therefore be ascending and disjoint (include/swb200.h).
+    const bool ascii_in = b->seq_encoding == SWB_SEQ_ASCII;
     for (int32_t i = 0; i < b->n_reads; ++i) {
         if (b->read_len[i] < 0 || b->read_off[i] < v.rbyte_base) { c->err = "negative read offset/length"; return -1; }
+        if (ascii_in && b->read_off[i] - v.rbyte_base < reads_bytes) { c->err = "ASCII read table entries must be ascending and must not overlap"; return -1; }
         reads_bytes = std::max<int64_t>(reads_bytes, b->read_off[i] - v.rbyte_base + b->read_len[i]); max_rl = std::max(max_rl, b->read_len[i]);
     }
     for (int32_t i = 0; i < b->n_windows; ++i) {
         if (b->win_len[i] < 0 || b->win_off[i] < v.wbyte_base) { c->err = "negative window offset/length"; return -1; }
+        if (ascii_in && b->win_off[i] - v.wbyte_base < win_bytes) { c->err = "ASCII window table entries must be ascending and must not overlap"; return -1; }
         win_bytes = std::max<int64_t>(win_bytes, b->win_off[i] - v.wbyte_base + b->win_len[i]); max_wl = std::max(max_wl, b->win_len[i]);
     }
 
@@ -477,7 +510,7 @@ static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t s
         int g2 = 128 / T2;
         while (g2 > 32 / T2 && (size_t)g2 * per2 > (size_t)c->smem_optin) g2 /= 2;
         if ((size_t)g2 * per2 <= (size_t)c->smem_optin) {
-            static bool attr2[SWB_MAX_DEVICES] = {};          // function attributes are per device: one flag per device, not one per process
+            static std::atomic<bool> attr2[SWB_MAX_DEVICES] = {};          // function attributes are per device: one flag per device, not one per process
             if (!attr2[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_exact2<MODE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr2[c->device % SWB_MAX_DEVICES] = true; }
             k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2, fewJobsLikely ? 1 : 0);
             c->tm.n_launches++;
@@ -520,7 +553,7 @@ static int launch_fast_one(swb_ctx* c, int bucket, int firstPair, int upperBound
     int groups = 128 / FAST_G;
     while (groups > 2 && groups * per > (size_t)c->smem_optin - 1024) groups /= 2;
     const int threads = groups * FAST_G;
-    static bool attr_set[SWB_MAX_DEVICES] = {};               // per template instantiation and device
+    static std::atomic<bool> attr_set[SWB_MAX_DEVICES] = {};               // per template instantiation and device
     if (!attr_set[c->device % SWB_MAX_DEVICES]) {
         cudaFuncSetAttribute(k_fast<R, DIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
         cudaFuncSetAttribute(k_fast<R, DIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
@@ -583,7 +616,7 @@ static int launch_rev_band(swb_ctx* c, int upperBoundPairs) {
     CUDA_TRY(c, cudaEventRecord(c->ev_rev_fork, c->stream));
 #define SWB_REVB_LAUNCH(cls, WI, WD) { \
         const size_t smem = (size_t)revb_stride_words(rows, WI + WD + 1) * 4 * T; \
-        static bool attr[SWB_MAX_DEVICES] = {}; \
+        static std::atomic<bool> attr[SWB_MAX_DEVICES] = {}; \
         if (!attr[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_rev_band<WI, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr[c->device % SWB_MAX_DEVICES] = true; } \
         CUDA_TRY(c, cudaStreamWaitEvent(c->rev_stream[cls], c->ev_rev_fork, 0)); \
         k_rev_band<WI, WD><<<blocks, T, smem, c->rev_stream[cls]>>>(d, d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, rows); \
@@ -626,7 +659,7 @@ static int launch_band_reg_one(swb_ctx* c, int listSlot, int njobs, int nextBase
     const SwbDev& d = c->d;
     const int rows = std::min(d.max_rlen, SWB_BANDREG_MAXROWS);
     const size_t smem = (size_t)bandreg_stride_words(rows) * 4 * SWB_BANDREG_THREADS;
-    static bool attr[SWB_MAX_DEVICES] = {};
+    static std::atomic<bool> attr[SWB_MAX_DEVICES] = {};
     if (!attr[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_band_reg<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr[c->device % SWB_MAX_DEVICES] = true; }
     k_band_reg<W><<<(njobs + SWB_BANDREG_THREADS - 1) / SWB_BANDREG_THREADS, SWB_BANDREG_THREADS, smem, st>>>(d, d.list[listSlot], njobs, nextBase, nextBaseW, resume, rows);
     c->tm.n_launches++;
@@ -1031,6 +1064,8 @@ struct TableStream {                 // upload frontier of one sequence table
     int32_t maxlen = 0;              // longest entry seen so far
     int32_t front = 0;               // entries [0, front) are on the device
     int64_t ulo = 0, uhi = 0;        // blob bytes [ulo, uhi) are on the device
+    bool ascii = false;              // encoded in place on the device: entries must be ascending and disjoint
+    int64_t prev_end = 0;            // end of the last entry seen (ASCII rule)
 };
 
 // make entries [front, upto] resident: their table rows, the blob bytes they cover (the resident byte interval stays
@@ -1044,11 +1079,15 @@ static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, TableStep& st
     const int32_t i0 = t.front, n = upto - t.front + 1;
     int64_t lo = INT64_MAX, hi = 0;
     int64_t minoff = 0; int32_t minlen = 0, ml = t.maxlen;
+    bool overlap = false; int64_t pe = t.prev_end;
     for (int32_t i = i0; i <= upto; ++i) {
         const int64_t o = t.off[i]; const int32_t l = t.len[i];
         lo = std::min<int64_t>(lo, o); hi = std::max<int64_t>(hi, o + l); minoff = std::min(minoff, o); minlen = std::min(minlen, l); ml = std::max(ml, l);
+        overlap |= o < pe; pe = std::max<int64_t>(pe, o + l);
     }
     if (minoff < 0 || minlen < 0) { c->err = "negative sequence offset/length"; return -1; }
+    if (t.ascii && overlap) { c->err = "ASCII sequence table entries must be ascending and must not overlap"; return -1; }
+    t.prev_end = pe;
     t.maxlen = ml;
     if (hi > t.cap) return -3;                              // the blob outgrew the buffer sized from the previous call: the caller restarts with a full scan
     cudaStream_t s = c->copy_stream;
@@ -1132,6 +1171,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     tw.blob = b->windows; tw.off = b->win_off; tw.len = b->win_len; tw.n = b->n_windows;
     tw.d_blob = d.windows; tw.d_off = d.win_off; tw.d_len = d.win_len; tw.d_bad = (uint8_t*)c->b_wbad.p;
     tr.cap = reads_bytes; tw.cap = win_bytes;
+    tr.ascii = tw.ascii = b->seq_encoding == SWB_SEQ_ASCII;
 
     // piece boundaries: small first pieces (the sweep starts early), growing by 1.3x -- slower than the ratio of the sweep's to
     // the copy's throughput, so the copies stay ahead -- up to an eighth of the batch, and shrinking again at the end: the sweep
@@ -1329,11 +1369,24 @@ extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* resul
     const bool off = (mode && !strcmp(mode, "off")) || getenv("SWB200_NO_PIPELINE");
     if (b && !off && !lanes && b->n_pairs >= 262144 && b->n_reads > 0 && b->n_windows > 0) {
         if (g_trace) c->trace.clear();
+        // on ANY failing exit earlier pieces may still have async copies reading the caller's host arrays and kernels in flight:
+        // drain every stream before the caller gets its buffers back, and leave no half-built batch behind
+        auto drain = [&]() {
+            cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->bulk_stream); cudaStreamSynchronize(c->bulk_stream2);
+            cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4); cudaStreamSynchronize(c->stream);
+            cudaGetLastError();
+        };
         int rc = align_batch_streamed(c, b, results, cigar_arena, cigar_cap, cigar_used, getenv("SWB200_ALWAYS_SCAN") != nullptr);
         if (rc == -3) {
             // a sequence blob larger than the buffers of the previous call: let everything queued so far drain, then size exactly
-            cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->bulk_stream); cudaStreamSynchronize(c->bulk_stream2);
+            drain();
             rc = align_batch_streamed(c, b, results, cigar_arena, cigar_cap, cigar_used, true);
+        }
+        if (rc != 0) {
+            const std::string keep = c->err;
+            drain();
+            c->err = keep;
+            if (rc != -2) { c->have_batch = false; c->computed = false; }
         }
         if (g_trace) { fprintf(stderr, "TRACE streamed:"); for (auto& e : c->trace) fprintf(stderr, " %s@%.2f", e.first, e.second - t_call); fprintf(stderr, " end@%.2f\n", now_ms() - t_call); }
         return rc;

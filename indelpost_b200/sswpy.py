@@ -16,6 +16,7 @@ from typing import NamedTuple, Optional, Sequence, Union
 import numpy as np
 
 from . import _lib as L
+from . import _swbhost as H
 from .batch import BatchAligner, dna_score_matrix
 
 STR_T = Union[str, bytes]
@@ -37,6 +38,7 @@ for _ch, _v in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("U", 0)):
     _LUT[ord(_ch.lower())] = _v
 
 _OPS = "MIDNSHP=X"
+_RESOLVER = None          # set by indelpost_b200.wave while a wave scheduler runs: (ssw, go8, ge8, start_idx, search_length) -> Alignment | None
 
 
 def _to_bytes(o: STR_T) -> bytes:  # obj_to_cstr_len, sswpy.pyx:45-55
@@ -66,6 +68,8 @@ class SSW:
         self._lib = L.load()
         self.score_matrix = dna_score_matrix(_c_int(match_score), _c_int(mismatch_penalty))  # buildDNAScoreMatrix
         self._mkey = self.score_matrix.tobytes()
+        self._ms, self._mm = match_score, mismatch_penalty
+        self._rid = self._wid = self._rkey = self._wkey = None
         self.read = None
         self.reference = None
         self._read_arr = None
@@ -93,13 +97,16 @@ class SSW:
             self._profile = None
         self.read = read
         self._read_arr = arr
+        self._rid = _SEQ_IDS.get(raw)            # None: this read is in no prefetched block
+        self._rkey = raw
         self.read_length = len(raw)
         self._profile = self._lib.ssw_init(arr.ctypes.data, len(raw), self.score_matrix.ctypes.data, 5, 2)
 
     def setReference(self, reference: STR_T):  # sswpy.pyx:180-197
         raw = _to_bytes(reference)
         self._ref_arr = np.ascontiguousarray(_LUT[np.frombuffer(raw, dtype=np.uint8)])
-        self._ref_key = self._ref_arr.tobytes()
+        self._wid = _SEQ_IDS.get(raw)
+        self._wkey = raw
         self.reference = reference
         self.ref_length = len(raw)
         self._memo.clear()
@@ -122,12 +129,24 @@ class SSW:
             raise ValueError("call setReference first")
         if not self._profile:
             raise ValueError("Must set profile first")
-        key = (self._read_arr.tobytes(), gap_open & 0xFF, gap_extension & 0xFF, start_idx, search_length)
+        go8, ge8 = gap_open & 0xFF, gap_extension & 0xFF
+        key = (self._rkey, go8, ge8, start_idx, search_length)
         hit = self._memo.get(key)
-        if hit is None and _PREFETCHED:
-            hit = _PREFETCHED.get((self._mkey, self._ref_key) + key)          # filled by prefetch_alignments()
         if hit is not None:
             return hit
+        if _BLOCKS and start_idx == 0 and search_length == self.ref_length:
+            if self._rid is None:
+                self._rid = _SEQ_IDS.get(self._rkey)
+            if self._wid is None:
+                self._wid = _SEQ_IDS.get(self._wkey)
+            if self._rid is not None and self._wid is not None:
+                hit = prefetched(self._mkey, self._rid, self._wid, go8, ge8, self.read_length)      # filled by prefetch_alignments()
+                if hit is not None:
+                    return hit
+        if _RESOLVER is not None:
+            hit = _RESOLVER(self, go8, ge8, start_idx, search_length)                                 # wave scheduler (wave.py)
+            if hit is not None:
+                return hit
         mask_len = self.read_length // 2  # align_c, sswpy.pyx:209-211
         mask_len = 15 if mask_len < 15 else mask_len
         ref_ptr = self._ref_arr.ctypes.data + start_idx
@@ -162,14 +181,97 @@ def _aligner(device: int) -> BatchAligner:
     return a
 
 
-def _blob(seqs: Sequence[STR_T]):
-    raws = [_to_bytes(s) for s in seqs]
-    lens = np.fromiter((len(r) for r in raws), dtype=np.int32, count=len(raws))
-    off = np.zeros(len(raws), dtype=np.int64)
-    if len(raws) > 1:
-        np.cumsum(lens[:-1], out=off[1:])
-    data = np.frombuffer(b"".join(raws), dtype=np.int8) if raws else np.zeros(0, np.int8)
-    return data, off, lens
+class AlignmentList(Sequence):
+    """Results of one batch: a sequence of ``Alignment`` tuples backed by the C ABI's fixed-stride records
+    (``records``, dtype RESULT_DTYPE = every s_align field, ssw.h:55-66) and the BAM-packed CIGAR arena
+    (``cigar_arena``).  An ``Alignment`` (and its "%d%s" CIGAR string, sswpy.pyx:283-298) is only built when an
+    element is asked for; vectorised consumers read ``records`` directly."""
+
+    __slots__ = ("records", "cigar_arena", "_lease", "_ra", "_aa")
+
+    def __init__(self, records: np.ndarray, cigar_arena: np.ndarray, lease=None):
+        self.records = records
+        self.cigar_arena = cigar_arena
+        self._lease = lease                       # keeps the pinned output buffers alive (returned to the aligner's pool on release)
+        self._ra = records.ctypes.data
+        self._aa = cigar_arena.ctypes.data
+
+    def __len__(self):
+        return self.records.shape[0]
+
+    def __getitem__(self, k):
+        n = self.records.shape[0]
+        if isinstance(k, slice):
+            return [H.alignment(self._ra, self._aa, i, Alignment) for i in range(*k.indices(n))]
+        k = int(k)
+        if k < 0:
+            k += n
+        if not 0 <= k < n:
+            raise IndexError("alignment index out of range")
+        return H.alignment(self._ra, self._aa, k, Alignment)
+
+    def __iter__(self):
+        n = self.records.shape[0]
+        for k0 in range(0, n, 4096):
+            yield from H.alignments(self._ra, self._aa, k0, min(n, k0 + 4096), Alignment)
+
+    def tolist(self):
+        return H.alignments(self._ra, self._aa, 0, self.records.shape[0], Alignment)
+
+    def __eq__(self, other):
+        if isinstance(other, AlignmentList):
+            other = other.tolist()
+        return self.tolist() == other
+
+    __hash__ = None
+
+
+class _Staging:
+    """reusable pinned host arrays for the inputs of one batch (the batched entry's contract: SURVEY.md 8b).  Two sets per
+    aligner, used alternately, so the arrays of the previous call stay untouched while a caller still looks at them."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def view(self, name, dtype, count):
+        dt = np.dtype(dtype)
+        need = max(1, count) * dt.itemsize + 16
+        b = self.bufs.get(name)
+        if b is None or b.nbytes < need:
+            if b is not None:
+                b.close()
+            b = self.bufs[name] = L.PinnedBuffer(need + need // 4)
+        return b.view(dt, count)
+
+    def table(self, name, seqs):
+        """str / bytes sequences -> (blob, off, len) in pinned memory, copied once, in C (csrc/swbhost.c)"""
+        n = len(seqs)
+        total = H.total_len(seqs)
+        blob = self.view(name + ".blob", np.int8, total)
+        off = self.view(name + ".off", np.int64, n)
+        ln = self.view(name + ".len", np.int32, n)
+        H.gather(seqs, blob.ctypes.data, total, off.ctypes.data, ln.ctypes.data, 0)
+        return blob, off, ln
+
+
+def _staging(a: BatchAligner) -> _Staging:
+    sets = getattr(a, "_staging_sets", None)
+    if sets is None:
+        sets = a._staging_sets = [_Staging(), _Staging()]
+        a._staging_turn = 0
+    a._staging_turn ^= 1
+    return sets[a._staging_turn]
+
+
+def _per_pair(v, default, n, name):
+    if v is None:
+        return None if default is None else np.full(n, default, dtype=np.int64)
+    a = np.asarray(v, dtype=np.int64)
+    if a.ndim == 0:
+        return np.full(n, int(a), dtype=np.int64)
+    if a.shape != (n,):
+        raise ValueError(f"{name} must be a scalar or have one entry per pair ({n}), got shape {a.shape}")
+    return a
 
 
 def align_batch(
@@ -185,63 +287,56 @@ def align_batch(
     mismatch_penalty: int = 2,
     device: int = 0,
     aligner: Optional[BatchAligner] = None,
-):
+) -> AlignmentList:
     """Align ``reads[pair_read[k]]`` against ``references[pair_ref[k]]`` for every k in ONE GPU batch.
 
     Each result equals what ``SSW(match_score, mismatch_penalty)`` + ``setReference`` + ``setRead`` +
     ``align(gap_open[k], gap_extension[k], start_idx[k], end_idx[k])`` returns (sswpy.pyx:227-304);
     ``gap_open`` / ``gap_extension`` / ``start_idx`` / ``end_idx`` may be scalars or per-pair sequences.
     Reads and references are de-duplicated tables: a locus' window is uploaded once however many reads
-    and gap-penalty grid points refer to it.  Returns ``list[Alignment]``.
+    and gap-penalty grid points refer to it.  The sequences are gathered straight into reusable pinned staging
+    arrays and the results come back as an ``AlignmentList`` (lazy ``Alignment`` tuples over the raw records).
     """
-    n = len(pair_read)
     pr = np.asarray(pair_read, dtype=np.int32)
     pw = np.asarray(pair_ref, dtype=np.int32)
-    if pw.shape[0] != n:
-        raise ValueError("pair_read and pair_ref must have the same length")
+    n = int(pr.shape[0])
+    if pr.ndim != 1 or pw.shape != (n,):
+        raise ValueError("pair_read and pair_ref must be one-dimensional and have the same length")
     if n and (pr.min() < 0 or pr.max() >= len(reads) or pw.min() < 0 or pw.max() >= len(references)):
         raise IndexError("pair index out of range")
-    rdata, roff, rlen = _blob(reads)
-    wdata, woff, wlen = _blob(references)
-
-    def per_pair(v, default):
-        if v is None:
-            return np.full(n, default, dtype=np.int64)
-        a = np.asarray(v, dtype=np.int64)
-        return np.full(n, int(a), dtype=np.int64) if a.ndim == 0 else a
-
-    go = per_pair(gap_open, 3)
-    ge = per_pair(gap_extension, 1)
-    s0 = per_pair(start_idx, 0)
-    e0 = per_pair(end_idx, 0)
-    ref_length = wlen[pw].astype(np.int64) if n else np.zeros(0, np.int64)
-    if n:
-        if (s0 < 0).any() or (e0 < 0).any():
-            raise ValueError("negative indexing not supported")
-        bad = (e0 > ref_length) | (s0 > ref_length)
-        if bad.any():
-            k = int(np.nonzero(bad)[0][0])
-            raise ValueError("start_idx: {} or end_idx: {} can't be greater than ref_length: {}".format(int(s0[k]), int(e0[k]), int(ref_length[k])))
-    e_final = np.where(e0 == 0, ref_length, e0)
-    search = (e_final - s0).astype(np.int32)
+    go = _per_pair(gap_open, 3, n, "gap_open")
+    ge = _per_pair(gap_extension, 1, n, "gap_extension")
+    s0 = _per_pair(start_idx, None, n, "start_idx")
+    e0 = _per_pair(end_idx, None, n, "end_idx")
     a = aligner or _aligner(device)
-    res, arena = a.align(
-        rdata, roff, rlen, wdata, woff, wlen, pr, pw,
-        (go & 0xFF).astype(np.uint8), (ge & 0xFF).astype(np.uint8),
-        ref_beg=s0.astype(np.int32), ref_len=search, mask_len=None,
-        mat=dna_score_matrix(match_score, mismatch_penalty), n=5, score_size=2, flag=1,
-        seq_encoding=L.SWB_SEQ_ASCII,
+    st = _staging(a)
+    rdata, roff, rlen = st.table("reads", reads)
+    wdata, woff, wlen = st.table("windows", references)
+    p_pr = st.view("pair_read", np.int32, n); p_pr[:] = pr
+    p_pw = st.view("pair_win", np.int32, n); p_pw[:] = pw
+    p_go = st.view("gap_open", np.uint8, n); np.bitwise_and(go, 0xFF, out=p_go, casting="unsafe")
+    p_ge = st.view("gap_ext", np.uint8, n); np.bitwise_and(ge, 0xFF, out=p_ge, casting="unsafe")
+    p_rb = p_rl = None
+    if s0 is not None or e0 is not None:
+        ref_length = wlen[pw].astype(np.int64) if n else np.zeros(0, np.int64)
+        s0 = np.zeros(n, np.int64) if s0 is None else s0
+        e0 = np.zeros(n, np.int64) if e0 is None else e0
+        if n:
+            if (s0 < 0).any() or (e0 < 0).any():
+                raise ValueError("negative indexing not supported")
+            bad = (e0 > ref_length) | (s0 > ref_length)
+            if bad.any():
+                k = int(np.nonzero(bad)[0][0])
+                raise ValueError("start_idx: {} or end_idx: {} can't be greater than ref_length: {}".format(int(s0[k]), int(e0[k]), int(ref_length[k])))
+        p_rb = st.view("ref_beg", np.int32, n); p_rb[:] = s0
+        p_rl = st.view("ref_len", np.int32, n); p_rl[:] = np.where(e0 == 0, ref_length, e0) - s0
+    res, arena, lease = a.align_leased(
+        rdata, roff, rlen, wdata, woff, wlen, p_pr, p_pw, p_go, p_ge, ref_beg=p_rb, ref_len=p_rl, mask_len=None,
+        mat=dna_score_matrix(match_score, mismatch_penalty), n=5, score_size=2, flag=1, seq_encoding=L.SWB_SEQ_ASCII,
     )
     if n and (res["status"] != 0).any():
         raise ValueError("Problem Running alignment, see stdout")
-    # Alignment tuples exactly like sswpy.pyx:283-298; the CIGAR tokens of the whole batch are formatted in one vectorised pass
-    # ("%d%s" per op, MAPSTR "MIDNSHP=X", ssw.h:171-190: op codes above 8 print as 'M')
-    ops_chars = np.array(list(_OPS + "M" * 7))
-    tok = np.char.add((arena >> 4).astype("U"), ops_chars[arena & 15]).tolist() if arena.shape[0] else []
-    out = [Alignment("".join(tok[o : o + l]) if l > 0 else None, a, b, c, d, e, f)
-           for o, l, a, b, c, d, e, f in zip(res["cigar_off"].tolist(), res["cigar_len"].tolist(), res["score1"].tolist(), res["score2"].tolist(),
-                                             res["ref_begin1"].tolist(), res["ref_end1"].tolist(), res["read_begin1"].tolist(), res["read_end1"].tolist())]
-    return out
+    return AlignmentList(res, arena, lease)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -252,14 +347,129 @@ def align_batch(
 # gap-penalty grid (varaln.pyx:1127-1143).  prefetch_alignments() computes that whole set in ONE GPU batch and
 # SSW.align() answers from it, so the unmodified per-call code runs at batch throughput.  Results are the same
 # tuples align() would compute; nothing is approximated.
+#
+# Storage: one _Block per prefetch call -- the raw result records of (pair, grid point) plus three small index dicts
+# (read id -> row, window id -> column, penalty pair -> grid slot).  Registering a block costs O(reads + windows + grid),
+# not O(pairs); an Alignment tuple is built when the control flow asks for that pair, and kept.
 
 INDELPOST_GRID = ((3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0))          # varaln.pyx:1127-1143
-_PREFETCHED: dict = {}
-_PREFETCH_LIMIT = 4_000_000
+_PREFETCH_LIMIT = 16_000_000            # pairs kept before the oldest blocks are dropped
+_SEQ_IDS: dict = {}                     # raw sequence bytes -> interned id
+_BLOCKS: dict = {}                      # (matrix bytes, window id) -> [blocks holding that window]
+_BLOCK_FIFO: dict = {}                  # id(block) -> block, oldest first
+_prefetched_pairs = 0
+
+
+_next_seq_id = 0
+
+
+def seq_id(raw: bytes) -> int:
+    """interned id of a sequence; ids are never reused (an SSW object may hold one across clear_prefetched())"""
+    global _next_seq_id
+    i = _SEQ_IDS.get(raw)
+    if i is None:
+        i = _SEQ_IDS[raw] = _next_seq_id
+        _next_seq_id += 1
+    return i
+
+
+class _Block:
+    __slots__ = ("alist", "n", "rows", "cols", "n_cols", "pairs", "grid", "made", "mkey", "wids")
+
+    def find(self, rid, wid, go8, ge8, rlen):
+        if self.pairs is not None:
+            p = self.pairs.get((rid, wid))
+        else:
+            r = self.rows.get(rid)
+            c = self.cols.get(wid)
+            p = None if r is None or c is None else r * self.n_cols + c
+        if p is None:
+            return None
+        g = self.grid.get((go8, ge8))
+        if g is None and go8 == (rlen & 0xFF):
+            g = self.grid.get(("len", ge8))
+            if g is None and ge8 == (rlen & 0xFF):
+                g = self.grid.get(("len", "len"))
+        if g is None:
+            return None
+        k = g * self.n + p
+        hit = self.made.get(k)
+        if hit is None:
+            hit = self.made[k] = self.alist[k]
+        return hit
 
 
 def clear_prefetched():
-    _PREFETCHED.clear()
+    global _prefetched_pairs
+    _BLOCKS.clear()
+    _BLOCK_FIFO.clear()
+    _SEQ_IDS.clear()
+    _prefetched_pairs = 0
+
+
+def drop_block(b) -> None:
+    """forget one prefetched block (lists are replaced, not edited: a concurrent reader keeps iterating its own copy)"""
+    global _prefetched_pairs
+    if _BLOCK_FIFO.pop(id(b), None) is None:
+        return
+    _prefetched_pairs -= len(b.alist)
+    for w in b.wids:
+        lst = _BLOCKS.get((b.mkey, w))
+        if lst is not None:
+            rest = [x for x in lst if x is not b]
+            if rest:
+                _BLOCKS[(b.mkey, w)] = rest
+            else:
+                _BLOCKS.pop((b.mkey, w), None)
+
+
+def register_block(alist: AlignmentList, rids, wids, pair_read, pair_ref, grid, mkey: bytes, cross: bool):
+    """make the results of a (pairs x grid) batch -- record k = g * n_pairs + p -- visible to SSW.align"""
+    global _prefetched_pairs
+    b = _Block()
+    b.alist, b.mkey, b.made = alist, mkey, {}
+    b.n = len(alist) // max(1, len(grid))
+    if cross:
+        b.rows = {r: i for i, r in enumerate(rids)}
+        b.cols = {w: i for i, w in enumerate(wids)}
+        b.n_cols, b.pairs = len(wids), None
+    else:
+        b.rows = b.cols = None
+        b.n_cols = 0
+        b.pairs = {(rids[r], wids[w]): p for p, (r, w) in enumerate(zip(pair_read.tolist(), pair_ref.tolist()))}
+    b.grid = {}
+    for g, (o, e) in enumerate(grid):
+        b.grid.setdefault((o if o == "len" else int(o) & 0xFF, e if e == "len" else int(e) & 0xFF), g)
+    b.wids = list(dict.fromkeys(wids))
+    for w in b.wids:
+        _BLOCKS[(mkey, w)] = _BLOCKS.get((mkey, w), []) + [b]
+    _BLOCK_FIFO[id(b)] = b
+    _prefetched_pairs += len(alist)
+    while _prefetched_pairs > _PREFETCH_LIMIT and len(_BLOCK_FIFO) > 1:
+        drop_block(next(iter(_BLOCK_FIFO.values())))
+    return b
+
+
+def prefetched(mkey: bytes, rid, wid, go8: int, ge8: int, rlen: int):
+    """the prefetched Alignment of (read id, window id, narrowed penalties) or None"""
+    blocks = _BLOCKS.get((mkey, wid))
+    if blocks:
+        for b in blocks:
+            hit = b.find(rid, wid, go8, ge8, rlen)
+            if hit is not None:
+                return hit
+    return None
+
+
+def grid_penalties(grid, rlen_of_pair: np.ndarray):
+    """(gap_open, gap_extension) arrays of shape [len(grid), n_pairs]; "len" stands for len(read) (localn.pyx:253-255)"""
+    n, g = rlen_of_pair.shape[0], len(grid)
+    go = np.empty((g, n), dtype=np.int64)
+    ge = np.empty((g, n), dtype=np.int64)
+    for k, (o, e) in enumerate(grid):
+        go[k] = rlen_of_pair if o == "len" else int(o)
+        ge[k] = rlen_of_pair if e == "len" else int(e)
+    return go, ge
 
 
 def prefetch_alignments(reads: Sequence[STR_T], references: Sequence[STR_T], pair_read=None, pair_ref=None, grid=INDELPOST_GRID,
@@ -268,35 +478,25 @@ def prefetch_alignments(reads: Sequence[STR_T], references: Sequence[STR_T], pai
     (gap_open, gap_extension) of ``grid`` in one GPU batch and keep the results for ``SSW.align``.  A grid entry whose
     gap_open is the string ``"len"`` stands for ``gap_open = len(read)`` (localn.pyx:253-255).  Returns the number of
     alignments computed."""
-    if pair_read is None or pair_ref is None:
-        pair_read = np.repeat(np.arange(len(reads), dtype=np.int32), len(references))
-        pair_ref = np.tile(np.arange(len(references), dtype=np.int32), len(reads))
-    pr = np.asarray(pair_read, dtype=np.int32)
-    pw = np.asarray(pair_ref, dtype=np.int32)
+    cross = pair_read is None or pair_ref is None
+    if cross:
+        pr = np.repeat(np.arange(len(reads), dtype=np.int32), len(references))
+        pw = np.tile(np.arange(len(references), dtype=np.int32), len(reads))
+    else:
+        pr = np.asarray(pair_read, dtype=np.int32)
+        pw = np.asarray(pair_ref, dtype=np.int32)
     n, g = pr.shape[0], len(grid)
     if n == 0 or g == 0:
         return 0
     raws_r = [_to_bytes(s) for s in reads]
-    rlen = np.fromiter((len(r) for r in raws_r), dtype=np.int64, count=len(raws_r))
-    go = np.empty((g, n), dtype=np.int64)
-    ge = np.empty((g, n), dtype=np.int64)
-    for k, (o, e) in enumerate(grid):
-        go[k] = rlen[pr] if o == "len" else int(o)
-        ge[k] = rlen[pr] if e == "len" else int(e)
-    alns = align_batch(reads, references, np.tile(pr, g), np.tile(pw, g), go.reshape(-1), ge.reshape(-1),
-                       match_score=match_score, mismatch_penalty=mismatch_penalty, device=device)
-    if len(_PREFETCHED) + len(alns) > _PREFETCH_LIMIT:
-        _PREFETCHED.clear()
+    raws_w = [_to_bytes(s) for s in references]
+    rlen = np.fromiter(map(len, raws_r), dtype=np.int64, count=len(raws_r))
+    go, ge = grid_penalties(grid, rlen[pr])
+    alist = align_batch(raws_r, raws_w, np.tile(pr, g), np.tile(pw, g), go.reshape(-1), ge.reshape(-1),
+                        match_score=match_score, mismatch_penalty=mismatch_penalty, device=device)
     mkey = dna_score_matrix(_c_int(match_score), _c_int(mismatch_penalty)).tobytes()
-    ref_keys = [_LUT[np.frombuffer(_to_bytes(s), dtype=np.uint8)].tobytes() for s in references]
-    read_keys = [_LUT[np.frombuffer(r, dtype=np.uint8)].tobytes() for r in raws_r]
-    ref_len = [len(k) for k in ref_keys]
-    gof, gef = go.reshape(-1), ge.reshape(-1)
-    for k, a in enumerate(alns):
-        p = k % n
-        r, w = int(pr[p]), int(pw[p])
-        _PREFETCHED[(mkey, ref_keys[w], read_keys[r], int(gof[k]) & 0xFF, int(gef[k]) & 0xFF, 0, ref_len[w])] = a
-    return len(alns)
+    register_block(alist, [seq_id(r) for r in raws_r], [seq_id(w) for w in raws_w], pr, pw, grid, mkey, cross)
+    return len(alist)
 
 
 # ---------------------------------------------------------------------------------------------

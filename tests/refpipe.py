@@ -102,19 +102,48 @@ def analyse(locus, fa, bam):
     return out
 
 
-def run_locus(locus, ssw_cls=None, calls=None):
-    """-> summary dict; with `calls` (a list) every SW call is recorded into it"""
+import contextlib
+import threading
+
+
+@contextlib.contextmanager
+def swapped(ssw_cls):
+    """`indelpost.localn.SSW = ssw_cls` for the duration of the block (process-wide: set it ONCE around concurrent tasks)"""
+    localn = load()[2]
+    saved = localn.SSW
+    localn.SSW = ssw_cls
+    try:
+        yield
+    finally:
+        localn.SSW = saved
+
+
+class ThreadCalls:
+    """list-like sink that keeps one call list per thread (for recording under the wave scheduler)"""
+
+    def __init__(self):
+        self._tl = threading.local()
+
+    def start(self, dest):
+        self._tl.dest = dest
+
+    def append(self, x):
+        self._tl.dest.append(x)
+
+
+def run_locus(locus, ssw_cls=None, calls=None, swap=True, bam_cls=None):
+    """-> summary dict; with `calls` (a list) every SW call is recorded into it.  swap=False: the caller has already
+    installed the SSW class (refpipe.swapped) -- required when several loci run concurrently."""
     indelpost, pysam, localn, RefSSW = load()
+    if not swap:
+        fa, bam = open_locus(locus, bam_cls)
+        return analyse(locus, fa, bam)
     cls = ssw_cls or RefSSW
     if calls is not None:
         cls = recording(cls, calls)
-    saved = localn.SSW
-    localn.SSW = cls
-    try:
-        fa, bam = open_locus(locus)
+    with swapped(cls):
+        fa, bam = open_locus(locus, bam_cls)
         return analyse(locus, fa, bam)
-    finally:
-        localn.SSW = saved
 
 
 def classify_call(call, locus):

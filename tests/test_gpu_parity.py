@@ -69,6 +69,49 @@ def test_gpu_ascii_encoding_and_bad_input():
     assert rg["ref_begin1"][3] == -1 and rg["cigar_len"][3] == 0
 
 
+def test_gpu_aliasing_table_entries():
+    """table entries that share blob bytes: fine for codes (nothing is rewritten), rejected for ASCII input -- the device encodes
+    ASCII tables in place and DNA_BASE_LUT is not idempotent ('A' -> 0 -> 4), so a shared byte would be encoded twice"""
+    from gpuutil import aligner, gpu_align
+    from indelpost_b200 import _lib as L
+
+    rng = np.random.default_rng(12)
+    win = rng.integers(0, 4, 400).astype(np.int8)
+    blob = np.concatenate([win[40:240], win[300:380]])           # read 0 = blob[0:150], read 1 = blob[50:200] (overlapping), read 2 = blob[200:280]
+    b = T.Batch(blob, np.array([0, 50, 200], np.int64), np.array([150, 150, 80], np.int32), win, np.array([0, 0], np.int64), np.array([400, 300], np.int32),
+                np.array([0, 1, 2, 1], np.int32), np.array([0, 0, 0, 1], np.int32), np.full(4, 3, np.uint8), np.full(4, 1, np.uint8))
+    rg, ag, _ = gpu_align(b)
+    flat = T.batch_from_lists([blob[0:150], blob[50:200], blob[200:280]], [win, win[:300]], [0, 1, 2, 1], [0, 0, 0, 1], 3, 1)
+    ro, ao = T.oracle().align_batch(flat)
+    T.compare(rg, ag, ro, ao, what="aliasing code tables")
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    b.reads = lut[b.reads].view(np.int8)
+    b.windows = lut[b.windows].view(np.int8)
+    b.seq_encoding = 1
+    with pytest.raises(L.SwbError, match="must not overlap"):
+        gpu_align(b)
+    b.read_off = np.array([200, 0, 50], np.int64)                # disjoint but not ascending
+    b.read_len = np.array([80, 40, 150], np.int32)
+    with pytest.raises(L.SwbError, match="ascending"):
+        gpu_align(b)
+    rg2, ag2, _ = gpu_align(flat)                                 # the context is usable after the rejected calls
+    T.compare(rg2, ag2, ro, ao, what="after rejected batches")
+
+
+def test_python_layer_rejects_short_per_pair_arrays():
+    from gpuutil import aligner
+
+    b = T.make_pairs(64, (60, 100), 200, seed=3)
+    a = aligner()
+    with pytest.raises(ValueError, match="one entry per pair"):
+        a.align(b.reads, b.read_off, b.read_len, b.windows, b.win_off, b.win_len, b.pair_read, b.pair_win, b.gap_open[:10], b.gap_ext, mat=b.mat)
+    with pytest.raises(ValueError, match="equal sizes"):
+        a.align(b.reads, b.read_off[:-1], b.read_len, b.windows, b.win_off, b.win_len, b.pair_read, b.pair_win, b.gap_open, b.gap_ext, mat=b.mat)
+    from indelpost_b200 import align_batch
+    with pytest.raises(ValueError, match="one entry per pair"):
+        align_batch(["ACGT" * 10], ["ACGT" * 30], [0, 0, 0], [0, 0, 0], gap_open=[3, 3])
+
+
 def test_sswpy_api_matches_reference_golden():
     """the reference's own sswpy.SSW outputs (tests/golden/sswpy_api.json) through our SSW class"""
     from indelpost_b200 import SSW, align_batch
@@ -155,8 +198,8 @@ def test_prefetch_serves_the_per_call_api():
         for r, rd in enumerate(reads):
             for go, ge in ((3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0), (len(rd), 1)):
                 got = localn.align(al, rd, go, ge)
-                key = (sswpy.dna_score_matrix(3, 2).tobytes(), al._ref_key, al._read_arr.tobytes(), go & 0xFF, ge & 0xFF, 0, len(win))
-                assert sswpy._PREFETCHED[key] is got         # served from the prefetched set
+                hit = sswpy.prefetched(sswpy.dna_score_matrix(3, 2).tobytes(), sswpy.seq_id(rd.encode()), sswpy.seq_id(win.encode()), go & 0xFF, ge & 0xFF, len(rd))
+                assert hit is got                              # served from the prefetched set
                 if (w, r, go, ge) in direct:
                     assert got == direct[(w, r, go, ge)]
     ip.clear_prefetched()
@@ -183,14 +226,14 @@ def test_prefetch_grid_search_covers_the_locus_calls():
             for go, ge in ((5, 0), (len(reads[r]), 1), (len(reads[r]), len(reads[r]))):
                 direct[(w, r, go, ge)] = localn.align(al, reads[r], go, ge)
     n = localn.prefetch_grid_search(Target(), reads, [ref, contig], True, 3, 1, 3, 2)
-    assert n == len(reads) * 2 * 8
+    assert n == len(reads) * 2 * 9          # 6 grid points + (len, 1) + (len, 0) + (len, len)
     for w, win in enumerate((ref, contig)):
         al = localn.make_aligner(win, 3, 2)
         for r, rd in enumerate(reads):
             for go, ge in localn.generate_grid(True, 3, 1, Target()) + [(len(rd), 1), (len(rd), len(rd))]:
                 got = localn.align(al, rd, go, ge)
-                key = (sswpy.dna_score_matrix(3, 2).tobytes(), al._ref_key, al._read_arr.tobytes(), go & 0xFF, ge & 0xFF, 0, len(win))
-                assert sswpy._PREFETCHED[key] is got
+                hit = sswpy.prefetched(sswpy.dna_score_matrix(3, 2).tobytes(), sswpy.seq_id(rd.encode()), sswpy.seq_id(win.encode()), go & 0xFF, ge & 0xFF, len(rd))
+                assert hit is got
                 if (w, r, go, ge) in direct:
                     assert got == direct[(w, r, go, ge)]
     ip.clear_prefetched()

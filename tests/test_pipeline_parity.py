@@ -128,3 +128,31 @@ def test_gpu_prefetch_behind_the_reference_pipeline():
         out = refpipe.run_locus(lc2, ssw_cls=SSW, calls=calls)
         clear_prefetched()
         _assert_same(spec, out_ref, calls_ref, out, calls)
+
+
+@pytest.mark.gpu
+def test_gpu_wave_runner_behind_the_reference_pipeline():
+    """all loci advance together as wave tasks: every miss of the unmodified control flow is served by ONE merged GPU batch per
+    wave (indelpost_b200/wave.py); outputs and call streams identical to the reference's own run"""
+    from indelpost_b200 import SSW, clear_prefetched, wave
+
+    specs = loci.parity_specs()
+    want = [reference_run(spec) for spec in specs]
+    got_calls = [[] for _ in specs]
+    sink = refpipe.ThreadCalls()
+    pysam = refpipe.load()[1]
+    tee = wave.tee_alignment_file(pysam.AlignmentFile)          # reads are registered as the pileup fetches them
+
+    def run(k):
+        sink.start(got_calls[k])
+        return refpipe.run_locus(loci.make_locus(**specs[k]), swap=False, bam_cls=tee)
+
+    clear_prefetched()
+    runner = wave.WaveRunner(max_inflight=64)
+    with refpipe.swapped(refpipe.recording(SSW, sink)):
+        outs = runner.map(run, range(len(specs)))
+    for k, spec in enumerate(specs):
+        _assert_same(spec, want[k][1], want[k][2], outs[k], got_calls[k])
+    n_calls = sum(len(c) for c in got_calls)
+    assert runner.stats["waves"] < n_calls / 100, runner.stats          # ~26 k calls, a few dozen GPU batches
+    clear_prefetched()

@@ -1,0 +1,153 @@
+"""Pipeline-level measurement (BASELINE.json configs 1 / 3 / 4): loci per second of the UNMODIFIED reference pipeline
+(`VariantAlignment` + `count_alleles` + `phase`, oracle/_ref_pipeline + stub pysam) on synthetic loci,
+
+   reference : on its own sswpy / ssw.c (one host process per worker, loci split evenly),
+   wave      : the same control flow with `indelpost.localn.SSW = indelpost_b200.SSW` under the wave scheduler
+               (indelpost_b200/wave.py): all loci of a worker advance together, one merged GPU batch per wave,
+
+and the check that both give identical outputs for every locus.  The host logic above the SW calls is the reference's own
+single-threaded Python/Cython in both arms (out of scope), so the ratio is Amdahl-bounded by the
+SW share of a locus (54-64 %); scaling beyond one host core is by processes (loci are independent).
+
+    python tools/bench_pipeline.py [--config cfg3] [--loci N] [--workers P] [--arms reference,wave] [--devices 0,1,...]
+
+Used by bench.py (`extra.pipeline`) on rank 0 with a bounded sample; standalone it prints one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = {
+    # BASELINE.json configs[0]: single 1-bp deletion locus, 200 x 150-bp reads
+    "cfg1": dict(kinds=[("del", 1)], n_reads=200, read_len=150, window=50),
+    # configs[2]: indel loci x 500 reads (150 bp), mixed indel types (del / ins 1-20 bp, 10 % complex)
+    "cfg3": dict(kinds=[("del", 1), ("ins", 2), ("del", 4), ("ins", 6), ("del", 9), ("ins", 12), ("hidden_del", 3), ("hidden_ins", 5), ("del", 17), ("complex", 6)],
+                 n_reads=500, read_len=150, window=50),
+    # configs[3]: high-depth amplicon, 250-bp reads vs ~1 kb windows (window=167), complex indels; depth bounded for the sample
+    "cfg4": dict(kinds=[("complex", 9), ("del", 12), ("ins", 15), ("complex", 14)], n_reads=2000, read_len=250, window=167, genome_len=6000, pos=3000),
+}
+
+
+def make_specs(config: str, n_loci: int, seed0: int = 5000):
+    c = CONFIGS[config]
+    specs = []
+    for k in range(n_loci):
+        kind, ev = c["kinds"][k % len(c["kinds"])]
+        sp = dict(seed=seed0 + k, kind=kind, ev_len=ev, n_reads=c["n_reads"], read_len=c["read_len"], window=c["window"])
+        if kind == "complex":
+            sp["ins_len"] = max(2, ev // 2)
+        for opt in ("genome_len", "pos"):
+            if opt in c:
+                sp[opt] = c[opt]
+        specs.append(sp)
+    return specs
+
+
+def _worker(arm, specs, device, q):
+    """one host process: its share of the loci through one arm -> (seconds, summaries, stats)"""
+    try:
+        import loci
+        import refpipe
+
+        lcs = [loci.make_locus(**sp) for sp in specs]          # generation is not part of the timed region
+        refpipe.load()
+        if arm == "reference":
+            t0 = time.perf_counter()
+            outs = [refpipe.run_locus(lc) for lc in lcs]
+            dt = time.perf_counter() - t0
+            q.put((dt, outs, {}))
+            return
+        from indelpost_b200 import SSW, clear_prefetched, wave
+        from indelpost_b200.sswpy import _aligner
+
+        al = _aligner(device)
+        tee = wave.tee_alignment_file(refpipe.load()[1].AlignmentFile)
+        runner = wave.WaveRunner(device=device, aligner=al, max_inflight=256)
+        with refpipe.swapped(SSW):
+            # warm-up: context, kernels, staging buffers
+            runner.map(lambda lc: refpipe.run_locus(lc, swap=False, bam_cls=tee), lcs[:1])
+            runner.stats = {k: 0 for k in runner.stats}
+            clear_prefetched()
+            t0 = time.perf_counter()
+            outs = runner.map(lambda lc: refpipe.run_locus(lc, swap=False, bam_cls=tee), lcs)
+            dt = time.perf_counter() - t0
+        q.put((dt, outs, dict(runner.stats)))
+    except BaseException as e:  # noqa: BLE001
+        import traceback
+        q.put((None, traceback.format_exc(), {}))
+
+
+def run_arm(arm, specs, workers, devices):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    shards = [specs[k::workers] for k in range(workers)]
+    procs = []
+    t0 = time.perf_counter()
+    for k, sh in enumerate(shards):
+        p = ctx.Process(target=_worker, args=(arm, sh, devices[k % len(devices)], q))
+        p.start()
+        procs.append(p)
+    parts = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    for dt, outs, st in parts:
+        if dt is None:
+            raise RuntimeError(f"{arm} worker failed:\n{outs}")
+    return parts, wall, shards
+
+
+def measure(config="cfg3", n_loci=32, workers=1, arms=("reference", "wave"), devices=(0,)):
+    specs = make_specs(config, n_loci)
+    n_reads = sum(sp["n_reads"] for sp in specs)
+    out = {"config": config, "loci": n_loci, "reads": n_reads, "workers": workers, "devices": list(devices),
+           "what": "unmodified reference VariantAlignment + count_alleles + phase per locus (stub pysam, synthetic loci); timed region = the pipeline calls, "
+                   "max over worker processes; host logic above the SW calls is the reference's own in both arms"}
+    by_arm = {}
+    for arm in arms:
+        parts, wall, shards = run_arm(arm, specs, workers, devices)
+        dt = max(p[0] for p in parts)
+        # results back in locus order: worker k got specs[k::workers]; parts arrive in completion order -> match by content
+        summaries = {}
+        for p in parts:
+            for o in p[1]:
+                summaries.setdefault(json.dumps(o, sort_keys=True, default=str), 0)
+                summaries[json.dumps(o, sort_keys=True, default=str)] += 1
+        by_arm[arm] = summaries
+        stats = {}
+        for p in parts:
+            for k, v in p[2].items():
+                stats[k] = stats.get(k, 0) + v
+        out[arm] = {"seconds": dt, "loci_per_s": n_loci / dt, "reads_per_s": n_reads / dt, "wall_incl_startup_s": wall}
+        if stats:
+            out[arm]["waves"] = stats.get("waves")
+            out[arm]["pairs_aligned"] = stats.get("pairs")
+            out[arm]["requests"] = stats.get("requests")
+    if "reference" in by_arm and "wave" in by_arm:
+        out["identical_outputs"] = by_arm["reference"] == by_arm["wave"]
+        out["speedup"] = out["wave"]["loci_per_s"] / out["reference"]["loci_per_s"]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--loci", type=int, default=32)
+    ap.add_argument("--workers", type=int, default=1)
+    ap.add_argument("--arms", default="reference,wave")
+    ap.add_argument("--devices", default="0")
+    a = ap.parse_args()
+    print(json.dumps(measure(a.config, a.loci, a.workers, tuple(a.arms.split(",")), tuple(int(x) for x in a.devices.split(",")))))
+
+
+if __name__ == "__main__":
+    main()
