@@ -14,29 +14,15 @@
 // the host only synchronises to read the few counters that size the next launch.  swb_align_batch additionally
 // pipelines large batches over two such contexts ("lanes") with chunk views of the caller's tables.
 // There is no CPU implementation behind any entry point: without a usable GPU every call fails.
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-#include <mutex>
-#include <algorithm>
-#include <atomic>
-#include <thread>
-#include <climits>
-
-#include "swb_common.cuh"
-#include "swb_exact.cuh"
-#include "swb_exact2.cuh"
+#include "swb_host.h"
+#define SWB_WITH_CERT_KERNEL          // k_certify_rest is defined (and launched) by this unit only
 #include "swb_cert.cuh"
-#include "swb_band.cuh"
-#include "swb_fast.cuh"
-#include "swb_revband.cuh"
-#include "swb_bandreg.cuh"
-#include "swb_bandwarp.cuh"
+#include "swb_band.cuh"               // launch geometry constants only: the band kernels are instantiated by swb_l_band.cu
+#include "swb_exact2.cuh"             // SWB_EXACT_SPARSE_MAX
+#include "swb_bandreg.cuh"            // SWB_BANDREG_* (instantiated by swb_l_bandreg.cu)
 #include "swb_indels.cuh"
 
 #define SWB_VERSION "swb200 0.1 (sm_100a)"
-#define SWB_MAX_DEVICES 64
 
 // ------------------------------------------------------------------------------------------------
 // small kernels
@@ -154,69 +140,11 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
 // context
 // ------------------------------------------------------------------------------------------------
 
-struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_BAND_R0, EV_BAND_ALL, EV_COUNT };
-
-struct swb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
-    cudaStream_t stream4 = nullptr; cudaEvent_t ev_join3; unsigned verify_pending = 0;   // second verification stream
-    cudaStream_t bulk_stream = nullptr;                                     // lowest priority: the forward DPX sweep (yields SM slots to the short, latency-bound kernels of the other lane)
-    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy;              // streamed path: host->device copies back to back on their own stream
-    cudaStream_t bulk_stream2 = nullptr;                                    // second one: consecutive forward slices of the streamed one-shot path overlap their tails
-    cudaEvent_t ev_bulk_fork, ev_bulk_join, ev_bulk_join2, ev_piece;
-    cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
-    cudaStream_t rev_stream[SWB_NREVB];                                     // banded reverse pass: one stream per band class
-    cudaEvent_t ev_rev_fork, ev_rev_join[SWB_NREVB];
-    cudaStream_t bandw_stream[SWB_BANDW_MAX]; cudaEvent_t ev_bandw_join[SWB_BANDW_MAX];   // register-band kernels: one stream per half-width
-    unsigned bandreg_used = 0; int bandreg_base = 0;                       // side streams the register-band kernels of the current round run on
-    cudaEvent_t ev[EV_COUNT];
-    std::string err;
-    SwbDev d;
-    bool have_batch = false, computed = false;
-    // device buffers
-    DevBuf b_reads, b_read_off, b_read_len, b_windows, b_win_off, b_win_len;
-    DevBuf b_pair_read, b_pair_win, b_ref_beg, b_ref_len, b_go, b_ge, b_mask, b_mat;
-    DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
-    DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe, b_fastcols;
-    DevBuf b_ind_off, b_ind_cnt, b_ind_rend, b_ind_recs, b_ind_misc, b_ind_cig, b_ind_coff, b_ind_clen, b_ind_rs, b_ind_qs;   // indel extraction
-    int fastMaxCols[SWB_NBUCKETS] = {};
-    int32_t* h_counters = nullptr;              // pinned mirror of counters
-    int32_t* h_snap[2] = {nullptr, nullptr};    // streamed path: counter snapshots of the piece in flight and the one before
-    cudaEvent_t ev_snap[2];
-    unsigned long long* h_bump = nullptr;       // pinned mirror of bump
-    swb_timing tm;
-    int smem_optin = 0;
-    int n_sm = 0;
-    int64_t chunk_pairs = 0;
-    std::vector<std::pair<const char*, double>> trace;
-    swb_ctx* sibling = nullptr;                 // second lane, created on demand by the pipelined swb_align_batch
-    bool pipelined_last = false;
-};
-
-// SWB200_TRACE=1: host wall-clock marks (after the host-side synchronisation points) dumped to stderr per swb_align_batch call
-#include <chrono>
-static const bool g_trace = getenv("SWB200_TRACE") != nullptr;
-static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-#define TR(ctx, name) do { if (g_trace) (ctx)->trace.push_back(std::make_pair((const char*)(name), now_ms())); } while (0)
+const bool g_trace = getenv("SWB200_TRACE") != nullptr;
 static std::string g_create_err;
 static std::mutex g_mu;
 static void destroy_ctx(swb_ctx* c);
 
-#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 
 extern "C" int swb_device_count(void) {
     int n = 0;
@@ -285,14 +213,8 @@ extern "C" swb_ctx* swb_create(int device) {
     for (int i = 0; i < 2; ++i) { chk(cudaMallocHost((void**)&c->h_snap[i], SWB_NCOUNTERS * sizeof(int32_t)), "cudaMallocHost"); mkEvent(&c->ev_snap[i]); }
     chk(cudaMallocHost((void**)&c->h_bump, 2 * sizeof(unsigned long long)), "cudaMallocHost");
     // opt in to large dynamic shared memory for the exact kernels
-    chk(cudaFuncSetAttribute(k_exact<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
-    chk(cudaFuncSetAttribute(k_exact<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
-    chk(cudaFuncSetAttribute(k_exact<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
-    chk(cudaFuncSetAttribute(k_exact<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin), "cudaFuncSetAttribute");
-    chk(cudaFuncSetAttribute(k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS)), "cudaFuncSetAttribute");
-    chk(cudaFuncSetAttribute(k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS)), "cudaFuncSetAttribute");
-    chk(cudaFuncSetAttribute(k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS)), "cudaFuncSetAttribute");
-    chk(cudaFuncSetAttribute(k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS)), "cudaFuncSetAttribute");
+    chk(swb_exact_set_attrs(c->smem_optin), "cudaFuncSetAttribute");
+    chk(swb_band_set_attrs(), "cudaFuncSetAttribute");
     if (prevDevice >= 0 && prevDevice != device) cudaSetDevice(prevDevice);      // leave the caller's current device as it was
     if (bad != cudaSuccess) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(bad);
@@ -461,16 +383,6 @@ static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v) {
 // compute
 // ------------------------------------------------------------------------------------------------
 
-// SWB200_DEBUG_SYNC=1: synchronise after every stage and name the one that faulted
-static int stage_check(swb_ctx* c, const char* name) {
-    static const bool dbg = getenv("SWB200_DEBUG_SYNC") != nullptr;
-    if (!dbg) return 0;
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { c->err = std::string("stage ") + name + ": " + cudaGetErrorString(e); fprintf(stderr, "libswb200: %s\n", c->err.c_str()); return -1; }
-    return 0;
-}
-
 static int read_counters(swb_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->d.counters, SWB_NCOUNTERS * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_bump, c->d.bump, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -489,144 +401,16 @@ static int launch_validate(swb_ctx* c, int8_t* blob, const int64_t* off, const i
     return 0;
 }
 
-// fewJobsLikely: the list is expected to hold a handful of jobs (overflow verification) but its length is only known on the
-// device: launch the dense and the one-job-per-warp schedule of k_exact2 side by side, the kernels pick by the real count
-template <int MODE, int DIR>
-static int launch_exact(swb_ctx* c, int listSlot, int upperBound, cudaStream_t st = nullptr, bool fewJobsLikely = false) {
-    if (upperBound <= 0) return 0;
-    if (!st) st = c->stream;
-    const SwbDev& d = c->d;
-    const int W = MODE ? 8 : 16;
-    const int segAlloc = (d.max_rlen + W - 1) / W;
-    const int per = exact_smem_per_group(MODE, d.n, d.max_rlen);
-    int groups = 128 / W;                                   // groups per block at 128 threads
-    while (groups > 32 / W && (size_t)groups * per > (size_t)c->smem_optin) groups /= 2;
-    if ((size_t)groups * per > (size_t)c->smem_optin) { c->err = "read too long for the exact kernel's shared-memory profile"; return -1; }
-    // packed variant (two SSE2 lanes per thread) whenever its 16-bit lanes cannot saturate; SWB200_OPT bit1 forces the scalar-lane kernel
-    const bool packed = !(d.opt & 2) && (MODE == 0 || (long long)d.max_score * d.max_rlen <= 32000);
-    if (packed) {
-        const int T2 = W / 2;
-        const int per2 = exact2_smem_per_group(MODE, d.n, d.max_rlen);
-        int g2 = 128 / T2;
-        while (g2 > 32 / T2 && (size_t)g2 * per2 > (size_t)c->smem_optin) g2 /= 2;
-        if ((size_t)g2 * per2 <= (size_t)c->smem_optin) {
-            static std::atomic<bool> attr2[SWB_MAX_DEVICES] = {};          // function attributes are per device: one flag per device, not one per process
-            if (!attr2[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_exact2<MODE, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr2[c->device % SWB_MAX_DEVICES] = true; }
-            k_exact2<MODE, DIR><<<(upperBound + g2 - 1) / g2, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2, fewJobsLikely ? 1 : 0);
-            c->tm.n_launches++;
-            if (fewJobsLikely) {
-                const int warps = g2 * T2 / 32;
-                k_exact2<MODE, DIR><<<(SWB_EXACT_SPARSE_MAX + warps - 1) / warps, g2 * T2, (size_t)g2 * per2, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per2, 2);
-                c->tm.n_launches++;
-            }
-            CUDA_TRY(c, cudaGetLastError());
-            return stage_check(c, MODE ? (DIR ? "exact2 word rev" : "exact2 word fwd") : (DIR ? "exact2 byte rev" : "exact2 byte fwd"));
-        }
-    }
-    const int threads = groups * W;
-    const int blocks = (upperBound + groups - 1) / groups;
-    k_exact<MODE, DIR><<<blocks, threads, (size_t)groups * per, st>>>(d, d.list[listSlot], d.counters + listSlot, segAlloc, per);
-    c->tm.n_launches++;
-    CUDA_TRY(c, cudaGetLastError());
-    return stage_check(c, MODE ? (DIR ? "exact word rev" : "exact word fwd") : (DIR ? "exact byte rev" : "exact byte fwd"));
-}
-
-// fast-path launch geometry: groups of FAST_G threads, 10 bytes of shared memory per column per group
-#define SWB_FAST_SMEM_COLS 1024     // windows longer than this keep their column bests in global memory
-
-template <int R, int DIR>
-static int launch_fast_one(swb_ctx* c, int bucket, int firstPair, int upperBoundPairs, cudaStream_t st) {
-    SwbDev& d = c->d;
-    const int colAlloc = (std::max(c->fastMaxCols[bucket], 8) + 7) & ~7;      // longest window among this bucket's pairs
-    const bool globalCols = colAlloc > SWB_FAST_SMEM_COLS;
-    const size_t per = (size_t)colAlloc * (globalCols ? 2 : 10);
-    // long windows: the global column-best scratch is bounded, the bucket is served in slices of the job list
-    int slicePairs = upperBoundPairs - firstPair;
-    if (globalCols) {
-        const size_t budget = (size_t)4 << 30;
-        const size_t perPairPair = (size_t)2 * colAlloc * 4;
-        const size_t evenBudget = std::max<size_t>(2, 2 * (budget / perPairPair));      // pairs per slice (even: lane pairs stay intact)
-        slicePairs = (size_t)slicePairs <= evenBudget ? slicePairs : (int)evenBudget;
-        CUDA_TRY(c, c->b_fastcols.ensure((size_t)((slicePairs + 1) / 2) * perPairPair + 16));
-        d.fast_cols = (uint32_t*)c->b_fastcols.p;
-    } else d.fast_cols = nullptr;
-    int groups = 128 / FAST_G;
-    while (groups > 2 && groups * per > (size_t)c->smem_optin - 1024) groups /= 2;
-    const int threads = groups * FAST_G;
-    static std::atomic<bool> attr_set[SWB_MAX_DEVICES] = {};               // per template instantiation and device
-    if (!attr_set[c->device % SWB_MAX_DEVICES]) {
-        cudaFuncSetAttribute(k_fast<R, DIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
-        cudaFuncSetAttribute(k_fast<R, DIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
-        attr_set[c->device % SWB_MAX_DEVICES] = true;
-    }
-    const int slot = (DIR ? LIST_FAST_REV : LIST_FAST_FWD) + bucket;
-    for (int off = firstPair; off < upperBoundPairs; off += slicePairs) {
-        const int n = std::min(slicePairs, upperBoundPairs - off);
-        const int ngroups = (n + 1) / 2;
-        const int blocks = (ngroups + groups - 1) / groups;
-        if (globalCols) k_fast<R, DIR, true><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
-        else k_fast<R, DIR, false><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
-        c->tm.n_launches++;
-    }
-    CUDA_TRY(c, cudaGetLastError());
-    return 0;
-}
-
-// one launch per non-empty read-length bucket (R = 2*(bucket+1) rows per thread) over the list ranges [first[b], counts[b])
-template <int DIR>
-static int launch_fast_range(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) {
-    for (int b = 0; b < SWB_NBUCKETS; ++b) {
-        const int n = counts[b], f = first ? first[b] : 0;
-        if (n <= f) continue;
-        int rc = 0;
-        switch (b) {
-            case 0: rc = launch_fast_one<2, DIR>(c, b, f, n, st); break;
-            case 1: rc = launch_fast_one<4, DIR>(c, b, f, n, st); break;
-            case 2: rc = launch_fast_one<6, DIR>(c, b, f, n, st); break;
-            case 3: rc = launch_fast_one<8, DIR>(c, b, f, n, st); break;
-            case 4: rc = launch_fast_one<10, DIR>(c, b, f, n, st); break;
-            case 5: rc = launch_fast_one<12, DIR>(c, b, f, n, st); break;
-            case 6: rc = launch_fast_one<14, DIR>(c, b, f, n, st); break;
-            case 7: rc = launch_fast_one<16, DIR>(c, b, f, n, st); break;
-        }
-        if (rc) return rc;
-    }
-    return 0;
-}
-
 template <int DIR>
 static int launch_fast(swb_ctx* c, const int* counts) {
     // the forward sweeps go to the low-priority stream (see swb_create), the reverse ones stay on the main stream
     if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_fork, c->stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_fork, 0)); }
-    const int rc = launch_fast_range<DIR>(c, nullptr, counts, DIR == 0 ? c->bulk_stream : c->stream);
+    const int rc = DIR == 0 ? swb_launch_fast_range_fwd(c, nullptr, counts, c->bulk_stream) : swb_launch_fast_range_rev(c, nullptr, counts, c->stream);
     if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join, c->bulk_stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_bulk_join, 0)); }
     if (rc) return rc;
     return stage_check(c, DIR ? "fast rev" : "fast fwd");
 }
 
-// banded reverse pass (swb_revband.cuh): one launch per band class, each on its own stream so that the classes
-// (a few thousand warps each) overlap; grids are sized by an upper bound (the classes were filled by the forward
-// sweep, no host round trip), blocks beyond the real count exit at once
-static int launch_rev_band(swb_ctx* c, int upperBoundPairs) {
-    if (upperBoundPairs <= 0 || (c->d.opt & 4)) return 0;
-    const SwbDev& d = c->d;
-    const int T = SWB_REVB_THREADS;
-    const int blocks = ((upperBoundPairs + 1) / 2 + T - 1) / T;
-    const int rows = std::min(d.max_rlen, 32 * SWB_NBUCKETS);
-    CUDA_TRY(c, cudaEventRecord(c->ev_rev_fork, c->stream));
-#define SWB_REVB_LAUNCH(cls, WI, WD) { \
-        const size_t smem = (size_t)revb_stride_words(rows, WI + WD + 1) * 4 * T; \
-        static std::atomic<bool> attr[SWB_MAX_DEVICES] = {}; \
-        if (!attr[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_rev_band<WI, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr[c->device % SWB_MAX_DEVICES] = true; } \
-        CUDA_TRY(c, cudaStreamWaitEvent(c->rev_stream[cls], c->ev_rev_fork, 0)); \
-        k_rev_band<WI, WD><<<blocks, T, smem, c->rev_stream[cls]>>>(d, d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, rows); \
-        c->tm.n_launches++; \
-        CUDA_TRY(c, cudaEventRecord(c->ev_rev_join[cls], c->rev_stream[cls])); }
-    SWB_REVB_CLASSES(SWB_REVB_LAUNCH)
-#undef SWB_REVB_LAUNCH
-    CUDA_TRY(c, cudaGetLastError());
-    return 0;
-}
 // the main stream waits for the band classes (after it has queued the wavefront sweep of the remaining pairs)
 static int join_rev_band(swb_ctx* c, int upperBoundPairs) {
     if (upperBoundPairs <= 0 || (c->d.opt & 4)) return 0;
@@ -646,25 +430,13 @@ static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound, 
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
     CUDA_TRY(c, cudaStreamWaitEvent(vs, c->ev_fork3, 0));
-    if (launch_exact<0, 0>(c, verifyList, upperBound, vs, /*fewJobsLikely=*/true)) return -1;      // confirms the overflow, or produces the byte-mode result
+    if (swb_launch_exact(c, 0, 0, verifyList, upperBound, vs, /*fewJobsLikely=*/true)) return -1;      // confirms the overflow, or produces the byte-mode result
     CUDA_TRY(c, cudaEventRecord(which ? c->ev_join3 : c->ev_join2, vs));
     c->verify_pending |= 1u << which;
     return 0;
 }
 static int certify_phase2_hook(swb_ctx* c, int total) { return total > 0 ? certify_and_verify_async(c, LIST_VERIFY2, total, 1) : 0; }
 
-// register-band kernels (swb_bandreg.cuh): one launch per exact half-width, spread over the side streams
-template <int W>
-static int launch_band_reg_one(swb_ctx* c, int listSlot, int njobs, int nextBase, int nextBaseW, int resume, cudaStream_t st) {
-    const SwbDev& d = c->d;
-    const int rows = std::min(d.max_rlen, SWB_BANDREG_MAXROWS);
-    const size_t smem = (size_t)bandreg_stride_words(rows) * 4 * SWB_BANDREG_THREADS;
-    static std::atomic<bool> attr[SWB_MAX_DEVICES] = {};
-    if (!attr[c->device % SWB_MAX_DEVICES]) { cudaFuncSetAttribute(k_band_reg<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 4096); attr[c->device % SWB_MAX_DEVICES] = true; }
-    k_band_reg<W><<<(njobs + SWB_BANDREG_THREADS - 1) / SWB_BANDREG_THREADS, SWB_BANDREG_THREADS, smem, st>>>(d, d.list[listSlot], njobs, nextBase, nextBaseW, resume, rows);
-    c->tm.n_launches++;
-    return 0;
-}
 static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBase, int nextBaseW, int resume) {
     int any = 0;
     for (int w = 1; w <= SWB_BANDW_MAX; ++w) any += njobsW[w - 1];
@@ -676,13 +448,7 @@ static int launch_band_reg(swb_ctx* c, int baseW, const int* njobsW, int nextBas
         if (n <= 0) continue;
         cudaStream_t st = c->bandw_stream[w - 1];
         CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_rev_fork, 0));
-        switch (w) {
-#define SWB_BR_CASE(W) case W: launch_band_reg_one<W>(c, baseW + W - 1, n, nextBase, nextBaseW, resume, st); break;
-            SWB_BR_CASE(1) SWB_BR_CASE(2) SWB_BR_CASE(3) SWB_BR_CASE(4) SWB_BR_CASE(5) SWB_BR_CASE(6) SWB_BR_CASE(7) SWB_BR_CASE(8)
-            SWB_BR_CASE(9) SWB_BR_CASE(10) SWB_BR_CASE(11) SWB_BR_CASE(12) SWB_BR_CASE(13) SWB_BR_CASE(14) SWB_BR_CASE(15) SWB_BR_CASE(16)
-            SWB_BR_CASE(17) SWB_BR_CASE(18) SWB_BR_CASE(19) SWB_BR_CASE(20) SWB_BR_CASE(21) SWB_BR_CASE(22) SWB_BR_CASE(23) SWB_BR_CASE(24)
-#undef SWB_BR_CASE
-        }
+        if ((w <= 12 ? swb_launch_band_reg_lo : swb_launch_band_reg_hi)(c, w, baseW + w - 1, n, nextBase, nextBaseW, resume, st)) return -1;
         CUDA_TRY(c, cudaEventRecord(c->ev_bandw_join[w - 1], st));
         c->bandreg_used |= 1u << (w - 1);
     }
@@ -741,26 +507,13 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
             CUDA_TRY(c, cudaEventRecord(c->ev_fork, s));
             CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             if (nWarp > 0) {
-                k_band_warp<<<(nWarp + SWB_BANDWARP_WARPS - 1) / SWB_BANDWARP_WARPS, 32 * SWB_BANDWARP_WARPS, 0, c->stream2>>>(d, d.list[baseWarp], nWarp, nxt);
-                c->tm.n_launches++;
+                if (swb_launch_band_warp(c, baseWarp, nWarp, nxt, c->stream2)) return -1;
                 CUDA_TRY(c, cudaMemsetAsync(d.counters + baseWarp, 0, 4, c->stream2));      // list consumed
             }
-            if (njobs[7] > 0) { k_band<0, SWB_BAND_THREADS><<<(njobs[7] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, SWB_BAND_THREADS, 0, c->stream2>>>(d, cur, 7, 7, nxt); c->tm.n_launches++; }
-            if (njobs[6] > 0) {
-                k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS><<<(njobs[6] + SWB_BAND_HUGE_THREADS - 1) / SWB_BAND_HUGE_THREADS, SWB_BAND_HUGE_THREADS,
-                                                                    band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS), c->stream2>>>(d, cur, 6, 6, nxt);
-                c->tm.n_launches++;
-            }
-            if (njobs[5] > 0) {
-                k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS><<<(njobs[5] + SWB_BAND_WIDE_THREADS - 1) / SWB_BAND_WIDE_THREADS, SWB_BAND_WIDE_THREADS,
-                                                                    band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS), c->stream2>>>(d, cur, 5, 5, nxt);
-                c->tm.n_launches++;
-            }
-            if (njobs[4] > 0) {
-                k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS><<<(njobs[4] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, SWB_BAND_MID_THREADS,
-                                                                  band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS), c->stream2>>>(d, cur, 4, 4, nxt);
-                c->tm.n_launches++;
-            }
+            if (swb_launch_band(c, 0, (njobs[7] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, cur, 7, 7, nxt, c->stream2)) return -1;
+            if (swb_launch_band(c, 4, (njobs[6] + SWB_BAND_HUGE_THREADS - 1) / SWB_BAND_HUGE_THREADS, cur, 6, 6, nxt, c->stream2)) return -1;
+            if (swb_launch_band(c, 3, (njobs[5] + SWB_BAND_WIDE_THREADS - 1) / SWB_BAND_WIDE_THREADS, cur, 5, 5, nxt, c->stream2)) return -1;
+            if (swb_launch_band(c, 2, (njobs[4] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, cur, 4, 4, nxt, c->stream2)) return -1;
             CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
         }
         // widened jobs: small batches are latency bound and re-run them with the (faster) register-band kernel of the doubled
@@ -769,10 +522,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         if (launch_band_reg(c, baseW, njobsW, nxt, regNext, round == 0 ? 0 : 1)) return -1;
         int blocks = 0;
         for (int k = 0; k < SWB_BAND_CLS_MID; ++k) blocks += (njobs[k] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
-        if (blocks > 0) {
-            k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS><<<blocks, SWB_BAND_THREADS, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS), s>>>(d, cur, 0, SWB_BAND_CLS_MID - 1, nxt);
-            c->tm.n_launches++;
-        }
+        if (swb_launch_band(c, 1, blocks, cur, 0, SWB_BAND_CLS_MID - 1, nxt, s)) return -1;
         if (side) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));
         if (join_band_reg(c)) return -1;
         CUDA_TRY(c, cudaGetLastError());
@@ -875,16 +625,16 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     const size_t np = (size_t)d.n_pairs;
     swb_timing& tm = c->tm;
     cudaStream_t s = c->stream;
-    if (launch_exact<0, 0>(c, LIST_BYTE_FWD, (int)np)) return -1;
-    if (launch_exact<1, 0>(c, LIST_WORD_FWD, (int)np)) return -1;
+    if (swb_launch_exact(c, 0, 0, LIST_BYTE_FWD, (int)np, nullptr, false)) return -1;
+    if (swb_launch_exact(c, 1, 0, LIST_WORD_FWD, (int)np, nullptr, false)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_FWD], s));
 
     // ---- reverse (ssw.c:875-891) ----------------------------------------------------------------
-    if (launch_rev_band(c, nFastTotal)) return -1;          // the pairs the forward sweep put into a band class
+    if (swb_launch_rev_band(c, nFastTotal)) return -1;          // the pairs the forward sweep put into a band class
     if (launch_fast<1>(c, fwdCounts)) return -1;            // the rest; rev bucket sizes are bounded by the fwd ones
     if (join_rev_band(c, nFastTotal)) return -1;
-    if (launch_exact<0, 1>(c, LIST_BYTE_REV, (int)np)) return -1;
-    if (launch_exact<1, 1>(c, LIST_WORD_REV, (int)np)) return -1;
+    if (swb_launch_exact(c, 0, 1, LIST_BYTE_REV, (int)np, nullptr, false)) return -1;
+    if (swb_launch_exact(c, 1, 1, LIST_WORD_REV, (int)np, nullptr, false)) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));
     TR(c, "fwd_rev_enqueued");
 
@@ -920,11 +670,11 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
         if (stage_check(c, "certify")) return -1;
         if (read_counters(c)) return -1;
         const int nverify3 = c->h_counters[LIST_BYTE_FWD];
-        if (nverify3 > 0 && launch_exact<0, 0>(c, LIST_BYTE_FWD, nverify3, nullptr, /*fewJobsLikely=*/true)) return -1;
+        if (nverify3 > 0 && swb_launch_exact(c, 0, 0, LIST_BYTE_FWD, nverify3, nullptr, /*fewJobsLikely=*/true)) return -1;
         if (nverify3 > 0 && read_counters(c)) return -1;
         const int nbyte = c->h_counters[CNT_BYTE_REV];
         if (nbyte > 0) {
-            if (launch_exact<0, 1>(c, LIST_BYTE_REV, nbyte)) return -1;
+            if (swb_launch_exact(c, 0, 1, LIST_BYTE_REV, nbyte, nullptr, false)) return -1;
             if (run_band_rounds(c, false, LIST_BAND)) return -1;
         }
     }
@@ -1255,7 +1005,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
             const bool second = (k & 1) && !global;
             cudaStream_t st = second ? c->bulk_stream2 : c->bulk_stream;
             CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_snap[k & 1], 0));
-            if (launch_fast_range<0>(c, done, upper, st)) return -1;
+            if (swb_launch_fast_range_fwd(c, done, upper, st)) return -1;
             (second ? used2 : used1) = true;
             for (int q = 0; q < SWB_NBUCKETS; ++q) done[q] = upper[q];
         }

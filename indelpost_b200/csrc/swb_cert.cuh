@@ -80,6 +80,7 @@ __device__ __forceinline__ void certify_pair(const SwbDev& d, int p, int verifyL
     list_push(d.list[verifyList], d.counters + verifyList, p);
 }
 
+#ifdef SWB_WITH_CERT_KERNEL   // defined by the one translation unit that launches it (swb200.cu)
 // certificate pass over the pairs whose traceback has finished (PST_BAND_DONE) and that still carry PST_NEED_CERT
 __global__ void k_certify_rest(SwbDev d, int32_t p0, int32_t p1, int verifyList)
 {
@@ -87,3 +88,4 @@ __global__ void k_certify_rest(SwbDev d, int32_t p0, int32_t p1, int verifyList)
     if (p >= p1) return;
     certify_pair(d, p, verifyList);
 }
+#endif

@@ -1,0 +1,35 @@
+// swb_l_band.cu — launches of the literal banded_sw kernel (swb_band.cuh) and the warp-per-alignment band kernel (swb_bandwarp.cuh)
+#include "swb_host.h"
+#include "swb_band.cuh"
+#include "swb_bandwarp.cuh"
+
+int swb_launch_band(swb_ctx* c, int which, int blocks, int listBase, int firstClass, int lastClass, int nextBase, cudaStream_t st) {
+    const SwbDev& d = c->d;
+    if (blocks <= 0) return 0;
+    switch (which) {
+        case 0: k_band<0, SWB_BAND_THREADS><<<blocks, SWB_BAND_THREADS, 0, st>>>(d, listBase, firstClass, lastClass, nextBase); break;
+        case 1: k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS><<<blocks, SWB_BAND_THREADS, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS), st>>>(d, listBase, firstClass, lastClass, nextBase); break;
+        case 2: k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS><<<blocks, SWB_BAND_MID_THREADS, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS), st>>>(d, listBase, firstClass, lastClass, nextBase); break;
+        case 3: k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS><<<blocks, SWB_BAND_WIDE_THREADS, band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS), st>>>(d, listBase, firstClass, lastClass, nextBase); break;
+        case 4: k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS><<<blocks, SWB_BAND_HUGE_THREADS, band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS), st>>>(d, listBase, firstClass, lastClass, nextBase); break;
+        default: return -1;
+    }
+    c->tm.n_launches++;
+    return 0;
+}
+
+int swb_launch_band_warp(swb_ctx* c, int listSlot, int njobs, int nextBase, cudaStream_t st) {
+    const SwbDev& d = c->d;
+    if (njobs <= 0) return 0;
+    k_band_warp<<<(njobs + SWB_BANDWARP_WARPS - 1) / SWB_BANDWARP_WARPS, 32 * SWB_BANDWARP_WARPS, 0, st>>>(d, d.list[listSlot], njobs, nextBase);
+    c->tm.n_launches++;
+    return 0;
+}
+
+cudaError_t swb_band_set_attrs() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_band<SWB_BAND_LOCAL_BW, SWB_BAND_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_LOCAL_BW, SWB_BAND_THREADS))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_band<SWB_BAND_MID_BW, SWB_BAND_MID_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_MID_BW, SWB_BAND_MID_THREADS))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_band<SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_WIDE_BW, SWB_BAND_WIDE_THREADS))) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_band<SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(SWB_BAND_HUGE_BW, SWB_BAND_HUGE_THREADS));
+}
