@@ -10,8 +10,13 @@ GCUPS := sum(readLen * windowLen) / seconds / 1e9 (one nominal forward matrix pe
 
 A "step" is one pass of the whole hot path (prepare, forward, reverse, banded traceback) over the batch.
   value : inputs already resident in HBM when the timed region starts (swb_upload done; K x swb_compute)
-  e2e   : the same through the one-shot C-ABI call swb_align_batch with pinned HOST buffers:
-          H2D of every input + kernels + D2H of results and CIGARs inside the timed region
+  e2e   : the same through the one-shot C-ABI call swb_align_batch with pinned HOST buffers (sequence tables 2-bit packed,
+          SWB_SEQ_PACKED2): H2D of every input + unpack + kernels + D2H of results and CIGARs inside the timed region;
+          `e2e_codes` is the same call with one-byte-per-base tables (the round-1 figure), `extra.e2e_api` the Python entry
+          `align_batch` from lists of ASCII sequences (host gather included)
+  extra : (1 GPU only) the other BASELINE configs and mixes, each resident + e2e with its own stage split: cfg4 / cfg5 shapes,
+          cfg2 with shared windows, indelPost's penalty mix, short reads, and the reference pipeline's loci/s on ssw.c vs
+          under the wave scheduler (tools/bench_pipeline.py)
 Multi-GPU (torchrun, one rank per GPU): the pairs shard across ranks with no collective in the data
 path (weak scaling: every rank aligns its own P pairs); torch.distributed is only the barrier and the
 max-over-ranks of the timed region.
@@ -48,7 +53,8 @@ def workload_config(pairs, n_gpus):
         "window_len": WIN_LEN,
         "distinct_windows": True,
         "parallelism": f"pair-sharded x{n_gpus}, no collective",
-        "l2_policy": "inputs (~550 MB/GPU) larger than the 126 MB L2; no explicit flush",
+        "l2_policy": "inputs (~550 MB/GPU unpacked) larger than the 126 MB L2; no explicit flush",
+        "e2e_host_buffers": "pinned; sequence tables 2-bit packed (SWB_SEQ_PACKED2), unpacked on the device",
     }
 
 
@@ -264,6 +270,136 @@ def bind_to_gpu_numa(local):
         print(f"NUMA binding skipped: {e}", file=sys.stderr)
 
 
+def pinned_args(L, b, bits=0):
+    """the batch's input arrays in pinned host memory (bits = 0: one code per byte; 2 / 4: packed tables)"""
+    from indelpost_b200.batch import pack_table
+
+    def pin(a):
+        buf = L.PinnedBuffer(a.nbytes)
+        v = buf.view(a.dtype, a.size)
+        v[:] = a.reshape(-1)
+        return buf, v
+
+    src = {k: getattr(b, k) for k in ("reads", "read_off", "read_len", "windows", "win_off", "win_len", "pair_read", "pair_win", "gap_open", "gap_ext")}
+    if bits:
+        src["reads"], src["read_off"] = pack_table(b.reads, b.read_off, b.read_len, bits=bits)
+        src["windows"], src["win_off"] = pack_table(b.windows, b.win_off, b.win_len, bits=bits)
+        src["reads"] = src["reads"].view(np.int8)
+        src["windows"] = src["windows"].view(np.int8)
+    keep, arrs = [], []
+    for k in ("reads", "read_off", "read_len", "windows", "win_off", "win_len", "pair_read", "pair_win", "gap_open", "gap_ext"):
+        buf, v = pin(src[k])
+        keep.append(buf)
+        arrs.append(v)
+    enc = {0: L.SWB_SEQ_CODES, 4: L.SWB_SEQ_PACKED4, 2: L.SWB_SEQ_PACKED2}[bits]
+    return keep, arrs, enc
+
+
+def measure_shape(al, L, b, steps=3, warmup=2, bits=2, peak_gcups=None):
+    """resident and end-to-end GCUPS of one synthetic batch on one GPU, with the stage split of the resident leg"""
+    kw = dict(mat=b.mat, n=5, score_size=2, flag=1)
+    keep, arrs, enc = pinned_args(L, b, bits)
+    keep0, arrs0, _ = pinned_args(L, b, 0)
+    al.upload(*arrs0, **kw)
+    for _ in range(warmup):
+        al.compute()
+    t0 = time.perf_counter()
+    stage = {}
+    for _ in range(steps):
+        al.compute()
+        tm = al.timing()
+        for k in ("ms_prepare", "ms_forward", "ms_reverse", "ms_traceback", "ms_band_round0", "ms_band_rest", "ms_certify"):
+            stage[k] = stage.get(k, 0.0) + tm[k] / steps
+    dt = (time.perf_counter() - t0) / steps
+    for _ in range(warmup):
+        al.align(*arrs, copy=False, seq_encoding=enc, **kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        al.align(*arrs, copy=False, seq_encoding=enc, **kw)
+    de = (time.perf_counter() - t0) / steps
+    t = al.timing()
+    cells = b.cells()
+    out = {"pairs": int(b.n_pairs), "resident_gcups": cells / dt / 1e9, "e2e_gcups": cells / de / 1e9, "ms_resident": dt * 1e3, "ms_e2e": de * 1e3,
+           "reads_per_s_resident": b.n_pairs / dt, "reads_per_s_e2e": b.n_pairs / de,
+           "h2d_bytes": int(t["h2d_bytes"]), "d2h_bytes": int(t["d2h_bytes"]), "stage_ms": {k: round(v, 3) for k, v in stage.items()},
+           "n_fast": int(tm["n_fast"]), "n_exact": int(tm["n_exact"])}
+    if peak_gcups and stage.get("ms_forward", 0) > 0:
+        out["forward_frac_of_dpx_peak"] = cells / (stage["ms_forward"] * 1e-3) / 1e9 / peak_gcups
+    for bf in keep + keep0:
+        bf.close()
+    return out
+
+
+def extra_measurements(al, L, T, peak_gcups):
+    """the other BASELINE configs / mixes on one GPU (bounded sizes: the whole block takes about a minute)"""
+    ex = {}
+    shapes = [
+        ("cfg2_shared_windows_5000x200", dict(n_pairs=1_000_000, read_len=150, win_len=400, seed=2, reads_per_window=200)),
+        ("cfg4_250x1000", dict(n_pairs=120_000, read_len=250, win_len=1000, seed=4, max_indel=30)),
+        ("cfg5_250x2000", dict(n_pairs=60_000, read_len=250, win_len=2000, seed=5, max_indel=10)),
+        ("reads_100x300", dict(n_pairs=400_000, read_len=100, win_len=300, seed=3)),
+        ("reads_75x300", dict(n_pairs=400_000, read_len=75, win_len=300, seed=6, max_indel=5)),
+        ("reads_50x300", dict(n_pairs=400_000, read_len=50, win_len=300, seed=7, max_indel=3)),
+    ]
+    cfgs = {}
+    for name, kw in shapes:
+        try:
+            cfgs[name] = measure_shape(al, L, T.make_pairs_fast(**kw), peak_gcups=peak_gcups)
+        except Exception as e:  # noqa: BLE001
+            cfgs[name] = {"error": repr(e)}
+    ex["configs"] = cfgs
+    # indelPost's own penalty mix (recorded call stream: ge = 0 on 40 % of the calls, go = len(read) on 6 %)
+    try:
+        n = 400_000
+        b = T.make_pairs_fast(n, 150, 300, seed=11, reads_per_window=500)
+        rng = np.random.default_rng(2)
+        combos = np.array([(3, 1), (5, 1), (3, 0), (5, 0), (4, 1), (4, 0), (150, 1)], dtype=np.uint8)
+        pick = rng.choice(7, size=n, p=[0.223, 0.18, 0.1344, 0.1344, 0.1344, 0.1344, 0.0594])
+        b.gap_open = np.ascontiguousarray(combos[pick, 0])
+        b.gap_ext = np.ascontiguousarray(combos[pick, 1])
+        ex["grid_mix"] = dict(measure_shape(al, L, b, peak_gcups=peak_gcups), workload="indelPost penalty mix, 150 bp x 300 bp, 500 reads per window")
+    except Exception as e:  # noqa: BLE001
+        ex["grid_mix"] = {"error": repr(e)}
+    # the Python entry point from lists of ASCII sequences: host gather + H2D + kernels + D2H, lazy result list
+    try:
+        from indelpost_b200 import align_batch
+
+        n = 200_000
+        b = T.make_pairs_fast(n, READ_LEN, WIN_LEN, seed=5)
+        lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+        rs = [lut[b.reads[o:o + l]].tobytes() for o, l in zip(b.read_off.tolist(), b.read_len.tolist())]
+        ws = [lut[b.windows[o:o + l]].tobytes() for o, l in zip(b.win_off.tolist(), b.win_len.tolist())]
+        for _ in range(2):
+            out = align_batch(rs, ws, b.pair_read, b.pair_win, 3, 1, match_score=3, mismatch_penalty=2, aligner=al)
+        t0 = time.perf_counter()
+        K = 3
+        for _ in range(K):
+            out = align_batch(rs, ws, b.pair_read, b.pair_win, 3, 1, match_score=3, mismatch_penalty=2, aligner=al)
+        dt = (time.perf_counter() - t0) / K
+        t1 = time.perf_counter()
+        first = out[:1000]
+        dmat = (time.perf_counter() - t1) / 1000
+        ex["e2e_api"] = {"call": "indelpost_b200.align_batch(list[bytes], list[bytes], ...) -> AlignmentList", "pairs": n, "gcups": b.cells() / dt / 1e9,
+                         "reads_per_s": n / dt, "ms": dt * 1e3, "us_per_materialised_alignment": dmat * 1e6, "sample_cigar": first[0].CIGAR}
+    except Exception as e:  # noqa: BLE001
+        ex["e2e_api"] = {"error": repr(e)}
+    return ex
+
+
+def pipeline_measurements():
+    """loci/s of the unmodified reference pipeline on ssw.c vs under the wave scheduler (needs oracle/_ref_pipeline)"""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_pipeline as BP
+
+        out = {}
+        for cfg, loci in (("cfg1", 4), ("cfg3", 12)):
+            out[cfg] = BP.measure(cfg, loci, workers=1)
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -291,20 +427,10 @@ def run_ours(args):
     b = T.make_pairs_fast(args.pairs, READ_LEN, WIN_LEN, seed=1000 + rank)
     cells = b.cells()
 
-    # pinned host staging for every input array (the batched entry point's contract)
-    def pin(a):
-        buf = L.PinnedBuffer(a.nbytes)
-        v = buf.view(a.dtype, a.size)
-        v[:] = a.reshape(-1)
-        return buf, v
-
-    keep = []
-    arrs = {}
-    for k in ("reads", "read_off", "read_len", "windows", "win_off", "win_len", "pair_read", "pair_win", "gap_open", "gap_ext"):
-        buf, v = pin(getattr(b, k))
-        keep.append(buf)
-        arrs[k] = v
-    args_pos = [arrs[k] for k in ("reads", "read_off", "read_len", "windows", "win_off", "win_len", "pair_read", "pair_win", "gap_open", "gap_ext")]
+    # pinned host staging for every input array (the batched entry point's contract): one-code-per-byte tables for the resident
+    # leg and `e2e_codes`, 2-bit packed tables for the headline end-to-end leg
+    keep, args_pos, _ = pinned_args(L, b, 0)
+    keep2, args_pk, enc_pk = pinned_args(L, b, 2)
     kw = dict(mat=b.mat, n=5, score_size=2, flag=1)
 
     def barrier():
@@ -339,24 +465,27 @@ def run_ours(args):
     dt = t1 - t0
     res, arena = al.download(n)
 
-    # ---- end-to-end leg (pinned host buffers -> results on host) ---------------------------------
-    for _ in range(min(2, args.warmup)):
-        al.align(*args_pos, copy=False, **kw)
-    barrier()
-    e0 = time.perf_counter()
-    h2d = d2h = 0
-    for _ in range(args.steps):
-        res2, arena2 = al.align(*args_pos, copy=False, **kw)
-        t = al.timing()
-        h2d, d2h = t["h2d_bytes"], t["d2h_bytes"]
-    barrier()
-    e1 = time.perf_counter()
-    dte = e1 - e0
+    # ---- end-to-end legs (pinned host buffers -> results on host) ---------------------------------
+    def e2e_leg(pos, enc):
+        for _ in range(min(2, args.warmup)):
+            al.align(*pos, copy=False, seq_encoding=enc, **kw)
+        barrier()
+        e0 = time.perf_counter()
+        hh = dd = 0
+        for _ in range(args.steps):
+            al.align(*pos, copy=False, seq_encoding=enc, **kw)
+            t = al.timing()
+            hh, dd = t["h2d_bytes"], t["d2h_bytes"]
+        barrier()
+        return time.perf_counter() - e0, hh, dd
+
+    dte_codes, h2d_codes, _ = e2e_leg(args_pos, L.SWB_SEQ_CODES)
+    dte, h2d, d2h = e2e_leg(args_pk, enc_pk)
 
     if world > 1:
-        tt = torch.tensor([dt, dte], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dt, dte, dte_codes], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt, dte = float(tt[0]), float(tt[1])
+        dt, dte, dte_codes = float(tt[0]), float(tt[1]), float(tt[2])
         cc = torch.tensor([float(cells)], dtype=torch.float64, device="cuda")
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
         total_cells = float(cc[0])
@@ -381,7 +510,7 @@ def run_ours(args):
         # dominant kernel family = forward sweep; algorithmic cells per launch = sum(readLen*winLen) of this rank
         fwd_ms = stage["ms_forward"] / args.steps
         achieved = cells / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
-        alg_bytes = int(h2d) + args.pairs * 40  # every input byte is read once by the sweep, one 40-byte result record written per pair
+        alg_bytes = int(h2d_codes) + args.pairs * 40  # every input byte (one code per byte on the device) is read once by the sweep, one 40-byte result record written per pair
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
         if os.path.exists(tp):
@@ -396,9 +525,13 @@ def run_ours(args):
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback"
         cores = host_cores()
-        sample_pairs = cores * 600
-        sb = T.make_pairs_fast(sample_pairs, READ_LEN, WIN_LEN, seed=77)
+        sample_pairs = max(cores * 250, min(args.pairs, cores * 1500))      # the reference arm's sample
+        sb = T.make_pairs_fast(sample_pairs, READ_LEN, WIN_LEN, seed=1234)
+        cpu_align_parallel(sb.subset(np.arange(min(sample_pairs, cores * 100))), cores)      # warm-up
         cdt, kind = cpu_align_parallel(sb, cores)
+        extra = None
+        if world == 1 and not args.no_extra:
+            extra = extra_measurements(al, L, T, peak_gcups)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -406,7 +539,9 @@ def run_ours(args):
             "reads_per_s": args.pairs * world * args.steps / dt,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "reads_per_s": args.pairs * world * args.steps / dte,
-                    "ms_per_step": 1e3 * dte / args.steps},
+                    "ms_per_step": 1e3 * dte / args.steps, "host_buffers": "pinned, 2-bit packed sequence tables (SWB_SEQ_PACKED2)"},
+            "e2e_codes": {"value": total_cells * args.steps / dte_codes / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d_codes), "ms_per_step": 1e3 * dte_codes / args.steps,
+                          "host_buffers": "pinned, one code per byte (the round-1 e2e figure)"},
             "gpu_launches": int(launches),
             "device_event_ms_per_step": ev_ms / args.steps,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
@@ -418,9 +553,13 @@ def run_ours(args):
                          "hbm": {"achieved_gbs": alg_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                                  "note": "algorithmic bytes = inputs read once (~0.009 B per cell): the path is integer-issue bound, not HBM bound"}},
             "cpu_baseline": {"value": sb.cells() / cdt / 1e9, "unit": UNIT, "cores": cores, "kind": kind, "reads_per_s": sample_pairs / cdt,
-                             "sample": f"{sample_pairs} pairs of the same workload, split evenly over {cores} threads"},
+                             "sample": f"{sample_pairs} pairs of the same workload, split evenly over {cores} threads (one warm-up pass first); the reference arm uses the same sample"},
         }
+        if extra is not None:
+            line["extra"] = extra
         result_line = line
+    if world == 1 and rank == 0 and not args.no_extra and result_line is not None:
+        result_line.setdefault("extra", {})["pipeline"] = pipeline_measurements()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -434,6 +573,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra configs / mixes / pipeline block (1-GPU runs add it by default)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line (rank 0): while the benchmark runs, file descriptor 1 points at stderr, so that
     # banners printed by native libraries (NCCL's version line, the reference's warnings) cannot land in front of it

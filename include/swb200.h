@@ -79,6 +79,8 @@ uint32_t swb_to_cigar_int(uint32_t length, char op_letter);
 
 #define SWB_SEQ_CODES 0   /* sequences are already 0..n-1 codes (what ssw_init / ssw_align take) */
 #define SWB_SEQ_ASCII 1   /* raw ASCII, encoded on the GPU with sswpy's DNA_BASE_LUT (sswpy.pyx:16-29) */
+#define SWB_SEQ_PACKED4 2 /* codes 0..15, two per byte (low nibble first): half the host->device bytes, N (code 4) representable */
+#define SWB_SEQ_PACKED2 3 /* codes 0..3, four per byte (bits 0-1 first): a quarter of the bytes, for sequences without N */
 
 /* per-pair status word (replaces the reference's fprintf(stderr) reporting) */
 #define SWB_OK              0
@@ -92,7 +94,11 @@ uint32_t swb_to_cigar_int(uint32_t length, char op_letter);
  * even share bytes).  SWB_SEQ_ASCII tables are encoded in place on the
  * device, so their entries must be in ascending offset order and must not
  * overlap (off[i] >= off[i-1] + len[i-1]); a table that breaks the rule
- * fails the call with -1. */
+ * fails the call with -1.
+ * SWB_SEQ_PACKED4 / SWB_SEQ_PACKED2: every entry starts on a byte boundary
+ * (off[i] = byte offset of its first byte, len[i] = length in BASES; the
+ * entry occupies ceil(len/2) resp. ceil(len/4) bytes) and is unpacked on the
+ * device; swb_pack_table() below produces such tables. */
 typedef struct {
     int32_t        n_pairs;
     int32_t        n_reads;
@@ -220,6 +226,13 @@ void  swb_host_free(void* p);
 
 /* sswpy.pyx:16-29 DNA_BASE_LUT on the host (for callers that want codes) */
 void swb_encode_dna(const char* ascii, int8_t* codes, int64_t len);
+
+/* Pack a sequence table for SWB_SEQ_PACKED4 (bits = 4) or SWB_SEQ_PACKED2 (bits = 2).  `blob` holds codes, or ASCII
+ * when src_ascii != 0 (then encoded with DNA_BASE_LUT first).  Entry i is written at dst + dst_off[i] (consecutive,
+ * byte aligned); returns the number of bytes written, or -1 if bits = 2 meets a code above 3 or an argument is bad.
+ * dst needs sum(ceil(len[i] * bits / 8)) bytes. */
+int64_t swb_pack_table(const int8_t* blob, const int64_t* off, const int32_t* len, int32_t n, int src_ascii, int bits,
+                       uint8_t* dst, int64_t* dst_off);
 
 const char* swb_version(void);
 

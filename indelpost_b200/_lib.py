@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libswb200.so")
 
 SWB_SEQ_CODES = 0
 SWB_SEQ_ASCII = 1
+SWB_SEQ_PACKED4 = 2
+SWB_SEQ_PACKED2 = 3
 SWB_OK = 0
 SWB_ERR_BYTE_ONLY = 1
 SWB_ERR_BAD_INPUT = 2
@@ -71,7 +73,7 @@ EXPORTS = (
     "swb_cigar_int_to_op", "swb_cigar_int_to_len", "swb_to_cigar_int",
     "swb_device_count", "swb_create", "swb_destroy", "swb_last_error",
     "swb_align_batch", "swb_upload", "swb_compute", "swb_download", "swb_get_timing",
-    "swb_host_alloc", "swb_host_free", "swb_encode_dna", "swb_version",
+    "swb_host_alloc", "swb_host_free", "swb_encode_dna", "swb_pack_table", "swb_version",
     "swb_indels", "swb_indels_from_cigars",
 )
 
@@ -115,6 +117,8 @@ def load():
     lib.swb_host_alloc.argtypes = [C.c_int64]
     lib.swb_host_free.argtypes = [C.c_void_p]
     lib.swb_encode_dna.argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
+    lib.swb_pack_table.restype = C.c_int64
+    lib.swb_pack_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.swb_version.restype = C.c_char_p
     lib.ssw_init.restype = C.c_void_p
     lib.ssw_init.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int8]

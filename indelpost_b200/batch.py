@@ -31,6 +31,27 @@ def _c(a, dtype):
     return a
 
 
+def pack_table(blob, off, length, bits: int = 4, ascii: bool = False, out=None, out_off=None):
+    """Pack a sequence table (codes, or ASCII with ``ascii=True``) for ``seq_encoding=SWB_SEQ_PACKED4`` (bits=4) or
+    ``SWB_SEQ_PACKED2`` (bits=2; no N): returns (packed_blob uint8, packed_off int64).  ``out`` / ``out_off`` may be
+    preallocated (pinned) arrays.  include/swb200.h: swb_pack_table."""
+    lib = L.load()
+    blob = np.ascontiguousarray(blob).view(np.int8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    length = np.ascontiguousarray(length, dtype=np.int32)
+    n = int(length.shape[0])
+    per = 8 // bits
+    need = int(((length.astype(np.int64) + per - 1) // per).sum())
+    dst = out if out is not None else np.empty(max(need, 1), dtype=np.uint8)
+    doff = out_off if out_off is not None else np.empty(max(n, 1), dtype=np.int64)
+    if dst.nbytes < need or doff.shape[0] < n:
+        raise ValueError("pack_table: output arrays too small")
+    used = lib.swb_pack_table(blob.ctypes.data, off.ctypes.data, length.ctypes.data, n, 1 if ascii else 0, int(bits), dst.ctypes.data, doff.ctypes.data)
+    if used < 0:
+        raise ValueError("pack_table: a code does not fit the packing (2 bits hold A/C/G/T only) or an argument is bad")
+    return dst[:used], doff[:n]
+
+
 class _OutLease:
     """a (results, cigar arena) pair of pinned buffers on loan from a BatchAligner's pool"""
 

@@ -29,13 +29,13 @@
 // ------------------------------------------------------------------------------------------------
 
 // one warp per sequence: ASCII -> code (in place) and range check; bad[s] = 1 if any code is outside [0, n)
-__global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int n, int ascii, uint8_t* bad, int64_t byte_base)
+__global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int n, int ascii, uint8_t* bad, int64_t byte_base, int shift)
 {
     // bad[s]: bit0 = code outside [0, n) (invalid input), bit1 = some code >= 4 (not usable by the DPX fast path as a window)
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nseq) return;
-    int8_t* s = blob + (off[w] - byte_base);
+    int8_t* s = blob + ((off[w] - byte_base) << shift);
     const int L = len[w];
     bool b = false, hi = false;
     for (int i = lane; i < L; i += 32) {
@@ -51,14 +51,14 @@ __global__ void k_encode_validate(int8_t* blob, const int64_t* off, const int32_
 
 // codes-only variant of k_encode_validate (nothing to rewrite): 8 lanes per sequence, aligned 16-byte loads, byte-parallel
 // range tests.  bad[s] as above.
-__global__ void k_validate_codes(const int8_t* __restrict__ blob, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int32_t nseq, int n, uint8_t* bad, int64_t byte_base)
+__global__ void k_validate_codes(const int8_t* __restrict__ blob, const int64_t* __restrict__ off, const int32_t* __restrict__ len, int32_t nseq, int n, uint8_t* bad, int64_t byte_base, int shift)
 {
     const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int sub = threadIdx.x & 7;
     const unsigned gm = 0xffu << ((threadIdx.x & 31) & ~7);
     bool b = false, hi = false;
     if (sidx < nseq) {
-        const int8_t* s = blob + (off[sidx] - byte_base);
+        const int8_t* s = blob + ((off[sidx] - byte_base) << shift);
         const int L = len[sidx];
         const uintptr_t a = reinterpret_cast<uintptr_t>(s);
         const int mis = (int)(a & 15);
@@ -84,6 +84,18 @@ __global__ void k_validate_codes(const int8_t* __restrict__ blob, const int64_t*
     b = (__ballot_sync(0xffffffffu, b) & gm) != 0;
     hi = (__ballot_sync(0xffffffffu, hi) & gm) != 0;
     if (sidx < nseq && sub == 0) bad[sidx] = (b ? 1 : 0) | (hi ? 2 : 0);
+}
+
+// SWB_SEQ_PACKED4 / PACKED2 -> one code per byte: packed byte i of the range becomes codes [i << shift, (i + 1) << shift)
+// (shift 1: two nibbles, low first; shift 2: four 2-bit fields, bits 0-1 first).  One thread per packed byte: a warp reads 32
+// consecutive bytes and writes 64 / 128 consecutive ones.
+__global__ void k_unpack(const uint8_t* __restrict__ src, int8_t* __restrict__ dst, int64_t nbytes, int shift)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbytes) return;
+    const uint32_t b = src[i];
+    if (shift == 1) *reinterpret_cast<uint16_t*>(dst + 2 * i) = (uint16_t)((b & 15u) | ((b >> 4) << 8));
+    else *reinterpret_cast<uint32_t*>(dst + 4 * i) = (b & 3u) | (((b >> 2) & 3u) << 8) | (((b >> 4) & 3u) << 16) | ((b >> 6) << 24);
 }
 
 __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_bad, int32_t p0, int32_t p1)
@@ -113,8 +125,8 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         d.res[p] = r;
         return;
     }
-    d.p_roff[p] = d.read_off[ri] - d.rbyte_base;
-    d.p_woff[p] = d.win_off[wi] - d.wbyte_base + rb;
+    d.p_roff[p] = (d.read_off[ri] - d.rbyte_base) << d.seq_shift;
+    d.p_woff[p] = ((d.win_off[wi] - d.wbyte_base) << d.seq_shift) + rb;
     d.p_rlen[p] = rl;
     d.p_wlen[p] = wl;
     d.p_mask[p] = d.mask_len ? d.mask_len[p] : (rl / 2 < 15 ? 15 : rl / 2);      // sswpy.pyx:209-211
@@ -236,7 +248,7 @@ static void destroy_ctx(swb_ctx* c) {
                       &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
                       &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
                       &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe, &c->b_fastcols,
-                      &c->b_ind_off, &c->b_ind_cnt, &c->b_ind_rend, &c->b_ind_recs, &c->b_ind_misc, &c->b_ind_cig, &c->b_ind_coff, &c->b_ind_clen, &c->b_ind_rs, &c->b_ind_qs };
+                      &c->b_ind_off, &c->b_ind_cnt, &c->b_ind_rend, &c->b_ind_recs, &c->b_ind_misc, &c->b_ind_cig, &c->b_ind_coff, &c->b_ind_clen, &c->b_ind_rs, &c->b_ind_qs, &c->b_reads_pk, &c->b_windows_pk };
     for (DevBuf* b : all) b->release();
     auto dS = [](cudaStream_t st) { if (st) cudaStreamDestroy(st); };
     auto dE = [](cudaEvent_t ev) { if (ev) cudaEventDestroy(ev); };
@@ -273,6 +285,29 @@ extern "C" void* swb_host_alloc(int64_t bytes) {
 }
 extern "C" void swb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+extern "C" int64_t swb_pack_table(const int8_t* blob, const int64_t* off, const int32_t* len, int32_t n, int src_ascii, int bits, uint8_t* dst, int64_t* dst_off) {
+    if ((bits != 2 && bits != 4) || n < 0 || (n > 0 && (!blob || !off || !len || !dst || !dst_off))) return -1;
+    const int per = 8 / bits;
+    const unsigned lim = bits == 2 ? 4u : 16u;
+    int64_t pos = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const int8_t* s = blob + off[i];
+        const int32_t l = len[i];
+        if (l < 0 || off[i] < 0) return -1;
+        dst_off[i] = pos;
+        for (int32_t k = 0; k < l; k += per) {
+            unsigned byte = 0;
+            for (int q = 0; q < per && k + q < l; ++q) {
+                const unsigned code = src_ascii ? (unsigned)swb_dna_code((unsigned char)s[k + q]) : (unsigned)(unsigned char)s[k + q];
+                if (code >= lim) return -1;
+                byte |= code << (bits * q);
+            }
+            dst[pos++] = (uint8_t)byte;
+        }
+    }
+    return pos;
+}
+
 extern "C" void swb_encode_dna(const char* ascii, int8_t* codes, int64_t len) {
     for (int64_t i = 0; i < len; ++i) codes[i] = swb_dna_code((unsigned char)ascii[i]);
 }
@@ -305,6 +340,17 @@ extern "C" int swb_upload(swb_ctx* c, const swb_batch* b) {
     return upload_view(c, b, v);
 }
 
+static inline int seq_shift_of(int enc) { return enc == SWB_SEQ_PACKED4 ? 1 : enc == SWB_SEQ_PACKED2 ? 2 : 0; }
+// bytes a sequence of len bases occupies in the caller's blob
+static inline int64_t seq_bytes(int32_t len, int shift) { return ((int64_t)len + (1 << shift) - 1) >> shift; }
+static int launch_unpack(swb_ctx* c, const uint8_t* src, int8_t* dst, int64_t nbytes, int shift, cudaStream_t st) {
+    if (nbytes <= 0) return 0;
+    k_unpack<<<(unsigned)((nbytes + 255) / 256), 256, 0, st>>>(src, dst, nbytes, shift);
+    c->tm.n_launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+
 // batch-level scalars of SwbDev (everything but the device pointers)
 static void set_batch_scalars(swb_ctx* c, const swb_batch* b, const ChunkView& v, int32_t max_rl, int32_t max_wl) {
     SwbDev& d = c->d;
@@ -313,6 +359,7 @@ static void set_batch_scalars(swb_ctx* c, const swb_batch* b, const ChunkView& v
     d.rbyte_base = v.rbyte_base; d.wbyte_base = v.wbyte_base;
     d.n = b->n; d.score_size = b->score_size; d.flag = b->flag; d.filters = b->filters; d.filterd = b->filterd;
     d.seq_encoding = b->seq_encoding;
+    d.seq_shift = seq_shift_of(b->seq_encoding);
     d.max_rlen = max_rl; d.max_wlen = max_wl;
     int bias = 0;
     for (int i = 0; i < b->n * b->n; ++i) if (b->mat[i] < bias) bias = b->mat[i];       // ssw.c:795-797
@@ -345,23 +392,36 @@ static int upload_view(swb_ctx* c, const swb_batch* b, const ChunkView& v) {
     // ASCII tables are encoded IN PLACE on the device and DNA_BASE_LUT is not idempotent ('A' -> 0 -> 4): entries that share
     // blob bytes would be encoded twice.  ASCII entries must therefore be ascending and disjoint (include/swb200.h).
     const bool ascii_in = b->seq_encoding == SWB_SEQ_ASCII;
+    if (b->seq_encoding < SWB_SEQ_CODES || b->seq_encoding > SWB_SEQ_PACKED2) { c->err = "unknown seq_encoding"; return -1; }
+    const int shift = seq_shift_of(b->seq_encoding);
     for (int32_t i = 0; i < b->n_reads; ++i) {
         if (b->read_len[i] < 0 || b->read_off[i] < v.rbyte_base) { c->err = "negative read offset/length"; return -1; }
         if (ascii_in && b->read_off[i] - v.rbyte_base < reads_bytes) { c->err = "ASCII read table entries must be ascending and must not overlap"; return -1; }
-        reads_bytes = std::max<int64_t>(reads_bytes, b->read_off[i] - v.rbyte_base + b->read_len[i]); max_rl = std::max(max_rl, b->read_len[i]);
+        reads_bytes = std::max<int64_t>(reads_bytes, b->read_off[i] - v.rbyte_base + seq_bytes(b->read_len[i], shift)); max_rl = std::max(max_rl, b->read_len[i]);
     }
     for (int32_t i = 0; i < b->n_windows; ++i) {
         if (b->win_len[i] < 0 || b->win_off[i] < v.wbyte_base) { c->err = "negative window offset/length"; return -1; }
         if (ascii_in && b->win_off[i] - v.wbyte_base < win_bytes) { c->err = "ASCII window table entries must be ascending and must not overlap"; return -1; }
-        win_bytes = std::max<int64_t>(win_bytes, b->win_off[i] - v.wbyte_base + b->win_len[i]); max_wl = std::max(max_wl, b->win_len[i]);
+        win_bytes = std::max<int64_t>(win_bytes, b->win_off[i] - v.wbyte_base + seq_bytes(b->win_len[i], shift)); max_wl = std::max(max_wl, b->win_len[i]);
     }
 
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D0], c->stream));
     const size_t np = (size_t)b->n_pairs;
+    if (shift) {
+        // packed input: the bytes land in a staging buffer and are unpacked on the device into the one-code-per-byte blobs
+        int8_t *pr = nullptr, *pw = nullptr;
+        if (up(c, c->b_reads_pk, b->reads, (size_t)reads_bytes, &pr)) return -1;
+        if (up(c, c->b_windows_pk, b->windows, (size_t)win_bytes, &pw)) return -1;
+        CUDA_TRY(c, c->b_reads.ensure(((size_t)reads_bytes << shift) + 16));   d.reads = (int8_t*)c->b_reads.p;
+        CUDA_TRY(c, c->b_windows.ensure(((size_t)win_bytes << shift) + 16));   d.windows = (int8_t*)c->b_windows.p;
+        if (launch_unpack(c, (const uint8_t*)pr, d.reads, reads_bytes, shift, c->stream)) return -1;
+        if (launch_unpack(c, (const uint8_t*)pw, d.windows, win_bytes, shift, c->stream)) return -1;
+    } else {
     if (up(c, c->b_reads, b->reads, (size_t)reads_bytes, &d.reads)) return -1;
+    if (up(c, c->b_windows, b->windows, (size_t)win_bytes, &d.windows)) return -1;
+    }
     if (up(c, c->b_read_off, b->read_off, (size_t)b->n_reads, &d.read_off)) return -1;
     if (up(c, c->b_read_len, b->read_len, (size_t)b->n_reads, &d.read_len)) return -1;
-    if (up(c, c->b_windows, b->windows, (size_t)win_bytes, &d.windows)) return -1;
     if (up(c, c->b_win_off, b->win_off, (size_t)b->n_windows, &d.win_off)) return -1;
     if (up(c, c->b_win_len, b->win_len, (size_t)b->n_windows, &d.win_len)) return -1;
     if (up(c, c->b_pair_read, b->pair_read, np, &d.pair_read)) return -1;
@@ -394,8 +454,8 @@ static int read_counters(swb_ctx* c) {
 // sequence table -> codes in place (ASCII input) + per-sequence validity flags
 static int launch_validate(swb_ctx* c, int8_t* blob, const int64_t* off, const int32_t* len, int32_t nseq, int ascii, uint8_t* bad, int64_t byte_base, cudaStream_t st) {
     if (nseq <= 0) return 0;
-    if (ascii) k_encode_validate<<<(nseq + 3) / 4, 128, 0, st>>>(blob, off, len, nseq, c->d.n, 1, bad, byte_base);
-    else k_validate_codes<<<(nseq + 15) / 16, 128, 0, st>>>(blob, off, len, nseq, c->d.n, bad, byte_base);
+    if (ascii) k_encode_validate<<<(nseq + 3) / 4, 128, 0, st>>>(blob, off, len, nseq, c->d.n, 1, bad, byte_base, c->d.seq_shift);
+    else k_validate_codes<<<(nseq + 15) / 16, 128, 0, st>>>(blob, off, len, nseq, c->d.n, bad, byte_base, c->d.seq_shift);
     c->tm.n_launches++;
     CUDA_TRY(c, cudaGetLastError());
     return 0;
@@ -771,11 +831,11 @@ extern "C" int swb_download(swb_ctx* c, swb_result* results, uint32_t* cigar_are
 // ------------------------------------------------------------------------------------------------
 
 // byte extent and longest entry of a sequence table; false on a negative offset / length
-static bool scan_table_range(const int64_t* off, const int32_t* len, int32_t i0, int32_t i1, int64_t& extent, int32_t& maxlen) {
+static bool scan_table_range(const int64_t* off, const int32_t* len, int32_t i0, int32_t i1, int64_t& extent, int32_t& maxlen, int shift) {
     int64_t ext = 0, minoff = 0; int32_t ml = 0, minlen = 0;
     for (int32_t i = i0; i < i1; ++i) {
         const int64_t o = off[i]; const int32_t l = len[i];
-        ext = std::max<int64_t>(ext, o + l); ml = std::max(ml, l); minoff = std::min(minoff, o); minlen = std::min(minlen, l);
+        ext = std::max<int64_t>(ext, o + seq_bytes(l, shift)); ml = std::max(ml, l); minoff = std::min(minoff, o); minlen = std::min(minlen, l);
     }
     extent = ext; maxlen = ml;
     return minoff >= 0 && minlen >= 0;
@@ -783,6 +843,7 @@ static bool scan_table_range(const int64_t* off, const int32_t* len, int32_t i0,
 // both tables, split over a few host threads when they are large (two million entries take ~3 ms on one core)
 static bool scan_tables(const swb_batch* b, int64_t& reads_bytes, int32_t& max_rl, int64_t& win_bytes, int32_t& max_wl) {
     const int NT = ((int64_t)b->n_reads + b->n_windows >= 400000) ? 6 : 1;      // 3 slices per table
+    const int shift = seq_shift_of(b->seq_encoding);
     struct Part { int64_t ext = 0; int32_t ml = 0; bool ok = true; };
     Part pr[3], pw[3];
     auto work = [&](int k) {
@@ -790,7 +851,7 @@ static bool scan_tables(const swb_batch* b, int64_t& reads_bytes, int32_t& max_r
         const int32_t n = which ? b->n_windows : b->n_reads;
         const int32_t i0 = (int32_t)((int64_t)n * sl / 3), i1 = (int32_t)((int64_t)n * (sl + 1) / 3);
         Part& q = which ? pw[sl] : pr[sl];
-        q.ok = which ? scan_table_range(b->win_off, b->win_len, i0, i1, q.ext, q.ml) : scan_table_range(b->read_off, b->read_len, i0, i1, q.ext, q.ml);
+        q.ok = which ? scan_table_range(b->win_off, b->win_len, i0, i1, q.ext, q.ml, shift) : scan_table_range(b->read_off, b->read_len, i0, i1, q.ext, q.ml, shift);
     };
     if (NT == 1) { for (int k = 0; k < 6; ++k) work(k); }
     else {
@@ -810,7 +871,8 @@ static bool scan_tables(const swb_batch* b, int64_t& reads_bytes, int32_t& max_r
 struct TableStream {                 // upload frontier of one sequence table
     const int8_t* blob; const int64_t* off; const int32_t* len; int32_t n;
     int8_t* d_blob; int64_t* d_off; int32_t* d_len; uint8_t* d_bad;
-    int64_t cap = 0;                 // bytes the device blob can hold
+    uint8_t* d_pk = nullptr; int shift = 0;      // packed input: the caller's bytes land in d_pk and are unpacked into d_blob (<< shift)
+    int64_t cap = 0;                 // caller-side blob bytes the device buffers can hold
     int32_t maxlen = 0;              // longest entry seen so far
     int32_t front = 0;               // entries [0, front) are on the device
     int64_t ulo = 0, uhi = 0;        // blob bytes [ulo, uhi) are on the device
@@ -832,8 +894,9 @@ static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, TableStep& st
     bool overlap = false; int64_t pe = t.prev_end;
     for (int32_t i = i0; i <= upto; ++i) {
         const int64_t o = t.off[i]; const int32_t l = t.len[i];
-        lo = std::min<int64_t>(lo, o); hi = std::max<int64_t>(hi, o + l); minoff = std::min(minoff, o); minlen = std::min(minlen, l); ml = std::max(ml, l);
-        overlap |= o < pe; pe = std::max<int64_t>(pe, o + l);
+        const int64_t e = o + seq_bytes(l, t.shift);
+        lo = std::min<int64_t>(lo, o); hi = std::max<int64_t>(hi, e); minoff = std::min(minoff, o); minlen = std::min(minlen, l); ml = std::max(ml, l);
+        overlap |= o < pe; pe = std::max<int64_t>(pe, e);
     }
     if (minoff < 0 || minlen < 0) { c->err = "negative sequence offset/length"; return -1; }
     if (t.ascii && overlap) { c->err = "ASCII sequence table entries must be ascending and must not overlap"; return -1; }
@@ -843,7 +906,10 @@ static int table_advance(swb_ctx* c, TableStream& t, int32_t upto, TableStep& st
     cudaStream_t s = c->copy_stream;
     auto copy = [&](int64_t a, int64_t b2) -> int {
         if (b2 <= a) return 0;
-        CUDA_TRY(c, cudaMemcpyAsync(t.d_blob + a, t.blob + a, (size_t)(b2 - a), cudaMemcpyHostToDevice, s));
+        if (t.shift) {
+            CUDA_TRY(c, cudaMemcpyAsync(t.d_pk + a, t.blob + a, (size_t)(b2 - a), cudaMemcpyHostToDevice, s));
+            if (launch_unpack(c, t.d_pk + a, t.d_blob + (a << t.shift), b2 - a, t.shift, s)) return -1;      // on the copy stream, right behind its bytes
+        } else CUDA_TRY(c, cudaMemcpyAsync(t.d_blob + a, t.blob + a, (size_t)(b2 - a), cudaMemcpyHostToDevice, s));
         c->tm.h2d_bytes += b2 - a;
         return 0;
     };
@@ -879,20 +945,27 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     memset(&c->tm, 0, sizeof c->tm);
     TR(c, "stream_begin");
     int64_t reads_bytes = 0, win_bytes = 0; int32_t max_rl = 0, max_wl = 0;
-    const bool scan = forceScan || c->b_reads.cap < 64 || c->b_windows.cap < 64;
+    if (b->seq_encoding < SWB_SEQ_CODES || b->seq_encoding > SWB_SEQ_PACKED2) { c->err = "unknown seq_encoding"; return -1; }
+    const int shift = seq_shift_of(b->seq_encoding);
+    const bool scan = forceScan || c->b_reads.cap < 64 || c->b_windows.cap < 64 || (shift && (c->b_reads_pk.cap < 64 || c->b_windows_pk.cap < 64));
     if (scan) {
         if (!scan_tables(b, reads_bytes, max_rl, win_bytes, max_wl)) { c->err = "negative sequence offset/length"; return -1; }
     } else {
         reads_bytes = (int64_t)c->b_reads.cap - 16; win_bytes = (int64_t)c->b_windows.cap - 16;      // what is already there; lengths follow from the pieces
+        if (shift) {                                         // caller-side (packed) bytes both the staging and the unpacked buffer can take
+            reads_bytes = std::min<int64_t>(reads_bytes >> shift, (int64_t)c->b_reads_pk.cap - 16);
+            win_bytes = std::min<int64_t>(win_bytes >> shift, (int64_t)c->b_windows_pk.cap - 16);
+        }
     }
     TR(c, "tables_scanned");
     const size_t np = (size_t)b->n_pairs, nr = (size_t)b->n_reads, nw = (size_t)b->n_windows;
 
     // device input buffers (filled piece by piece below)
-    CUDA_TRY(c, c->b_reads.ensure((size_t)reads_bytes + 16));   d.reads = (int8_t*)c->b_reads.p;
+    if (shift) { CUDA_TRY(c, c->b_reads_pk.ensure((size_t)reads_bytes + 16)); CUDA_TRY(c, c->b_windows_pk.ensure((size_t)win_bytes + 16)); }
+    CUDA_TRY(c, c->b_reads.ensure(((size_t)reads_bytes << shift) + 16));   d.reads = (int8_t*)c->b_reads.p;
     CUDA_TRY(c, c->b_read_off.ensure(nr * 8 + 16));             d.read_off = (int64_t*)c->b_read_off.p;
     CUDA_TRY(c, c->b_read_len.ensure(nr * 4 + 16));             d.read_len = (int32_t*)c->b_read_len.p;
-    CUDA_TRY(c, c->b_windows.ensure((size_t)win_bytes + 16));   d.windows = (int8_t*)c->b_windows.p;
+    CUDA_TRY(c, c->b_windows.ensure(((size_t)win_bytes << shift) + 16));   d.windows = (int8_t*)c->b_windows.p;
     CUDA_TRY(c, c->b_win_off.ensure(nw * 8 + 16));              d.win_off = (int64_t*)c->b_win_off.p;
     CUDA_TRY(c, c->b_win_len.ensure(nw * 4 + 16));              d.win_len = (int32_t*)c->b_win_len.p;
     CUDA_TRY(c, c->b_pair_read.ensure(np * 4 + 16));            d.pair_read = (int32_t*)c->b_pair_read.p;
@@ -921,6 +994,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     tw.blob = b->windows; tw.off = b->win_off; tw.len = b->win_len; tw.n = b->n_windows;
     tw.d_blob = d.windows; tw.d_off = d.win_off; tw.d_len = d.win_len; tw.d_bad = (uint8_t*)c->b_wbad.p;
     tr.cap = reads_bytes; tw.cap = win_bytes;
+    tr.shift = tw.shift = shift; tr.d_pk = (uint8_t*)c->b_reads_pk.p; tw.d_pk = (uint8_t*)c->b_windows_pk.p;
     tr.ascii = tw.ascii = b->seq_encoding == SWB_SEQ_ASCII;
 
     // piece boundaries: small first pieces (the sweep starts early), growing by 1.3x -- slower than the ratio of the sweep's to
@@ -1055,7 +1129,7 @@ static bool plan_chunks(const swb_batch* b, std::vector<ChunkPlan>& plans)
 {
     const int64_t np = b->n_pairs;
     const bool off = getenv("SWB200_NO_PIPELINE") != nullptr;
-    if (off || np < 524288 || b->n_reads <= 0 || b->n_windows <= 0) return false;
+    if (off || np < 524288 || b->n_reads <= 0 || b->n_windows <= 0 || seq_shift_of(b->seq_encoding)) return false;
     // Chunk sizes: a small first chunk so that the kernels start while most of the batch is still crossing PCIe, then
     // growing ones (per-chunk fixed latencies -- host round trips, tail rounds -- favour few, large chunks).
     // SWB200_CHUNK_PLAN overrides the relative sizes ("1,2,3"), SWB200_CHUNK_PAIRS forces equal chunks of that many pairs.

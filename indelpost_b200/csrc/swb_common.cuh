@@ -52,6 +52,7 @@ struct SwbDev {
     int32_t bias;       // |min(mat)| (ssw.c:795-799)
     int8_t  score_size; uint8_t flag; uint16_t filters; int32_t filterd;
     int32_t seq_encoding;
+    int32_t seq_shift;  // device blobs hold one code per byte; a caller offset o (bytes, packed input) maps to (o - byte_base) << seq_shift
     int32_t max_rlen, max_wlen;
     int32_t max_score;  // max(mat): bound on the score gained per read base
     int32_t fast_ok;    // batch-level eligibility of the DPX fast path (matrix range, n >= 4, score_size)

@@ -50,6 +50,7 @@ struct swb_ctx {
     SwbDev d;
     bool have_batch = false, computed = false;
     // device buffers
+    DevBuf b_reads_pk, b_windows_pk;              // packed input (SWB_SEQ_PACKED4 / PACKED2) as uploaded, before k_unpack
     DevBuf b_reads, b_read_off, b_read_len, b_windows, b_win_off, b_win_len;
     DevBuf b_pair_read, b_pair_win, b_ref_beg, b_ref_len, b_go, b_ge, b_mask, b_mat;
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;

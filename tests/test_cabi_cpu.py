@@ -49,6 +49,27 @@ def test_host_helpers_without_gpu():
     assert m[0, 0] == 3 and m[0, 1] == -2 and (m[4] == 0).all() and (m[:, 4] == 0).all()
 
 
+def test_pack_table_layouts():
+    """swb_pack_table: SWB_SEQ_PACKED4 = two codes per byte, low nibble first; SWB_SEQ_PACKED2 = four per byte, bits 0-1 first;
+    every entry starts on a byte boundary; ASCII goes through DNA_BASE_LUT; 2 bits refuse N"""
+    from indelpost_b200.batch import pack_table
+
+    codes = np.array([0, 1, 2, 3, 4, 3, 2,   1, 0, 3], dtype=np.int8)
+    off = np.array([0, 7], dtype=np.int64)
+    ln = np.array([7, 3], dtype=np.int32)
+    pk, po = pack_table(codes, off, ln, bits=4)
+    assert po.tolist() == [0, 4]
+    assert pk.tolist() == [0x10, 0x32, 0x34, 0x02, 0x01, 0x03]
+    with pytest.raises(ValueError):
+        pack_table(codes, off, ln, bits=2)                   # code 4 (N) does not fit two bits
+    codes2 = np.array([0, 1, 2, 3, 3, 2,   1], dtype=np.int8)
+    pk2, po2 = pack_table(codes2, np.array([0, 6], dtype=np.int64), np.array([6, 1], dtype=np.int32), bits=2)
+    assert po2.tolist() == [0, 2]
+    assert pk2.tolist() == [0b11100100, 0b1011, 0b01]
+    pk3, _ = pack_table(np.frombuffer(b"ACGTNacgu", dtype=np.int8), np.array([0], dtype=np.int64), np.array([9], dtype=np.int32), bits=4, ascii=True)
+    assert pk3.tolist() == [0x10, 0x32, 0x04, 0x21, 0x00]
+
+
 def test_no_cpu_fallback_without_gpu():
     from indelpost_b200 import _lib as L
 

@@ -392,6 +392,45 @@ def test_gpu_streamed_batch_ascii_subranges_and_masks(monkeypatch):
     T.compare(r2[sub].copy(), a2, ro, ao, what="streamed (ASCII, sub-ranges, masks) vs oracle")
 
 
+def _packed(b, bits):
+    """the same batch with its sequence tables packed for SWB_SEQ_PACKED4 / PACKED2 (include/swb200.h)"""
+    import copy
+    from indelpost_b200.batch import pack_table
+
+    q = copy.copy(b)
+    q.reads, q.read_off = pack_table(b.reads, b.read_off, b.read_len, bits=bits)
+    q.windows, q.win_off = pack_table(b.windows, b.win_off, b.win_len, bits=bits)
+    q.reads = q.reads.view(np.int8); q.windows = q.windows.view(np.int8)
+    q.seq_encoding = 2 if bits == 4 else 3
+    return q
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", [4, 2])
+def test_gpu_packed_input_equals_codes(bits, monkeypatch):
+    """4-bit and 2-bit packed sequence tables (unpacked on the device) give the results of the one-code-per-byte tables: single
+    pass (ragged lengths, sub-ranges, N bases for 4 bits) and streamed path (pieces unpacked behind their copies)"""
+    from gpuutil import gpu_align
+
+    b = T.make_pairs(3000, (31, 150), (180, 400), seed=61, grid=True, n_rate=0.01 if bits == 4 else 0.0)
+    rng = np.random.default_rng(8)
+    wl = b.win_len[b.pair_win]
+    b.ref_beg = rng.integers(0, 20, size=b.n_pairs).astype(np.int32)
+    b.ref_len = (wl - b.ref_beg - rng.integers(0, 20, size=b.n_pairs)).astype(np.int32)
+    r0, a0, _ = gpu_align(b)
+    r1, a1, tm1 = gpu_align(_packed(b, bits))
+    T.compare(r1, a1, r0, a0, what=f"{bits}-bit packed vs codes (single pass)")
+    ro, ao = T.oracle().align_batch(b)
+    T.compare(r1, a1, ro, ao, what=f"{bits}-bit packed vs oracle")
+    big = T.make_pairs_fast(300000, 101, 251, seed=12, reads_per_window=20)
+    big = big.subset(np.random.default_rng(4).permutation(big.n_pairs))      # upload frontier jumps around
+    r2, a2, tm2 = gpu_align(_packed(big, bits))                              # >= 262144 pairs: streamed
+    monkeypatch.setenv("SWB200_NO_PIPELINE", "1")
+    r3, a3, tm3 = gpu_align(big)
+    T.compare(r2, a2, r3, a3, what=f"{bits}-bit packed streamed vs codes single pass")
+    assert tm2["h2d_bytes"] < tm3["h2d_bytes"] * (0.75 if bits == 4 else 0.55)
+
+
 def test_multi_gpu_aligner_shards_and_stitches():
     """host-side sharding over several contexts (here: two contexts on the available device(s))"""
     import torch
