@@ -168,6 +168,9 @@ typedef struct {
     float   ms_band_rest;    /* band-doubling rounds                                             */
     float   ms_certify;      /* overflow certificate + exact 8-bit verification of the remainder */
     int32_t band_rounds;
+    int32_t n_sw_certified;  /* 8-bit-final pairs with scores past 128+go+ge that the sandwich sweep certified (forward pass) */
+    int32_t n_sw_rejected;   /* ... that it sent to the exact striped emulation                                               */
+    int32_t n_sw_verified;   /* overflow verifications settled by the sandwich lower bound instead of the exact 8-bit pass    */
 } swb_timing;
 
 int         swb_device_count(void);

@@ -54,6 +54,7 @@ class SwbTiming(C.Structure):
         ("n_fast", C.c_int64), ("n_exact", C.c_int64), ("n_launches", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_band_round0", C.c_float), ("ms_band_rest", C.c_float), ("ms_certify", C.c_float), ("band_rounds", C.c_int32),
+        ("n_sw_certified", C.c_int32), ("n_sw_rejected", C.c_int32), ("n_sw_verified", C.c_int32),
     ]
 
     def as_dict(self):

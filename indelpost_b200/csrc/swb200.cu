@@ -141,7 +141,10 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         const bool wordSem = d.score_size == 1 || (d.max_score * rl + d.bias >= 255);
         d.p_mode[p] = wordSem ? 1 : 0;
         const int b = (lp16 + 31) / 32 - 1;
-        list_push(d.list[LIST_FAST_FWD + b], d.counters + CNT_FAST_FWD + b, p);
+        // 8-bit-final pairs whose scores can pass 128+go+ge (where the 8-bit pass may deviate from Gotoh) take the sandwich sweep
+        const bool sw = !wordSem && !(d.opt & 128) && d.max_score * rl >= 128 + go + ge;
+        if (sw) list_push(d.list[LIST_SW_FWD + b], d.counters + CNT_SW_FWD + b, p);
+        else list_push(d.list[LIST_FAST_FWD + b], d.counters + CNT_FAST_FWD + b, p);
         if (wl > *(volatile int32_t*)(d.counters + CNT_FAST_MAXCOLS + b)) atomicMax(d.counters + CNT_FAST_MAXCOLS + b, wl);   // test first: one hot address
     }
     else if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
@@ -461,11 +464,27 @@ static int launch_validate(swb_ctx* c, int8_t* blob, const int64_t* off, const i
     return 0;
 }
 
+// counts: plain fast-path list lengths per bucket; c->swCounts: what k_prepare put on the sandwich lists.  The plain forward sweep
+// appends to a bucket's sandwich list (16-bit-semantics pairs whose result turned out to be the 8-bit pass's), so the sandwich
+// launches are sized by the sum (the kernels read the real list length)
 template <int DIR>
 static int launch_fast(swb_ctx* c, const int* counts) {
     // the forward sweeps go to the low-priority stream (see swb_create), the reverse ones stay on the main stream
     if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_fork, c->stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_fork, 0)); }
-    const int rc = DIR == 0 ? swb_launch_fast_range_fwd(c, nullptr, counts, c->bulk_stream) : swb_launch_fast_range_rev(c, nullptr, counts, c->stream);
+    int rc;
+    if (DIR == 0) {
+        int ub[SWB_NBUCKETS];
+        for (int b = 0; b < SWB_NBUCKETS; ++b) ub[b] = counts[b] + c->swCounts[b];
+        rc = swb_launch_fast_range_fwd(c, nullptr, counts, c->bulk_stream);
+        if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_fwd(c, ub, c->bulk_stream);
+    } else {
+        // reverse lists are filled by the forward sweeps: a bucket's plain list is bounded by its plain + sandwich forward counts
+        // (sandwich pairs that ended in the safe zone take the plain reverse pass), its sandwich list by the sandwich forward count
+        int ub[SWB_NBUCKETS];
+        for (int b = 0; b < SWB_NBUCKETS; ++b) ub[b] = counts[b] + c->swCounts[b];
+        rc = swb_launch_fast_range_rev(c, nullptr, ub, c->stream);
+        if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_rev(c, ub, c->stream);
+    }
     if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join, c->bulk_stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_bulk_join, 0)); }
     if (rc) return rc;
     return stage_check(c, DIR ? "fast rev" : "fast fwd");
@@ -490,7 +509,17 @@ static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound, 
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
     CUDA_TRY(c, cudaStreamWaitEvent(vs, c->ev_fork3, 0));
-    if (swb_launch_exact(c, 0, 0, verifyList, upperBound, vs, /*fewJobsLikely=*/true)) return -1;      // confirms the overflow, or produces the byte-mode result
+    // first the sandwich lower bound (a DPX sweep, microseconds for a handful of pairs); what it cannot settle goes on to the exact
+    // 8-bit pass, which confirms the overflow or produces the byte-mode result
+    int xList = verifyList;
+    if (!(d.opt & 128)) {
+        const int xs = LIST_VERIFYX + which;
+        CUDA_TRY(c, cudaMemsetAsync(d.counters + xs, 0, 4, vs));
+        const int rc = swb_launch_sandwich_verify(c, verifyList, xs, upperBound, vs);
+        if (rc < 0) return -1;
+        if (rc == 0) xList = xs;
+    }
+    if (swb_launch_exact(c, 0, 0, xList, upperBound, vs, /*fewJobsLikely=*/true)) return -1;
     CUDA_TRY(c, cudaEventRecord(which ? c->ev_join3 : c->ev_join2, vs));
     c->verify_pending |= 1u << which;
     return 0;
@@ -759,6 +788,7 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     memcpy(&tm.cells_band, c->h_counters + CNT_CELLS_BAND, 8);
     tm.n_fast = c->h_counters[CNT_FAST_DONE] - c->h_counters[CNT_VERIFY_BYTE];
     tm.n_exact = c->h_counters[CNT_EXACT_JOBS];
+    tm.n_sw_certified = c->h_counters[CNT_SW_CERTIFIED]; tm.n_sw_rejected = c->h_counters[CNT_SW_REJECTED]; tm.n_sw_verified = c->h_counters[CNT_SW_VERIFIED];
     c->computed = true;
     TR(c, "compute_end");
     return 0;
@@ -780,7 +810,10 @@ static int swb_compute_impl(swb_ctx* c) {
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
     if (read_counters(c)) return -1;                        // bucket sizes for the fast path launches
     int fwdCounts[SWB_NBUCKETS]; int nFastTotal = 0;
-    for (int b = 0; b < SWB_NBUCKETS; ++b) { fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; nFastTotal += fwdCounts[b]; c->fastMaxCols[b] = c->h_counters[CNT_FAST_MAXCOLS + b]; }
+    for (int b = 0; b < SWB_NBUCKETS; ++b) {
+        fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; c->swCounts[b] = c->h_counters[CNT_SW_FWD + b];
+        nFastTotal += fwdCounts[b] + c->swCounts[b]; c->fastMaxCols[b] = c->h_counters[CNT_FAST_MAXCOLS + b];
+    }
 
     // ---- forward (ssw.c:842-860) --------------------------------------------------------------------
     //   fast path: one 16-bit Gotoh sweep per pair (pairs it cannot decide are appended to the exact lists)
@@ -1085,6 +1118,20 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
         }
     }
     if (npieces == 0) { CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], s)); CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s)); }
+    // the sandwich lists are swept once, after the last piece (short reads: a minority of a mixed batch)
+    int nSw = 0;
+    for (int q = 0; q < SWB_NBUCKETS; ++q) { c->swCounts[q] = npieces > 0 ? c->h_snap[(npieces - 1) & 1][CNT_SW_FWD + q] : 0; nSw += c->swCounts[q]; }
+    int nFwdPlain = 0;
+    for (int q = 0; q < SWB_NBUCKETS; ++q) nFwdPlain += done[q];
+    if ((nSw > 0 || nFwdPlain > 0) && npieces > 0 && !(d.opt & 128)) {
+        // after every plain forward slice (they append to the sandwich lists) and the last piece's prepare
+        int ub[SWB_NBUCKETS];
+        for (int q = 0; q < SWB_NBUCKETS; ++q) ub[q] = done[q] + c->swCounts[q];
+        CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_snap[(npieces - 1) & 1], 0));
+        if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_join2, 0)); }
+        if (swb_launch_sandwich_fwd(c, ub, c->bulk_stream)) return -1;
+        used1 = true;
+    }
     if (used1) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join, c->bulk_stream)); CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_bulk_join, 0)); }
     if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_bulk_join2, 0)); }
     // only the table entries some pair refers to are resident: a later swb_compute on this context must not touch the rest
@@ -1096,7 +1143,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     d.seq_encoding = SWB_SEQ_CODES;
     c->have_batch = true;
     int nFastTotal = 0;
-    for (int q = 0; q < SWB_NBUCKETS; ++q) nFastTotal += done[q];
+    for (int q = 0; q < SWB_NBUCKETS; ++q) nFastTotal += done[q] + c->swCounts[q];
     TR(c, "pieces_enqueued");
     if (compute_tail(c, done, nFastTotal)) return -1;
     return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);
@@ -1119,6 +1166,7 @@ static void add_timing(swb_timing& a, const swb_timing& t) {
     a.ms_traceback += t.ms_traceback; a.ms_h2d += t.ms_h2d; a.ms_d2h += t.ms_d2h;
     a.cells_forward += t.cells_forward; a.cells_reverse += t.cells_reverse; a.cells_band += t.cells_band;
     a.n_fast += t.n_fast; a.n_exact += t.n_exact; a.n_launches += t.n_launches; a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes;
+    a.n_sw_certified += t.n_sw_certified; a.n_sw_rejected += t.n_sw_rejected; a.n_sw_verified += t.n_sw_verified;
     a.ms_band_round0 += t.ms_band_round0; a.ms_band_rest += t.ms_band_rest; a.ms_certify += t.ms_certify; a.band_rounds += t.band_rounds;
 }
 

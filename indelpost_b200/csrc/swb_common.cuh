@@ -7,8 +7,8 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 132
-#define SWB_NCOUNTERS 168
+#define SWB_NLISTS 152
+#define SWB_NCOUNTERS 200
 
 // ---------------------------------------------------------------------------------------------
 // Device-resident batch ("workspace").  One per context, grown on demand.
@@ -63,7 +63,7 @@ struct SwbDev {
     int64_t rbyte_base, wbyte_base;   // byte offset of the slice inside the caller's blobs
     uint32_t* fast_cols;   // global column-best storage of the fast path when windows are too long for shared memory (null otherwise)
     int32_t one;        // always 1, but opaque to the compiler: x * one + c compiles to a real IMAD (FMA pipe) instead of an ALU-pipe add
-    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass, bit4 = no register-band kernel, bit5 = single traceback phase, bit6 = no warp-per-alignment band kernel
+    int32_t opt;        // experiment switches (SWB200_OPT): bit0 = certificate inline in k_band instead of the separate pass, bit1 = scalar-lane exact kernel, bit2 = no banded reverse pass, bit4 = no register-band kernel, bit5 = single traceback phase, bit6 = no warp-per-alignment band kernel, bit7 = no sandwich sweep (unsafe-zone 8-bit pairs and overflow verifications go to the exact kernels)
 };
 
 // list[] slots; counters[i] is the length of list[i] for i < SWB_NLISTS
@@ -75,12 +75,18 @@ struct SwbDev {
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
        LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
        LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104,
-       LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129, LIST_BANDWARP_NEXT = 130 };
+       LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129, LIST_BANDWARP_NEXT = 130,
+       // sandwich sweep (swb_fast.cuh, SW = 1): 8-bit-final pairs whose scores can pass 128+go+ge, per read-length bucket, forward / reverse;
+       // LIST_VERIFYX (+1): pairs whose overflow neither the CIGAR certificate nor the sandwich lower bound could prove (exact 8-bit pass)
+       LIST_SW_FWD = 132, LIST_SW_REV = 140, LIST_VERIFYX = 148 };
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
-       CNT_CELLS_FWD = 136, CNT_CELLS_REV = 138, CNT_CELLS_BAND = 140, CNT_BAND_OVERFLOW = 142, CNT_CIGAR_OVERFLOW = 143,
-       CNT_FAST_DONE = 144, CNT_CERT_FAIL = 145, CNT_VERIFY_BYTE = 146, CNT_EXACT_JOBS = 147,
-       CNT_FAST_MAXCOLS = 152 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
+       CNT_SW_FWD = 132, CNT_SW_REV = 140,
+       CNT_CELLS_FWD = 160, CNT_CELLS_REV = 162, CNT_CELLS_BAND = 164, CNT_BAND_OVERFLOW = 166, CNT_CIGAR_OVERFLOW = 167,
+       CNT_FAST_DONE = 168, CNT_CERT_FAIL = 169, CNT_VERIFY_BYTE = 170, CNT_EXACT_JOBS = 171,
+       CNT_SW_CERTIFIED = 172,     // unsafe-zone pairs the sandwich certified (forward); CNT_SW_REJECTED: those it sent to the exact path
+       CNT_SW_REJECTED = 173, CNT_SW_VERIFIED = 174,   // overflow verifications settled by the sandwich lower bound
+       CNT_FAST_MAXCOLS = 176 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
 #define SWB_BANDW_MAX 24           // widest half-width the register-band kernel is instantiated for
 #define SWB_BANDREG_MAXROWS 320    // longest read segment it stages in shared memory
 // banded reverse pass (swb_revband.cuh): band classes as (rows below, columns right of) the main diagonal

@@ -27,6 +27,16 @@
 // wavefront as (value, row) and stored per column in shared memory by the last thread; best score, first
 // best column (ssw.c:325-333 / 530-534), mask rule and the reverse pass' "first column whose maximum
 // equals score1" (ssw.c:337/539) are resolved by a short scan after the sweep.
+//
+// SW = 1, the "sandwich" sweep: for 8-bit-final pairs whose scores can pass 128+go+ge the result IS the 8-bit pass
+// with its signed lazy-F exit test (ssw.c:309-311), which differs from Gotoh only when that test mis-reads a live vertical-gap
+// chain -- possible only while the chain's value lies in W = [128, 127+go-ge].  Next to Gotoh (U) the sweep carries a lower
+// bound L: the same recurrence, but a vertical-gap CONTINUATION is dropped whenever the interval [L's value, U's value] of the
+// chain meets W, and E opens from H without F (ssw.c computes E before the lazy correction).  L <= H(8-bit) <= U cell by cell; if
+// in every column L equals U at U's column-best cell (the smallest row holding the column maximum), every output of the 8-bit pass
+// is Gotoh's.  One bit per column and lane ("L differs at the column best") rides in bit 15 of the row word down the wavefront.
+// Pairs with a flagged column go to the exact kernels.  The same sweep settles overflow verifications (PST_HAVE_WORD): if L's
+// maximum reaches 255-bias the 8-bit pass certainly overflowed.
 #pragma once
 #include <type_traits>
 #include "swb_common.cuh"
@@ -50,35 +60,17 @@ struct FastLane {
     int p;                                    // pair index (-1: lane unused)
 };
 
-// job list entry j -> pairs (jobs[2j], jobs[2j+1]); an odd tail is paired with itself
-template <int R, int DIR, bool GCOLS>
-__global__ void __launch_bounds__(128)
-k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc, int pairOffset, int pairLimit)
+// One group's lane pair: staging, sweep, post-sweep scans.  job list entry j -> pairs (jobs[2j], jobs[2j+1]); an odd tail is paired with itself
+template <int R, int DIR, bool GCOLS, int SW>
+__device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __restrict__ jobs, const int npairs, const int grp, const bool valid,
+                                           const int colAlloc, const int verifyX, unsigned char* smem_raw, const uint32_t* s_rowtab)
 {
     constexpr int G = FAST_G;
     constexpr int BKT = R / 2 - 1;                               // read-length bucket this instantiation serves
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_rowtab[SWB_MAX_N];
-
-    // this launch serves the slice [pairOffset, pairOffset + pairLimit) of the job list (pairOffset is even)
-    jobs += pairOffset;
-    const int npairs = min(max(*njobs_ptr - pairOffset, 0), pairLimit);
-    const int ngroups = (npairs + 1) >> 1;
-    const int groupsPerBlock = blockDim.x / G;
-    if (blockIdx.x * groupsPerBlock >= ngroups) return;
     const int lane = threadIdx.x & 31;
     const int g = lane % G;
     const int groupInBlock = threadIdx.x / G;
-    const int grp = blockIdx.x * groupsPerBlock + groupInBlock;
-    const bool valid = grp < ngroups;
-
-    // per-read-base score table: byte nt = 16 * mat[nt][rb]  (qP_word's profile cell, ssw.c:402, scaled)
-    if (threadIdx.x < d.n) {
-        uint32_t t = 0;
-        for (int nt = 0; nt < 4; ++nt) t |= (uint32_t)(uint8_t)(int8_t)(FAST_SCALE * d.mat[nt * d.n + threadIdx.x]) << (8 * nt);
-        s_rowtab[threadIdx.x] = t;
-    }
 
     FastLane ln[2];
 #pragma unroll
@@ -103,7 +95,6 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             q.off = G * R - q.Lp;
         }
     }
-    __syncthreads();
 
     // ---- shared memory: per group, per column: selector (u16), column best value (u32), its row (u32) ----
     // short windows: everything in shared memory (10 bytes per column).  Long windows: only the selectors stay in
@@ -142,6 +133,17 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         tA[k] = a; tB[k] = b;
         H[k] = FAST_CPACK; E[k] = FAST_CPACK;
     }
+    uint32_t HL[SW ? R : 1], EL[SW ? R : 1];                    // the lower-bound recurrence (SW only)
+    if constexpr (SW) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) { HL[k] = FAST_CPACK; EL[k] = FAST_CPACK; }
+    }
+    // SW: drop window W = [128, 127 + go - ge] as sign-bit tests: (hiX - contL) has lane bit 15 set iff contL <= hi,
+    // (contU + loY) iff contU >= lo (all lane values are below 0x8000, no carry between the lanes)
+    uint32_t geP = pack2(FAST_SCALE * ln[0].ge, FAST_SCALE * ln[1].ge);
+    uint32_t hiX = pack2(FAST_SCALE * (127 + ln[0].go - ln[0].ge) + FAST_C + 0x8000, FAST_SCALE * (127 + ln[1].go - ln[1].ge) + FAST_C + 0x8000);
+    const uint32_t loY = pack2(0x8000 - (FAST_SCALE * 128 + FAST_C), 0x8000 - (FAST_SCALE * 128 + FAST_C));
+    if constexpr (SW) asm volatile("" : "+r"(geP), "+r"(hiX));
     uint32_t goP = pack2(FAST_SCALE * ln[0].go, FAST_SCALE * ln[1].go);
     uint32_t ngeP = pack2(-FAST_SCALE * ln[0].ge, -FAST_SCALE * ln[1].ge);
     uint32_t rowBase = pack2(g * R, g * R);
@@ -159,6 +161,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     if (!valid) nsteps = max(nsteps, 0);
 
     uint32_t outH = FAST_CPACK, outF = FAST_CPACK, outV = 0, outRow = 0, prevInH = FAST_CPACK;
+    uint32_t outHL = FAST_CPACK, outFL = FAST_CPACK, prevInHL = FAST_CPACK, runL = 0;
     const uint32_t targetV = pack2(ln[0].target >= 0 ? FAST_SCALE * ln[0].target + FAST_C : 0x7fff, ln[1].target >= 0 ? FAST_SCALE * ln[1].target + FAST_C : 0x7fff);
     bool done = false;                                         // reverse pass: both lanes have hit their target
 
@@ -179,14 +182,22 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         uint32_t inV = __shfl_up_sync(FULL, outV, 1, G);
         uint32_t inRow = __shfl_up_sync(FULL, outRow, 1, G);
         inH = inH * m1 + c0; inF = inF * m1 + c0; inV *= m1; inRow *= m1;
+        uint32_t inHL = 0, inFL = 0;
+        if constexpr (SW) {
+            inHL = __shfl_up_sync(FULL, outHL, 1, G) * m1 + c0;
+            inFL = __shfl_up_sync(FULL, outFL, 1, G) * m1 + c0;
+        }
         const int c = t - g;
         if (!CHECKED || (c >= 0 && c < maxcols && !done)) {
             const uint32_t sel = selS[c];
             uint32_t F = inF, hd = prevInH, cm = 0;
             prevInH = inH;
+            [[maybe_unused]] uint32_t FL = inFL, hdL = prevInHL, cmL = 0;
+            prevInHL = inHL;
 #pragma unroll
             for (int k = 0; k < R; k += 2) {
                 uint32_t key[2];
+                [[maybe_unused]] uint32_t keyL[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int kk = k + u;
@@ -197,14 +208,38 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                     key[u] = h * one - (uint32_t)(kk * 0x00010001);              // value - rowInThread: a true IMAD (FMA pipe), no lane borrow
                     const uint32_t hg = h - goP;                                 // FMA-pipe IADD; no lane borrow: h >= 0x4000 > 16*go
                     E[kk] = __viaddmax_s16x2(E[kk], ngeP, hg);                   // max(E - ge, H - go)
-                    F = __viaddmax_s16x2(F, ngeP, hg);                           // max(F - ge, H - go)
+                    if constexpr (!SW) {
+                        F = __viaddmax_s16x2(F, ngeP, hg);                       // max(F - ge, H - go)
+                    } else {
+                        // the lower bound L: H without F first (E opens from it), then the vertical gap
+                        uint32_t hn = __viaddmax_s16x2(hdL, s, EL[kk]);
+                        hn = vmax2(hn, FAST_CPACK);
+                        const uint32_t hL = vmax2(hn, FL);
+                        hdL = HL[kk]; HL[kk] = hL;
+                        keyL[u] = hL * one - (uint32_t)(kk * 0x00010001);
+                        EL[kk] = __viaddmax_s16x2(EL[kk], ngeP, hn - goP);
+                        // continuations of the two chains (every F lane is >= 0x4000 - 16*go > 16*ge: no borrow); L's is dropped
+                        // when [contL, contU] meets W
+                        const uint32_t contU = F - geP;
+                        uint32_t contL = FL - geP;
+                        const uint32_t z = (hiX - contL) & (contU + loY);
+                        const uint32_t drop = prmt(z, 0u, 0xBB99u);              // 0xFFFF in the lanes where both sign bits are set
+                        contL &= ~drop;
+                        F = vmax2(contU, hg);
+                        FL = vmax2(contL, hL - goP);
+                    }
                 }
                 cm = k == 0 ? vmax2(key[0], key[1]) : __vimax3_s16x2(cm, key[0], key[1]);   // column best over keys, two rows per ALU instruction
+                if constexpr (SW) cmL = k == 0 ? vmax2(keyL[0], keyL[1]) : __vimax3_s16x2(cmL, keyL[0], keyL[1]);
             }
             outH = H[R - 1]; outF = F;
+            if constexpr (SW) { outHL = HL[R - 1]; outFL = FL; runL = vmax2(runL, cmL); }
             // local column best -> (value, absolute row); merge with the rows above (they win ties)
             const uint32_t lv = (cm + 0x000F000Fu) & 0xFFF0FFF0u;
-            const uint32_t lrow = lv - cm + rowBase;
+            uint32_t lrow = lv - cm + rowBase;
+            // SW: bit 15 of the lane = "L differs from U at this thread's column-best cell" (equal keys <=> same value in the same row);
+            // it travels with the row word, so the column's final word carries the flag of the cell that won
+            if constexpr (SW) lrow += ((cm ^ cmL) + 0x7FFF7FFFu) & 0x80008000u;
             const uint32_t x = inV + 0x80008000u - lv;                       // lane bit15 set <=> inV >= lv (inV lanes are < 0x8000)
             const uint32_t keep = prmt(x, 0u, 0xBB99u);                 // 0xFFFF in lanes where the upstream value stays
             outV = vmax2(inV, lv);
@@ -251,12 +286,31 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
         const int p = q.p;
         swb_result& r = d.res[p];
         const bool wordSem = d.p_mode[p] != 0;
+        if (DIR == 0 && SW && (d.p_state[p] & PST_HAVE_WORD)) {
+            // overflow verification of a provisional 16-bit result: L <= H(8-bit), so L reaching 255-bias proves the overflow
+            int mv = (int)((runL >> sh) & 0xffffu);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) mv = max(mv, __shfl_xor_sync(GM, mv, o, G));
+            if (g == 0) {
+                const int ml = mv > FAST_C ? (((mv + 15) & ~15) - FAST_C) / FAST_SCALE : 0;
+                if (ml >= 255 - d.bias) atomicAdd(d.counters + CNT_SW_VERIFIED, 1);
+                else if (verifyX >= 0) list_push(d.list[verifyX], d.counters + verifyX, p);
+            }
+            continue;
+        }
         if (DIR == 0) {
             // best score and first column reaching it
             int bv = 0, bc = 0x7fffffff;
+            uint32_t fl = 0;                                    // SW: some column's best cell differs between L and U
             for (int c = g; c < q.ncols; c += G) {
                 const int v = (int)((colv[c] >> sh) & 0xffffu);
                 if (v > bv) { bv = v; bc = c; }
+                if constexpr (SW) fl |= colr[c];
+            }
+            if constexpr (SW) {
+                fl = (fl >> sh) & 0x8000u;
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) fl |= __shfl_xor_sync(GM, fl, o, G);
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) {
@@ -265,7 +319,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             }
             const int T = bv > FAST_C ? (bv - FAST_C) / FAST_SCALE : 0;
             int end_ref, end_read;
-            if (T > 0) { end_ref = bc; end_read = min((int)((colr[bc] >> sh) & 0xffffu) - q.off, q.L - 1); }
+            if (T > 0) { end_ref = bc; end_read = min((int)((colr[bc] >> sh) & 0x7fffu) - q.off, q.L - 1); }
             else { end_ref = wordSem ? 0 : -1; end_read = 0; }                      // ssw.c:427 / 220
             // sub-optimal score outside the mask (ssw.c:366-379 byte, 568-581 word)
             const int edgeL = max(end_ref - q.mask, 0);
@@ -299,9 +353,17 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                 bool accept;
                 if (wordSem) accept = d.score_size == 1 || T >= limit;            // else the result is a byte-mode one: exact path decides
                 else accept = T < limit && T < 128 + q.go + q.ge;                  // safe zone of the signed lazy-F test
+                const bool unsafeZone = !wordSem && T < limit && T >= 128 + q.go + q.ge;
+                if (SW && unsafeZone) {                                            // ... or certified by the sandwich
+                    accept = fl == 0;
+                    atomicAdd(d.counters + (accept ? CNT_SW_CERTIFIED : CNT_SW_REJECTED), 1);
+                }
                 if (!accept) {
                     d.p_mode[p] = 0; d.p_state[p] = 0;
-                    list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
+                    // a 16-bit-semantics sweep whose score stays below the 8-bit limit: the result is the 8-bit pass's.  It is swept again
+                    // in 8-bit semantics (16-row padding, the other mask edge) by the sandwich flavour, which runs after this launch
+                    if (!SW && wordSem && d.score_size == 2 && !(d.opt & 128)) list_push(d.list[LIST_SW_FWD + BKT], d.counters + CNT_SW_FWD + BKT, p);
+                    else list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
                 } else {
                     r.score1 = (uint16_t)T; r.ref_end1 = end_ref; r.read_end1 = end_read;
                     d.p_csafe[p] = cs;
@@ -313,13 +375,14 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                         // reverse pass: banded (swb_revband.cuh) when the score deficit B = mx*rows - T bounds the deviation
                         // of every path scoring T from the main diagonal to one of the band classes, else the wavefront sweep
                         int cls = -1;
-                        if (T > 0 && q.ge > 0 && !(d.opt & 4)) {
+                        if (T > 0 && q.ge > 0 && !(d.opt & 4) && !(SW && unsafeZone)) {
                             const int B = d.max_score * (end_read + 1) - T;
                             int wd = 0, wi = 0;
                             if (B >= q.go) { wd = (B - q.go) / q.ge + 1; wi = (B - q.go + q.ge) / (d.max_score + q.ge); }
                             cls = revb_class(wi, wd);
                         }
                         if (cls >= 0) list_push(d.list[LIST_REVB + cls], d.counters + LIST_REVB + cls, p);
+                        else if (SW && unsafeZone) list_push(d.list[LIST_SW_REV + BKT], d.counters + CNT_SW_REV + BKT, p);   // the reverse pass needs its own certificate
                         else list_push(d.list[LIST_FAST_REV + BKT], d.counters + CNT_FAST_REV + BKT, p);
                     }
                     else d.p_state[p] |= PST_BAND_DONE;                            // no reverse pass / traceback will follow
@@ -335,8 +398,15 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) hc = min(hc, __shfl_xor_sync(GM, hc, o, G));
+            uint32_t fl = 0;                                    // SW: a column up to the hit whose best cell differs between L and U
+            if constexpr (SW) {
+                if (hc != 0x7fffffff) for (int c = g; c <= hc; c += G) fl |= colr[c];
+                fl = (fl >> sh) & 0x8000u;
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) fl |= __shfl_xor_sync(GM, fl, o, G);
+            }
             if (g == 0) {
-                if (hc == 0x7fffffff || q.target <= 0) {
+                if (hc == 0x7fffffff || q.target <= 0 || fl) {
                     // no column reaches score1 (or score 0 corner): let the exact path reproduce ssw.c literally
                     const int md = d.p_mode[p];
                     d.p_state[p] &= ~PST_FAST;
@@ -344,7 +414,7 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                 } else {
                     warp_count(d.counters + CNT_CELLS_REV, (unsigned long long)q.Lp * (hc + 1));
                     r.ref_begin1 = r.ref_end1 - hc;                                 // ssw.c:885-886
-                    r.read_begin1 = r.read_end1 - ((int)((colr[hc] >> sh) & 0xffffu) - q.off);
+                    r.read_begin1 = r.read_end1 - ((int)((colr[hc] >> sh) & 0x7fffu) - q.off);
                     const int f = d.flag;
                     const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
                                          ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));
@@ -352,5 +422,39 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
                 }
             }
         }
+    }
+}
+
+// Grid: one block per FAST-group bundle of the list slice; a launch whose grid is smaller than the slice (the sandwich flavour is
+// launched against an upper bound of its list) strides over it.
+template <int R, int DIR, bool GCOLS, int SW = 0>
+__global__ void __launch_bounds__(128)
+k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc, int pairOffset, int pairLimit, int verifyX = -1)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_rowtab[SWB_MAX_N];
+    // this launch serves the slice [pairOffset, pairOffset + pairLimit) of the job list (pairOffset is even)
+    jobs += pairOffset;
+    const int npairs = min(max(*njobs_ptr - pairOffset, 0), pairLimit);
+    const int ngroups = (npairs + 1) >> 1;
+    const int groupsPerBlock = blockDim.x / FAST_G;
+    if (blockIdx.x * groupsPerBlock >= ngroups) return;
+    // per-read-base score table: byte nt = 16 * mat[nt][rb]  (qP_word's profile cell, ssw.c:402, scaled)
+    if (threadIdx.x < d.n) {
+        uint32_t t = 0;
+        for (int nt = 0; nt < 4; ++nt) t |= (uint32_t)(uint8_t)(int8_t)(FAST_SCALE * d.mat[nt * d.n + threadIdx.x]) << (8 * nt);
+        s_rowtab[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if constexpr (SW) {
+        for (int g0 = blockIdx.x * groupsPerBlock; g0 < ngroups; g0 += gridDim.x * groupsPerBlock) {
+            const int grp = g0 + threadIdx.x / FAST_G;
+            fast_group<R, DIR, GCOLS, SW>(d, jobs, npairs, grp, grp < ngroups, colAlloc, verifyX, smem_raw, s_rowtab);
+            __syncwarp();                                       // the group's shared-memory columns are reused by its next lane pair
+        }
+    } else {
+        // the plain sweep is launched with one block per bundle of its list (no loop: the loop state costs the hot kernel registers)
+        const int grp = blockIdx.x * groupsPerBlock + threadIdx.x / FAST_G;
+        fast_group<R, DIR, GCOLS, SW>(d, jobs, npairs, grp, grp < ngroups, colAlloc, verifyX, smem_raw, s_rowtab);
     }
 }

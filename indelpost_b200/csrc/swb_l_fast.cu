@@ -1,13 +1,18 @@
-// swb_l_fast.cu — launches of the DPX sweep (swb_fast.cuh); compiled once per direction (-DSWB_FAST_DIR=0 / 1)
+// swb_l_fast.cu — launches of the DPX sweep (swb_fast.cuh); compiled once per direction and per flavour
+// (-DSWB_FAST_DIR=0 / 1, -DSWB_FAST_SW=0 plain Gotoh / 1 sandwich), so the instantiations build in parallel
 #include "swb_host.h"
 #include "swb_fast.cuh"
 
-// fast-path launch geometry: groups of FAST_G threads, 10 bytes of shared memory per column per group
+#ifndef SWB_FAST_SW
+#define SWB_FAST_SW 0
+#endif
 
-template <int R, int DIR>
-static int launch_fast_one(swb_ctx* c, int bucket, int firstPair, int upperBoundPairs, cudaStream_t st) {
+// fast-path launch geometry: groups of FAST_G threads, 10 bytes of shared memory per column per group
+// listBase: first of the SWB_NBUCKETS job lists this launch family reads; verifyX >= 0: overflow-verification launch (SW forward only)
+template <int R, int DIR, int SW>
+static int launch_fast_one(swb_ctx* c, int listBase, int bucket, int maxCols, int firstPair, int upperBoundPairs, cudaStream_t st, int verifyX = -1) {
     SwbDev& d = c->d;
-    const int colAlloc = (std::max(c->fastMaxCols[bucket], 8) + 7) & ~7;      // longest window among this bucket's pairs
+    const int colAlloc = (std::max(maxCols, 8) + 7) & ~7;                     // longest window among this bucket's pairs
     const bool globalCols = colAlloc > SWB_FAST_SMEM_COLS;
     const size_t per = (size_t)colAlloc * (globalCols ? 2 : 10);
     // long windows: the global column-best scratch is bounded, the bucket is served in slices of the job list
@@ -25,47 +30,75 @@ static int launch_fast_one(swb_ctx* c, int bucket, int firstPair, int upperBound
     const int threads = groups * FAST_G;
     static std::atomic<bool> attr_set[SWB_MAX_DEVICES] = {};               // per template instantiation and device
     if (!attr_set[c->device % SWB_MAX_DEVICES]) {
-        cudaFuncSetAttribute(k_fast<R, DIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
-        cudaFuncSetAttribute(k_fast<R, DIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
+        cudaFuncSetAttribute(k_fast<R, DIR, false, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
+        cudaFuncSetAttribute(k_fast<R, DIR, true, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
         attr_set[c->device % SWB_MAX_DEVICES] = true;
     }
-    const int slot = (DIR ? LIST_FAST_REV : LIST_FAST_FWD) + bucket;
+    const int slot = listBase + bucket;
     for (int off = firstPair; off < upperBoundPairs; off += slicePairs) {
         const int n = std::min(slicePairs, upperBoundPairs - off);
         const int ngroups = (n + 1) / 2;
-        const int blocks = (ngroups + groups - 1) / groups;
-        if (globalCols) k_fast<R, DIR, true><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
-        else k_fast<R, DIR, false><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs);
+        int blocks = (ngroups + groups - 1) / groups;
+        // the sandwich lists are launched against an upper bound of their length (the forward sweep appends to them): a bounded
+        // grid that strides over the list instead of tens of thousands of blocks that find nothing to do
+        if (SW) blocks = std::min(blocks, c->n_sm * 8);
+        if (globalCols) k_fast<R, DIR, true, SW><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs, verifyX);
+        else k_fast<R, DIR, false, SW><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs, verifyX);
         c->tm.n_launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
     return 0;
 }
 
-// one launch per non-empty read-length bucket (R = 2*(bucket+1) rows per thread) over the list ranges [first[b], counts[b])
-template <int DIR>
-static int launch_fast_range(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) {
+template <int DIR, int SW>
+static int launch_fast_bucket(swb_ctx* c, int listBase, int b, int rowsBucket, int maxCols, int f, int n, cudaStream_t st, int verifyX = -1) {
+    switch (rowsBucket) {      // R = 2 * (bucket + 1) rows per thread
+        case 0: return launch_fast_one<2, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 1: return launch_fast_one<4, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 2: return launch_fast_one<6, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 3: return launch_fast_one<8, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 4: return launch_fast_one<10, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 5: return launch_fast_one<12, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 6: return launch_fast_one<14, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 7: return launch_fast_one<16, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+    }
+    return -1;
+}
+
+// one launch per non-empty read-length bucket over the list ranges [first[b], counts[b])
+template <int DIR, int SW>
+static int launch_fast_range(swb_ctx* c, int listBase, const int* first, const int* counts, cudaStream_t st) {
     for (int b = 0; b < SWB_NBUCKETS; ++b) {
         const int n = counts[b], f = first ? first[b] : 0;
         if (n <= f) continue;
-        int rc = 0;
-        switch (b) {
-            case 0: rc = launch_fast_one<2, DIR>(c, b, f, n, st); break;
-            case 1: rc = launch_fast_one<4, DIR>(c, b, f, n, st); break;
-            case 2: rc = launch_fast_one<6, DIR>(c, b, f, n, st); break;
-            case 3: rc = launch_fast_one<8, DIR>(c, b, f, n, st); break;
-            case 4: rc = launch_fast_one<10, DIR>(c, b, f, n, st); break;
-            case 5: rc = launch_fast_one<12, DIR>(c, b, f, n, st); break;
-            case 6: rc = launch_fast_one<14, DIR>(c, b, f, n, st); break;
-            case 7: rc = launch_fast_one<16, DIR>(c, b, f, n, st); break;
-        }
+        const int rc = launch_fast_bucket<DIR, SW>(c, listBase, b, b, c->fastMaxCols[b], f, n, st);
         if (rc) return rc;
     }
     return 0;
 }
 
+#if SWB_FAST_SW == 0
 #if SWB_FAST_DIR == 0
-int swb_launch_fast_range_fwd(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) { return launch_fast_range<0>(c, first, counts, st); }
+int swb_launch_fast_range_fwd(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) { return launch_fast_range<0, 0>(c, LIST_FAST_FWD, first, counts, st); }
 #else
-int swb_launch_fast_range_rev(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) { return launch_fast_range<1>(c, first, counts, st); }
+int swb_launch_fast_range_rev(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) { return launch_fast_range<1, 0>(c, LIST_FAST_REV, first, counts, st); }
+#endif
+#else
+#if SWB_FAST_DIR == 0
+int swb_launch_sandwich_fwd(swb_ctx* c, const int* counts, cudaStream_t st) { return launch_fast_range<0, 1>(c, LIST_SW_FWD, nullptr, counts, st); }
+// overflow verification of the pairs in list `listSlot` (any read length of the batch: the widest bucket's instantiation, reads are
+// end-aligned in its rows); pairs the lower bound cannot settle are appended to list `xSlot`.  Returns 1 if the batch's windows are
+// too long for the shared-memory column scratch (the caller then goes to the exact kernel directly).
+int swb_launch_sandwich_verify(swb_ctx* c, int listSlot, int xSlot, int upperBound, cudaStream_t st) {
+    const SwbDev& d = c->d;
+    int maxCols = 0;
+    for (int b = 0; b < SWB_NBUCKETS; ++b) maxCols = std::max(maxCols, c->fastMaxCols[b]);
+    const int lp16 = (std::min(d.max_rlen, 32 * SWB_NBUCKETS) + 15) & ~15;
+    if (maxCols > SWB_FAST_SMEM_COLS || d.max_rlen > 32 * SWB_NBUCKETS || upperBound <= 0) return 1;
+    const int rb = std::max(0, (lp16 + 31) / 32 - 1);
+    return launch_fast_bucket<0, 1>(c, listSlot, 0, rb, maxCols, 0, upperBound, st, xSlot);
+}
+#else
+int swb_launch_sandwich_rev(swb_ctx* c, const int* counts, cudaStream_t st) { return launch_fast_range<1, 1>(c, LIST_SW_REV, nullptr, counts, st); }
+#endif
 #endif

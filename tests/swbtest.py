@@ -533,6 +533,34 @@ def make_overflow_zone_pairs(n_pairs: int, seed: int = 1) -> Batch:
     return b
 
 
+def make_sandwich_adversarial_pairs(n_pairs: int, seed: int = 1) -> Batch:
+    """Adversarial set for the sandwich certificate of 8-bit-final results (swb_fast.cuh, SW = 1): short reads (62-83 bp, the 8-bit
+    pass cannot overflow) with an insertion placed where the running score is around 128 + go, so that the signed lazy-F exit test
+    (ssw.c:309-311) really drops vertical gaps and the 8-bit result differs from Gotoh for some pairs -- those must not be certified."""
+    rng = np.random.default_rng(seed)
+    grid = [(3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0)]
+    wins, reads, go, ge = [], [], [], []
+    for p in range(n_pairs):
+        wl = int(rng.integers(150, 300))
+        W = rng.integers(0, 4, size=wl, dtype=np.int8)
+        L = int(rng.integers(62, 84))
+        q = int(rng.integers(40, 52))                          # left flank scores ~120-156: the gap opens around 128 + go
+        k = int(rng.integers(1, 10))
+        span = L - k
+        start = int(rng.integers(0, wl - span))
+        ins = rng.integers(0, 4, size=k, dtype=np.int8)
+        r = np.concatenate([W[start:start + q], ins, W[start + q:start + span]]).astype(np.int8)
+        for _ in range(int(rng.integers(0, 3))):
+            x = int(rng.integers(0, r.shape[0]))
+            r[x] = (r[x] + 1 + rng.integers(0, 3)) % 4
+        g = grid[int(rng.integers(0, 6))]
+        wins.append(W); reads.append(r); go.append(g[0]); ge.append(g[1])
+    idx = np.arange(n_pairs, dtype=np.int32)
+    b = batch_from_lists(reads, wins, idx, idx, go, ge)
+    b.mat = dna_matrix(3, 2)
+    return b
+
+
 def oracle_parallel(b: Batch, threads: int = 8):
     """oracle over a batch using several threads (ctypes releases the GIL)"""
     from concurrent.futures import ThreadPoolExecutor

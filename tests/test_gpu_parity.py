@@ -392,6 +392,55 @@ def test_gpu_streamed_batch_ascii_subranges_and_masks(monkeypatch):
     T.compare(r2[sub].copy(), a2, ro, ao, what="streamed (ASCII, sub-ranges, masks) vs oracle")
 
 
+def test_gpu_sandwich_certificate_adversarial():
+    """the sandwich sweep (swb_fast.cuh, SW = 1) certifies 8-bit-final results whose scores pass 128+go+ge; on a set built so that
+    the 8-bit pass really deviates from Gotoh (insertions opened around score 128) every result must still equal the oracle's --
+    a deviating pair that got certified would show up here -- and most of the zone must stay off the exact path"""
+    from gpuutil import gpu_align
+
+    b = T.make_sandwich_adversarial_pairs(40000, seed=5)
+    rg, ag, tm = gpu_align(b)
+    ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+    T.compare(rg, ag, ro, ao, what="sandwich adversarial set vs oracle")
+    # how many pairs really deviate: 8-bit result (score_size 2) vs plain Gotoh (score_size 1, 16-bit kernel only)
+    import dataclasses
+    r16, _ = T.oracle_parallel(dataclasses.replace(b, score_size=1), threads=min(16, os.cpu_count() or 1))
+    dev = np.zeros(b.n_pairs, dtype=bool)
+    for f in ("score1", "ref_end1", "read_end1", "ref_begin1", "read_begin1"):
+        dev |= ro[f] != r16[f]
+    zone = tm["n_sw_certified"] + tm["n_sw_rejected"]
+    assert zone > 0.5 * b.n_pairs, (zone, b.n_pairs)
+    assert dev.sum() > 0, "the generator no longer produces deviating pairs"
+    assert tm["n_sw_certified"] <= zone - 0.5 * dev.sum(), (tm, int(dev.sum()))      # deviating pairs are rejected (forward or reverse)
+    assert tm["n_sw_certified"] > 0.7 * zone, tm
+
+
+def test_gpu_sandwich_short_read_fuzz():
+    """30-100 bp reads x 300 bp windows under indelPost's penalty grid, N bases, junk tails: the zone the sandwich serves, bit-exact"""
+    from gpuutil import gpu_align
+
+    for seed, kw in ((31, dict(read_len=(30, 100), win_len=300, grid=True, max_indel=10)),
+                     (32, dict(read_len=(44, 84), win_len=(120, 400), grid=True, max_indel=6, n_rate=0.01, junk_tail=0.2)),
+                     (33, dict(read_len=(60, 84), win_len=300, grid=True, max_indel=3, low_complexity=0.3))):
+        b = T.make_pairs(20000, seed=seed, **kw)
+        rg, ag, tm = gpu_align(b)
+        ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+        T.compare(rg, ag, ro, ao, what=f"short-read fuzz seed {seed} vs oracle")
+        assert tm["n_sw_certified"] + tm["n_sw_rejected"] > 0
+
+
+def test_gpu_overflow_verification_by_sandwich():
+    """pairs whose CIGAR certificate fails (insertion opened around score 128, provisional 16-bit result) are settled by the sandwich
+    lower bound; results stay bit-exact and most verifications never reach the exact 8-bit pass"""
+    from gpuutil import gpu_align
+
+    b = T.make_overflow_zone_pairs(30000, seed=9)
+    rg, ag, tm = gpu_align(b)
+    ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+    T.compare(rg, ag, ro, ao, what="overflow zone vs oracle")
+    assert tm["n_sw_verified"] > 0, tm
+
+
 def _packed(b, bits):
     """the same batch with its sequence tables packed for SWB_SEQ_PACKED4 / PACKED2 (include/swb200.h)"""
     import copy
