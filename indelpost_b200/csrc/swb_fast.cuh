@@ -33,8 +33,9 @@
 // chain -- possible only while the chain's value lies in W = [128, 127+go-ge].  Next to Gotoh (U) the sweep carries a lower
 // bound L: the same recurrence, but a vertical-gap CONTINUATION is dropped whenever the interval [L's value, U's value] of the
 // chain meets W, and E opens from H without F (ssw.c computes E before the lazy correction).  L <= H(8-bit) <= U cell by cell; if
-// in every column L equals U at U's column-best cell (the smallest row holding the column maximum), every output of the 8-bit pass
-// is Gotoh's.  One bit per column and lane ("L differs at the column best") rides in bit 15 of the row word down the wavefront.
+// L equals U at the cells the outputs are read from -- the best cell (smallest row holding the maximum) of the best column, of the
+// sub-optimal column and, in the reverse pass, of the hit column -- every output of the 8-bit pass is Gotoh's (the 8-bit column
+// maxima lie between L's and U's, and the columns scanned before those are strictly lower in U already).  One bit per column and lane ("L differs at the column best") rides in bit 15 of the row word down the wavefront.
 // Pairs with a flagged column go to the exact kernels.  The same sweep settles overflow verifications (PST_HAVE_WORD): if L's
 // maximum reaches 255-bias the 8-bit pass certainly overflowed.
 #pragma once
@@ -301,16 +302,9 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
         if (DIR == 0) {
             // best score and first column reaching it
             int bv = 0, bc = 0x7fffffff;
-            uint32_t fl = 0;                                    // SW: some column's best cell differs between L and U
             for (int c = g; c < q.ncols; c += G) {
                 const int v = (int)((colv[c] >> sh) & 0xffffu);
                 if (v > bv) { bv = v; bc = c; }
-                if constexpr (SW) fl |= colr[c];
-            }
-            if constexpr (SW) {
-                fl = (fl >> sh) & 0x8000u;
-#pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) fl |= __shfl_xor_sync(GM, fl, o, G);
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) {
@@ -347,6 +341,15 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
             for (int o = G / 2; o > 0; o >>= 1) cs = min(cs, __shfl_xor_sync(GM, cs, o, G));
             const int s2 = sv > FAST_C ? (sv - FAST_C) / FAST_SCALE : 0;
             const int r2 = s2 > 0 ? si : 0;
+            // SW: the 8-bit pass's column maxima lie between L's and U's, so its outputs are U's as soon as L equals U at the two
+            // cells they are read from: the best cell of the best column (score1, ref_end1, read_end1; every earlier column and every
+            // row above stay below it in U already) and the best cell of the sub-optimal column (score2, ref_end2)
+            uint32_t fl = 0;
+            if constexpr (SW) {
+                if (T > 0) fl |= colr[bc];
+                if (s2 > 0 && q.mask >= 15) fl |= colr[si];
+                fl = (fl >> sh) & 0x8000u;
+            }
             if (g == 0) {
                 warp_count(d.counters + CNT_CELLS_FWD, (unsigned long long)q.Lp * q.ncols);
                 const int limit = 255 - d.bias;                                    // 8-bit pass overflows at max + bias >= 255 (ssw.c:327)
@@ -398,13 +401,10 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) hc = min(hc, __shfl_xor_sync(GM, hc, o, G));
-            uint32_t fl = 0;                                    // SW: a column up to the hit whose best cell differs between L and U
-            if constexpr (SW) {
-                if (hc != 0x7fffffff) for (int c = g; c <= hc; c += G) fl |= colr[c];
-                fl = (fl >> sh) & 0x8000u;
-#pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) fl |= __shfl_xor_sync(GM, fl, o, G);
-            }
+            // SW: the 8-bit reverse pass stops at the first column whose maximum equals score1; every earlier column stays below it in U
+            // already, so L has to equal U only at the best cell of the hit column
+            uint32_t fl = 0;
+            if constexpr (SW) { if (hc != 0x7fffffff) fl = (colr[hc] >> sh) & 0x8000u; }
             if (g == 0) {
                 if (hc == 0x7fffffff || q.target <= 0 || fl) {
                     // no column reaches score1 (or score 0 corner): let the exact path reproduce ssw.c literally

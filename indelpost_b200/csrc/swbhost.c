@@ -4,8 +4,8 @@
  * int8 array (sswpy.pyx:149-170), turning an s_align into the 7-field Alignment tuple with its "%d%s" CIGAR string
  * (sswpy.pyx:283-298) -- is done here in C as well, for whole batches:
  *
- *   gather(seqs, dest, cap, off, len, byte0)      copy a sequence of str / bytes straight into a (pinned) staging blob and
- *                                                 fill the offset / length tables of include/swb200.h's swb_batch
+ *   gather(seqs, dest, cap, off, len, byte0)      copy a sequence of str / bytes straight into a (pinned) staging blob (GIL released,
+ *                                                 several threads for large tables) and fill the offset / length tables of swb_batch
  *   alignment(res, arena, k, cls)                 swb_result record k -> cls(CIGAR, score1, score2, ref_begin1, ref_end1,
  *   alignments(res, arena, k0, k1, cls)           read_begin1, read_end1)   (one, or a list for a range)
  *
@@ -15,6 +15,7 @@
 #include <Python.h>
 #include <stdint.h>
 #include <string.h>
+#include <pthread.h>
 
 /* same layout as swb_result (include/swb200.h) */
 typedef struct {
@@ -23,6 +24,21 @@ typedef struct {
     uint16_t flag, status;
     int64_t cigar_off;
 } swb_result_t;
+
+/* gather: pass 1 (GIL held) collects (pointer, length) of every item and fills the offset / length tables; pass 2 copies the
+ * bytes -- with the GIL released and, for large tables, split over a few threads by byte count (the objects are kept alive by the
+ * caller's sequence, which `fast` references; bytes / compact-ASCII str buffers are immutable).
+ * Returns the end byte, or -(needed capacity) - 1 when `cap` is too small (nothing copied: the caller grows its buffer and calls again). */
+typedef struct { const char** ptr; const int64_t* off; const int32_t* len; char* dest; Py_ssize_t i0, i1; } gather_job;
+
+static void* gather_worker(void* a)
+{
+    const gather_job* j = (const gather_job*)a;
+    for (Py_ssize_t i = j->i0; i < j->i1; ++i) memcpy(j->dest + j->off[i], j->ptr[i], (size_t)j->len[i]);
+    return NULL;
+}
+
+#define GATHER_MAX_THREADS 8
 
 static PyObject* host_gather(PyObject* self, PyObject* args)
 {
@@ -37,6 +53,8 @@ static PyObject* host_gather(PyObject* self, PyObject* args)
     int32_t* len = (int32_t*)(uintptr_t)len_a;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
     PyObject** items = PySequence_Fast_ITEMS(fast);
+    const char** ptr = (const char**)PyMem_Malloc((size_t)(n > 0 ? n : 1) * sizeof(char*));
+    if (!ptr) { Py_DECREF(fast); return PyErr_NoMemory(); }
     long long pos = byte0;
     for (Py_ssize_t i = 0; i < n; ++i) {
         PyObject* o = items[i];
@@ -44,14 +62,37 @@ static PyObject* host_gather(PyObject* self, PyObject* args)
         if (PyBytes_Check(o)) { p = PyBytes_AS_STRING(o); l = PyBytes_GET_SIZE(o); }
         else if (PyUnicode_Check(o)) {
             if (PyUnicode_IS_COMPACT_ASCII(o)) { p = (const char*)PyUnicode_1BYTE_DATA(o); l = PyUnicode_GET_LENGTH(o); }
-            else { p = PyUnicode_AsUTF8AndSize(o, &l); if (!p) { Py_DECREF(fast); return NULL; } }   /* obj_to_cstr_len encodes utf8, sswpy.pyx:45-55 */
-        } else { Py_DECREF(fast); PyErr_SetString(PyExc_TypeError, "expected str or bytes"); return NULL; }
-        if (l > INT32_MAX) { Py_DECREF(fast); PyErr_SetString(PyExc_OverflowError, "sequence too long"); return NULL; }
-        if (pos + l > cap) { Py_DECREF(fast); PyErr_SetString(PyExc_BufferError, "gather: staging buffer too small"); return NULL; }
-        memcpy(dest + pos, p, (size_t)l);
-        off[i] = pos; len[i] = (int32_t)l;
+            else { p = PyUnicode_AsUTF8AndSize(o, &l); if (!p) { PyMem_Free(ptr); Py_DECREF(fast); return NULL; } }   /* obj_to_cstr_len encodes utf8, sswpy.pyx:45-55 (the utf8 copy is cached in the object) */
+        } else { PyMem_Free(ptr); Py_DECREF(fast); PyErr_SetString(PyExc_TypeError, "expected str or bytes"); return NULL; }
+        if (l > INT32_MAX) { PyMem_Free(ptr); Py_DECREF(fast); PyErr_SetString(PyExc_OverflowError, "sequence too long"); return NULL; }
+        ptr[i] = p; off[i] = pos; len[i] = (int32_t)l;
         pos += l;
     }
+    if (pos > cap) { PyMem_Free(ptr); Py_DECREF(fast); return PyLong_FromLongLong(-pos - 1); }
+    const long long total = pos - byte0;
+    int nt = total >= (8ll << 20) ? GATHER_MAX_THREADS : (total >= (1ll << 20) ? 2 : 1);
+    if (nt > n) nt = n > 0 ? (int)n : 1;
+    Py_BEGIN_ALLOW_THREADS
+    gather_job jobs[GATHER_MAX_THREADS];
+    pthread_t th[GATHER_MAX_THREADS];
+    int started[GATHER_MAX_THREADS];
+    Py_ssize_t i0 = 0;
+    for (int t = 0; t < nt; ++t) {
+        /* entries [i0, i1): up to the t+1-th share of the bytes */
+        const long long until = byte0 + total * (t + 1) / nt;
+        Py_ssize_t i1 = i0;
+        if (t + 1 == nt) i1 = n;
+        else while (i1 < n && off[i1] < until) ++i1;
+        jobs[t].ptr = ptr; jobs[t].off = off; jobs[t].len = len; jobs[t].dest = dest; jobs[t].i0 = i0; jobs[t].i1 = i1;
+        started[t] = 0;
+        if (t + 1 < nt && i1 > i0) started[t] = pthread_create(&th[t], NULL, gather_worker, &jobs[t]) == 0;
+        if (!started[t] && t + 1 < nt) gather_worker(&jobs[t]);
+        i0 = i1;
+    }
+    gather_worker(&jobs[nt - 1]);                     /* the calling thread takes the last share */
+    for (int t = 0; t + 1 < nt; ++t) if (started[t]) pthread_join(th[t], NULL);
+    Py_END_ALLOW_THREADS
+    PyMem_Free(ptr);
     Py_DECREF(fast);
     return PyLong_FromLongLong(pos);
 }

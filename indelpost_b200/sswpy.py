@@ -244,14 +244,21 @@ class _Staging:
         return b.view(dt, count)
 
     def table(self, name, seqs):
-        """str / bytes sequences -> (blob, off, len) in pinned memory, copied once, in C (csrc/swbhost.c)"""
+        """str / bytes sequences -> (blob, off, len) in pinned memory, copied once, in C (csrc/swbhost.c).  The blob keeps the
+        capacity of earlier calls; if this table does not fit, gather reports the size it needs and is called again."""
         n = len(seqs)
-        total = H.total_len(seqs)
-        blob = self.view(name + ".blob", np.int8, total)
         off = self.view(name + ".off", np.int64, n)
         ln = self.view(name + ".len", np.int32, n)
-        H.gather(seqs, blob.ctypes.data, total, off.ctypes.data, ln.ctypes.data, 0)
-        return blob, off, ln
+        b = self.bufs.get(name + ".blob")
+        cap = b.nbytes - 16 if b is not None else 0
+        if cap <= 0:
+            cap = max(1 << 16, H.total_len(seqs))
+        while True:
+            blob = self.view(name + ".blob", np.int8, cap)
+            end = H.gather(seqs, blob.ctypes.data, cap, off.ctypes.data, ln.ctypes.data, 0)
+            if end >= 0:
+                return blob[:end], off, ln
+            cap = -end - 1
 
 
 def _staging(a: BatchAligner) -> _Staging:

@@ -22,8 +22,16 @@ def test_gather_copies_str_and_bytes_into_the_staging_blob():
     for s, o, l in zip(seqs, off, ln):
         want = s if isinstance(s, bytes) else s.encode()
         assert raw[o: o + l] == want
-    with pytest.raises(BufferError):
-        H.gather(seqs, blob.ctypes.data, total - 1, off.ctypes.data, ln.ctypes.data, 0)
+    # too small a buffer: nothing is copied, the needed capacity comes back as -(need) - 1
+    assert H.gather(seqs, blob.ctypes.data, total - 1, off.ctypes.data, ln.ctypes.data, 0) == -total - 1
+    # a table large enough for the threaded copy (GIL released, shares split by byte count)
+    rng = np.random.default_rng(3)
+    big = [bytes(rng.integers(65, 90, size=int(k), dtype=np.uint8)) for k in rng.integers(0, 700, size=40000)]
+    tb = sum(map(len, big))
+    bb = np.zeros(tb, np.int8); bo = np.zeros(len(big), np.int64); bl = np.zeros(len(big), np.int32)
+    assert H.gather(big, bb.ctypes.data, tb, bo.ctypes.data, bl.ctypes.data, 0) == tb
+    assert bb.view(np.uint8).tobytes() == b"".join(big)
+    assert bo.tolist() == np.concatenate([[0], np.cumsum([len(x) for x in big])[:-1]]).tolist()
     with pytest.raises(TypeError):
         H.gather(["ACGT", 5], blob.ctypes.data, total, off.ctypes.data, ln.ctypes.data, 0)
     # non-ASCII text is encoded as UTF-8 like obj_to_cstr_len does (sswpy.pyx:45-55)
