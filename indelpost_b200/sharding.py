@@ -60,13 +60,32 @@ def stitch(parts: Sequence[Tuple[np.ndarray, np.ndarray]]) -> Tuple[np.ndarray, 
 
 
 def slice_pairs(arrs: dict, p0: int, p1: int) -> dict:
-    """per-pair arrays restricted to [p0, p1); tables are passed whole (the library uploads only the slices a
-    chunk touches when it pipelines, and a shard's tables are small next to the DP work)"""
+    """per-pair arrays restricted to [p0, p1)"""
     out = dict(arrs)
     for k in ("pair_read", "pair_win", "gap_open", "gap_ext", "ref_beg", "ref_len", "mask_len"):
         if out.get(k) is not None:
             out[k] = np.ascontiguousarray(out[k][p0:p1])
     return out
+
+
+def slice_table(blob, off, length, idx, seq_encoding: int = L.SWB_SEQ_CODES):
+    """the part of a sequence table the (valid) indices in `idx` refer to: (blob slice, rebased offsets, lengths, first index).
+    A shard uploads these instead of the whole table (each GPU gets only the sequences its pairs touch).  Entries are
+    taken as an index RANGE [min, max], so out-of-range pair indices still fail inside the library like they do unsharded."""
+    n = int(np.asarray(length).shape[0])
+    idx = np.asarray(idx)
+    ok = idx[(idx >= 0) & (idx < n)]
+    if ok.shape[0] == 0 or n == 0:
+        return blob[:0], np.zeros(0, np.int64), np.zeros(0, np.int32), 0
+    i0, i1 = int(ok.min()), int(ok.max()) + 1
+    o = np.asarray(off, dtype=np.int64)[i0:i1]
+    ln = np.asarray(length, dtype=np.int32)[i0:i1]
+    per = {L.SWB_SEQ_PACKED4: 2, L.SWB_SEQ_PACKED2: 4}.get(int(seq_encoding), 1)
+    nbytes = (ln.astype(np.int64) + per - 1) // per
+    if (o < 0).any() or (ln < 0).any():
+        return blob, np.asarray(off, dtype=np.int64)[i0:i1], ln, i0          # let the library report the bad table
+    b0, b1 = int(o.min()), int((o + nbytes).max())
+    return blob[b0:b1], np.ascontiguousarray(o - b0), np.ascontiguousarray(ln), i0
 
 
 class MultiGpuAligner:
@@ -94,10 +113,21 @@ class MultiGpuAligner:
         cells = pair_cells(read_len, win_len, arrs["pair_read"], arrs["pair_win"], arrs["ref_len"], arrs["ref_beg"])
         bounds = shard_bounds(cells, len(self.aligners))
 
+        enc = int(kw.get("seq_encoding", L.SWB_SEQ_CODES))
+        reads_a, windows_a = np.asarray(reads), np.asarray(windows)
+        n_reads, n_windows = int(np.asarray(read_len).shape[0]), int(np.asarray(win_len).shape[0])
+
         def run(k):
             p0, p1 = bounds[k]
             s = slice_pairs(arrs, p0, p1)
-            return self.aligners[k].align(reads, read_off, read_len, windows, win_off, win_len, s["pair_read"], s["pair_win"],
+            # only the table slices this shard refers to travel to its GPU; indices are rebased to the slice, indices outside
+            # the tables are kept out of range
+            rb, ro, rl, r0 = slice_table(reads_a, read_off, read_len, s["pair_read"], enc)
+            wb, wo, wl, w0 = slice_table(windows_a, win_off, win_len, s["pair_win"], enc)
+            pr, pw = s["pair_read"], s["pair_win"]
+            pr = np.where((pr >= 0) & (pr < n_reads), pr - r0, -1).astype(np.int32)
+            pw = np.where((pw >= 0) & (pw < n_windows), pw - w0, -1).astype(np.int32)
+            return self.aligners[k].align(rb, ro, rl, wb, wo, wl, pr, pw,
                                           s["gap_open"], s["gap_ext"], ref_beg=s["ref_beg"], ref_len=s["ref_len"], mask_len=s["mask_len"], **kw)
 
         parts = list(self.pool.map(run, range(len(self.aligners))))

@@ -72,3 +72,23 @@ def test_two_rank_gloo_job_matches_single_process(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29531", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert "GLOO_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_slice_table_rebases_offsets_and_keeps_bad_indices_out():
+    """a shard uploads only the table entries its pairs refer to (sharding.slice_table): index range, rebased byte offsets,
+    packed tables by their packed byte extents"""
+    from indelpost_b200 import _lib as L
+    from indelpost_b200.sharding import slice_table
+
+    blob = np.arange(100, dtype=np.int8)
+    off = np.array([0, 10, 30, 60, 90], dtype=np.int64)
+    ln = np.array([10, 20, 30, 30, 10], dtype=np.int32)
+    b, o, l, i0 = slice_table(blob, off, ln, np.array([3, 2, 2, -1, 99]))
+    assert i0 == 2 and l.tolist() == [30, 30] and o.tolist() == [0, 30] and b.tolist() == list(range(30, 90))
+    b, o, l, i0 = slice_table(blob, off, ln, np.array([-5, 77]))
+    assert b.shape[0] == 0 and o.shape[0] == 0 and i0 == 0
+    # 2-bit packed: an entry of len bases occupies ceil(len / 4) bytes
+    poff = np.array([0, 3, 8], dtype=np.int64)
+    pln = np.array([10, 20, 7], dtype=np.int32)
+    b, o, l, i0 = slice_table(np.arange(10, dtype=np.int8), poff, pln, np.array([1, 2]), L.SWB_SEQ_PACKED2)
+    assert i0 == 1 and o.tolist() == [0, 5] and b.tolist() == list(range(3, 10))
