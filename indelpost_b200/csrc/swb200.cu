@@ -143,9 +143,14 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         const int b = (lp16 + 31) / 32 - 1;
         // 8-bit-final pairs whose scores can pass 128+go+ge (where the 8-bit pass may deviate from Gotoh) take the sandwich sweep
         const bool sw = !wordSem && !(d.opt & 128) && d.max_score * rl >= 128 + go + ge;
+        // forward family: the 8-thread-group sweep (rows per thread = padded length / 8: no pad rows for 150 bp) when the matrix fits its
+        // scale and the read its buckets, else the 16-thread-group sweep of the read's 32-row bucket
+        const int b8 = (d.fast8_ok && !sw && d.max_score * rl <= 767) ? f8_bucket(wordSem ? ((rl + 7) & ~7) : lp16) : -1;
+        int fam = b;
         if (sw) list_push(d.list[LIST_SW_FWD + b], d.counters + CNT_SW_FWD + b, p);
+        else if (b8 >= 0) { fam = SWB_NBUCKETS + b8; list_push(d.list[LIST_F8_FWD + b8], d.counters + CNT_F8_FWD + b8, p); }
         else list_push(d.list[LIST_FAST_FWD + b], d.counters + CNT_FAST_FWD + b, p);
-        if (wl > *(volatile int32_t*)(d.counters + CNT_FAST_MAXCOLS + b)) atomicMax(d.counters + CNT_FAST_MAXCOLS + b, wl);   // test first: one hot address
+        if (wl > *(volatile int32_t*)(d.counters + CNT_FAST_MAXCOLS + fam)) atomicMax(d.counters + CNT_FAST_MAXCOLS + fam, wl);   // test first: one hot address
     }
     else if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
     else list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
@@ -375,6 +380,8 @@ static void set_batch_scalars(swb_ctx* c, const swb_batch* b, const ChunkView& v
     // long enough to hide the overflow verification of the pairs traced back first; measured crossover ~200 k pairs)
     if (b->n_pairs < 200000) d.opt |= 32;
     d.one = 1;
+    { bool f8 = true; for (int i = 0; i < b->n * b->n; ++i) if (b->mat[i] > 3 || b->mat[i] < -4) f8 = false;
+      d.fast8_ok = (f8 && !getenv("SWB200_NO_G8")) ? 1 : 0; }
     d.fast_ok = (small && b->n >= 4 && mx > 0 && (b->score_size == 1 || b->score_size == 2) && !getenv("SWB200_NO_FAST")) ? 1 : 0;
 }
 
@@ -464,24 +471,29 @@ static int launch_validate(swb_ctx* c, int8_t* blob, const int64_t* off, const i
     return 0;
 }
 
-// counts: plain fast-path list lengths per bucket; c->swCounts: what k_prepare put on the sandwich lists.  The plain forward sweep
-// appends to a bucket's sandwich list (16-bit-semantics pairs whose result turned out to be the 8-bit pass's), so the sandwich
-// launches are sized by the sum (the kernels read the real list length)
+// counts: plain forward list lengths per family (SWB_NFWD entries: 16-thread-group buckets, then 8-thread-group buckets);
+// c->swCounts: what k_prepare put on the sandwich lists.  The plain forward sweeps append to a bucket's sandwich list (16-bit-semantics
+// pairs whose result turned out to be the 8-bit pass's) and to its reverse list, so the follow-up launches are sized by an upper
+// bound per 32-row bucket (the kernels read the real list length)
+static void bucket_upper_bounds(const swb_ctx* c, const int* counts, int* ub) {
+    // 8-thread-group bucket j (padded length <= 32, 56, 80, 104, 128, 152) -> the 32-row buckets its reads can belong to
+    static const int map8[SWB_NF8][2] = {{0, 0}, {1, 1}, {1, 2}, {2, 3}, {3, 3}, {4, 4}};
+    for (int b = 0; b < SWB_NBUCKETS; ++b) ub[b] = counts[b] + c->swCounts[b];
+    for (int j = 0; j < SWB_NF8; ++j) for (int b = map8[j][0]; b <= map8[j][1]; ++b) ub[b] += counts[SWB_NBUCKETS + j];
+}
+
 template <int DIR>
 static int launch_fast(swb_ctx* c, const int* counts) {
     // the forward sweeps go to the low-priority stream (see swb_create), the reverse ones stay on the main stream
     if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_fork, c->stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_fork, 0)); }
     int rc;
+    int ub[SWB_NBUCKETS];
+    bucket_upper_bounds(c, counts, ub);
     if (DIR == 0) {
-        int ub[SWB_NBUCKETS];
-        for (int b = 0; b < SWB_NBUCKETS; ++b) ub[b] = counts[b] + c->swCounts[b];
-        rc = swb_launch_fast_range_fwd(c, nullptr, counts, c->bulk_stream);
+        rc = swb_launch_fast8_range_fwd(c, nullptr, counts, c->bulk_stream);
+        if (!rc) rc = swb_launch_fast_range_fwd(c, nullptr, counts, c->bulk_stream);
         if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_fwd(c, ub, c->bulk_stream);
     } else {
-        // reverse lists are filled by the forward sweeps: a bucket's plain list is bounded by its plain + sandwich forward counts
-        // (sandwich pairs that ended in the safe zone take the plain reverse pass), its sandwich list by the sandwich forward count
-        int ub[SWB_NBUCKETS];
-        for (int b = 0; b < SWB_NBUCKETS; ++b) ub[b] = counts[b] + c->swCounts[b];
         rc = swb_launch_fast_range_rev(c, nullptr, ub, c->stream);
         if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_rev(c, ub, c->stream);
     }
@@ -809,11 +821,12 @@ static int swb_compute_impl(swb_ctx* c) {
     if (stage_check(c, "prepare")) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
     if (read_counters(c)) return -1;                        // bucket sizes for the fast path launches
-    int fwdCounts[SWB_NBUCKETS]; int nFastTotal = 0;
-    for (int b = 0; b < SWB_NBUCKETS; ++b) {
-        fwdCounts[b] = c->h_counters[CNT_FAST_FWD + b]; c->swCounts[b] = c->h_counters[CNT_SW_FWD + b];
-        nFastTotal += fwdCounts[b] + c->swCounts[b]; c->fastMaxCols[b] = c->h_counters[CNT_FAST_MAXCOLS + b];
+    int fwdCounts[SWB_NFWD]; int nFastTotal = 0;
+    for (int f = 0; f < SWB_NFWD; ++f) {
+        fwdCounts[f] = c->h_counters[f < SWB_NBUCKETS ? CNT_FAST_FWD + f : CNT_F8_FWD + (f - SWB_NBUCKETS)];
+        nFastTotal += fwdCounts[f]; c->fastMaxCols[f] = c->h_counters[CNT_FAST_MAXCOLS + f];
     }
+    for (int b = 0; b < SWB_NBUCKETS; ++b) { c->swCounts[b] = c->h_counters[CNT_SW_FWD + b]; nFastTotal += c->swCounts[b]; }
 
     // ---- forward (ssw.c:842-860) --------------------------------------------------------------------
     //   fast path: one 16-bit Gotoh sweep per pair (pairs it cannot decide are appended to the exact lists)
@@ -1055,7 +1068,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     }
     const int npieces = (int)bounds.size() - 1;
 
-    int done[SWB_NBUCKETS] = {};
+    int done[SWB_NFWD] = {};
     bool used2 = false, used1 = false;
     // The host runs one piece ahead: piece k+1's copies and prepare kernel are queued before it waits for piece k's
     // fast-list lengths, so PCIe never idles during a host round trip.
@@ -1100,9 +1113,9 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
         CUDA_TRY(c, cudaEventSynchronize(c->ev_snap[k & 1]));
         TR(c, "piece_ready");
         const int32_t* hc = c->h_snap[k & 1];
-        int upper[SWB_NBUCKETS]; bool any = false, global = false;
-        for (int q = 0; q < SWB_NBUCKETS; ++q) {
-            const int cnt = hc[CNT_FAST_FWD + q];
+        int upper[SWB_NFWD]; bool any = false, global = false;
+        for (int q = 0; q < SWB_NFWD; ++q) {
+            const int cnt = hc[q < SWB_NBUCKETS ? CNT_FAST_FWD + q : CNT_F8_FWD + (q - SWB_NBUCKETS)];
             upper[q] = last ? cnt : (cnt & ~1);                  // lane pairs stay intact: an odd leftover waits for the next piece
             c->fastMaxCols[q] = hc[CNT_FAST_MAXCOLS + q];
             if (upper[q] > done[q]) any = true;
@@ -1112,9 +1125,10 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
             const bool second = (k & 1) && !global;
             cudaStream_t st = second ? c->bulk_stream2 : c->bulk_stream;
             CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_snap[k & 1], 0));
+            if (swb_launch_fast8_range_fwd(c, done, upper, st)) return -1;
             if (swb_launch_fast_range_fwd(c, done, upper, st)) return -1;
             (second ? used2 : used1) = true;
-            for (int q = 0; q < SWB_NBUCKETS; ++q) done[q] = upper[q];
+            for (int q = 0; q < SWB_NFWD; ++q) done[q] = upper[q];
         }
     }
     if (npieces == 0) { CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], s)); CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s)); }
@@ -1122,11 +1136,11 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     int nSw = 0;
     for (int q = 0; q < SWB_NBUCKETS; ++q) { c->swCounts[q] = npieces > 0 ? c->h_snap[(npieces - 1) & 1][CNT_SW_FWD + q] : 0; nSw += c->swCounts[q]; }
     int nFwdPlain = 0;
-    for (int q = 0; q < SWB_NBUCKETS; ++q) nFwdPlain += done[q];
+    for (int q = 0; q < SWB_NFWD; ++q) nFwdPlain += done[q];
     if ((nSw > 0 || nFwdPlain > 0) && npieces > 0 && !(d.opt & 128)) {
         // after every plain forward slice (they append to the sandwich lists) and the last piece's prepare
         int ub[SWB_NBUCKETS];
-        for (int q = 0; q < SWB_NBUCKETS; ++q) ub[q] = done[q] + c->swCounts[q];
+        bucket_upper_bounds(c, done, ub);
         CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_snap[(npieces - 1) & 1], 0));
         if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_join2, 0)); }
         if (swb_launch_sandwich_fwd(c, ub, c->bulk_stream)) return -1;
@@ -1143,7 +1157,8 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     d.seq_encoding = SWB_SEQ_CODES;
     c->have_batch = true;
     int nFastTotal = 0;
-    for (int q = 0; q < SWB_NBUCKETS; ++q) nFastTotal += done[q] + c->swCounts[q];
+    for (int q = 0; q < SWB_NFWD; ++q) nFastTotal += done[q];
+    for (int q = 0; q < SWB_NBUCKETS; ++q) nFastTotal += c->swCounts[q];
     TR(c, "pieces_enqueued");
     if (compute_tail(c, done, nFastTotal)) return -1;
     return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);

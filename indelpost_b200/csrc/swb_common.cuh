@@ -7,7 +7,9 @@
 
 #define SWB_MAX_N 32            // largest substitution-matrix edge the kernels stage in shared memory
 #define SWB_NBUCKETS 8          // fast-path read-length buckets: bucket b holds padded lengths <= 32*(b+1) (R = 2*(b+1) rows per thread)
-#define SWB_NLISTS 152
+#define SWB_NF8 6               // forward-only read-length buckets of the 8-thread-per-lane-pair sweep: padded lengths <= 32, 56, 80, 104, 128, 152 (R = 4 .. 19 rows per thread)
+#define SWB_NFWD (SWB_NBUCKETS + SWB_NF8)   // forward list families: [0, 8) 16-thread groups, [8, 14) 8-thread groups
+#define SWB_NLISTS 160
 #define SWB_NCOUNTERS 200
 
 // ---------------------------------------------------------------------------------------------
@@ -57,6 +59,7 @@ struct SwbDev {
     int32_t max_score;  // max(mat): bound on the score gained per read base
     int32_t fast_ok;    // batch-level eligibility of the DPX fast path (matrix range, n >= 4, score_size)
     int32_t fast_max_cols;
+    int32_t fast8_ok;   // the 8-thread-group sweep may be used: every matrix entry in [-4, 3] (its scores are scaled by 32 into one signed byte)
     // chunk view: the uploaded tables are slices of the caller's tables (pipelined swb_align_batch)
     int32_t ridx_base, widx_base;     // first read / window index present in the slice
     int32_t n_reads_total, n_windows_total;
@@ -78,15 +81,16 @@ enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 
        LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129, LIST_BANDWARP_NEXT = 130,
        // sandwich sweep (swb_fast.cuh, SW = 1): 8-bit-final pairs whose scores can pass 128+go+ge, per read-length bucket, forward / reverse;
        // LIST_VERIFYX (+1): pairs whose overflow neither the CIGAR certificate nor the sandwich lower bound could prove (exact 8-bit pass)
-       LIST_SW_FWD = 132, LIST_SW_REV = 140, LIST_VERIFYX = 148 };
+       LIST_SW_FWD = 132, LIST_SW_REV = 140, LIST_VERIFYX = 148,
+       LIST_F8_FWD = 150 };      // SWB_NF8 lists: forward sweep with 8 threads per lane pair (swb_fast.cuh, G = 8)
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
-       CNT_SW_FWD = 132, CNT_SW_REV = 140,
+       CNT_SW_FWD = 132, CNT_SW_REV = 140, CNT_F8_FWD = 150,
        CNT_CELLS_FWD = 160, CNT_CELLS_REV = 162, CNT_CELLS_BAND = 164, CNT_BAND_OVERFLOW = 166, CNT_CIGAR_OVERFLOW = 167,
        CNT_FAST_DONE = 168, CNT_CERT_FAIL = 169, CNT_VERIFY_BYTE = 170, CNT_EXACT_JOBS = 171,
        CNT_SW_CERTIFIED = 172,     // unsafe-zone pairs the sandwich certified (forward); CNT_SW_REJECTED: those it sent to the exact path
        CNT_SW_REJECTED = 173, CNT_SW_VERIFIED = 174,   // overflow verifications settled by the sandwich lower bound
-       CNT_FAST_MAXCOLS = 176 };   // [SWB_NBUCKETS] longest window among the fast-path pairs of each bucket
+       CNT_FAST_MAXCOLS = 176 };   // [SWB_NFWD] longest window among the fast-path pairs of each forward list family
 #define SWB_BANDW_MAX 24           // widest half-width the register-band kernel is instantiated for
 #define SWB_BANDREG_MAXROWS 320    // longest read segment it stages in shared memory
 // banded reverse pass (swb_revband.cuh): band classes as (rows below, columns right of) the main diagonal
@@ -98,6 +102,9 @@ __host__ __device__ __forceinline__ int revb_class(int wi, int wd) {
 #undef SWB_REVB_PICK
     return -1;
 }
+// bucket of the 8-thread-group forward sweep for a padded read length (rows the result counts: 8-padded in 16-bit semantics, 16-padded in
+// 8-bit semantics); -1: too long
+__host__ __device__ __forceinline__ int f8_bucket(int lp) { return lp <= 32 ? 0 : lp <= 56 ? 1 : lp <= 80 ? 2 : lp <= 104 ? 3 : lp <= 128 ? 4 : lp <= 152 ? 5 : -1; }
 // p_state flags
 enum { PST_FAST = 1,        // forward result produced by the DPX fast path
        PST_NEED_CERT = 2,   // word-mode result accepted provisionally: the 8-bit pass still has to be shown to overflow

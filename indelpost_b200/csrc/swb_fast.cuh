@@ -62,12 +62,18 @@ struct FastLane {
 };
 
 // One group's lane pair: staging, sweep, post-sweep scans.  job list entry j -> pairs (jobs[2j], jobs[2j+1]); an odd tail is paired with itself
-template <int R, int DIR, bool GCOLS, int SW>
+template <int R, int DIR, bool GCOLS, int SW, int G>
 __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __restrict__ jobs, const int npairs, const int grp, const bool valid,
                                            const int colAlloc, const int verifyX, unsigned char* smem_raw, const uint32_t* s_rowtab)
 {
-    constexpr int G = FAST_G;
-    constexpr int BKT = R / 2 - 1;                               // read-length bucket this instantiation serves
+    static_assert(G == 16 || (G == 8 && SW == 0 && DIR == 0), "8-thread groups: plain forward sweep only");
+    static_assert(R <= (G == 8 ? 32 : 16), "row tags must fit the scale");
+    // representation (see the header): 16 threads x R <= 16 rows with scale 16 / bias 0x4000, or 8 threads x R <= 32 rows with scale 32 /
+    // bias 0x2000 (5 tag bits; scores up to 767, matrix entries in [-4, 3] so that 32 * s fits the signed byte PRMT sign-extends)
+    constexpr int SC = G == 8 ? 32 : FAST_SCALE;
+    constexpr int CB = G == 8 ? 0x2000 : FAST_C;
+    constexpr uint32_t CP = (uint32_t)CB * 0x00010001u;
+    constexpr uint32_t TAGS = (uint32_t)(SC - 1) * 0x00010001u;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int g = lane % G;
@@ -102,25 +108,53 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
     // shared memory (2 bytes per column) and the column bests go to a global scratch (written once per step by the
     // last thread, re-read by the post-sweep scans from L2), which keeps the occupancy register-limited.
     // (a template parameter, not a run-time pointer choice, so the shared-memory case keeps LDS/STS in the hot loop)
-    uint32_t* colv; uint32_t* colr; uint16_t* selS;
+    // 8-thread groups keep the two row bytes of a column in 16 bits (8 bytes per column: twice as many groups per warp share the SM's
+    // shared memory); 16-thread groups keep the 32-bit row word, whose lane bit 15 carries the sandwich flag
+    using RowT = std::conditional_t<G == 8, uint16_t, uint32_t>;
+    uint32_t* colv; RowT* colr; uint16_t* selS;
     if constexpr (GCOLS) {
         selS = reinterpret_cast<uint16_t*>(smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * 2));
         colv = d.fast_cols + (size_t)grp * 2 * colAlloc;
-        colr = colv + colAlloc;
+        colr = reinterpret_cast<RowT*>(colv + colAlloc);
     } else {
-        unsigned char* gbase = smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * 10);
+        unsigned char* gbase = smem_raw + (size_t)groupInBlock * ((size_t)colAlloc * (6 + sizeof(RowT)));
         colv = reinterpret_cast<uint32_t*>(gbase);
-        colr = colv + colAlloc;
+        colr = reinterpret_cast<RowT*>(colv + colAlloc);
         selS = reinterpret_cast<uint16_t*>(colr + colAlloc);
     }
+    // row of lane s (0 / 1) in a column's row word, and its sandwich flag
+    auto rowOf = [&](int c, int s) -> int { return G == 8 ? (int)((colr[c] >> (8 * s)) & 0xffu) : (int)((colr[c] >> (16 * s)) & 0x7fffu); };
 
     const int maxcols = max(ln[0].ncols, ln[1].ncols);
-    for (int c = g; c < maxcols; c += G) {
-        int bA = 0, bB = 0;
-        if (c < ln[0].ncols) bA = DIR ? ln[0].ref[ln[0].ncols - 1 - c] : ln[0].ref[c];
-        if (c < ln[1].ncols) bB = DIR ? ln[1].ref[ln[1].ncols - 1 - c] : ln[1].ref[c];
-        // PRMT selector: byte0 = tabA[bA], byte1 = sign(byte0), byte2 = tabB[bB], byte3 = sign(byte2)
-        selS[c] = (uint16_t)(0xC480u | (uint32_t)(bA & 3) * 0x11u | (uint32_t)(bB & 3) * 0x1100u);
+    // PRMT selector per column: byte0 = tabA[bA], byte1 = sign(byte0), byte2 = tabB[bB], byte3 = sign(byte2).  The windows are read as
+    // aligned 16-byte chunks spread over the group's threads (up to 15 bytes before / after a window are touched: every sequence blob is
+    // a device allocation with 16 bytes of slack), lane A's bases first, then lane B's are OR-ed in.
+    for (int c = g; c < maxcols; c += G) selS[c] = (uint16_t)0xC480u;
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int len = ln[s].ncols;
+        if (len > 0) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(ln[s].ref);
+            const int mis = (int)(a & 15);
+            const uint4* base = reinterpret_cast<const uint4*>(a - mis);
+            const int nch = (mis + len + 15) >> 4;
+            const uint32_t mul = s ? 0x1100u : 0x11u;
+            for (int ch = g; ch < nch; ch += G) {
+                const uint4 v = __ldg(base + ch);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                const int i0 = ch * 16 - mis;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int idx = i0 + q;
+                    if ((unsigned)idx < (unsigned)len) {
+                        const int c = DIR ? len - 1 - idx : idx;
+                        selS[c] |= (uint16_t)(((w[q >> 2] >> (8 * (q & 3))) & 3u) * mul);
+                    }
+                }
+            }
+        }
+        __syncwarp();
     }
 
     // ---- per-row registers (slot g*R+k of the lane holds read row slot - off) -------------------------
@@ -132,21 +166,21 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
         if (rA < 0) a = 0x80808080u; else if (rA < ln[0].L) a = s_rowtab[DIR ? ln[0].read[ln[0].L - 1 - rA] : ln[0].read[rA]];
         if (rB < 0) b = 0x80808080u; else if (rB < ln[1].L) b = s_rowtab[DIR ? ln[1].read[ln[1].L - 1 - rB] : ln[1].read[rB]];
         tA[k] = a; tB[k] = b;
-        H[k] = FAST_CPACK; E[k] = FAST_CPACK;
+        H[k] = CP; E[k] = CP;
     }
     uint32_t HL[SW ? R : 1], EL[SW ? R : 1];                    // the lower-bound recurrence (SW only)
     if constexpr (SW) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) { HL[k] = FAST_CPACK; EL[k] = FAST_CPACK; }
+        for (int k = 0; k < R; ++k) { HL[k] = CP; EL[k] = CP; }
     }
     // SW: drop window W = [128, 127 + go - ge] as sign-bit tests: (hiX - contL) has lane bit 15 set iff contL <= hi,
     // (contU + loY) iff contU >= lo (all lane values are below 0x8000, no carry between the lanes)
-    uint32_t geP = pack2(FAST_SCALE * ln[0].ge, FAST_SCALE * ln[1].ge);
-    uint32_t hiX = pack2(FAST_SCALE * (127 + ln[0].go - ln[0].ge) + FAST_C + 0x8000, FAST_SCALE * (127 + ln[1].go - ln[1].ge) + FAST_C + 0x8000);
-    const uint32_t loY = pack2(0x8000 - (FAST_SCALE * 128 + FAST_C), 0x8000 - (FAST_SCALE * 128 + FAST_C));
+    uint32_t geP = pack2(SC * ln[0].ge, SC * ln[1].ge);
+    uint32_t hiX = pack2(SC * (127 + ln[0].go - ln[0].ge) + CB + 0x8000, SC * (127 + ln[1].go - ln[1].ge) + CB + 0x8000);
+    const uint32_t loY = pack2(0x8000 - (SC * 128 + CB), 0x8000 - (SC * 128 + CB));
     if constexpr (SW) asm volatile("" : "+r"(geP), "+r"(hiX));
-    uint32_t goP = pack2(FAST_SCALE * ln[0].go, FAST_SCALE * ln[1].go);
-    uint32_t ngeP = pack2(-FAST_SCALE * ln[0].ge, -FAST_SCALE * ln[1].ge);
+    uint32_t goP = pack2(SC * ln[0].go, SC * ln[1].go);
+    uint32_t ngeP = pack2(-SC * ln[0].ge, -SC * ln[1].ge);
     uint32_t rowBase = pack2(g * R, g * R);
     const uint32_t one = (uint32_t)d.one;
     // keep the loop invariants in registers (ptxas otherwise rematerialises them every step)
@@ -161,19 +195,20 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
     for (int o = 16; o > 0; o >>= 1) nsteps = max(nsteps, __shfl_xor_sync(FULL, nsteps, o));
     if (!valid) nsteps = max(nsteps, 0);
 
-    uint32_t outH = FAST_CPACK, outF = FAST_CPACK, outV = 0, outRow = 0, prevInH = FAST_CPACK;
-    uint32_t outHL = FAST_CPACK, outFL = FAST_CPACK, prevInHL = FAST_CPACK, runL = 0;
-    const uint32_t targetV = pack2(ln[0].target >= 0 ? FAST_SCALE * ln[0].target + FAST_C : 0x7fff, ln[1].target >= 0 ? FAST_SCALE * ln[1].target + FAST_C : 0x7fff);
+    uint32_t outH = CP, outF = CP, outV = 0, outRow = 0, prevInH = CP;
+    uint32_t outHL = CP, outFL = CP, prevInHL = CP, runL = 0;
+    const uint32_t targetV = pack2(ln[0].target >= 0 ? SC * ln[0].target + CB : 0x7fff, ln[1].target >= 0 ? SC * ln[1].target + CB : 0x7fff);
     bool done = false;                                         // reverse pass: both lanes have hit their target
 
     // boundary of the first thread of a group as masks (loop invariants kept in registers: no per-step predicate set-up)
     // boundary lane (g == 0): inputs become the constants of row -1.  Done as x * m1 + c0 with an opaque m1 in {0, 1}: a true
     // IMAD (FMA pipe) instead of a LOP3 on the ALU pipe that bounds this loop
-    uint32_t m1 = g == 0 ? 0u : 1u, c0 = g == 0 ? FAST_CPACK : 0u;
+    uint32_t m1 = g == 0 ? 0u : 1u, c0 = g == 0 ? CP : 0u;
     asm volatile("" : "+r"(m1), "+r"(c0));
     // steps in which every thread of the warp is on a valid column need no range check: [G-1, smallest maxcols of the warp's groups)
     int steadyEnd = valid ? maxcols : 0;
     steadyEnd = min(steadyEnd, __shfl_xor_sync(FULL, steadyEnd, 16));
+    if (G == 8) steadyEnd = min(steadyEnd, __shfl_xor_sync(FULL, steadyEnd, 8));
     if (DIR == 1) steadyEnd = 0;                                // the reverse sweep stops early: keep it checked
 
     auto step = [&](const int t, auto checkedTag) {
@@ -202,9 +237,10 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int kk = k + u;
+                    if (kk >= R) { key[u] = 0; if constexpr (SW) keyL[u] = 0; break; }      // odd R: the last pair has one row (keys are >= CB > 0)
                     const uint32_t s = prmt(tA[kk], tB[kk], sel);
                     uint32_t h = __viaddmax_s16x2(hd, s, E[kk]);                 // max(Hdiag + s, E)
-                    h = __vimax3_s16x2(h, F, FAST_CPACK);                        // max(., F, 0)
+                    h = __vimax3_s16x2(h, F, CP);                        // max(., F, 0)
                     hd = H[kk]; H[kk] = h;
                     key[u] = h * one - (uint32_t)(kk * 0x00010001);              // value - rowInThread: a true IMAD (FMA pipe), no lane borrow
                     const uint32_t hg = h - goP;                                 // FMA-pipe IADD; no lane borrow: h >= 0x4000 > 16*go
@@ -214,7 +250,7 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
                     } else {
                         // the lower bound L: H without F first (E opens from it), then the vertical gap
                         uint32_t hn = __viaddmax_s16x2(hdL, s, EL[kk]);
-                        hn = vmax2(hn, FAST_CPACK);
+                        hn = vmax2(hn, CP);
                         const uint32_t hL = vmax2(hn, FL);
                         hdL = HL[kk]; HL[kk] = hL;
                         keyL[u] = hL * one - (uint32_t)(kk * 0x00010001);
@@ -236,7 +272,7 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
             outH = H[R - 1]; outF = F;
             if constexpr (SW) { outHL = HL[R - 1]; outFL = FL; runL = vmax2(runL, cmL); }
             // local column best -> (value, absolute row); merge with the rows above (they win ties)
-            const uint32_t lv = (cm + 0x000F000Fu) & 0xFFF0FFF0u;
+            const uint32_t lv = (cm + TAGS) & ~TAGS;
             uint32_t lrow = lv - cm + rowBase;
             // SW: bit 15 of the lane = "L differs from U at this thread's column-best cell" (equal keys <=> same value in the same row);
             // it travels with the row word, so the column's final word carries the flag of the cell that won
@@ -245,7 +281,7 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
             const uint32_t keep = prmt(x, 0u, 0xBB99u);                 // 0xFFFF in lanes where the upstream value stays
             outV = vmax2(inV, lv);
             outRow = (inRow & keep) | (lrow & ~keep);
-            if (g == G - 1) { colv[c] = outV; colr[c] = outRow; }
+            if (g == G - 1) { colv[c] = outV; colr[c] = G == 8 ? (RowT)prmt(outRow, 0u, 0x4420u) : (RowT)outRow; }
         }
     };
 
@@ -287,13 +323,15 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
         const int p = q.p;
         swb_result& r = d.res[p];
         const bool wordSem = d.p_mode[p] != 0;
+        // read-length bucket of the 16-thread-group lists this pair continues on (this instantiation's own for G = 16)
+        const int BKT = G == 8 ? max(0, (((d.p_rlen[p] + 15) & ~15) + 31) / 32 - 1) : R / 2 - 1;
         if (DIR == 0 && SW && (d.p_state[p] & PST_HAVE_WORD)) {
             // overflow verification of a provisional 16-bit result: L <= H(8-bit), so L reaching 255-bias proves the overflow
             int mv = (int)((runL >> sh) & 0xffffu);
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) mv = max(mv, __shfl_xor_sync(GM, mv, o, G));
             if (g == 0) {
-                const int ml = mv > FAST_C ? (((mv + 15) & ~15) - FAST_C) / FAST_SCALE : 0;
+                const int ml = mv > CB ? (((mv + (SC - 1)) & ~(SC - 1)) - CB) / SC : 0;
                 if (ml >= 255 - d.bias) atomicAdd(d.counters + CNT_SW_VERIFIED, 1);
                 else if (verifyX >= 0) list_push(d.list[verifyX], d.counters + verifyX, p);
             }
@@ -311,14 +349,14 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
                 const int ov = __shfl_xor_sync(GM, bv, o, G), oc = __shfl_xor_sync(GM, bc, o, G);
                 if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
             }
-            const int T = bv > FAST_C ? (bv - FAST_C) / FAST_SCALE : 0;
+            const int T = bv > CB ? (bv - CB) / SC : 0;
             int end_ref, end_read;
-            if (T > 0) { end_ref = bc; end_read = min((int)((colr[bc] >> sh) & 0x7fffu) - q.off, q.L - 1); }
+            if (T > 0) { end_ref = bc; end_read = min(rowOf(bc, s) - q.off, q.L - 1); }
             else { end_ref = wordSem ? 0 : -1; end_read = 0; }                      // ssw.c:427 / 220
             // sub-optimal score outside the mask (ssw.c:366-379 byte, 568-581 word)
             const int edgeL = max(end_ref - q.mask, 0);
             const int edgeR = min(end_ref + q.mask, q.ncols) + (wordSem ? 0 : 1);
-            int sv = FAST_C, si = 0x7fffffff;
+            int sv = CB, si = 0x7fffffff;
             for (int c = g; c < q.ncols; c += G) {
                 if (c < edgeL || c >= edgeR) {
                     const int v = (int)((colv[c] >> sh) & 0xffffu);
@@ -332,14 +370,14 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
             }
             // first column whose maximum reaches 128+go+ge: every F value before it is < 128+ge, so the signed lazy-F test
             // (ssw.c:311) is correct there and the 8-bit pass is exact Gotoh up to that column (used by the certificate)
-            const int thr = FAST_C + FAST_SCALE * (128 + q.go + q.ge);
+            const int thr = CB + SC * (128 + q.go + q.ge);
             int cs = q.ncols;
             for (int c = g; c < q.ncols; c += G) {
                 if ((int)((colv[c] >> sh) & 0xffffu) >= thr) { cs = c; break; }
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) cs = min(cs, __shfl_xor_sync(GM, cs, o, G));
-            const int s2 = sv > FAST_C ? (sv - FAST_C) / FAST_SCALE : 0;
+            const int s2 = sv > CB ? (sv - CB) / SC : 0;
             const int r2 = s2 > 0 ? si : 0;
             // SW: the 8-bit pass's column maxima lie between L's and U's, so its outputs are U's as soon as L equals U at the two
             // cells they are read from: the best cell of the best column (score1, ref_end1, read_end1; every earlier column and every
@@ -414,7 +452,7 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
                 } else {
                     warp_count(d.counters + CNT_CELLS_REV, (unsigned long long)q.Lp * (hc + 1));
                     r.ref_begin1 = r.ref_end1 - hc;                                 // ssw.c:885-886
-                    r.read_begin1 = r.read_end1 - ((int)((colr[hc] >> sh) & 0x7fffu) - q.off);
+                    r.read_begin1 = r.read_end1 - (rowOf(hc, s) - q.off);
                     const int f = d.flag;
                     const bool noCigar = (7 & f) == 0 || ((2 & f) != 0 && (int)r.score1 < (int)d.filters) ||
                                          ((4 & f) != 0 && (r.ref_end1 - r.ref_begin1 > d.filterd || r.read_end1 - r.read_begin1 > d.filterd));
@@ -427,8 +465,8 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
 
 // Grid: one block per FAST-group bundle of the list slice; a launch whose grid is smaller than the slice (the sandwich flavour is
 // launched against an upper bound of its list) strides over it.
-template <int R, int DIR, bool GCOLS, int SW = 0>
-__global__ void __launch_bounds__(128)
+template <int R, int DIR, bool GCOLS, int SW = 0, int G = FAST_G>
+__global__ void __launch_bounds__(128, (G == 8 && R > 16) ? 4 : 0)      // 19 rows per thread: cap at 128 registers (4 blocks per SM)
 k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ njobs_ptr, int colAlloc, int pairOffset, int pairLimit, int verifyX = -1)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -437,24 +475,24 @@ k_fast(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict__ n
     jobs += pairOffset;
     const int npairs = min(max(*njobs_ptr - pairOffset, 0), pairLimit);
     const int ngroups = (npairs + 1) >> 1;
-    const int groupsPerBlock = blockDim.x / FAST_G;
+    const int groupsPerBlock = blockDim.x / G;
     if (blockIdx.x * groupsPerBlock >= ngroups) return;
     // per-read-base score table: byte nt = 16 * mat[nt][rb]  (qP_word's profile cell, ssw.c:402, scaled)
     if (threadIdx.x < d.n) {
         uint32_t t = 0;
-        for (int nt = 0; nt < 4; ++nt) t |= (uint32_t)(uint8_t)(int8_t)(FAST_SCALE * d.mat[nt * d.n + threadIdx.x]) << (8 * nt);
+        for (int nt = 0; nt < 4; ++nt) t |= (uint32_t)(uint8_t)(int8_t)((G == 8 ? 32 : FAST_SCALE) * d.mat[nt * d.n + threadIdx.x]) << (8 * nt);
         s_rowtab[threadIdx.x] = t;
     }
     __syncthreads();
     if constexpr (SW) {
         for (int g0 = blockIdx.x * groupsPerBlock; g0 < ngroups; g0 += gridDim.x * groupsPerBlock) {
-            const int grp = g0 + threadIdx.x / FAST_G;
-            fast_group<R, DIR, GCOLS, SW>(d, jobs, npairs, grp, grp < ngroups, colAlloc, verifyX, smem_raw, s_rowtab);
+            const int grp = g0 + threadIdx.x / G;
+            fast_group<R, DIR, GCOLS, SW, G>(d, jobs, npairs, grp, grp < ngroups, colAlloc, verifyX, smem_raw, s_rowtab);
             __syncwarp();                                       // the group's shared-memory columns are reused by its next lane pair
         }
     } else {
         // the plain sweep is launched with one block per bundle of its list (no loop: the loop state costs the hot kernel registers)
-        const int grp = blockIdx.x * groupsPerBlock + threadIdx.x / FAST_G;
-        fast_group<R, DIR, GCOLS, SW>(d, jobs, npairs, grp, grp < ngroups, colAlloc, verifyX, smem_raw, s_rowtab);
+        const int grp = blockIdx.x * groupsPerBlock + threadIdx.x / G;
+        fast_group<R, DIR, GCOLS, SW, G>(d, jobs, npairs, grp, grp < ngroups, colAlloc, verifyX, smem_raw, s_rowtab);
     }
 }

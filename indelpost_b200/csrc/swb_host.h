@@ -56,7 +56,7 @@ struct swb_ctx {
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
     DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe, b_fastcols;
     DevBuf b_ind_off, b_ind_cnt, b_ind_rend, b_ind_recs, b_ind_misc, b_ind_cig, b_ind_coff, b_ind_clen, b_ind_rs, b_ind_qs;   // indel extraction
-    int fastMaxCols[SWB_NBUCKETS] = {};
+    int fastMaxCols[SWB_NFWD] = {};              // longest window per forward list family
     int swCounts[SWB_NBUCKETS] = {};             // sandwich forward list lengths of the current batch
     int32_t* h_counters = nullptr;              // pinned mirror of counters
     int32_t* h_snap[2] = {nullptr, nullptr};    // streamed path: counter snapshots of the piece in flight and the one before
@@ -95,6 +95,8 @@ cudaError_t swb_exact_set_attrs(int smem_optin);
 // swb_l_fast.cu (compiled once per direction): one launch per non-empty read-length bucket over the list ranges [first[b], counts[b])
 int swb_launch_fast_range_fwd(swb_ctx* c, const int* first, const int* counts, cudaStream_t st);
 int swb_launch_fast_range_rev(swb_ctx* c, const int* first, const int* counts, cudaStream_t st);
+// (-DSWB_FAST_G8) the forward sweep with 8 threads per lane pair; first / counts hold SWB_NFWD entries, this family reads [SWB_NBUCKETS, SWB_NFWD)
+int swb_launch_fast8_range_fwd(swb_ctx* c, const int* first, const int* counts, cudaStream_t st);
 // (-DSWB_FAST_SW=1) the sandwich flavour: 8-bit-final pairs whose scores can pass 128+go+ge, and overflow verifications
 int swb_launch_sandwich_fwd(swb_ctx* c, const int* counts, cudaStream_t st);
 int swb_launch_sandwich_rev(swb_ctx* c, const int* counts, cudaStream_t st);

@@ -9,12 +9,12 @@
 
 // fast-path launch geometry: groups of FAST_G threads, 10 bytes of shared memory per column per group
 // listBase: first of the SWB_NBUCKETS job lists this launch family reads; verifyX >= 0: overflow-verification launch (SW forward only)
-template <int R, int DIR, int SW>
+template <int R, int DIR, int SW, int G = FAST_G>
 static int launch_fast_one(swb_ctx* c, int listBase, int bucket, int maxCols, int firstPair, int upperBoundPairs, cudaStream_t st, int verifyX = -1) {
     SwbDev& d = c->d;
     const int colAlloc = (std::max(maxCols, 8) + 7) & ~7;                     // longest window among this bucket's pairs
     const bool globalCols = colAlloc > SWB_FAST_SMEM_COLS;
-    const size_t per = (size_t)colAlloc * (globalCols ? 2 : 10);
+    const size_t per = (size_t)colAlloc * (globalCols ? 2 : (G == 8 ? 8 : 10));
     // long windows: the global column-best scratch is bounded, the bucket is served in slices of the job list
     int slicePairs = upperBoundPairs - firstPair;
     if (globalCols) {
@@ -25,13 +25,13 @@ static int launch_fast_one(swb_ctx* c, int listBase, int bucket, int maxCols, in
         CUDA_TRY(c, c->b_fastcols.ensure((size_t)((slicePairs + 1) / 2) * perPairPair + 16));
         d.fast_cols = (uint32_t*)c->b_fastcols.p;
     } else d.fast_cols = nullptr;
-    int groups = 128 / FAST_G;
+    int groups = 128 / G;
     while (groups > 2 && groups * per > (size_t)c->smem_optin - 1024) groups /= 2;
-    const int threads = groups * FAST_G;
+    const int threads = groups * G;
     static std::atomic<bool> attr_set[SWB_MAX_DEVICES] = {};               // per template instantiation and device
     if (!attr_set[c->device % SWB_MAX_DEVICES]) {
-        cudaFuncSetAttribute(k_fast<R, DIR, false, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
-        cudaFuncSetAttribute(k_fast<R, DIR, true, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
+        cudaFuncSetAttribute(k_fast<R, DIR, false, SW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
+        cudaFuncSetAttribute(k_fast<R, DIR, true, SW, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin - 1024);
         attr_set[c->device % SWB_MAX_DEVICES] = true;
     }
     const int slot = listBase + bucket;
@@ -42,8 +42,8 @@ static int launch_fast_one(swb_ctx* c, int listBase, int bucket, int maxCols, in
         // the sandwich lists are launched against an upper bound of their length (the forward sweep appends to them): a bounded
         // grid that strides over the list instead of tens of thousands of blocks that find nothing to do
         if (SW) blocks = std::min(blocks, c->n_sm * 8);
-        if (globalCols) k_fast<R, DIR, true, SW><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs, verifyX);
-        else k_fast<R, DIR, false, SW><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs, verifyX);
+        if (globalCols) k_fast<R, DIR, true, SW, G><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs, verifyX);
+        else k_fast<R, DIR, false, SW, G><<<blocks, threads, groups * per, st>>>(d, d.list[slot], d.counters + slot, colAlloc, off, slicePairs, verifyX);
         c->tm.n_launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -77,7 +77,27 @@ static int launch_fast_range(swb_ctx* c, int listBase, const int* first, const i
     return 0;
 }
 
-#if SWB_FAST_SW == 0
+#ifdef SWB_FAST_G8
+// forward sweep with 8 threads per lane pair: families SWB_NBUCKETS .. SWB_NFWD-1 (first / counts / c->fastMaxCols are indexed by family)
+int swb_launch_fast8_range_fwd(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) {
+    for (int b = 0; b < SWB_NF8; ++b) {
+        const int fam = SWB_NBUCKETS + b;
+        const int n = counts[fam], f = first ? first[fam] : 0;
+        if (n <= f) continue;
+        int rc = -1;
+        switch (b) {      // rows per thread = padded length / 8
+            case 0: rc = launch_fast_one<4, 0, 0, 8>(c, LIST_F8_FWD, b, c->fastMaxCols[fam], f, n, st); break;
+            case 1: rc = launch_fast_one<7, 0, 0, 8>(c, LIST_F8_FWD, b, c->fastMaxCols[fam], f, n, st); break;
+            case 2: rc = launch_fast_one<10, 0, 0, 8>(c, LIST_F8_FWD, b, c->fastMaxCols[fam], f, n, st); break;
+            case 3: rc = launch_fast_one<13, 0, 0, 8>(c, LIST_F8_FWD, b, c->fastMaxCols[fam], f, n, st); break;
+            case 4: rc = launch_fast_one<16, 0, 0, 8>(c, LIST_F8_FWD, b, c->fastMaxCols[fam], f, n, st); break;
+            case 5: rc = launch_fast_one<19, 0, 0, 8>(c, LIST_F8_FWD, b, c->fastMaxCols[fam], f, n, st); break;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+#elif SWB_FAST_SW == 0
 #if SWB_FAST_DIR == 0
 int swb_launch_fast_range_fwd(swb_ctx* c, const int* first, const int* counts, cudaStream_t st) { return launch_fast_range<0, 0>(c, LIST_FAST_FWD, first, counts, st); }
 #else
@@ -92,7 +112,7 @@ int swb_launch_sandwich_fwd(swb_ctx* c, const int* counts, cudaStream_t st) { re
 int swb_launch_sandwich_verify(swb_ctx* c, int listSlot, int xSlot, int upperBound, cudaStream_t st) {
     const SwbDev& d = c->d;
     int maxCols = 0;
-    for (int b = 0; b < SWB_NBUCKETS; ++b) maxCols = std::max(maxCols, c->fastMaxCols[b]);
+    for (int f = 0; f < SWB_NFWD; ++f) maxCols = std::max(maxCols, c->fastMaxCols[f]);
     const int lp16 = (std::min(d.max_rlen, 32 * SWB_NBUCKETS) + 15) & ~15;
     if (maxCols > SWB_FAST_SMEM_COLS || d.max_rlen > 32 * SWB_NBUCKETS || upperBound <= 0) return 1;
     const int rb = std::max(0, (lp16 + 31) / 32 - 1);
