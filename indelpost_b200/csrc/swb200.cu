@@ -151,6 +151,8 @@ __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_
         else if (b8 >= 0) { fam = SWB_NBUCKETS + b8; list_push(d.list[LIST_F8_FWD + b8], d.counters + CNT_F8_FWD + b8, p); }
         else list_push(d.list[LIST_FAST_FWD + b], d.counters + CNT_FAST_FWD + b, p);
         if (wl > *(volatile int32_t*)(d.counters + CNT_FAST_MAXCOLS + fam)) atomicMax(d.counters + CNT_FAST_MAXCOLS + fam, wl);   // test first: one hot address
+        // the pair may continue on its 32-row bucket's lists (reverse sweep, sandwich re-sweep): that bucket's launches size their columns by it too
+        if (fam != b && wl > *(volatile int32_t*)(d.counters + CNT_FAST_MAXCOLS + b)) atomicMax(d.counters + CNT_FAST_MAXCOLS + b, wl);
     }
     else if (d.score_size == 1) list_push(d.list[LIST_WORD_FWD], d.counters + CNT_WORD_FWD, p);
     else list_push(d.list[LIST_BYTE_FWD], d.counters + CNT_BYTE_FWD, p);
