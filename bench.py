@@ -512,13 +512,13 @@ def run_ours(args):
         achieved = cells / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else 0.0
         alg_bytes = int(h2d_codes) + args.pairs * 40  # every input byte (one code per byte on the device) is read once by the sweep, one 40-byte result record written per pair
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
             k = tj["kernels"].get("k_fast_fwd")
             if k:
                 traffic = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["pairs"] * args.pairs
-                traffic_src = tj["source"] + ": dram__bytes_read.sum + dram__bytes_write.sum of k_fast<10,0>, scaled per pair"
+                traffic_src = tj["source"] + ": dram__bytes_read.sum + dram__bytes_write.sum of k_fast<19,0,false,0,8> (forward sweep), scaled per pair"
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured"

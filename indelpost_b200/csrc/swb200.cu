@@ -226,7 +226,7 @@ extern "C" swb_ctx* swb_create(int device) {
     mkStream(&c->copy_stream, prGreatest); mkEvent(&c->ev_copy);
     mkEvent(&c->ev_bulk_join2); mkEvent(&c->ev_piece);
     mkEvent(&c->ev_bulk_fork); mkEvent(&c->ev_bulk_join);
-    mkEvent(&c->ev_fork3);
+    mkEvent(&c->ev_fork3); mkEvent(&c->ev_x_fork); mkEvent(&c->ev_x_join);
     mkEvent(&c->ev_rev_fork);
     for (int i = 0; i < SWB_BANDW_MAX; ++i) { mkStream(&c->bandw_stream[i], prMid); mkEvent(&c->ev_bandw_join[i]); }
     for (int i = 0; i < SWB_NREVB; ++i) { mkStream(&c->rev_stream[i], prMid); mkEvent(&c->ev_rev_join[i]); }
@@ -267,7 +267,7 @@ static void destroy_ctx(swb_ctx* c) {
     if (c->h_bump) cudaFreeHost(c->h_bump);
     for (int i = 0; i < 2; ++i) { if (c->h_snap[i]) cudaFreeHost(c->h_snap[i]); dE(c->ev_snap[i]); }
     dS(c->stream);
-    dS(c->stream3); dE(c->ev_fork3);
+    dS(c->stream3); dE(c->ev_fork3); dE(c->ev_x_fork); dE(c->ev_x_join);
     dS(c->stream4); dE(c->ev_join3);
     dS(c->bulk_stream); dE(c->ev_bulk_fork); dE(c->ev_bulk_join);
     dS(c->bulk_stream2); dE(c->ev_bulk_join2); dE(c->ev_piece);
@@ -728,16 +728,34 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     const size_t np = (size_t)d.n_pairs;
     swb_timing& tm = c->tm;
     cudaStream_t s = c->stream;
-    if (swb_launch_exact(c, 0, 0, LIST_BYTE_FWD, (int)np, nullptr, false)) return -1;
-    if (swb_launch_exact(c, 1, 0, LIST_WORD_FWD, (int)np, nullptr, false)) return -1;
+    // ---- exact striped emulation, forward and reverse, on a side stream: these kernels serve a minority (pairs the fast path cannot
+    //      decide) but each is a long chain of dependent steps whatever the count, so they run beside the reverse pass of the fast-path
+    //      pairs instead of in front of and behind it.  Their reverse passes read LIST_BYTE_REV / LIST_WORD_REV, which only they fill;
+    //      fast-path pairs whose reverse sweep gives up go to LIST_BYTE_REV2 / LIST_WORD_REV2 and are served after the join.
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_FWD], s));
+    cudaStream_t xs = c->stream3;
+    CUDA_TRY(c, cudaEventRecord(c->ev_x_fork, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(xs, c->ev_x_fork, 0));
+    if (swb_launch_exact(c, 0, 0, LIST_BYTE_FWD, (int)np, xs, false)) return -1;
+    if (swb_launch_exact(c, 1, 0, LIST_WORD_FWD, (int)np, xs, false)) return -1;
+    if (swb_launch_exact(c, 0, 1, LIST_BYTE_REV, (int)np, xs, false)) return -1;
+    if (swb_launch_exact(c, 1, 1, LIST_WORD_REV, (int)np, xs, false)) return -1;
+    CUDA_TRY(c, cudaEventRecord(c->ev_x_join, xs));
 
     // ---- reverse (ssw.c:875-891) ----------------------------------------------------------------
     if (swb_launch_rev_band(c, nFastTotal)) return -1;          // the pairs the forward sweep put into a band class
     if (launch_fast<1>(c, fwdCounts)) return -1;            // the rest; rev bucket sizes are bounded by the fwd ones
     if (join_rev_band(c, nFastTotal)) return -1;
-    if (swb_launch_exact(c, 0, 1, LIST_BYTE_REV, (int)np, nullptr, false)) return -1;
-    if (swb_launch_exact(c, 1, 1, LIST_WORD_REV, (int)np, nullptr, false)) return -1;
+    CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_x_join, 0));
+    // fast-path pairs handed to the exact reverse pass (rare: no column reached score1, or the sandwich rejected the reverse sweep):
+    // their lists are sized on the host, one more counter read only when there are any
+    if (read_counters(c)) return -1;
+    {
+        const int n2b = c->h_counters[LIST_BYTE_REV2], n2w = c->h_counters[LIST_WORD_REV2];
+        if (n2b > 0 && swb_launch_exact(c, 0, 1, LIST_BYTE_REV2, n2b, nullptr, false)) return -1;
+        if (n2w > 0 && swb_launch_exact(c, 1, 1, LIST_WORD_REV2, n2w, nullptr, false)) return -1;
+        if ((n2b > 0 || n2w > 0) && read_counters(c)) return -1;
+    }
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_REV], s));
     TR(c, "fwd_rev_enqueued");
 
@@ -753,7 +771,7 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_WORD_FWD, 0, 4, s));
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_FWD, 0, 4, s));      // reused as the leftovers' verify list
     int nFirst = 0;
-    if (run_band_rounds(c, false, LIST_BAND_FIRST, &nFirst, /*firstRoundOnly=*/true)) return -1;      // its re-queues join phase 2's rounds
+    if (run_band_rounds(c, false, LIST_BAND_FIRST, &nFirst, /*firstRoundOnly=*/true, false, nullptr, /*haveCounters=*/true)) return -1;      // its re-queues join phase 2's rounds
     if (certify && nFirst > 0 && certify_and_verify_async(c, LIST_VERIFY, nFirst)) return -1;
     // phase 2; its first round is followed at once by the certificate + verification of its own pairs (hook), which
     // then overlap the re-queue rounds

@@ -1,8 +1,9 @@
 // swb_bandreg.cuh — banded_sw (ssw.c:588-772) with the rolling band rows in REGISTERS, for the first band width of
 // the "regular" jobs: half-width W = |refLen - readLen| + 1 <= SWB_BANDW_MAX known at compile time, refLen >= 2W + 2
 // (the band is narrower than the matrix, so none of the reference's buffer-reuse quirks is reachable, see below),
-// matrix edge n <= 8.  Everything else — wider or irregular bands, band doubling (ssw.c:668-669) — goes to the literal
-// kernel k_band (swb_band.cuh), which also provides the traceback walk used here.
+// matrix edge n <= 8.  Band doubling (ssw.c:668-669) continues in place through the 2W, 4W ... instantiations while the band stays
+// regular and within SWB_BANDW_MAX (bandreg_solve).  Everything else — wider or irregular bands — goes to the warp-per-alignment
+// kernel or the literal kernel k_band (swb_band.cuh), which also provides the traceback walk used here.
 //
 // Slot algebra (ssw.c:92-95, set_u): cell (i, j) of row i lives in slot u = j - max(0, i - W) + 1 of the rolling
 // buffers; x = u - 1 below.
@@ -23,6 +24,8 @@
 #include "swb_fast.cuh"
 
 #define SWB_BANDREG_THREADS 64
+#define SWB_BANDREG_INPLACE 1          // band doublings a register-band kernel performs itself before it re-queues the job ...
+#define SWB_BANDREG_INPLACE_MAXW 14    // ... up to this doubled half-width (a kernel needs the registers of its widest band: wider chains would halve the occupancy of the W = 9 .. 12 kernels)
 
 struct BandRegPar { const int8_t* read; const int8_t* ref; int readLen, refLen; };
 
@@ -179,57 +182,24 @@ __device__ __forceinline__ int bandreg_dp(const BandGeom& g, const uint8_t* selT
     return best;
 }
 
-template <int W>
-__global__ void __launch_bounds__(SWB_BANDREG_THREADS)
-k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, int nextBaseW, int resume, int rowsAlloc)
+// One band width for one staged job: DP, then either the traceback, or -- the running maximum still below score1 (ssw.c:668-669) --
+// the doubled width right here while it is still a regular register band (the staging does not depend on W), so that a widened job
+// costs its own thread a second DP instead of the whole batch another round of latency-bound launches.  Widths beyond the register
+// kernels go to the warp-per-alignment / literal kernels of the next round.
+template <int W, int DEPTH = 0>
+__device__ __forceinline__ void bandreg_solve(const SwbDev& d, const int p, swb_result& r, BandGeom g, const uint8_t* selT, const uint8_t* rowT,
+                                              const unsigned long long* s_rowTab, uint32_t* region, const int strideW, const int go, const int ge,
+                                              const int score, const int best0, const int nextBase, const int nextBaseW)
 {
     constexpr int NX = 2 * W + 1;
     constexpr int NW = (NX + 7) / 8;                      // direction words per row
-    constexpr int T = SWB_BANDREG_THREADS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long s_rowTab[8];            // per read base: its scores against every window base, 8 x int8
-    if (threadIdx.x < 8) {
-        unsigned long long tab = 0;
-        if ((int)threadIdx.x < d.n) for (int nt = 0; nt < d.n; ++nt) tab |= (unsigned long long)(uint8_t)d.mat[nt * d.n + threadIdx.x] << (8 * nt);
-        s_rowTab[threadIdx.x] = tab;
-    }
-    __syncthreads();
-    const int t = blockIdx.x * T + threadIdx.x;
-    if (t >= njobs) return;
-    const int p = jobs[t];
-    BandGeom g; g.w = W; g.width_d = NX; g.strideW = NW;
-    {
-        const swb_result& r0 = d.res[p];
-        g.refLen = r0.ref_end1 - r0.ref_begin1 + 1;       // ssw.c:897-899
-        g.readLen = r0.read_end1 - r0.read_begin1 + 1;
-    }
-
-    // ---- staging: every thread copies its own window / read segment into its shared-memory region ------------------
-    const int strideW = bandreg_stride_words(rowsAlloc);
-    const int selCols = bandreg_sel_cols(rowsAlloc);
-    uint32_t* const region = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)threadIdx.x * strideW;
-    uint8_t* selW = reinterpret_cast<uint8_t*>(region);
-    uint8_t* rowW = reinterpret_cast<uint8_t*>(region + selCols / 4);
-    {
-        const swb_result& r0 = d.res[p];
-        for_each_byte16_pair(d.windows + d.p_woff[p] + r0.ref_begin1, g.refLen, [&](int c, uint32_t v) { selW[c] = (uint8_t)(v & 7u); },
-                             d.reads + d.p_roff[p] + r0.read_begin1, g.readLen, [&](int i, uint32_t v) { rowW[i] = (uint8_t)(v & 7u); });
-        const int ncols = min(g.refLen + NX + 1, selCols);
-        for (int c = g.refLen; c < ncols; ++c) selW[c] = 0;
-    }
-    const uint8_t* selT = selW;
-    const uint8_t* rowT = rowW;
-
-    swb_result& r = d.res[p];
-    const int score = r.score1;
-    const int go = d.gap_open[p], ge = d.gap_ext[p];
+    g.w = W; g.width_d = NX; g.strideW = NW;
     const int len = g.refLen > g.readLen ? g.refLen : g.readLen;
-
     // ---- scratch for the packed direction words -----------------------------------------------------------------
     const long long need = (long long)NW * 4 * g.readLen;
     const unsigned long long off = warp_bump(&d.bump[0], (unsigned long long)need);
     if ((long long)off + need > d.band_cap) {               // out of scratch: the literal kernel retries in a later round
-        d.t_bw[p] = W; d.t_best[p] = 0;
+        d.t_bw[p] = W; d.t_best[p] = best0;
         atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1);
         const int c = band_class(W, g.refLen);
         list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
@@ -239,15 +209,21 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
 
     long long cells = 0;
     // a widened job carries its running maximum along (ssw.c:661 is not reset)
-    const int best0 = resume ? d.t_best[p] : 0;
     const int best = go >= ge ? bandreg_dp<W, true>(g, selT, rowT, s_rowTab, go, ge, d.one, dir, best0, cells)
                               : bandreg_dp<W, false>(g, selT, rowT, s_rowTab, go, ge, d.one, dir, best0, cells);
     warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
 
-    if (best < score && W * 2 <= len) {                     // ssw.c:668-669: widen and redo in the next round
+    if (best < score && W * 2 <= len) {                     // ssw.c:668-669: widen and redo
+        // (one doubling in place: a kernel's register count is that of its widest band, and a second doubling is rare)
+        if constexpr (2 * W <= SWB_BANDREG_INPLACE_MAXW && DEPTH < SWB_BANDREG_INPLACE) {
+            if (g.refLen >= 4 * W + 2) {                    // still narrower than the matrix: the 2W register band, in place
+                bandreg_solve<2 * W, DEPTH + 1>(d, p, r, g, selT, rowT, s_rowTab, region, strideW, go, ge, score, best, nextBase, nextBaseW);
+                return;
+            }
+        }
         d.t_bw[p] = 2 * W; d.t_best[p] = best;
         if (nextBaseW >= 0 && 2 * W <= SWB_BANDW_MAX && g.refLen >= 4 * W + 2) {
-            list_push(d.list[nextBaseW + 2 * W - 1], d.counters + nextBaseW + 2 * W - 1, p);      // still regular: this kernel's 2W instantiation
+            list_push(d.list[nextBaseW + 2 * W - 1], d.counters + nextBaseW + 2 * W - 1, p);      // still regular: this kernel's 2W instantiation, next round
         } else {
             requeue_band(d, nextBase, p, 2 * W, g.refLen, g.readLen, r);                            // warp-per-alignment or literal kernel
         }
@@ -257,7 +233,6 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
     // ---- traceback: one walk (ops buffered in registers), allocate, emit reversed ---------------------------------
     BandOps ops;
     constexpr bool regRows = NW <= BAND_ROWWORDS;
-    __syncwarp();                                           // the region is reused as the traceback window: all lanes are done with their selectors
     const int wrows = min(32, (strideW - 1) / NW);
     int l = bandreg_traceback<NW>(dir, g, region, wrows, ops, nullptr, 0);
     const bool literal = l == -2;
@@ -275,4 +250,47 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
         bandreg_traceback<NW>(dir, g, region, wrows, ops, d.cigar + coff, l);
     }
     d.p_state[p] |= PST_BAND_DONE;
+}
+
+template <int W>
+__global__ void __launch_bounds__(SWB_BANDREG_THREADS)
+k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, int nextBaseW, int resume, int rowsAlloc)
+{
+    constexpr int NX = 2 * W + 1;
+    constexpr int T = SWB_BANDREG_THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long s_rowTab[8];            // per read base: its scores against every window base, 8 x int8
+    if (threadIdx.x < 8) {
+        unsigned long long tab = 0;
+        if ((int)threadIdx.x < d.n) for (int nt = 0; nt < d.n; ++nt) tab |= (unsigned long long)(uint8_t)d.mat[nt * d.n + threadIdx.x] << (8 * nt);
+        s_rowTab[threadIdx.x] = tab;
+    }
+    __syncthreads();
+    const int t = blockIdx.x * T + threadIdx.x;
+    if (t >= njobs) return;
+    const int p = jobs[t];
+    BandGeom g; g.w = W; g.width_d = NX; g.strideW = (NX + 7) / 8;
+    {
+        const swb_result& r0 = d.res[p];
+        g.refLen = r0.ref_end1 - r0.ref_begin1 + 1;       // ssw.c:897-899
+        g.readLen = r0.read_end1 - r0.read_begin1 + 1;
+    }
+
+    // ---- staging: every thread copies its own window / read segment into its shared-memory region ------------------
+    // (the region does not depend on W: selectors for every column a band of up to SWB_BANDW_MAX can touch)
+    const int strideW = bandreg_stride_words(rowsAlloc);
+    const int selCols = bandreg_sel_cols(rowsAlloc);
+    uint32_t* const region = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)threadIdx.x * strideW;
+    uint8_t* selW = reinterpret_cast<uint8_t*>(region);
+    uint8_t* rowW = reinterpret_cast<uint8_t*>(region + selCols / 4);
+    {
+        const swb_result& r0 = d.res[p];
+        for_each_byte16_pair(d.windows + d.p_woff[p] + r0.ref_begin1, g.refLen, [&](int c, uint32_t v) { selW[c] = (uint8_t)(v & 7u); },
+                             d.reads + d.p_roff[p] + r0.read_begin1, g.readLen, [&](int i, uint32_t v) { rowW[i] = (uint8_t)(v & 7u); });
+        const int ncols = min(g.refLen + 2 * SWB_BANDW_MAX + 2, selCols);
+        for (int c = g.refLen; c < ncols; ++c) selW[c] = 0;
+    }
+    swb_result& r = d.res[p];
+    // a job this kernel re-runs at a doubled width carries its running maximum along (ssw.c:661 is not reset)
+    bandreg_solve<W>(d, p, r, g, selW, rowW, s_rowTab, region, strideW, d.gap_open[p], d.gap_ext[p], r.score1, resume ? d.t_best[p] : 0, nextBase, nextBaseW);
 }

@@ -76,6 +76,7 @@ struct SwbDev {
 // certified first; _NEXT: jobs that kernel widened once.  LIST_BANDWARP*: wide bands, one warp per alignment (swb_bandwarp.cuh);
 // _NEXT is two lists used alternately by the re-queue rounds.
 enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 3, LIST_VERIFY = 4, LIST_VERIFY2 = 5,
+       LIST_BYTE_REV2 = 6, LIST_WORD_REV2 = 7,      // fast-path pairs handed to the exact reverse pass (the exact path itself uses LIST_*_REV, concurrently)
        LIST_FAST_FWD = 8, LIST_FAST_REV = 16, LIST_BAND = 24, LIST_BAND_NEXT = 32, LIST_BAND_FIRST = 40, LIST_REVB = 48,
        LIST_BANDW = 56, LIST_BANDW_FIRST = 80, LIST_BANDW_NEXT = 104,
        LIST_BANDWARP = 128, LIST_BANDWARP_FIRST = 129, LIST_BANDWARP_NEXT = 130,

@@ -448,7 +448,7 @@ __device__ __forceinline__ void fast_group(const SwbDev& d, const int32_t* __res
                     // no column reaches score1 (or score 0 corner): let the exact path reproduce ssw.c literally
                     const int md = d.p_mode[p];
                     d.p_state[p] &= ~PST_FAST;
-                    list_push(d.list[md ? LIST_WORD_REV : LIST_BYTE_REV], d.counters + (md ? CNT_WORD_REV : CNT_BYTE_REV), p);
+                    list_push(d.list[md ? LIST_WORD_REV2 : LIST_BYTE_REV2], d.counters + (md ? LIST_WORD_REV2 : LIST_BYTE_REV2), p);
                 } else {
                     warp_count(d.counters + CNT_CELLS_REV, (unsigned long long)q.Lp * (hc + 1));
                     r.ref_begin1 = r.ref_end1 - hc;                                 // ssw.c:885-886

@@ -35,7 +35,8 @@ enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0
 struct swb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
-    cudaStream_t stream4 = nullptr; cudaEvent_t ev_join3; unsigned verify_pending = 0;   // second verification stream
+    cudaStream_t stream4 = nullptr; cudaEvent_t ev_join3; cudaEvent_t ev_x_fork, ev_x_join;     // exact path beside the fast reverse pass (on stream3)
+    unsigned verify_pending = 0;   // second verification stream
     cudaStream_t bulk_stream = nullptr;                                     // lowest priority: the forward DPX sweep (yields SM slots to the short, latency-bound kernels of the other lane)
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_copy;              // streamed path: host->device copies back to back on their own stream
     cudaStream_t bulk_stream2 = nullptr;                                    // second one: consecutive forward slices of the streamed one-shot path overlap their tails

@@ -160,7 +160,7 @@ k_rev_band(SwbDev d, const int32_t* __restrict__ jobs, const int32_t* __restrict
             // no cell reaches score1: let the exact path reproduce ssw.c literally (flag = 2 case)
             const int md = d.p_mode[p];
             d.p_state[p] &= ~PST_FAST;
-            list_push(d.list[md ? LIST_WORD_REV : LIST_BYTE_REV], d.counters + (md ? CNT_WORD_REV : CNT_BYTE_REV), p);
+            list_push(d.list[md ? LIST_WORD_REV2 : LIST_BYTE_REV2], d.counters + (md ? LIST_WORD_REV2 : LIST_BYTE_REV2), p);
         } else {
             warp_count(d.counters + CNT_CELLS_REV, (unsigned long long)(s ? LB : LA) * (hc + 1));
             r.ref_begin1 = r.ref_end1 - hc;

@@ -144,6 +144,50 @@ def test_sswpy_api_matches_reference_golden():
     assert [list(o) for o in outs] == wants
 
 
+def test_link_level_dropin_of_reference_sswpy():
+    """the reference's UNMODIFIED sswpy.pyx, cythonized against include/compat/ssw.h and linked against libswb200.so
+    instead of ssw.c (oracle/build_ref_sswpy_dropin.py), returns the reference's own outputs (tests/golden/sswpy_api.json) -- every
+    SSW.align() of that module is a GPU call through ssw_init / ssw_align / align_destroy"""
+    d = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "oracle", "_ref_sswpy", "sswpy_dropin")
+    if not os.path.isdir(d):
+        pytest.skip("oracle/_ref_sswpy not built (needs the reference tree at build time)")
+    sys.path.insert(0, os.path.abspath(d))
+    try:
+        import sswpy as dropin
+    finally:
+        sys.path.pop(0)
+    assert "oracle/_ref_sswpy" in dropin.__file__.replace(os.sep, "/")
+    cases = json.load(open(os.path.join(GOLDEN_DIR, "sswpy_api.json")))
+    n_ok = 0
+    for c in cases:
+        ref, read = c["ref"], c["read"]
+        if c["bytes_input"]:
+            ref, read = ref.encode(), read.encode()
+        a = dropin.SSW(c["match"], c["mismatch"])
+        a.setReference(ref)
+        a.setRead(read)
+        if c["err"]:
+            with pytest.raises(ValueError):
+                a.align(**c["kw"])
+            continue
+        got = a.align(**c["kw"])
+        assert list(got) == c["out"], (c["kw"], list(got), c["out"])
+        n_ok += 1
+    assert n_ok >= 15
+    # the reference's convenience wrappers on top of it (sswpy.pyx:339-396) and ours give the same
+    from indelpost_b200 import force_align, format_force_align
+
+    read, ref = "ACGTTGCATGCATTACGATCGATC", "GGGGACGTTGCATGCATTACGATCGATCTTTT"
+    want = dropin.force_align(read, ref)
+    got = force_align(read, ref)
+    assert list(got) == list(want)
+    assert format_force_align(read, ref, got) == dropin.format_force_align(read, ref, want)
+    with pytest.raises(ValueError, match="No solution found"):
+        force_align("A", "CCCCCC")
+    with pytest.raises(ValueError, match="one overhang"):
+        force_align(read, ref, force_overhang=True)
+
+
 def test_sswpy_memo_returns_identical_results():
     """repeated SSW.align calls with identical inputs are served from the aligner's memo (update_read_info
     repeats retarget's alignment); a new reference or different penalties must not hit it"""
