@@ -619,9 +619,10 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
             if (swb_launch_band(c, 2, (njobs[4] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, cur, 4, 4, nxt, c->stream2)) return -1;
             CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
         }
-        // widened jobs: small batches are latency bound and re-run them with the (faster) register-band kernel of the doubled
-        // width; large ones hand them to the literal kernel, which keeps doubling in place and so never needs a third round
-        const int regNext = (round == 0 && d.n_pairs < 200000) ? LIST_BANDW_NEXT : -1;
+        // widened jobs: the register-band kernels double once in place (up to half-width 14); what doubles beyond that but still fits a
+        // register band (16 .. 24) is re-run in the next round by the kernel of the doubled width, whose latency is half the literal
+        // kernel's; the literal / warp kernels take the rest and keep doubling in place
+        const int regNext = round == 0 ? LIST_BANDW_NEXT : -1;
         if (launch_band_reg(c, baseW, njobsW, nxt, regNext, round == 0 ? 0 : 1)) return -1;
         int blocks = 0;
         for (int k = 0; k < SWB_BAND_CLS_MID; ++k) blocks += (njobs[k] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
