@@ -199,6 +199,21 @@ class BatchAligner:
             a = arena[: used.value]
             return (res.copy(), a.copy()) if copy else (res, a)
 
+    def align_into(self, res: np.ndarray, arena: np.ndarray, *args, **kw) -> int:
+        """one-shot into caller-owned (ideally pinned) output arrays: `res` (RESULT_DTYPE, one record per pair) and `arena`
+        (uint32).  Returns the number of arena entries used, or -(needed) if the arena is too small (nothing valid written).
+        This is what a sharder uses to let every GPU write its slice of ONE result array (no stitching copies)."""
+        b, keep = self._make_batch(*args, **kw)
+        if res.shape[0] < b.n_pairs or res.dtype != L.RESULT_DTYPE or not res.flags.c_contiguous or arena.dtype != np.uint32:
+            raise ValueError("align_into: res must be a contiguous RESULT_DTYPE array with one record per pair, arena uint32")
+        used = C.c_int64(0)
+        rc = self.lib.swb_align_batch(self.ctx, C.byref(b), res.ctypes.data, arena.ctypes.data, int(arena.shape[0]), C.byref(used))
+        if rc == -2:
+            return -int(used.value)
+        if rc != 0:
+            raise L.SwbError(self._err())
+        return int(used.value)
+
     def align_leased(self, *args, cigar_cap: int | None = None, **kw):
         """like align(), but the outputs land in pinned buffers taken from a pool and stay valid for as long as the returned
         lease object lives (the buffers go back to the pool when it is released) -- no copy of the records"""

@@ -291,6 +291,33 @@ k_band_reg(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase, 
         for (int c = g.refLen; c < ncols; ++c) selW[c] = 0;
     }
     swb_result& r = d.res[p];
+    if constexpr (W == 1) {
+        // Gapless shortcut.  refLen == readLen and the main diagonal of the sub-matrix scores exactly score1, where score1 is the true
+        // Smith-Waterman maximum (fast-path pairs: their result is plain Gotoh).  Every band cell is <= the true local score <= score1,
+        // and H(i,i) >= the diagonal prefix sum; were some H(i,i) larger, following the diagonal from there would end above score1.  So
+        // H(i,i) equals the prefix sum, the diagonal candidate m = H(i-1,i-1) + s attains it, the tie rule `gmax <= m` (ssw.c:663) picks
+        // the diagonal in every cell of the walk, the maximum reaches score1 at the first width, and the traceback (ssw.c:672-751) emits
+        // the single op readLen M.  The majority of a real pileup (reads without an indel against their window) ends here.
+        if (!resume && g.refLen == g.readLen && (d.p_state[p] & PST_FAST)) {
+            int s0 = 0, s1 = 0;
+            const int n = g.readLen;
+            int i = 0;
+            for (; i + 1 < n; i += 2) {
+                const unsigned long long t0 = s_rowTab[rowW[i]], t1 = s_rowTab[rowW[i + 1]];
+                s0 += (int)prmt((uint32_t)t0, (uint32_t)(t0 >> 32), bandreg_sel(selW[i], d.one));
+                s1 += (int)prmt((uint32_t)t1, (uint32_t)(t1 >> 32), bandreg_sel(selW[i + 1], d.one));
+            }
+            if (i < n) { const unsigned long long t0 = s_rowTab[rowW[i]]; s0 += (int)prmt((uint32_t)t0, (uint32_t)(t0 >> 32), bandreg_sel(selW[i], d.one)); }
+            if (s0 + s1 == (int)r.score1) {
+                const unsigned long long coff = warp_bump(&d.bump[1], 1ull);
+                r.cigar_len = 1; r.cigar_off = (int64_t)coff;
+                if ((long long)coff + 1 > d.cigar_cap) { atomicAdd(d.counters + CNT_CIGAR_OVERFLOW, 1); return; }
+                d.cigar[coff] = ((uint32_t)n << 4) | 0u;
+                d.p_state[p] |= PST_BAND_DONE;
+                return;
+            }
+        }
+    }
     // a job this kernel re-runs at a doubled width carries its running maximum along (ssw.c:661 is not reset)
     bandreg_solve<W>(d, p, r, g, selW, rowW, s_rowTab, region, strideW, d.gap_open[p], d.gap_ext[p], r.score1, resume ? d.t_best[p] : 0, nextBase, nextBaseW);
 }

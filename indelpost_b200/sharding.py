@@ -88,8 +88,30 @@ def slice_table(blob, off, length, idx, seq_encoding: int = L.SWB_SEQ_CODES):
     return blob[b0:b1], np.ascontiguousarray(o - b0), np.ascontiguousarray(ln), i0
 
 
+def sampled_bounds(read_len, win_len, pair_read, pair_win, ref_len, ref_beg, n_shards: int, stride: int = 16) -> List[Tuple[int, int]]:
+    """shard_bounds over every `stride`-th pair (a 16th of the gathers and of the prefix sum): the cut positions are good to
+    `stride` pairs, which is far below what a shard's balance needs"""
+    n = int(np.asarray(pair_read).shape[0])
+    if n_shards <= 1 or n == 0:
+        return [(0, n)] + [(n, n)] * (max(1, n_shards) - 1)
+    if n < 64 * stride:
+        stride = 1
+    sl = slice(0, n, stride)
+    cells = pair_cells(read_len, win_len, pair_read[sl], pair_win[sl], None if ref_len is None else ref_len[sl], None if ref_beg is None else ref_beg[sl])
+    b = shard_bounds(cells, n_shards)
+    cuts = [min(n, p0 * stride) for p0, _ in b] + [n]
+    cuts[0] = 0
+    return [(cuts[k], cuts[k + 1]) for k in range(n_shards)]
+
+
 class MultiGpuAligner:
-    """one BatchAligner per device, one host thread per device, no collective"""
+    """one BatchAligner per device, one host thread per device, no collective.
+
+    Every shard (a contiguous range of pairs, balanced by nominal DP cells) uploads only the table slices its pairs refer to
+    and writes its records straight into its slice of ONE pinned result array; CIGARs go to the shard's own region of one
+    pinned arena (`cigar_off` of the records is rebased to the arena start, so `arena[off : off + len]` works as for a single
+    GPU -- the regions are not packed, unused entries between them are never referenced).  The returned arrays are views of
+    buffers owned by this object, valid until its next `align`."""
 
     def __init__(self, devices: Sequence[int]):
         from .batch import BatchAligner
@@ -97,38 +119,76 @@ class MultiGpuAligner:
         self.devices = list(devices)
         self.aligners = [BatchAligner(d) for d in self.devices]
         self.pool = ThreadPoolExecutor(max_workers=len(self.devices))
+        self._res = None
+        self._arena = None
 
     def close(self):
         for a in self.aligners:
             a.close()
         self.pool.shutdown(wait=False)
+        for b in (self._res, self._arena):
+            if b is not None:
+                b.close()
+        self._res = self._arena = None
+
+    def _out(self, n_pairs: int, arena_entries: int):
+        need_r = max(1, n_pairs) * L.RESULT_DTYPE.itemsize
+        if self._res is None or self._res.nbytes < need_r:
+            if self._res is not None:
+                self._res.close()
+            self._res = L.PinnedBuffer(need_r + need_r // 8)
+        need_a = max(64, arena_entries) * 4
+        if self._arena is None or self._arena.nbytes < need_a:
+            if self._arena is not None:
+                self._arena.close()
+            self._arena = L.PinnedBuffer(need_a + need_a // 8)
+        return self._res.view(L.RESULT_DTYPE, n_pairs), self._arena.view(np.uint32, self._arena.nbytes // 4)
 
     def align(self, reads, read_off, read_len, windows, win_off, win_len, pair_read, pair_win, gap_open, gap_ext,
-              ref_beg=None, ref_len=None, mask_len=None, **kw):
+              ref_beg=None, ref_len=None, mask_len=None, copy: bool = True, cigar_per_pair: int = 8, **kw):
         arrs = dict(pair_read=np.asarray(pair_read, np.int32), pair_win=np.asarray(pair_win, np.int32),
                     gap_open=np.asarray(gap_open, np.uint8), gap_ext=np.asarray(gap_ext, np.uint8),
                     ref_beg=None if ref_beg is None else np.asarray(ref_beg, np.int32),
                     ref_len=None if ref_len is None else np.asarray(ref_len, np.int32),
                     mask_len=None if mask_len is None else np.asarray(mask_len, np.int32))
-        cells = pair_cells(read_len, win_len, arrs["pair_read"], arrs["pair_win"], arrs["ref_len"], arrs["ref_beg"])
-        bounds = shard_bounds(cells, len(self.aligners))
-
+        n = int(arrs["pair_read"].shape[0])
+        bounds = sampled_bounds(read_len, win_len, arrs["pair_read"], arrs["pair_win"], arrs["ref_len"], arrs["ref_beg"], len(self.aligners))
         enc = int(kw.get("seq_encoding", L.SWB_SEQ_CODES))
         reads_a, windows_a = np.asarray(reads), np.asarray(windows)
-        n_reads, n_windows = int(np.asarray(read_len).shape[0]), int(np.asarray(win_len).shape[0])
+        # arena regions: a fixed budget per pair (grown and retried if a shard reports it needs more)
+        per = max(2, int(cigar_per_pair))
+        while True:
+            abase = [0]
+            for p0, p1 in bounds:
+                abase.append(abase[-1] + max(64, per * (p1 - p0)))
+            res, arena = self._out(n, abase[-1])
 
-        def run(k):
-            p0, p1 = bounds[k]
-            s = slice_pairs(arrs, p0, p1)
-            # only the table slices this shard refers to travel to its GPU; indices are rebased to the slice, indices outside
-            # the tables are kept out of range
-            rb, ro, rl, r0 = slice_table(reads_a, read_off, read_len, s["pair_read"], enc)
-            wb, wo, wl, w0 = slice_table(windows_a, win_off, win_len, s["pair_win"], enc)
-            pr, pw = s["pair_read"], s["pair_win"]
-            pr = np.where((pr >= 0) & (pr < n_reads), pr - r0, -1).astype(np.int32)
-            pw = np.where((pw >= 0) & (pw < n_windows), pw - w0, -1).astype(np.int32)
-            return self.aligners[k].align(rb, ro, rl, wb, wo, wl, pr, pw,
-                                          s["gap_open"], s["gap_ext"], ref_beg=s["ref_beg"], ref_len=s["ref_len"], mask_len=s["mask_len"], **kw)
+            def run(k):
+                p0, p1 = bounds[k]
+                if p1 <= p0:
+                    return 0
+                s = slice_pairs_view(arrs, p0, p1)
+                # only the table slices this shard refers to travel to its GPU; pair indices are rebased by subtraction (an index
+                # outside the caller's tables stays outside the slice)
+                rb, ro, rl, r0 = slice_table(reads_a, read_off, read_len, s["pair_read"], enc)
+                wb, wo, wl, w0 = slice_table(windows_a, win_off, win_len, s["pair_win"], enc)
+                pr = s["pair_read"] - np.int32(r0) if r0 else s["pair_read"]
+                pw = s["pair_win"] - np.int32(w0) if w0 else s["pair_win"]
+                used = self.aligners[k].align_into(res[p0:p1], arena[abase[k]:abase[k + 1]], rb, ro, rl, wb, wo, wl, pr, pw,
+                                                   s["gap_open"], s["gap_ext"], ref_beg=s["ref_beg"], ref_len=s["ref_len"], mask_len=s["mask_len"], **kw)
+                if used >= 0 and abase[k]:
+                    r = res[p0:p1]
+                    np.add(r["cigar_off"], abase[k], out=r["cigar_off"], where=r["cigar_len"] > 0)
+                return used
 
-        parts = list(self.pool.map(run, range(len(self.aligners))))
-        return stitch(parts)
+            used = list(self.pool.map(run, range(len(self.aligners))))
+            if min(used) >= 0:
+                break
+            per = max(per * 2, max((-u + (p1 - p0) - 1) // max(1, p1 - p0) for u, (p0, p1) in zip(used, bounds) if u < 0) + 1)
+        a = arena[: abase[-1]]
+        return (res.copy(), a.copy()) if copy else (res, a)
+
+
+def slice_pairs_view(arrs: dict, p0: int, p1: int) -> dict:
+    """per-pair arrays restricted to [p0, p1) as views (a contiguous range of a contiguous array is contiguous)"""
+    return {k: (None if v is None else v[p0:p1]) for k, v in arrs.items()}

@@ -92,3 +92,23 @@ def test_slice_table_rebases_offsets_and_keeps_bad_indices_out():
     pln = np.array([10, 20, 7], dtype=np.int32)
     b, o, l, i0 = slice_table(np.arange(10, dtype=np.int8), poff, pln, np.array([1, 2]), L.SWB_SEQ_PACKED2)
     assert i0 == 1 and o.tolist() == [0, 5] and b.tolist() == list(range(3, 10))
+
+
+def test_sampled_bounds_cover_and_balance():
+    """sharding.sampled_bounds: contiguous cover of all pairs, balanced by cells within the sampling stride"""
+    from indelpost_b200.sharding import pair_cells, sampled_bounds
+
+    rng = np.random.default_rng(5)
+    n = 50000
+    read_len = rng.integers(50, 250, size=3000).astype(np.int32)
+    win_len = rng.integers(200, 1000, size=400).astype(np.int32)
+    pr = rng.integers(0, 3000, size=n).astype(np.int32)
+    pw = np.sort(rng.integers(0, 400, size=n)).astype(np.int32)
+    for k in (1, 2, 3, 8):
+        b = sampled_bounds(read_len, win_len, pr, pw, None, None, k)
+        assert len(b) == k and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(k - 1))
+        cells = pair_cells(read_len, win_len, pr, pw)
+        tot = [int(cells[p0:p1].sum()) for p0, p1 in b]
+        assert max(tot) <= 1.1 * (sum(tot) / k) + 1
+    assert sampled_bounds(read_len, win_len, pr[:0], pw[:0], None, None, 4) == [(0, 0)] * 4
