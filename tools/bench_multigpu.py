@@ -50,9 +50,10 @@ def main():
             for _ in range(a.steps):
                 r, ar = m.align(*args, **kw)
             dt = (time.perf_counter() - t0) / a.steps
+            # (the result arrays are views of the sharder's pinned buffers: read them before close())
+            sig = (int(r["score1"].astype(np.int64).sum()), int(r["ref_begin1"].astype(np.int64).sum()), int(r["cigar_len"].astype(np.int64).sum()))
         finally:
             m.close()
-        sig = (int(r["score1"].astype(np.int64).sum()), int(r["ref_begin1"].astype(np.int64).sum()), int(r["cigar_len"].astype(np.int64).sum()))
         if ref is None:
             ref = sig
         out["by_gpus"][str(n)] = {"gcups": b.cells() / dt / 1e9, "reads_per_s": a.pairs / dt, "ms": dt * 1e3, "identical_to_1gpu": sig == ref}
