@@ -195,6 +195,10 @@ int swb_download(swb_ctx* ctx, swb_result* results, uint32_t* cigar_arena,
 
 int swb_get_timing(const swb_ctx* ctx, swb_timing* out);
 
+/* Host helper for callers that stitch the outputs of several contexts (one per GPU) into one result array and one arena:
+ * adds `base` to cigar_off of every record that has a CIGAR. */
+void swb_rebase_cigar_offsets(swb_result* results, int64_t n, int64_t base);
+
 /* ------------------------------------------------------------------ */
 /* 3. CIGAR -> indel records                     */
 /* ------------------------------------------------------------------ */

@@ -1440,6 +1440,11 @@ extern "C" int swb_indels_from_cigars(swb_ctx* c, int32_t n, const uint32_t* cig
                       (const int32_t*)c->b_ind_qs.p, n, indel_off, indel_cnt, read_end, indels, cap, used);
 }
 
+extern "C" void swb_rebase_cigar_offsets(swb_result* results, int64_t n, int64_t base) {
+    if (!results || base == 0) return;
+    for (int64_t i = 0; i < n; ++i) if (results[i].cigar_len > 0) results[i].cigar_off += base;
+}
+
 extern "C" int swb_get_timing(const swb_ctx* c, swb_timing* out) {
     if (!c || !out) return -1;
     *out = c->tm;

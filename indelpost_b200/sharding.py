@@ -177,8 +177,7 @@ class MultiGpuAligner:
                 used = self.aligners[k].align_into(res[p0:p1], arena[abase[k]:abase[k + 1]], rb, ro, rl, wb, wo, wl, pr, pw,
                                                    s["gap_open"], s["gap_ext"], ref_beg=s["ref_beg"], ref_len=s["ref_len"], mask_len=s["mask_len"], **kw)
                 if used >= 0 and abase[k]:
-                    r = res[p0:p1]
-                    np.add(r["cigar_off"], abase[k], out=r["cigar_off"], where=r["cigar_len"] > 0)
+                    self.aligners[k].lib.swb_rebase_cigar_offsets(res[p0:p1].ctypes.data, p1 - p0, abase[k])      # in C, GIL released
                 return used
 
             used = list(self.pool.map(run, range(len(self.aligners))))
