@@ -198,6 +198,10 @@ int swb_get_timing(const swb_ctx* ctx, swb_timing* out);
 /* Host helper for callers that stitch the outputs of several contexts (one per GPU) into one result array and one arena:
  * adds `base` to cigar_off of every record that has a CIGAR. */
 void swb_rebase_cigar_offsets(swb_result* results, int64_t n, int64_t base);
+/* ... and uploads only the part of a sequence table a shard refers to: byte extent [extent[0], extent[1]) of entries
+ * off[0..n) / len[0..n) (shift = 0 one byte per base, 1 SWB_SEQ_PACKED4, 2 SWB_SEQ_PACKED2) and their offsets rebased to
+ * extent[0] in out_off.  Returns -1 on a negative offset or length. */
+int swb_slice_table(const int64_t* off, const int32_t* len, int64_t n, int shift, int64_t* out_off, int64_t* extent);
 
 /* ------------------------------------------------------------------ */
 /* 3. CIGAR -> indel records                     */

@@ -73,7 +73,7 @@ EXPORTS = (
     "ssw_init", "init_destroy", "ssw_align", "align_destroy",
     "swb_cigar_int_to_op", "swb_cigar_int_to_len", "swb_to_cigar_int",
     "swb_device_count", "swb_create", "swb_destroy", "swb_last_error",
-    "swb_align_batch", "swb_upload", "swb_compute", "swb_download", "swb_get_timing", "swb_rebase_cigar_offsets",
+    "swb_align_batch", "swb_upload", "swb_compute", "swb_download", "swb_get_timing", "swb_rebase_cigar_offsets", "swb_slice_table",
     "swb_host_alloc", "swb_host_free", "swb_encode_dna", "swb_pack_table", "swb_version",
     "swb_indels", "swb_indels_from_cigars",
 )
@@ -111,6 +111,8 @@ def load():
     lib.swb_get_timing.argtypes = [C.c_void_p, C.POINTER(SwbTiming)]
     lib.swb_rebase_cigar_offsets.restype = None
     lib.swb_rebase_cigar_offsets.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    lib.swb_slice_table.restype = C.c_int
+    lib.swb_slice_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.swb_indels.restype = C.c_int
     lib.swb_indels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.swb_indels_from_cigars.restype = C.c_int

@@ -1445,6 +1445,18 @@ extern "C" void swb_rebase_cigar_offsets(swb_result* results, int64_t n, int64_t
     for (int64_t i = 0; i < n; ++i) if (results[i].cigar_len > 0) results[i].cigar_off += base;
 }
 
+extern "C" int swb_slice_table(const int64_t* off, const int32_t* len, int64_t n, int shift, int64_t* out_off, int64_t* extent) {
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (off[i] < 0 || len[i] < 0) return -1;
+        lo = std::min<int64_t>(lo, off[i]); hi = std::max<int64_t>(hi, off[i] + seq_bytes(len[i], shift));
+    }
+    if (n <= 0) { lo = 0; hi = 0; }
+    for (int64_t i = 0; i < n; ++i) out_off[i] = off[i] - lo;
+    extent[0] = lo; extent[1] = hi;
+    return 0;
+}
+
 extern "C" int swb_get_timing(const swb_ctx* c, swb_timing* out) {
     if (!c || !out) return -1;
     *out = c->tm;

@@ -13,20 +13,24 @@ from __future__ import annotations
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Sequence, Tuple
 
+import ctypes as C
+
 import numpy as np
 
 from . import _lib as L
 
 
 def pair_cells(read_len, win_len, pair_read, pair_win, ref_len=None, ref_beg=None) -> np.ndarray:
-    """nominal DP cells of every pair: readLen * searched window length"""
-    rl = np.asarray(read_len, dtype=np.int64)[np.asarray(pair_read, dtype=np.int64).clip(0, max(len(read_len) - 1, 0))]
+    """nominal DP cells of every pair: readLen * searched window length (the tables are gathered as they are: no conversion pass
+    over a table that may be far longer than the pair list)"""
+    read_len, win_len = np.asarray(read_len), np.asarray(win_len)
+    rl = read_len[np.asarray(pair_read).clip(0, max(len(read_len) - 1, 0))].astype(np.int64)
     if ref_len is not None:
-        wl = np.asarray(ref_len, dtype=np.int64)
+        wl = np.asarray(ref_len).astype(np.int64)
     else:
-        wl = np.asarray(win_len, dtype=np.int64)[np.asarray(pair_win, dtype=np.int64).clip(0, max(len(win_len) - 1, 0))]
+        wl = win_len[np.asarray(pair_win).clip(0, max(len(win_len) - 1, 0))].astype(np.int64)
         if ref_beg is not None:
-            wl = wl - np.asarray(ref_beg, dtype=np.int64)
+            wl = wl - np.asarray(ref_beg).astype(np.int64)
     return rl * np.maximum(wl, 0)
 
 
@@ -68,24 +72,35 @@ def slice_pairs(arrs: dict, p0: int, p1: int) -> dict:
     return out
 
 
-def slice_table(blob, off, length, idx, seq_encoding: int = L.SWB_SEQ_CODES):
+def slice_table(blob, off, length, idx, seq_encoding: int = L.SWB_SEQ_CODES, scratch: dict = None, key: str = ""):
     """the part of a sequence table the (valid) indices in `idx` refer to: (blob slice, rebased offsets, lengths, first index).
     A shard uploads these instead of the whole table (each GPU gets only the sequences its pairs touch).  Entries are
     taken as an index RANGE [min, max], so out-of-range pair indices still fail inside the library like they do unsharded."""
     n = int(np.asarray(length).shape[0])
     idx = np.asarray(idx)
-    ok = idx[(idx >= 0) & (idx < n)]
-    if ok.shape[0] == 0 or n == 0:
+    if idx.shape[0] == 0 or n == 0:
         return blob[:0], np.zeros(0, np.int64), np.zeros(0, np.int32), 0
-    i0, i1 = int(ok.min()), int(ok.max()) + 1
-    o = np.asarray(off, dtype=np.int64)[i0:i1]
-    ln = np.asarray(length, dtype=np.int32)[i0:i1]
-    per = {L.SWB_SEQ_PACKED4: 2, L.SWB_SEQ_PACKED2: 4}.get(int(seq_encoding), 1)
-    nbytes = (ln.astype(np.int64) + per - 1) // per
-    if (o < 0).any() or (ln < 0).any():
-        return blob, np.asarray(off, dtype=np.int64)[i0:i1], ln, i0          # let the library report the bad table
-    b0, b1 = int(o.min()), int((o + nbytes).max())
-    return blob[b0:b1], np.ascontiguousarray(o - b0), np.ascontiguousarray(ln), i0
+    i0, i1 = int(idx.min()), int(idx.max()) + 1          # two reductions; the masked path only when an index is out of range
+    if i0 < 0 or i1 > n:
+        ok = idx[(idx >= 0) & (idx < n)]
+        if ok.shape[0] == 0:
+            return blob[:0], np.zeros(0, np.int64), np.zeros(0, np.int32), 0
+        i0, i1 = int(ok.min()), int(ok.max()) + 1
+    o = np.ascontiguousarray(np.asarray(off)[i0:i1], dtype=np.int64)
+    ln = np.ascontiguousarray(np.asarray(length)[i0:i1], dtype=np.int32)
+    shift = {L.SWB_SEQ_PACKED4: 1, L.SWB_SEQ_PACKED2: 2}.get(int(seq_encoding), 0)
+    if scratch is not None:                                  # reuse the rebased-offset array across calls (no first-touch page faults)
+        buf = scratch.get(key)
+        if buf is None or buf.shape[0] < i1 - i0:
+            buf = scratch[key] = np.empty(max(1024, (i1 - i0) + (i1 - i0) // 8), dtype=np.int64)
+        out_off = buf[: i1 - i0]
+    else:
+        out_off = np.empty(i1 - i0, dtype=np.int64)
+    ext = (C.c_int64 * 2)()
+    # one pass in C (GIL released): byte extent [b0, b1) of the entries and their offsets rebased to b0; -1: a negative offset / length
+    if L.load().swb_slice_table(o.ctypes.data, ln.ctypes.data, i1 - i0, shift, out_off.ctypes.data, ext) != 0:
+        return blob, o, ln, i0                                              # let the library report the bad table
+    return blob[int(ext[0]):int(ext[1])], out_off, ln, i0
 
 
 def sampled_bounds(read_len, win_len, pair_read, pair_win, ref_len, ref_beg, n_shards: int, stride: int = 16) -> List[Tuple[int, int]]:
@@ -121,6 +136,7 @@ class MultiGpuAligner:
         self.pool = ThreadPoolExecutor(max_workers=len(self.devices))
         self._res = None
         self._arena = None
+        self._scratch = [dict() for _ in self.devices]
 
     def close(self):
         for a in self.aligners:
@@ -170,8 +186,8 @@ class MultiGpuAligner:
                 s = slice_pairs_view(arrs, p0, p1)
                 # only the table slices this shard refers to travel to its GPU; pair indices are rebased by subtraction (an index
                 # outside the caller's tables stays outside the slice)
-                rb, ro, rl, r0 = slice_table(reads_a, read_off, read_len, s["pair_read"], enc)
-                wb, wo, wl, w0 = slice_table(windows_a, win_off, win_len, s["pair_win"], enc)
+                rb, ro, rl, r0 = slice_table(reads_a, read_off, read_len, s["pair_read"], enc, self._scratch[k], "r")
+                wb, wo, wl, w0 = slice_table(windows_a, win_off, win_len, s["pair_win"], enc, self._scratch[k], "w")
                 pr = s["pair_read"] - np.int32(r0) if r0 else s["pair_read"]
                 pw = s["pair_win"] - np.int32(w0) if w0 else s["pair_win"]
                 used = self.aligners[k].align_into(res[p0:p1], arena[abase[k]:abase[k + 1]], rb, ro, rl, wb, wo, wl, pr, pw,
