@@ -1140,7 +1140,7 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
             upper[q] = last ? cnt : (cnt & ~1);                  // lane pairs stay intact: an odd leftover waits for the next piece
             c->fastMaxCols[q] = hc[CNT_FAST_MAXCOLS + q];
             if (upper[q] > done[q]) any = true;
-            if (c->fastMaxCols[q] > SWB_FAST_SMEM_COLS) global = true;   // shared column scratch: slices must not overlap
+            if (c->fastMaxCols[q] > fast_smem_cols(q)) global = true;   // shared column scratch: slices must not overlap
         }
         if (any) {
             const bool second = (k & 1) && !global;

@@ -27,7 +27,7 @@
 #define SWB_BANDWARP_WARPS 4                   // warps (jobs) per block
 #define SWB_BANDWARP_MAXREF (32 * SWB_BANDWARP_C)
 
-__global__ void __launch_bounds__(32 * SWB_BANDWARP_WARPS)
+__global__ void __launch_bounds__(32 * SWB_BANDWARP_WARPS, 6)      // latency bound: 24 warps per SM (<= 80 registers) beat 16
 k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
 {
     constexpr int C = SWB_BANDWARP_C;

@@ -14,7 +14,12 @@
 #include "swb_common.cuh"
 
 #define SWB_MAX_DEVICES 64
-#define SWB_FAST_SMEM_COLS 1024     // fast path: windows longer than this keep their column bests in global memory
+// fast path: windows longer than this keep their column bests in global memory (written once per step by a group's last thread) and
+// only the 2-byte selectors in shared memory -- beyond it the per-column shared memory, not the registers, would set the occupancy
+// (four 128-thread blocks per SM: 8 groups x 10 bytes or 16 groups x 8 bytes per column)
+#define SWB_FAST_SMEM_COLS 704
+#define SWB_FAST8_SMEM_COLS 448
+static inline int fast_smem_cols(int fam) { return fam >= SWB_NBUCKETS ? SWB_FAST8_SMEM_COLS : SWB_FAST_SMEM_COLS; }
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;

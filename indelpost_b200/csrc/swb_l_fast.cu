@@ -10,10 +10,11 @@
 // fast-path launch geometry: groups of FAST_G threads, 10 bytes of shared memory per column per group
 // listBase: first of the SWB_NBUCKETS job lists this launch family reads; verifyX >= 0: overflow-verification launch (SW forward only)
 template <int R, int DIR, int SW, int G = FAST_G>
-static int launch_fast_one(swb_ctx* c, int listBase, int bucket, int maxCols, int firstPair, int upperBoundPairs, cudaStream_t st, int verifyX = -1) {
+static int launch_fast_one(swb_ctx* c, int listBase, int bucket, int maxCols, int firstPair, int upperBoundPairs, cudaStream_t st, int verifyX = -1, bool forceSmem = false) {
     SwbDev& d = c->d;
     const int colAlloc = (std::max(maxCols, 8) + 7) & ~7;                     // longest window among this bucket's pairs
-    const bool globalCols = colAlloc > SWB_FAST_SMEM_COLS;
+    // (forceSmem: a launch that may run beside another one of its family must not use the shared global column scratch)
+    const bool globalCols = !forceSmem && colAlloc > (G == 8 ? SWB_FAST8_SMEM_COLS : SWB_FAST_SMEM_COLS);
     const size_t per = (size_t)colAlloc * (globalCols ? 2 : (G == 8 ? 8 : 10));
     // long windows: the global column-best scratch is bounded, the bucket is served in slices of the job list
     int slicePairs = upperBoundPairs - firstPair;
@@ -51,16 +52,16 @@ static int launch_fast_one(swb_ctx* c, int listBase, int bucket, int maxCols, in
 }
 
 template <int DIR, int SW>
-static int launch_fast_bucket(swb_ctx* c, int listBase, int b, int rowsBucket, int maxCols, int f, int n, cudaStream_t st, int verifyX = -1) {
+static int launch_fast_bucket(swb_ctx* c, int listBase, int b, int rowsBucket, int maxCols, int f, int n, cudaStream_t st, int verifyX = -1, bool forceSmem = false) {
     switch (rowsBucket) {      // R = 2 * (bucket + 1) rows per thread
-        case 0: return launch_fast_one<2, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
-        case 1: return launch_fast_one<4, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
-        case 2: return launch_fast_one<6, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
-        case 3: return launch_fast_one<8, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
-        case 4: return launch_fast_one<10, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
-        case 5: return launch_fast_one<12, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
-        case 6: return launch_fast_one<14, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
-        case 7: return launch_fast_one<16, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX);
+        case 0: return launch_fast_one<2, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
+        case 1: return launch_fast_one<4, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
+        case 2: return launch_fast_one<6, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
+        case 3: return launch_fast_one<8, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
+        case 4: return launch_fast_one<10, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
+        case 5: return launch_fast_one<12, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
+        case 6: return launch_fast_one<14, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
+        case 7: return launch_fast_one<16, DIR, SW>(c, listBase, b, maxCols, f, n, st, verifyX, forceSmem);
     }
     return -1;
 }
@@ -114,9 +115,9 @@ int swb_launch_sandwich_verify(swb_ctx* c, int listSlot, int xSlot, int upperBou
     int maxCols = 0;
     for (int f = 0; f < SWB_NFWD; ++f) maxCols = std::max(maxCols, c->fastMaxCols[f]);
     const int lp16 = (std::min(d.max_rlen, 32 * SWB_NBUCKETS) + 15) & ~15;
-    if (maxCols > SWB_FAST_SMEM_COLS || d.max_rlen > 32 * SWB_NBUCKETS || upperBound <= 0) return 1;
+    if (maxCols > 1024 || d.max_rlen > 32 * SWB_NBUCKETS || upperBound <= 0) return 1;      // 10 KB of shared memory per lane pair at most
     const int rb = std::max(0, (lp16 + 31) / 32 - 1);
-    return launch_fast_bucket<0, 1>(c, listSlot, 0, rb, maxCols, 0, upperBound, st, xSlot);
+    return launch_fast_bucket<0, 1>(c, listSlot, 0, rb, maxCols, 0, upperBound, st, xSlot, /*forceSmem=*/true);      // two verifications may run side by side
 }
 #else
 int swb_launch_sandwich_rev(swb_ctx* c, const int* counts, cudaStream_t st) { return launch_fast_range<1, 1>(c, LIST_SW_REV, nullptr, counts, st); }
