@@ -17,6 +17,15 @@
 // doubled band is still one of the two kinds, and jobs the other band kernels widened into this kernel's range arrive with their
 // width and running maximum in t_bw / t_best.  Anything else -- the walk leaving the band, a doubled band that slides and is wider
 // than the matrix, scratch exhausted -- hands the job to the literal kernel with the state it needs to carry on exactly.
+//
+// Q = 8 (round 2): bands of half-width 25 .. 51 keep only 4-5 of a warp's 32 column blocks busy, so FOUR alignments share a warp,
+// eight lanes each.  The 16-column blocks are dealt to the lanes cyclically (block b -> lane b mod 8) and block b still works on
+// row s - b at step s, so the pipeline is the same; a band of 2W + 1 <= 103 columns touches at most seven consecutive blocks in a
+// row, so at any step a lane has at most one block in the band (its registers are reset when it moves on to block b + 8: the cells
+// above a block's first band row are out of band, i.e. zero).  A lane stays with a block for one step after the block's last column
+// has left the band, because that step hands H(i-1, last column) -- the diagonal neighbour of the band's first cell in row i -- to
+// the next lane.  Only regular bands (refLen >= 2W + 2) come here; the direction words keep the column layout, so the traceback is
+// the same walk.
 #pragma once
 #include "swb_common.cuh"
 #include "swb_band.cuh"
@@ -26,12 +35,31 @@
 #define SWB_BANDWARP_ROWWORDS 64               // direction words per row (column layout)
 #define SWB_BANDWARP_WARPS 4                   // warps (jobs) per block
 #define SWB_BANDWARP_MAXREF (32 * SWB_BANDWARP_C)
+#define SWB_BANDQ_MAXW 51                     // widest half-width of the eight-lanes-per-alignment schedule (see below)
 
+// jobs whose band fits the eight-lane schedule
+__device__ __forceinline__ bool bandq_ok(int bw, int refLen) { return bw <= SWB_BANDQ_MAXW && refLen >= 2 * bw + 2; }
+
+// splits a warp-kernel job list by schedule: eight lanes per alignment (listQ) / a whole warp (listW)
+__global__ void k_bandwarp_split(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int listQ, int listW)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= njobs) return;
+    const int p = jobs[t];
+    const swb_result& r = d.res[p];
+    const int refLen = r.ref_end1 - r.ref_begin1 + 1, readLen = r.read_end1 - r.read_begin1 + 1;
+    const int dl = refLen - readLen;
+    const int W = d.t_bw[p] != 0 ? d.t_bw[p] : (dl < 0 ? -dl : dl) + 1;
+    const int dst = bandq_ok(W, refLen) ? listQ : listW;
+    list_push(d.list[dst], d.counters + dst, p);
+}
+
+template <int Q>
 __global__ void __launch_bounds__(32 * SWB_BANDWARP_WARPS, 6)      // latency bound: 24 warps per SM (<= 80 registers) beat 16
-k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
+k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobsMax, const int32_t* __restrict__ njobs_ptr, int nextBase)
 {
     constexpr int C = SWB_BANDWARP_C;
-    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int JPW = 32 / Q;                            // alignments per warp
     __shared__ unsigned long long s_rowTab[8];            // per read base: its scores against every window base, 8 x int8
     if (threadIdx.x < 8) {
         unsigned long long tab = 0;
@@ -39,10 +67,15 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
         s_rowTab[threadIdx.x] = tab;
     }
     __syncthreads();
-    __shared__ uint8_t s_read[SWB_BANDWARP_WARPS][SWB_BANDREG_MAXROWS];      // the job's read codes: one shared-memory load per row
+    __shared__ uint8_t s_read[SWB_BANDWARP_WARPS * JPW][SWB_BANDREG_MAXROWS];      // the job's read codes: one shared-memory load per row
+    const int njobs = njobs_ptr ? min(njobsMax, *njobs_ptr) : njobsMax;
     const int lane = threadIdx.x & 31;
-    const int job = blockIdx.x * SWB_BANDWARP_WARPS + (threadIdx.x >> 5);
-    if (job >= njobs) return;                              // whole warp
+    const int ql = lane % Q;                               // lane within the alignment's group
+    const int grp = lane / Q;
+    const unsigned GM = Q == 32 ? 0xffffffffu : (((1u << Q) - 1u) << (grp * Q));
+    const int slot = (threadIdx.x >> 5) * JPW + grp;
+    const int job = (blockIdx.x * SWB_BANDWARP_WARPS + (threadIdx.x >> 5)) * JPW + grp;
+    if (job >= njobs) return;                              // whole group
     const int p = jobs[job];
     swb_result& r = d.res[p];
     const int refLen = r.ref_end1 - r.ref_begin1 + 1;      // ssw.c:897-899
@@ -57,57 +90,82 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
     const int8_t* ref = d.windows + d.p_woff[p] + r.ref_begin1;
     const int8_t* read = d.reads + d.p_roff[p] + r.read_begin1;
 
-    auto to_literal = [&](int bw, int best) {              // lane 0 only
+    auto to_literal = [&](int bw, int best) {              // group lane 0 only
         d.t_bw[p] = bw; d.t_best[p] = best;
         const int c = band_class(bw, refLen);
         list_push(d.list[nextBase + c], d.counters + nextBase + c, p);
     };
+    auto to_next = [&](int bw, int best) {                 // group lane 0 only: warp-per-alignment kernel of the next round, else literal
+        d.t_bw[p] = bw; d.t_best[p] = best;
+        requeue_band(d, nextBase, p, bw, refLen, readLen, r);
+    };
 
-    for (int k = lane; k < readLen; k += 32) s_read[threadIdx.x >> 5][k] = (uint8_t)(read[k] & 7);
-    __syncwarp();
-    const uint8_t* rd = s_read[threadIdx.x >> 5];
+    for (int k = ql; k < readLen; k += Q) s_read[slot][k] = (uint8_t)(read[k] & 7);
+    __syncwarp(GM);
+    const uint8_t* rd = s_read[slot];
 
     // scratch for the direction words (column layout)
     unsigned long long off = 0;
     const long long need = (long long)SWB_BANDWARP_ROWWORDS * 4 * readLen;
-    if (lane == 0) off = atomicAdd(&d.bump[0], (unsigned long long)need);
-    off = __shfl_sync(FULL, off, 0);
+    if (ql == 0) off = atomicAdd(&d.bump[0], (unsigned long long)need);
+    off = __shfl_sync(GM, off, grp * Q);
     if ((long long)off + need > d.band_cap) {
-        if (lane == 0) { atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1); to_literal(W, 0); }
+        if (ql == 0) { atomicAdd(d.counters + CNT_BAND_OVERFLOW, 1); to_literal(W, 0); }
         return;
     }
     uint32_t* dir = reinterpret_cast<uint32_t*>(d.band + off);
 
-    // this lane's window columns as PRMT selectors (byte rc of the score row, sign-extended), 16 x 4 bits packed would need
-    // unpacking per cell: keep the codes, 4 per register
-    const int j0 = lane * C;
+    // a block's window columns as codes, 4 per register (PRMT selectors are rebuilt per cell: bandreg_sel)
     uint32_t codes[C / 4];
+    auto load_codes = [&](int b) {
+        const int j0 = b * C;
 #pragma unroll
-    for (int q = 0; q < C / 4; ++q) {
-        uint32_t w = 0;
+        for (int q = 0; q < C / 4; ++q) {
+            uint32_t w = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { const int j = j0 + 4 * q + k; if (j < refLen) w |= (uint32_t)(ref[j] & 7) << (8 * k); }
-        codes[q] = w;
-    }
+            for (int k = 0; k < 4; ++k) { const int j = j0 + 4 * q + k; if (j < refLen) w |= (uint32_t)(ref[j] & 7) << (8 * k); }
+            codes[q] = w;
+        }
+    };
+    if constexpr (Q == 32) load_codes(ql);
+    const int nblocks = (refLen + C - 1) / C;
 
     int bestIn;                                            // running maximum before the current width's pass
     for (;;) {                                             // band doubling, ssw.c:612-669 (the direction words do not depend on W)
     bestIn = best;
     // a band that never slides and is wider than the matrix: the last column loses its upper neighbour (see above)
-    const bool cutLast = refLen < 2 * W + 2;
+    const bool cutLast = Q == 32 && refLen < 2 * W + 2;
     int Hp[C], Ev[C];                                      // H of the previous row / vertical-gap state, per own column
 #pragma unroll
     for (int k = 0; k < C; ++k) { Hp[k] = 0; Ev[k] = 0; }
-    int outH = 0, outF = 0, outDiag = 0;                   // what lane+1 receives at the next step
-    const int nsteps = readLen + 31;
+    int cb = Q == 32 ? ql : -1;                            // block this lane's registers hold
+    int outH = 0, outF = 0, outDiag = 0;                   // what the next lane receives at the next step
+    const int nsteps = readLen + (Q == 32 ? 31 : nblocks);
     for (int s = 0; s < nsteps; ++s) {
-        int inH = __shfl_up_sync(FULL, outH, 1), inF = __shfl_up_sync(FULL, outF, 1), inDiag = __shfl_up_sync(FULL, outDiag, 1);
-        if (lane == 0) { inH = 0; inF = 0; inDiag = 0; }
-        const int i = s - lane;                            // the row this lane is on
-        if (i < 0 || i >= readLen) continue;
+        // left neighbour = the lane of block b - 1 (cyclic for Q = 8)
+        const int src = grp * Q + (ql + Q - 1) % Q;
+        int inH = __shfl_sync(GM, outH, src), inF = __shfl_sync(GM, outF, src), inDiag = __shfl_sync(GM, outDiag, src);
+        int b;
+        if constexpr (Q == 32) b = ql;
+        else {
+            // the (at most eight) consecutive blocks that can hold band cells of their row at this step, plus the one-step hand-over
+            const int t17 = s - W - 16;
+            const int lo = t17 >= 0 ? (t17 + 16) / 17 : -((-t17) / 17);      // ceil(t17 / 17)
+            b = lo + (((ql - lo) % Q) + Q) % Q;
+        }
+        if (b == 0) { inH = 0; inF = 0; inDiag = 0; }
+        const int i = s - b;                               // the row block b is on
+        if (b < 0 || b >= nblocks || i < 0 || i >= readLen) { if (Q != 32) { outH = 0; outF = 0; outDiag = 0; } continue; }
+        if (Q != 32 && b != cb) {                          // moved on to the next block of this lane: nothing above it is in the band yet
+#pragma unroll
+            for (int k = 0; k < C; ++k) { Hp[k] = 0; Ev[k] = 0; }
+            load_codes(b);
+            cb = b;
+        }
+        const int j0 = b * C;
         const int beg = i - W > 0 ? i - W : 0;             // band of row i (ssw.c:630-631)
         const int end = i + W < refLen - 1 ? i + W : refLen - 1;
-        outDiag = Hp[C - 1];                               // row i-1's value of this lane's last column: diagonal neighbour of lane+1's first
+        outDiag = Hp[C - 1];                               // row i-1's value of this block's last column: diagonal neighbour of the next block's first
         if (end < j0 || beg >= j0 + C) { outH = 0; outF = 0; continue; }
         const unsigned long long tab = s_rowTab[rd[i]];
         const uint32_t tabLo = (uint32_t)tab, tabHi = (uint32_t)(tab >> 32);
@@ -135,23 +193,24 @@ k_band_warp(SwbDev d, const int32_t* __restrict__ jobs, int njobs, int nextBase)
         const bool lastIn = j0 + C - 1 >= beg && j0 + C - 1 <= end;
         outH = lastIn ? hLeft : 0; outF = lastIn ? f : 0;
 #pragma unroll
-        for (int q = 0; q < C / 8; ++q) dir[(size_t)i * SWB_BANDWARP_ROWWORDS + lane * (C / 8) + q] = words[q];
+        for (int q = 0; q < C / 8; ++q) dir[(size_t)i * SWB_BANDWARP_ROWWORDS + b * (C / 8) + q] = words[q];
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
-    __syncwarp();
+    for (int o = Q / 2; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(GM, best, o, Q));
+    __syncwarp(GM);
     {
         long long cells = 0;                               // statistics: cells of the band inside the matrix
-        for (int i = lane; i < readLen; i += 32) cells += min(i + W, refLen - 1) - max(i - W, 0) + 1;
+        for (int i = ql; i < readLen; i += Q) cells += min(i + W, refLen - 1) - max(i - W, 0) + 1;
         warp_count(d.counters + CNT_CELLS_BAND, (unsigned long long)cells);
     }
     if (!(best < score && W * 2 <= len)) break;            // ssw.c:668-669
-    W *= 2;                                                // widen and redo: here while the band is still one of the two kinds
-    if (!(refLen >= 2 * W + 2 || W >= readLen - 1)) { if (lane == 0) to_literal(W, best); return; }
+    W *= 2;                                                // widen and redo: here while the band still fits this schedule
+    if (Q == 32) { if (!(refLen >= 2 * W + 2 || W >= readLen - 1)) { if (ql == 0) to_literal(W, best); return; } }
+    else if (!bandq_ok(W, refLen)) { if (ql == 0) to_next(W, best); return; }
     }
-    if (lane != 0) return;
+    if (ql != 0) return;
 
-    // ---- traceback (ssw.c:672-751), lane 0, column layout; the word of the row above is fetched one step ahead ------------
+    // ---- traceback (ssw.c:672-751), group lane 0, column layout -----------------------------------------------------------
     __threadfence_block();
     BandOps ops; ops.n = 0;
     int i = readLen - 1, j = refLen - 1, e = 0, state = 2, op = 0, prev_op = 0;

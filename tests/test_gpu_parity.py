@@ -436,6 +436,20 @@ def test_gpu_streamed_batch_ascii_subranges_and_masks(monkeypatch):
     T.compare(r2[sub].copy(), a2, ro, ao, what="streamed (ASCII, sub-ranges, masks) vs oracle")
 
 
+def test_gpu_mid_width_bands_eight_lanes_per_alignment():
+    """banded_sw with half-widths of 25-51 (indels of 24-50 bases, and narrower bands that double into that range): the warp band
+    kernel's eight-lanes-per-alignment schedule (swb_bandwarp.cuh, Q = 8), with band doubling in place, under indelPost's penalty grid"""
+    from gpuutil import gpu_align
+
+    for seed, kw in ((71, dict(read_len=(150, 250), win_len=(500, 700), max_indel=50, grid=True)),
+                     (72, dict(read_len=(120, 250), win_len=(400, 512), max_indel=40, grid=True, low_complexity=0.2, sub_rate=0.03)),
+                     (73, dict(read_len=250, win_len=1000, max_indel=30, go=3, ge=1))):
+        b = T.make_pairs(5000, seed=seed, **kw)
+        rg, ag, tm = gpu_align(b)
+        ro, ao = T.oracle_parallel(b, threads=min(16, os.cpu_count() or 1))
+        T.compare(rg, ag, ro, ao, what=f"mid-width bands seed {seed} vs oracle")
+
+
 def test_gpu_sandwich_certificate_adversarial():
     """the sandwich sweep (swb_fast.cuh, SW = 1) certifies 8-bit-final results whose scores pass 128+go+ge; on a set built so that
     the 8-bit pass really deviates from Gotoh (insertions opened around score 128) every result must still equal the oracle's --
