@@ -230,6 +230,8 @@ extern "C" swb_ctx* swb_create(int device) {
     mkEvent(&c->ev_rev_fork);
     for (int i = 0; i < SWB_BANDW_MAX; ++i) { mkStream(&c->bandw_stream[i], prMid); mkEvent(&c->ev_bandw_join[i]); }
     for (int i = 0; i < SWB_NREVB; ++i) { mkStream(&c->rev_stream[i], prMid); mkEvent(&c->ev_rev_join[i]); }
+    for (int i = 0; i < SWB_NSIDE; ++i) { mkStream(&c->side_stream[i], prMid); mkEvent(&c->ev_side_join[i]); }
+    mkEvent(&c->ev_side_split);
     mkEvent(&c->ev_fork); mkEvent(&c->ev_join); mkEvent(&c->ev_join2);
     chk(cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t)), "cudaMallocHost");
     for (int i = 0; i < 2; ++i) { chk(cudaMallocHost((void**)&c->h_snap[i], SWB_NCOUNTERS * sizeof(int32_t)), "cudaMallocHost"); mkEvent(&c->ev_snap[i]); }
@@ -274,6 +276,8 @@ static void destroy_ctx(swb_ctx* c) {
     dS(c->copy_stream); dE(c->ev_copy);
     dE(c->ev_rev_fork);
     for (int i = 0; i < SWB_NREVB; ++i) { dS(c->rev_stream[i]); dE(c->ev_rev_join[i]); }
+    for (int i = 0; i < SWB_NSIDE; ++i) { dS(c->side_stream[i]); dE(c->ev_side_join[i]); }
+    dE(c->ev_side_split);
     for (int i = 0; i < SWB_BANDW_MAX; ++i) { dS(c->bandw_stream[i]); dE(c->ev_bandw_join[i]); }
     dS(c->stream2); dE(c->ev_fork); dE(c->ev_join); dE(c->ev_join2);
     cudaGetLastError();
@@ -607,17 +611,19 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         // the wider classes go to the side stream so their long, latency-bound threads overlap the bulk
         const bool side = njobs[4] > 0 || njobs[5] > 0 || njobs[6] > 0 || njobs[7] > 0 || nWarp > 0;
         if (side) {
+            // every wide kernel is a chain of dependent steps as long as its longest job, whatever the job count: one side stream each,
+            // so that a round costs the longest of them and not their sum
             CUDA_TRY(c, cudaEventRecord(c->ev_fork, s));
-            CUDA_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            for (int k = 0; k < SWB_NSIDE; ++k) CUDA_TRY(c, cudaStreamWaitEvent(c->side_stream[k], c->ev_fork, 0));
             if (nWarp > 0) {
-                if (swb_launch_band_warp(c, baseWarp, nWarp, nxt, c->stream2)) return -1;
-                CUDA_TRY(c, cudaMemsetAsync(d.counters + baseWarp, 0, 4, c->stream2));      // list consumed
+                if (swb_launch_band_warp(c, baseWarp, nWarp, nxt, c->side_stream[0], c->side_stream[1], c->ev_side_split)) return -1;
+                CUDA_TRY(c, cudaMemsetAsync(d.counters + baseWarp, 0, 4, c->side_stream[0]));      // list consumed (by the split kernel)
             }
-            if (swb_launch_band(c, 0, (njobs[7] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, cur, 7, 7, nxt, c->stream2)) return -1;
-            if (swb_launch_band(c, 4, (njobs[6] + SWB_BAND_HUGE_THREADS - 1) / SWB_BAND_HUGE_THREADS, cur, 6, 6, nxt, c->stream2)) return -1;
-            if (swb_launch_band(c, 3, (njobs[5] + SWB_BAND_WIDE_THREADS - 1) / SWB_BAND_WIDE_THREADS, cur, 5, 5, nxt, c->stream2)) return -1;
-            if (swb_launch_band(c, 2, (njobs[4] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, cur, 4, 4, nxt, c->stream2)) return -1;
-            CUDA_TRY(c, cudaEventRecord(c->ev_join, c->stream2));
+            if (swb_launch_band(c, 0, (njobs[7] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS, cur, 7, 7, nxt, c->side_stream[2])) return -1;
+            if (swb_launch_band(c, 4, (njobs[6] + SWB_BAND_HUGE_THREADS - 1) / SWB_BAND_HUGE_THREADS, cur, 6, 6, nxt, c->side_stream[3])) return -1;
+            if (swb_launch_band(c, 3, (njobs[5] + SWB_BAND_WIDE_THREADS - 1) / SWB_BAND_WIDE_THREADS, cur, 5, 5, nxt, c->side_stream[4])) return -1;
+            if (swb_launch_band(c, 2, (njobs[4] + SWB_BAND_MID_THREADS - 1) / SWB_BAND_MID_THREADS, cur, 4, 4, nxt, c->side_stream[5])) return -1;
+            for (int k = 0; k < SWB_NSIDE; ++k) CUDA_TRY(c, cudaEventRecord(c->ev_side_join[k], c->side_stream[k]));
         }
         // widened jobs: the register-band kernels double once in place (up to half-width 14); what doubles beyond that but still fits a
         // register band (16 .. 24) is re-run in the next round by the kernel of the doubled width, whose latency is half the literal
@@ -627,7 +633,7 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
         int blocks = 0;
         for (int k = 0; k < SWB_BAND_CLS_MID; ++k) blocks += (njobs[k] + SWB_BAND_THREADS - 1) / SWB_BAND_THREADS;
         if (swb_launch_band(c, 1, blocks, cur, 0, SWB_BAND_CLS_MID - 1, nxt, s)) return -1;
-        if (side) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));
+        if (side) for (int k = 0; k < SWB_NSIDE; ++k) CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_side_join[k], 0));
         if (join_band_reg(c)) return -1;
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "band")) return -1;
@@ -1281,7 +1287,9 @@ extern "C" int swb_align_batch(swb_ctx* c, const swb_batch* b, swb_result* resul
         // drain every stream before the caller gets its buffers back, and leave no half-built batch behind
         auto drain = [&]() {
             cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->bulk_stream); cudaStreamSynchronize(c->bulk_stream2);
-            cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4); cudaStreamSynchronize(c->stream);
+            cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4);
+            for (int k = 0; k < SWB_NSIDE; ++k) cudaStreamSynchronize(c->side_stream[k]);
+            cudaStreamSynchronize(c->stream);
             cudaGetLastError();
         };
         int rc = align_batch_streamed(c, b, results, cigar_arena, cigar_cap, cigar_used, getenv("SWB200_ALWAYS_SCAN") != nullptr);

@@ -14,6 +14,7 @@
 #include "swb_common.cuh"
 
 #define SWB_MAX_DEVICES 64
+#define SWB_NSIDE 6
 // fast path: windows longer than this keep their column bests in global memory (written once per step by a group's last thread) and
 // only the 2-byte selectors in shared memory -- beyond it the per-column shared memory, not the registers, would set the occupancy
 // (four 128-thread blocks per SM: 8 groups x 10 bytes or 16 groups x 8 bytes per column)
@@ -47,6 +48,7 @@ struct swb_ctx {
     cudaStream_t bulk_stream2 = nullptr;                                    // second one: consecutive forward slices of the streamed one-shot path overlap their tails
     cudaEvent_t ev_bulk_fork, ev_bulk_join, ev_bulk_join2, ev_piece;
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_fork3;
+    cudaStream_t side_stream[SWB_NSIDE] = {}; cudaEvent_t ev_side_join[SWB_NSIDE], ev_side_split;      // wide band kernels of a traceback round, one stream each
     cudaStream_t rev_stream[SWB_NREVB];                                     // banded reverse pass: one stream per band class
     cudaEvent_t ev_rev_fork, ev_rev_join[SWB_NREVB];
     cudaStream_t bandw_stream[SWB_BANDW_MAX]; cudaEvent_t ev_bandw_join[SWB_BANDW_MAX];   // register-band kernels: one stream per half-width
@@ -114,5 +116,5 @@ int swb_launch_band_reg_lo(swb_ctx* c, int w, int listSlot, int njobs, int nextB
 int swb_launch_band_reg_hi(swb_ctx* c, int w, int listSlot, int njobs, int nextBase, int nextBaseW, int resume, cudaStream_t st);
 // swb_l_band.cu: the literal banded_sw kernel (which = 0: rows in global memory, 1: local, 2: mid, 3: wide, 4: huge) and the warp-per-alignment one
 int swb_launch_band(swb_ctx* c, int which, int blocks, int listBase, int firstClass, int lastClass, int nextBase, cudaStream_t st);
-int swb_launch_band_warp(swb_ctx* c, int listSlot, int njobs, int nextBase, cudaStream_t st);
+int swb_launch_band_warp(swb_ctx* c, int listSlot, int njobs, int nextBase, cudaStream_t st, cudaStream_t st2, cudaEvent_t evSplit);
 cudaError_t swb_band_set_attrs();

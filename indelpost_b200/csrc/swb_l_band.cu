@@ -20,14 +20,17 @@ int swb_launch_band(swb_ctx* c, int which, int blocks, int listBase, int firstCl
 
 // wide-band jobs: split by schedule on the device (no host round trip: both kernels are launched against the list's length as an
 // upper bound and read their real job counts), eight lanes per alignment for half-widths up to SWB_BANDQ_MAXW, a whole warp otherwise
-int swb_launch_band_warp(swb_ctx* c, int listSlot, int njobs, int nextBase, cudaStream_t st) {
+int swb_launch_band_warp(swb_ctx* c, int listSlot, int njobs, int nextBase, cudaStream_t st, cudaStream_t st2, cudaEvent_t evSplit) {
     const SwbDev& d = c->d;
     if (njobs <= 0) return 0;
     CUDA_TRY(c, cudaMemsetAsync(d.counters + LIST_BANDQ_TMP, 0, 8, st));      // LIST_BANDQ_TMP, LIST_BANDW_TMP
     k_bandwarp_split<<<(njobs + 127) / 128, 128, 0, st>>>(d, d.list[listSlot], njobs, LIST_BANDQ_TMP, LIST_BANDW_TMP);
+    CUDA_TRY(c, cudaEventRecord(evSplit, st));
+    CUDA_TRY(c, cudaStreamWaitEvent(st2, evSplit, 0));
     constexpr int JQ = SWB_BANDWARP_WARPS * 4;
+    // the two schedules side by side (st: eight lanes per alignment, st2: a warp per alignment)
     k_band_warp<8><<<(njobs + JQ - 1) / JQ, 32 * SWB_BANDWARP_WARPS, 0, st>>>(d, d.list[LIST_BANDQ_TMP], njobs, d.counters + LIST_BANDQ_TMP, nextBase);
-    k_band_warp<32><<<(njobs + SWB_BANDWARP_WARPS - 1) / SWB_BANDWARP_WARPS, 32 * SWB_BANDWARP_WARPS, 0, st>>>(d, d.list[LIST_BANDW_TMP], njobs, d.counters + LIST_BANDW_TMP, nextBase);
+    k_band_warp<32><<<(njobs + SWB_BANDWARP_WARPS - 1) / SWB_BANDWARP_WARPS, 32 * SWB_BANDWARP_WARPS, 0, st2>>>(d, d.list[LIST_BANDW_TMP], njobs, d.counters + LIST_BANDW_TMP, nextBase);
     c->tm.n_launches += 3;
     CUDA_TRY(c, cudaGetLastError());
     return 0;
