@@ -382,9 +382,11 @@ static void set_batch_scalars(swb_ctx* c, const swb_batch* b, const ChunkView& v
     for (int i = 0; i < b->n * b->n; ++i) { mx = std::max<int>(mx, b->mat[i]); if (b->mat[i] > 7 || b->mat[i] < -7) small = false; }
     d.max_score = mx;
     { const char* o = getenv("SWB200_OPT"); d.opt = o ? atoi(o) : 0; }
-    // small batches are latency bound: one traceback phase (the two-phase split only pays once the traceback of the bulk is
-    // long enough to hide the overflow verification of the pairs traced back first; measured crossover ~200 k pairs)
-    if (b->n_pairs < 200000) d.opt |= 32;
+    // one traceback phase.  (The two-phase split -- pairs that can fail the overflow certificate traced back first, so that their
+    // exact 8-bit verification hides behind the bulk of the traceback -- paid while that verification took ~3 ms; the sandwich
+    // lower bound settles it in ~0.1 ms now and the second phase only costs a second low-occupancy tail: 4.35 -> 3.79 ms on
+    // config 2.  SWB200_TWO_PHASE=1 brings it back.)
+    if (!getenv("SWB200_TWO_PHASE")) d.opt |= 32;
     d.one = 1;
     { bool f8 = true; for (int i = 0; i < b->n * b->n; ++i) if (b->mat[i] > 3 || b->mat[i] < -4) f8 = false;
       d.fast8_ok = (f8 && !getenv("SWB200_NO_G8")) ? 1 : 0; }
