@@ -232,6 +232,8 @@ extern "C" swb_ctx* swb_create(int device) {
     for (int i = 0; i < SWB_NREVB; ++i) { mkStream(&c->rev_stream[i], prMid); mkEvent(&c->ev_rev_join[i]); }
     for (int i = 0; i < SWB_NSIDE; ++i) { mkStream(&c->side_stream[i], prMid); mkEvent(&c->ev_side_join[i]); }
     mkEvent(&c->ev_side_split);
+    for (int i = 0; i < SWB_MAX_PARTS; ++i) mkEvent(&c->ev_part_fwd[i]);
+    chk(cudaEventCreate(&c->ev_fwd_end), "cudaEventCreate");
     mkEvent(&c->ev_fork); mkEvent(&c->ev_join); mkEvent(&c->ev_join2);
     chk(cudaMallocHost((void**)&c->h_counters, SWB_NCOUNTERS * sizeof(int32_t)), "cudaMallocHost");
     for (int i = 0; i < 2; ++i) { chk(cudaMallocHost((void**)&c->h_snap[i], SWB_NCOUNTERS * sizeof(int32_t)), "cudaMallocHost"); mkEvent(&c->ev_snap[i]); }
@@ -278,6 +280,8 @@ static void destroy_ctx(swb_ctx* c) {
     for (int i = 0; i < SWB_NREVB; ++i) { dS(c->rev_stream[i]); dE(c->ev_rev_join[i]); }
     for (int i = 0; i < SWB_NSIDE; ++i) { dS(c->side_stream[i]); dE(c->ev_side_join[i]); }
     dE(c->ev_side_split);
+    for (int i = 0; i < SWB_MAX_PARTS; ++i) dE(c->ev_part_fwd[i]);
+    dE(c->ev_fwd_end);
     for (int i = 0; i < SWB_BANDW_MAX; ++i) { dS(c->bandw_stream[i]); dE(c->ev_bandw_join[i]); }
     dS(c->stream2); dE(c->ev_fork); dE(c->ev_join); dE(c->ev_join2);
     cudaGetLastError();
@@ -490,24 +494,25 @@ static void bucket_upper_bounds(const swb_ctx* c, const int* counts, int* ub) {
     for (int j = 0; j < SWB_NF8; ++j) for (int b = map8[j][0]; b <= map8[j][1]; ++b) ub[b] += counts[SWB_NBUCKETS + j];
 }
 
-template <int DIR>
-static int launch_fast(swb_ctx* c, const int* counts) {
-    // the forward sweeps go to the low-priority stream (see swb_create), the reverse ones stay on the main stream
-    if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_fork, c->stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_fork, 0)); }
-    int rc;
+// forward sweeps of the current part on the low-priority stream (see swb_create); the caller orders that stream behind the prepare
+// kernels and records the event the part's tail waits for
+static int launch_fast_fwd(swb_ctx* c, const int* counts) {
     int ub[SWB_NBUCKETS];
     bucket_upper_bounds(c, counts, ub);
-    if (DIR == 0) {
-        rc = swb_launch_fast8_range_fwd(c, nullptr, counts, c->bulk_stream);
-        if (!rc) rc = swb_launch_fast_range_fwd(c, nullptr, counts, c->bulk_stream);
-        if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_fwd(c, ub, c->bulk_stream);
-    } else {
-        rc = swb_launch_fast_range_rev(c, nullptr, ub, c->stream);
-        if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_rev(c, ub, c->stream);
-    }
-    if (DIR == 0) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join, c->bulk_stream)); CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_bulk_join, 0)); }
+    int rc = swb_launch_fast8_range_fwd(c, nullptr, counts, c->bulk_stream);
+    if (!rc) rc = swb_launch_fast_range_fwd(c, nullptr, counts, c->bulk_stream);
+    if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_fwd(c, ub, c->bulk_stream);
     if (rc) return rc;
-    return stage_check(c, DIR ? "fast rev" : "fast fwd");
+    return stage_check(c, "fast fwd");
+}
+// reverse sweeps (wavefront) of the current part on the main stream
+static int launch_fast_rev(swb_ctx* c, const int* counts) {
+    int ub[SWB_NBUCKETS];
+    bucket_upper_bounds(c, counts, ub);
+    int rc = swb_launch_fast_range_rev(c, nullptr, ub, c->stream);
+    if (!rc && !(c->d.opt & 128)) rc = swb_launch_sandwich_rev(c, ub, c->stream);
+    if (rc) return rc;
+    return stage_check(c, "fast rev");
 }
 
 // the main stream waits for the band classes (after it has queued the wavefront sweep of the remaining pairs)
@@ -523,8 +528,9 @@ static int certify_and_verify_async(swb_ctx* c, int verifyList, int upperBound, 
     SwbDev& d = c->d;
     cudaStream_t s = c->stream;
     cudaStream_t vs = which ? c->stream4 : c->stream3;       // the two verifications of a compute run side by side (each is a long, serial kernel over a handful of pairs)
-    const size_t np = (size_t)d.n_pairs;
-    k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, verifyList);
+    const Part& pt = c->parts[c->cur_part];
+    const size_t np = (size_t)std::max<int32_t>(pt.p1 - pt.p0, 1);
+    k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, pt.p0, pt.p1, verifyList);
     c->tm.n_launches++;
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaEventRecord(c->ev_fork3, s));
@@ -692,6 +698,14 @@ static int compute_setup_lens(swb_ctx* c) {
     return 0;
 }
 
+// make part k's job lists and counters the current ones (for the launches queued from now on)
+static void use_part(swb_ctx* c, int k) {
+    const Part& pt = c->parts[k];
+    for (int i = 0; i < SWB_NLISTS; ++i) c->d.list[i] = pt.lists + (size_t)i * pt.perList;
+    c->d.counters = pt.counters;
+    c->cur_part = k;
+}
+
 // workspace for the batch described by c->d (grow-only buffers), counters cleared, start event recorded
 static int compute_setup(swb_ctx* c) {
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -711,9 +725,28 @@ static int compute_setup(swb_ctx* c) {
     CUDA_TRY(c, c->b_state.ensure(np + 16));      d.p_state = (uint8_t*)c->b_state.p;
     CUDA_TRY(c, c->b_csafe.ensure(np * 4 + 16));  d.p_csafe = (int32_t*)c->b_csafe.p;
     CUDA_TRY(c, c->b_res.ensure(np * sizeof(swb_result) + 16)); d.res = (swb_result*)c->b_res.p;
-    CUDA_TRY(c, c->b_lists.ensure((size_t)SWB_NLISTS * (np + 32) * 4));
-    for (int i = 0; i < SWB_NLISTS; ++i) d.list[i] = (int32_t*)c->b_lists.p + (size_t)i * (np + 32);
-    CUDA_TRY(c, c->b_counters.ensure(SWB_NCOUNTERS * 4)); d.counters = (int32_t*)c->b_counters.p;
+    // Parts: a large batch is cut into contiguous pair ranges with a job-list / counter set each, so that the latency-bound stages
+    // (reverse, traceback) of one part run beside the forward sweep of the next instead of behind the whole sweep.  Kernels get SwbDev
+    // by value, so a launch keeps the set that was current when it was queued (use_part).
+    {
+        const char* e = getenv("SWB200_PARTS");
+        int want = c->force_parts ? c->force_parts : e ? atoi(e) : (np >= 1500000 ? 4 : np >= 700000 ? 3 : np >= 300000 ? 2 : 1);
+        c->nparts = std::max(1, std::min(want, SWB_MAX_PARTS));
+        size_t perList = 0;
+        for (int k = 0; k < c->nparts; ++k) {
+            Part& pt = c->parts[k];
+            pt.p0 = (int32_t)((np * k / c->nparts) & ~(size_t)1); pt.p1 = k + 1 == c->nparts ? (int32_t)np : (int32_t)((np * (k + 1) / c->nparts) & ~(size_t)1);
+            perList = std::max(perList, (size_t)(pt.p1 - pt.p0) + 32);
+        }
+        CUDA_TRY(c, c->b_lists.ensure((size_t)c->nparts * SWB_NLISTS * perList * 4));
+        CUDA_TRY(c, c->b_counters.ensure((size_t)c->nparts * SWB_NCOUNTERS * 4));
+        for (int k = 0; k < c->nparts; ++k) {
+            c->parts[k].lists = (int32_t*)c->b_lists.p + (size_t)k * SWB_NLISTS * perList;
+            c->parts[k].perList = perList;
+            c->parts[k].counters = (int32_t*)c->b_counters.p + (size_t)k * SWB_NCOUNTERS;
+        }
+        use_part(c, 0);
+    }
     CUDA_TRY(c, c->b_bump.ensure(2 * 8));         d.bump = (unsigned long long*)c->b_bump.p;
     CUDA_TRY(c, c->b_tbw.ensure(np * 4 + 16));    d.t_bw = (int32_t*)c->b_tbw.p;
     CUDA_TRY(c, c->b_tbest.ensure(np * 4 + 16));  d.t_best = (int32_t*)c->b_tbest.p;
@@ -723,20 +756,25 @@ static int compute_setup(swb_ctx* c) {
 
     cudaStream_t s = c->stream;
     TR(c, "compute_begin");
-    CUDA_TRY(c, cudaMemsetAsync(d.counters, 0, SWB_NCOUNTERS * 4, s));
+    CUDA_TRY(c, cudaMemsetAsync(c->b_counters.p, 0, (size_t)c->nparts * SWB_NCOUNTERS * 4, s));
     CUDA_TRY(c, cudaMemsetAsync(d.bump, 0, 16, s));
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_START], s));
+    tm.ms_band_round0 = tm.ms_band_rest = tm.ms_certify = 0; tm.band_rounds = 0;
+    tm.n_sw_certified = tm.n_sw_rejected = tm.n_sw_verified = 0;
     return 0;
 }
 
 static int swb_compute_impl(swb_ctx* c);
 
-// everything after the fast-path forward sweeps: exact forward passes, reverse, banded traceback, certificate, timings
-static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
+// everything after the fast-path forward sweeps of the CURRENT part (pairs [pt.p0, pt.p1)): exact forward passes, reverse, banded
+// traceback, certificate; its stage times and statistics are added to c->tm.  fwdDone: recorded behind the part's forward sweeps.
+static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal, cudaEvent_t fwdDone) {
     SwbDev& d = c->d;
-    const size_t np = (size_t)d.n_pairs;
+    const Part& pt = c->parts[c->cur_part];
+    const size_t np = (size_t)(pt.p1 - pt.p0);               // upper bound of every list of this part
     swb_timing& tm = c->tm;
     cudaStream_t s = c->stream;
+    if (fwdDone) CUDA_TRY(c, cudaStreamWaitEvent(s, fwdDone, 0));
     // ---- exact striped emulation, forward and reverse, on a side stream: these kernels serve a minority (pairs the fast path cannot
     //      decide) but each is a long chain of dependent steps whatever the count, so they run beside the reverse pass of the fast-path
     //      pairs instead of in front of and behind it.  Their reverse passes read LIST_BYTE_REV / LIST_WORD_REV, which only they fill;
@@ -753,7 +791,7 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
 
     // ---- reverse (ssw.c:875-891) ----------------------------------------------------------------
     if (swb_launch_rev_band(c, nFastTotal)) return -1;          // the pairs the forward sweep put into a band class
-    if (launch_fast<1>(c, fwdCounts)) return -1;            // the rest; rev bucket sizes are bounded by the fwd ones
+    if (launch_fast_rev(c, fwdCounts)) return -1;           // the rest; rev bucket sizes are bounded by the fwd ones
     if (join_rev_band(c, nFastTotal)) return -1;
     CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_x_join, 0));
     // fast-path pairs handed to the exact reverse pass (rare: no column reached score1, or the sandwich rejected the reverse sweep):
@@ -773,7 +811,6 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     //          pass over them; their exact 8-bit verification is launched on the side stream (grid sized by an upper
     //          bound, the kernel reads the real count) while
     // phase 2: the bulk of the traceback runs on the main stream.
-    tm.band_rounds = 0;
     c->verify_pending = 0;
     const bool certify = nFastTotal > 0 && d.score_size == 2;
     CUDA_TRY(c, cudaMemsetAsync(d.counters + CNT_BYTE_REV, 0, 4, s));      // consumed by the reverse stage; reused by the verification
@@ -794,7 +831,7 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     // ---- leftovers: certificate for the pairs finished in re-queue rounds (rarely fails), byte-mode redo for verified
     //      pairs whose 8-bit pass did not overflow (never observed in practice)
     if (certify) {
-        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, 0, (int32_t)np, LIST_BYTE_FWD);
+        k_certify_rest<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(d, pt.p0, pt.p1, LIST_BYTE_FWD);
         tm.n_launches++;
         CUDA_TRY(c, cudaGetLastError());
         if (stage_check(c, "certify")) return -1;
@@ -812,32 +849,57 @@ static int compute_tail(swb_ctx* c, const int* fwdCounts, int nFastTotal) {
     if (read_counters(c)) return -1;
     if (c->h_counters[CNT_CIGAR_OVERFLOW] > 0) {
         // device arena too small: grow to the exact requirement and redo (rare; the default is 16 ops/pair)
-        size_t need = (size_t)c->h_bump[1] + 1024;
+        // (sized from what this part's pairs needed so far, scaled to the whole batch; the redo repeats if that is still short)
+        size_t need = (size_t)((double)c->h_bump[1] * (double)d.n_pairs / (double)std::max<int32_t>(1, pt.p1)) + (size_t)c->h_bump[1] / 4 + 1024;
+        cudaStreamSynchronize(c->bulk_stream); cudaStreamSynchronize(c->bulk_stream2);      // later parts' sweeps still run
         CUDA_TRY(c, c->b_cigar.ensure(need * 4));
-        return swb_compute_impl(c);
+        const int rc = swb_compute_impl(c);                 // the whole batch again, every part, from the device-resident inputs
+        return rc ? rc : 1;                                 // 1: the step is complete, the caller must not go on with its own parts
     }
+    // this part's stage times (its reverse / traceback stages overlap the forward sweep of the next part, so the stages of a
+    // multi-part step do not add up to ms_total) and statistics
+    {
+        float t = 0;
+        cudaEventElapsedTime(&t, c->ev[EV_FWD], c->ev[EV_REV]); tm.ms_reverse += t;
+        cudaEventElapsedTime(&t, c->ev[EV_REV], c->ev[EV_BAND]); tm.ms_traceback += t;
+        cudaEventElapsedTime(&t, c->ev[EV_REV], c->ev[EV_BAND_R0]); tm.ms_band_round0 += t;
+        cudaEventElapsedTime(&t, c->ev[EV_BAND_R0], c->ev[EV_BAND_ALL]); tm.ms_band_rest += t;
+        cudaEventElapsedTime(&t, c->ev[EV_BAND_ALL], c->ev[EV_BAND]); tm.ms_certify += t;
+        int64_t v = 0;
+        memcpy(&v, c->h_counters + CNT_CELLS_FWD, 8); tm.cells_forward += v;
+        memcpy(&v, c->h_counters + CNT_CELLS_REV, 8); tm.cells_reverse += v;
+        memcpy(&v, c->h_counters + CNT_CELLS_BAND, 8); tm.cells_band += v;
+        tm.n_fast += c->h_counters[CNT_FAST_DONE] - c->h_counters[CNT_VERIFY_BYTE];
+        tm.n_exact += c->h_counters[CNT_EXACT_JOBS];
+        tm.n_sw_certified += c->h_counters[CNT_SW_CERTIFIED]; tm.n_sw_rejected += c->h_counters[CNT_SW_REJECTED]; tm.n_sw_verified += c->h_counters[CNT_SW_VERIFIED];
+    }
+    return 0;
+}
+
+// after the last part's tail: whole-step times
+static int compute_finish(swb_ctx* c) {
+    swb_timing& tm = c->tm;
     cudaEventElapsedTime(&tm.ms_prepare, c->ev[EV_START], c->ev[EV_PREP]);
-    cudaEventElapsedTime(&tm.ms_forward, c->ev[EV_PREP], c->ev[EV_FWD]);
-    cudaEventElapsedTime(&tm.ms_reverse, c->ev[EV_FWD], c->ev[EV_REV]);
-    cudaEventElapsedTime(&tm.ms_traceback, c->ev[EV_REV], c->ev[EV_BAND]);
+    cudaEventElapsedTime(&tm.ms_forward, c->ev[EV_PREP], c->ev_fwd_end);      // first forward launch .. end of the last part's sweeps
     cudaEventElapsedTime(&tm.ms_total, c->ev[EV_START], c->ev[EV_BAND]);
-    cudaEventElapsedTime(&tm.ms_band_round0, c->ev[EV_REV], c->ev[EV_BAND_R0]);
-    cudaEventElapsedTime(&tm.ms_band_rest, c->ev[EV_BAND_R0], c->ev[EV_BAND_ALL]);
-    cudaEventElapsedTime(&tm.ms_certify, c->ev[EV_BAND_ALL], c->ev[EV_BAND]);
-    memcpy(&tm.cells_forward, c->h_counters + CNT_CELLS_FWD, 8);
-    memcpy(&tm.cells_reverse, c->h_counters + CNT_CELLS_REV, 8);
-    memcpy(&tm.cells_band, c->h_counters + CNT_CELLS_BAND, 8);
-    tm.n_fast = c->h_counters[CNT_FAST_DONE] - c->h_counters[CNT_VERIFY_BYTE];
-    tm.n_exact = c->h_counters[CNT_EXACT_JOBS];
-    tm.n_sw_certified = c->h_counters[CNT_SW_CERTIFIED]; tm.n_sw_rejected = c->h_counters[CNT_SW_REJECTED]; tm.n_sw_verified = c->h_counters[CNT_SW_VERIFIED];
     c->computed = true;
     TR(c, "compute_end");
     return 0;
 }
 
+// counters of the current part (already in c->h_counters) -> forward list lengths per family, sandwich list lengths, column maxima
+static int part_counts(swb_ctx* c, const int32_t* hc, int* fwdCounts) {
+    int nFast = 0;
+    for (int f = 0; f < SWB_NFWD; ++f) {
+        fwdCounts[f] = hc[f < SWB_NBUCKETS ? CNT_FAST_FWD + f : CNT_F8_FWD + (f - SWB_NBUCKETS)];
+        nFast += fwdCounts[f]; c->fastMaxCols[f] = std::max(c->fastMaxCols[f], hc[CNT_FAST_MAXCOLS + f]);
+    }
+    for (int b = 0; b < SWB_NBUCKETS; ++b) { c->swCounts[b] = hc[CNT_SW_FWD + b]; nFast += c->swCounts[b]; }
+    return nFast;
+}
+
 static int swb_compute_impl(swb_ctx* c) {
     if (compute_setup(c)) return -1;
-    SwbDev& d = c->d;
     const size_t np = (size_t)d.n_pairs;
     swb_timing& tm = c->tm;
     cudaStream_t s = c->stream;
@@ -845,23 +907,58 @@ static int swb_compute_impl(swb_ctx* c) {
     if (launch_validate(c, d.reads, d.read_off, d.read_len, d.n_reads, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_rbad.p, d.rbyte_base, s)) return -1;
     if (launch_validate(c, d.windows, d.win_off, d.win_len, d.n_windows, d.seq_encoding == SWB_SEQ_ASCII, (uint8_t*)c->b_wbad.p, d.wbyte_base, s)) return -1;
     d.seq_encoding = SWB_SEQ_CODES;                         // tables are codes from now on (repeat computes must not re-encode)
-    if (np) { k_prepare<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, 0, (int32_t)np); tm.n_launches++; }
+    for (int k = 0; k < c->nparts; ++k) {
+        const Part& pt = c->parts[k];
+        if (pt.p1 <= pt.p0) continue;
+        use_part(c, k);
+        k_prepare<<<(unsigned)((pt.p1 - pt.p0 + 255) / 256), 256, 0, s>>>(d, (uint8_t*)c->b_rbad.p, (uint8_t*)c->b_wbad.p, pt.p0, pt.p1);
+        tm.n_launches++;
+    }
     CUDA_TRY(c, cudaGetLastError());
     if (stage_check(c, "prepare")) return -1;
     CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
-    if (read_counters(c)) return -1;                        // bucket sizes for the fast path launches
-    int fwdCounts[SWB_NFWD]; int nFastTotal = 0;
-    for (int f = 0; f < SWB_NFWD; ++f) {
-        fwdCounts[f] = c->h_counters[f < SWB_NBUCKETS ? CNT_FAST_FWD + f : CNT_F8_FWD + (f - SWB_NBUCKETS)];
-        nFastTotal += fwdCounts[f]; c->fastMaxCols[f] = c->h_counters[CNT_FAST_MAXCOLS + f];
+    // list lengths of every part in one round trip
+    std::vector<int32_t> hc((size_t)c->nparts * SWB_NCOUNTERS);
+    CUDA_TRY(c, cudaMemcpyAsync(hc.data(), c->b_counters.p, hc.size() * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    for (int f = 0; f < SWB_NFWD; ++f) c->fastMaxCols[f] = 0;
+    int fwdCounts[SWB_MAX_PARTS][SWB_NFWD], swc[SWB_MAX_PARTS][SWB_NBUCKETS], nFast[SWB_MAX_PARTS];
+    bool global = false;
+    for (int k = 0; k < c->nparts; ++k) {
+        nFast[k] = part_counts(c, hc.data() + (size_t)k * SWB_NCOUNTERS, fwdCounts[k]);
+        memcpy(swc[k], c->swCounts, sizeof c->swCounts);
     }
-    for (int b = 0; b < SWB_NBUCKETS; ++b) { c->swCounts[b] = c->h_counters[CNT_SW_FWD + b]; nFastTotal += c->swCounts[b]; }
+    for (int f = 0; f < SWB_NFWD; ++f) if (c->fastMaxCols[f] > fast_smem_cols(f)) global = true;
+    if (global && c->nparts > 1) {
+        // long windows keep their column bests in ONE global scratch: a part's reverse sweep must not run beside the next part's forward
+        // sweep.  Redo as a single part (rare shape for a large batch; costs one more prepare).
+        c->force_parts = 1;
+        const int rc = swb_compute_impl(c);
+        c->force_parts = 0;
+        return rc;
+    }
 
-    // ---- forward (ssw.c:842-860) --------------------------------------------------------------------
+    // ---- forward (ssw.c:842-860), part after part on the low-priority stream; then the tails, each behind its own part's sweeps ----
     //   fast path: one 16-bit Gotoh sweep per pair (pairs it cannot decide are appended to the exact lists)
     //   exact path: 8-bit pass, then 16-bit pass for the pairs that overflowed
-    if (launch_fast<0>(c, fwdCounts)) return -1;
-    return compute_tail(c, fwdCounts, nFastTotal);
+    CUDA_TRY(c, cudaEventRecord(c->ev_bulk_fork, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_fork, 0));
+    for (int k = 0; k < c->nparts; ++k) {
+        use_part(c, k);
+        memcpy(c->swCounts, swc[k], sizeof c->swCounts);
+        if (launch_fast_fwd(c, fwdCounts[k])) return -1;
+        CUDA_TRY(c, cudaEventRecord(c->ev_part_fwd[k], c->bulk_stream));
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_fwd_end, c->bulk_stream));
+    for (int k = 0; k < c->nparts; ++k) {
+        use_part(c, k);
+        memcpy(c->swCounts, swc[k], sizeof c->swCounts);
+        if (k > 0 && c->parts[k].p1 <= c->parts[k].p0) continue;
+        const int rc = compute_tail(c, fwdCounts[k], nFast[k], c->ev_part_fwd[k]);
+        if (rc < 0) return rc;
+        if (rc == 1) return 0;                              // redone with a larger CIGAR arena
+    }
+    return compute_finish(c);
 }
 
 extern "C" int swb_compute(swb_ctx* c) {
@@ -1094,15 +1191,26 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
         }
         for (int64_t szk : sizes) if (szk > 0) bounds.push_back(std::min<int64_t>(bounds.back() + szk, (int64_t)np));
         bounds.back() = (int64_t)np;
+        // a piece belongs to one part (compute_setup): cut the pieces that straddle a part boundary
+        for (int k = 1; k < c->nparts; ++k) {
+            const int64_t cut = c->parts[k].p0;
+            auto it = std::lower_bound(bounds.begin(), bounds.end(), cut);
+            if (it == bounds.end() || *it != cut) bounds.insert(it, cut);
+        }
     }
     const int npieces = (int)bounds.size() - 1;
+    auto part_of = [&](int k) { int q = 0; while (q + 1 < c->nparts && bounds[k] >= c->parts[q + 1].p0) ++q; return q; };
 
-    int done[SWB_NFWD] = {};
-    bool used2 = false, used1 = false;
+    int done[SWB_MAX_PARTS][SWB_NFWD] = {};
+    int swc[SWB_MAX_PARTS][SWB_NBUCKETS] = {};
+    int nFastPart[SWB_MAX_PARTS] = {};
+    for (int q = 0; q < SWB_NFWD; ++q) c->fastMaxCols[q] = 0;
+    bool used2 = false, serialize = false;
     // The host runs one piece ahead: piece k+1's copies and prepare kernel are queued before it waits for piece k's
     // fast-list lengths, so PCIe never idles during a host round trip.
     auto enqueue_piece = [&](int k) -> int {
         const int32_t p0 = (int32_t)bounds[k], p1 = (int32_t)bounds[k + 1];
+        use_part(c, part_of(k));                             // the piece's prepare kernel and counter snapshot go to its part's set
         int32_t rmax = -1, wmax = -1;
         for (int32_t p = p0; p < p1; ++p) {
             const int32_t r = b->pair_read[p], w = b->pair_win[p];
@@ -1138,45 +1246,54 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     if (npieces > 0) { const int e0 = enqueue_piece(0); if (e0) return e0; }
     for (int k = 0; k < npieces; ++k) {
         const bool last = k + 1 == npieces;
+        const int pk = part_of(k);
+        const bool lastOfPart = last || part_of(k + 1) != pk;
         if (!last) { const int e1 = enqueue_piece(k + 1); if (e1) return e1; }
         CUDA_TRY(c, cudaEventSynchronize(c->ev_snap[k & 1]));
         TR(c, "piece_ready");
+        use_part(c, pk);
         const int32_t* hc = c->h_snap[k & 1];
         int upper[SWB_NFWD]; bool any = false, global = false;
         for (int q = 0; q < SWB_NFWD; ++q) {
             const int cnt = hc[q < SWB_NBUCKETS ? CNT_FAST_FWD + q : CNT_F8_FWD + (q - SWB_NBUCKETS)];
-            upper[q] = last ? cnt : (cnt & ~1);                  // lane pairs stay intact: an odd leftover waits for the next piece
-            c->fastMaxCols[q] = hc[CNT_FAST_MAXCOLS + q];
-            if (upper[q] > done[q]) any = true;
+            upper[q] = lastOfPart ? cnt : (cnt & ~1);            // lane pairs stay intact: an odd leftover waits for the part's next piece
+            c->fastMaxCols[q] = std::max(c->fastMaxCols[q], hc[CNT_FAST_MAXCOLS + q]);
+            if (upper[q] > done[pk][q]) any = true;
             if (c->fastMaxCols[q] > fast_smem_cols(q)) global = true;   // shared column scratch: slices must not overlap
         }
+        if (global) serialize = true;                        // ... and no part's reverse sweep may run beside another part's forward sweep
         if (any) {
             const bool second = (k & 1) && !global;
             cudaStream_t st = second ? c->bulk_stream2 : c->bulk_stream;
             CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_snap[k & 1], 0));
-            if (swb_launch_fast8_range_fwd(c, done, upper, st)) return -1;
-            if (swb_launch_fast_range_fwd(c, done, upper, st)) return -1;
-            (second ? used2 : used1) = true;
-            for (int q = 0; q < SWB_NFWD; ++q) done[q] = upper[q];
+            if (swb_launch_fast8_range_fwd(c, done[pk], upper, st)) return -1;
+            if (swb_launch_fast_range_fwd(c, done[pk], upper, st)) return -1;
+            if (second) used2 = true;
+            for (int q = 0; q < SWB_NFWD; ++q) done[pk][q] = upper[q];
+        }
+        if (lastOfPart) {
+            // the part's sandwich lists are swept once, after its last piece: behind every plain forward slice of the part (they
+            // append to the sandwich lists) and the piece's prepare kernel
+            int nSw = 0, nFwdPlain = 0;
+            for (int q = 0; q < SWB_NBUCKETS; ++q) { swc[pk][q] = hc[CNT_SW_FWD + q]; nSw += swc[pk][q]; }
+            for (int q = 0; q < SWB_NFWD; ++q) nFwdPlain += done[pk][q];
+            nFastPart[pk] = nSw + nFwdPlain;
+            memcpy(c->swCounts, swc[pk], sizeof c->swCounts);
+            CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_snap[k & 1], 0));
+            if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_join2, 0)); }
+            if ((nSw > 0 || nFwdPlain > 0) && !(d.opt & 128)) {
+                int ub[SWB_NBUCKETS];
+                bucket_upper_bounds(c, done[pk], ub);
+                if (swb_launch_sandwich_fwd(c, ub, c->bulk_stream)) return -1;
+            }
+            CUDA_TRY(c, cudaEventRecord(c->ev_part_fwd[pk], c->bulk_stream));
         }
     }
-    if (npieces == 0) { CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], s)); CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s)); }
-    // the sandwich lists are swept once, after the last piece (short reads: a minority of a mixed batch)
-    int nSw = 0;
-    for (int q = 0; q < SWB_NBUCKETS; ++q) { c->swCounts[q] = npieces > 0 ? c->h_snap[(npieces - 1) & 1][CNT_SW_FWD + q] : 0; nSw += c->swCounts[q]; }
-    int nFwdPlain = 0;
-    for (int q = 0; q < SWB_NFWD; ++q) nFwdPlain += done[q];
-    if ((nSw > 0 || nFwdPlain > 0) && npieces > 0 && !(d.opt & 128)) {
-        // after every plain forward slice (they append to the sandwich lists) and the last piece's prepare
-        int ub[SWB_NBUCKETS];
-        bucket_upper_bounds(c, done, ub);
-        CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_snap[(npieces - 1) & 1], 0));
-        if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(c->bulk_stream, c->ev_bulk_join2, 0)); }
-        if (swb_launch_sandwich_fwd(c, ub, c->bulk_stream)) return -1;
-        used1 = true;
+    if (npieces == 0) {
+        CUDA_TRY(c, cudaEventRecord(c->ev[EV_H2D1], s)); CUDA_TRY(c, cudaEventRecord(c->ev[EV_PREP], s));
+        for (int k = 0; k < c->nparts; ++k) CUDA_TRY(c, cudaEventRecord(c->ev_part_fwd[k], c->bulk_stream));
     }
-    if (used1) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join, c->bulk_stream)); CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_bulk_join, 0)); }
-    if (used2) { CUDA_TRY(c, cudaEventRecord(c->ev_bulk_join2, c->bulk_stream2)); CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_bulk_join2, 0)); }
+    CUDA_TRY(c, cudaEventRecord(c->ev_fwd_end, c->bulk_stream));
     // only the table entries some pair refers to are resident: a later swb_compute on this context must not touch the rest
     d.n_reads = tr.front; d.n_windows = tw.front;
     if (!scan) {                                            // lengths as seen by the pieces (every entry a pair refers to)
@@ -1185,11 +1302,18 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     }
     d.seq_encoding = SWB_SEQ_CODES;
     c->have_batch = true;
-    int nFastTotal = 0;
-    for (int q = 0; q < SWB_NFWD; ++q) nFastTotal += done[q];
-    for (int q = 0; q < SWB_NBUCKETS; ++q) nFastTotal += c->swCounts[q];
     TR(c, "pieces_enqueued");
-    if (compute_tail(c, done, nFastTotal)) return -1;
+    // the tails, part after part, each behind its own part's forward sweeps (behind all of them if the column scratch is shared)
+    bool redone = false;
+    for (int k = 0; k < c->nparts; ++k) {
+        if (k > 0 && c->parts[k].p1 <= c->parts[k].p0) continue;
+        use_part(c, k);
+        memcpy(c->swCounts, swc[k], sizeof c->swCounts);
+        const int rc = compute_tail(c, done[k], nFastPart[k], c->ev_part_fwd[serialize ? c->nparts - 1 : k]);
+        if (rc < 0) return rc;
+        if (rc == 1) { redone = true; break; }              // redone with a larger CIGAR arena
+    }
+    if (!redone && compute_finish(c)) return -1;
     return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);
 }
 

@@ -38,6 +38,10 @@ struct DevBuf {
 
 enum { EV_START = 0, EV_PREP, EV_FWD, EV_REV, EV_BAND, EV_H2D0, EV_H2D1, EV_D2H0, EV_D2H1, EV_BAND_R0, EV_BAND_ALL, EV_COUNT };
 
+#define SWB_MAX_PARTS 4
+// a contiguous range of the batch's pairs with its own job lists and counters (see compute_setup)
+struct Part { int32_t p0 = 0, p1 = 0; int32_t* lists = nullptr; size_t perList = 0; int32_t* counters = nullptr; };
+
 struct swb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main; wide band classes; overflow verification
@@ -64,6 +68,8 @@ struct swb_ctx {
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
     DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe, b_fastcols;
     DevBuf b_ind_off, b_ind_cnt, b_ind_rend, b_ind_recs, b_ind_misc, b_ind_cig, b_ind_coff, b_ind_clen, b_ind_rs, b_ind_qs;   // indel extraction
+    Part parts[SWB_MAX_PARTS]; int nparts = 1, cur_part = 0, force_parts = 0;
+    cudaEvent_t ev_part_fwd[SWB_MAX_PARTS] = {}; cudaEvent_t ev_fwd_end = nullptr;      // behind a part's forward sweeps / behind the last one (timed)
     int fastMaxCols[SWB_NFWD] = {};              // longest window per forward list family
     int swCounts[SWB_NBUCKETS] = {};             // sandwich forward list lengths of the current batch
     int32_t* h_counters = nullptr;              // pinned mirror of counters
