@@ -730,7 +730,10 @@ static int compute_setup(swb_ctx* c) {
     // by value, so a launch keeps the set that was current when it was queued (use_part).
     {
         const char* e = getenv("SWB200_PARTS");
-        int want = c->force_parts ? c->force_parts : e ? atoi(e) : (np >= 1500000 ? 4 : np >= 700000 ? 3 : np >= 300000 ? 2 : 1);
+        // Default ONE part.  Measured on config 2 (1 M pairs): 18.2 ms with one part, 19.6 / 21.1 / 22.3 ms with 2 / 3 / 4 -- the forward
+        // sweep keeps every register of an SM busy, so the latency-bound kernels of the other part wait for block slots and then
+        // share the issue ports; their stages take 8-11 ms instead of 5.7.  SWB200_PARTS=k keeps the experiment reachable.
+        int want = c->force_parts ? c->force_parts : e ? atoi(e) : 1;
         c->nparts = std::max(1, std::min(want, SWB_MAX_PARTS));
         size_t perList = 0;
         for (int k = 0; k < c->nparts; ++k) {
@@ -900,7 +903,7 @@ static int part_counts(swb_ctx* c, const int32_t* hc, int* fwdCounts) {
 
 static int swb_compute_impl(swb_ctx* c) {
     if (compute_setup(c)) return -1;
-    const size_t np = (size_t)d.n_pairs;
+    SwbDev& d = c->d;
     swb_timing& tm = c->tm;
     cudaStream_t s = c->stream;
     // ---- prepare ------------------------------------------------------------------------------
