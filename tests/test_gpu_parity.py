@@ -395,6 +395,26 @@ def test_gpu_pipelined_batch_equals_single_pass(monkeypatch):
     T.compare(r2[sub].copy(), a2, ro, ao, what="streamed vs oracle")
 
 
+def test_gpu_parts_equal_single_part(monkeypatch):
+    """SWB200_PARTS=k cuts a batch into pair ranges with their own job lists (a part's reverse / traceback stages run beside the next
+    part's forward sweep): same results as one part, in the resident path and in the streamed one-shot path (pieces cut at the
+    part boundaries, 2-bit packed tables)"""
+    from gpuutil import gpu_align
+
+    b = T.make_pairs(9001, (40, 150), (150, 400), seed=91, grid=True, n_rate=0.004, max_indel=30)
+    r0, a0, _ = gpu_align(b)
+    monkeypatch.setenv("SWB200_PARTS", "3")
+    r1, a1, _ = gpu_align(b)
+    T.compare(r1, a1, r0, a0, what="3 parts vs 1 part (single pass)")
+    big = T.make_pairs_fast(300001, 120, 300, seed=14, reads_per_window=30)
+    monkeypatch.setenv("SWB200_PARTS", "4")
+    r2, a2, _ = gpu_align(_packed(big, 2))
+    monkeypatch.delenv("SWB200_PARTS")
+    monkeypatch.setenv("SWB200_NO_PIPELINE", "1")
+    r3, a3, _ = gpu_align(big)
+    T.compare(r2, a2, r3, a3, what="4 parts streamed vs 1 part single pass")
+
+
 def test_gpu_streamed_batch_unordered_tables(monkeypatch):
     """streamed path with pairs that refer to the sequence tables in random order (the upload frontier jumps to the
     end with the first piece) and ASCII input"""
