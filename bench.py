@@ -394,7 +394,7 @@ def pipeline_measurements():
 
         out = {}
         for cfg, loci in (("cfg1", 4), ("cfg3", 12)):
-            out[cfg] = BP.measure(cfg, loci, workers=1)
+            out[cfg] = BP.measure(cfg, loci, workers=1, repeats=2)
         # the same at equal host parallelism: W worker processes in both arms (the wave arm's workers share GPU 0)
         w = max(2, min(8, host_cores() // 2))
         out["cfg3_%d_workers" % w] = BP.measure("cfg3", 6 * w, workers=w)

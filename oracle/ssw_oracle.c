@@ -8,9 +8,10 @@
  * Parity pinning: the reference ships no tests or golden vectors
  * (SURVEY.md §4), so this restatement is pinned against the reference's own
  * ssw.c compiled unmodified into oracle/_ref/libssw_ref.so (oracle/Makefile)
- * — tests/test_oracle_vs_ref.py fuzzes the two against each other when the
+ * — tests/test_oracle.py fuzzes the two against each other when the
  * _ref library is present, and tests/golden/ holds vectors generated from
- * _ref by tests/golden/make_golden.py.
+ * _ref by tests/golden/make_golden.py; at pipeline level tests/test_pipeline_parity.py
+ * plugs it into the unmodified reference pipeline (oracle/_ref_pipeline).
  *
  * It is a scalar, intrinsic-free restatement: each SSE2 register of the
  * reference becomes an array of W lanes (W=16 unsigned bytes in "byte mode",
