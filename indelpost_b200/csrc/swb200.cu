@@ -98,6 +98,25 @@ __global__ void k_unpack(const uint8_t* __restrict__ src, int8_t* __restrict__ d
     else *reinterpret_cast<uint32_t*>(dst + 4 * i) = (b & 3u) | (((b >> 2) & 3u) << 8) | (((b >> 4) & 3u) << 16) | ((b >> 6) << 24);
 }
 
+// early download (one-shot path): the pairs re-queued by the first traceback round -- the only ones whose records still change --
+// are remembered in LIST_LATE (one block per source list) ...
+__global__ void k_collect_late(SwbDev d, int nxtBase, int nxtW, int warpNxt)
+{
+    const int b = blockIdx.x;
+    const int src = b < SWB_NBANDCLASS ? nxtBase + b : b < SWB_NBANDCLASS + SWB_BANDW_MAX ? nxtW + (b - SWB_NBANDCLASS) : warpNxt;
+    const int n = d.counters[src];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = n > 0 ? atomicAdd(d.counters + LIST_LATE, n) : 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d.list[LIST_LATE][base + i] = d.list[src][i];
+}
+// ... and their final records are gathered into a compact array once the step is complete
+__global__ void k_gather_late(const swb_result* __restrict__ res, const int32_t* __restrict__ late, int n, swb_result* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = res[late[i]];
+}
+
 __global__ void k_prepare(SwbDev d, const uint8_t* read_bad, const uint8_t* win_bad, int32_t p0, int32_t p1)
 {
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,7 +250,7 @@ extern "C" swb_ctx* swb_create(int device) {
     for (int i = 0; i < SWB_BANDW_MAX; ++i) { mkStream(&c->bandw_stream[i], prMid); mkEvent(&c->ev_bandw_join[i]); }
     for (int i = 0; i < SWB_NREVB; ++i) { mkStream(&c->rev_stream[i], prMid); mkEvent(&c->ev_rev_join[i]); }
     for (int i = 0; i < SWB_NSIDE; ++i) { mkStream(&c->side_stream[i], prMid); mkEvent(&c->ev_side_join[i]); }
-    mkEvent(&c->ev_side_split);
+    mkEvent(&c->ev_side_split); mkEvent(&c->ev_early);
     for (int i = 0; i < SWB_MAX_PARTS; ++i) mkEvent(&c->ev_part_fwd[i]);
     chk(cudaEventCreate(&c->ev_fwd_end), "cudaEventCreate");
     mkEvent(&c->ev_fork); mkEvent(&c->ev_join); mkEvent(&c->ev_join2);
@@ -262,7 +281,7 @@ static void destroy_ctx(swb_ctx* c) {
                       &c->b_ref_beg, &c->b_ref_len, &c->b_go, &c->b_ge, &c->b_mask, &c->b_mat, &c->b_roff, &c->b_woff, &c->b_rlen, &c->b_wlen,
                       &c->b_pmask, &c->b_mode, &c->b_res, &c->b_lists, &c->b_counters, &c->b_colmax, &c->b_band, &c->b_cigar, &c->b_bump,
                       &c->b_tbw, &c->b_tbest, &c->b_rbad, &c->b_wbad, &c->b_state, &c->b_csafe, &c->b_fastcols,
-                      &c->b_ind_off, &c->b_ind_cnt, &c->b_ind_rend, &c->b_ind_recs, &c->b_ind_misc, &c->b_ind_cig, &c->b_ind_coff, &c->b_ind_clen, &c->b_ind_rs, &c->b_ind_qs, &c->b_reads_pk, &c->b_windows_pk };
+                      &c->b_ind_off, &c->b_ind_cnt, &c->b_ind_rend, &c->b_ind_recs, &c->b_ind_misc, &c->b_ind_cig, &c->b_ind_coff, &c->b_ind_clen, &c->b_ind_rs, &c->b_ind_qs, &c->b_reads_pk, &c->b_windows_pk, &c->b_late };
     for (DevBuf* b : all) b->release();
     auto dS = [](cudaStream_t st) { if (st) cudaStreamDestroy(st); };
     auto dE = [](cudaEvent_t ev) { if (ev) cudaEventDestroy(ev); };
@@ -279,7 +298,9 @@ static void destroy_ctx(swb_ctx* c) {
     dE(c->ev_rev_fork);
     for (int i = 0; i < SWB_NREVB; ++i) { dS(c->rev_stream[i]); dE(c->ev_rev_join[i]); }
     for (int i = 0; i < SWB_NSIDE; ++i) { dS(c->side_stream[i]); dE(c->ev_side_join[i]); }
-    dE(c->ev_side_split);
+    dE(c->ev_side_split); dE(c->ev_early);
+    if (c->h_late_rec) cudaFreeHost(c->h_late_rec);
+    if (c->h_late_idx) cudaFreeHost(c->h_late_idx);
     for (int i = 0; i < SWB_MAX_PARTS; ++i) dE(c->ev_part_fwd[i]);
     dE(c->ev_fwd_end);
     for (int i = 0; i < SWB_BANDW_MAX; ++i) { dS(c->bandw_stream[i]); dE(c->ev_bandw_join[i]); }
@@ -655,6 +676,23 @@ static int run_band_rounds(swb_ctx* c, bool record, int firstBase = LIST_BAND, i
             return 0;
         }
         if (read_counters(c)) return -1;
+        if (round == 0 && record && c->early.active && !c->early.started && c->nparts == 1) {
+            // Early download: every record except those of the pairs just re-queued is final now (the certificate only touches
+            // p_state; a verification that overturns a 16-bit result is detected at the end and falls back to a full download).
+            // The records and the CIGARs emitted so far cross PCIe beside the re-queue rounds instead of behind them.
+            const int64_t arenaNow = (int64_t)c->h_bump[1];
+            if (arenaNow <= c->early.cap && c->h_counters[CNT_CIGAR_OVERFLOW] == 0) {
+                k_collect_late<<<SWB_NBANDCLASS + SWB_BANDW_MAX + 1, 128, 0, s>>>(d, nxt, LIST_BANDW_NEXT, warpNxt);
+                c->tm.n_launches++;
+                CUDA_TRY(c, cudaEventRecord(c->ev_copy, s));
+                CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+                CUDA_TRY(c, cudaEventRecord(c->ev[EV_D2H0], c->copy_stream));
+                if (d.n_pairs) CUDA_TRY(c, cudaMemcpyAsync(c->early.results, d.res, (size_t)d.n_pairs * sizeof(swb_result), cudaMemcpyDeviceToHost, c->copy_stream));
+                if (arenaNow) CUDA_TRY(c, cudaMemcpyAsync(c->early.arena, d.cigar, (size_t)arenaNow * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+                CUDA_TRY(c, cudaEventRecord(c->ev_early, c->copy_stream));
+                c->early.started = true; c->early.arena_done = arenaNow;
+            }
+        }
         if (total > 0 && c->h_counters[CNT_BAND_OVERFLOW] >= total) {
             // nothing fitted: the scratch is smaller than a single band; grow it
             if (++stalls > 8 || c->b_band.cap >= ((size_t)64 << 30)) { c->err = "banded traceback scratch exhausted"; return -1; }
@@ -1107,6 +1145,42 @@ static int table_encode(swb_ctx* c, TableStream& t, const TableStep& st, int asc
     return launch_validate(c, t.d_blob, t.d_off + st.i0, t.d_len + st.i0, st.n, ascii, t.d_bad + st.i0, 0, c->stream);
 }
 
+// second half of the early download (see run_band_rounds): the records of the late pairs, compacted on the device, and the CIGARs
+// emitted after the first round.  Returns 0 when the caller's arrays are complete, 1 when the full download must be used instead.
+static int finish_early_download(swb_ctx* c, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used) {
+    const SwbDev& d = c->d;
+    cudaStream_t s = c->stream;
+    const int64_t used = (int64_t)c->h_bump[1];
+    const int nLate = c->h_counters[LIST_LATE];
+    if (c->h_counters[CNT_VERIFY_BYTE] > 0 || nLate > d.n_pairs / 8 || used > cigar_cap || c->h_counters[CNT_CIGAR_OVERFLOW] > 0) return 1;
+    if (cigar_used) *cigar_used = used;
+    if (nLate > 0) {
+        CUDA_TRY(c, c->b_late.ensure((size_t)nLate * sizeof(swb_result) + 16));
+        if ((size_t)nLate > c->h_late_cap) {
+            if (c->h_late_rec) cudaFreeHost(c->h_late_rec);
+            if (c->h_late_idx) cudaFreeHost(c->h_late_idx);
+            c->h_late_rec = nullptr; c->h_late_idx = nullptr; c->h_late_cap = 0;
+            const size_t cap = (size_t)nLate + (size_t)nLate / 2 + 1024;
+            CUDA_TRY(c, cudaMallocHost((void**)&c->h_late_rec, cap * sizeof(swb_result)));
+            CUDA_TRY(c, cudaMallocHost((void**)&c->h_late_idx, cap * sizeof(int32_t)));
+            c->h_late_cap = cap;
+        }
+        k_gather_late<<<(nLate + 255) / 256, 256, 0, s>>>(d.res, d.list[LIST_LATE], nLate, (swb_result*)c->b_late.p);
+        c->tm.n_launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_late_rec, c->b_late.p, (size_t)nLate * sizeof(swb_result), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_late_idx, d.list[LIST_LATE], (size_t)nLate * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (used > c->early.arena_done) CUDA_TRY(c, cudaMemcpyAsync(cigar_arena + c->early.arena_done, d.cigar + c->early.arena_done, (size_t)(used - c->early.arena_done) * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaEventRecord(c->ev[EV_D2H1], s));
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_early));           // the bulk of the records (copy stream)
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    for (int i = 0; i < nLate; ++i) results[c->h_late_idx[i]] = c->h_late_rec[i];
+    c->tm.d2h_bytes = (int64_t)d.n_pairs * (int64_t)sizeof(swb_result) + used * 4 + (int64_t)nLate * (int64_t)(sizeof(swb_result) + 4);
+    cudaEventElapsedTime(&c->tm.ms_h2d, c->ev[EV_H2D0], c->ev[EV_H2D1]);
+    c->tm.ms_d2h = 0;                                        // overlapped with the re-queue rounds
+    return 0;
+}
+
 // forceScan = false: trust the buffer capacities left by the previous call (steady state: the same kind of batch again) and
 // check every piece against them; returns -3 if a blob does not fit, the caller then repeats the call with forceScan = true
 static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* results, uint32_t* cigar_arena, int64_t cigar_cap, int64_t* cigar_used, bool forceScan) {
@@ -1306,6 +1380,8 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
     d.seq_encoding = SWB_SEQ_CODES;
     c->have_batch = true;
     TR(c, "pieces_enqueued");
+    c->early.active = c->nparts == 1 && !getenv("SWB200_NO_EARLY_D2H");
+    c->early.started = false; c->early.results = results; c->early.arena = cigar_arena; c->early.cap = cigar_arena ? cigar_cap : 0;
     // the tails, part after part, each behind its own part's forward sweeps (behind all of them if the column scratch is shared)
     bool redone = false;
     for (int k = 0; k < c->nparts; ++k) {
@@ -1316,7 +1392,14 @@ static int align_batch_streamed(swb_ctx* c, const swb_batch* b, swb_result* resu
         if (rc < 0) return rc;
         if (rc == 1) { redone = true; break; }              // redone with a larger CIGAR arena
     }
+    c->early.active = false;
     if (!redone && compute_finish(c)) return -1;
+    if (c->early.started) {
+        const int rc = redone ? 1 : finish_early_download(c, results, cigar_arena, cigar_cap, cigar_used);
+        c->early.started = false;
+        if (rc <= 0) return rc;                              // done (0) or failed (< 0); 1: fall back to the full download
+        CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));      // the early copies must not land after the full ones
+    }
     return swb_download(c, results, cigar_arena, cigar_cap, cigar_used);
 }
 

@@ -84,7 +84,8 @@ enum { LIST_BYTE_FWD = 0, LIST_WORD_FWD = 1, LIST_BYTE_REV = 2, LIST_WORD_REV = 
        // LIST_VERIFYX (+1): pairs whose overflow neither the CIGAR certificate nor the sandwich lower bound could prove (exact 8-bit pass)
        LIST_SW_FWD = 132, LIST_SW_REV = 140, LIST_VERIFYX = 148,
        LIST_F8_FWD = 150,
-       LIST_BANDQ_TMP = 156, LIST_BANDW_TMP = 157 };      // a round's warp-kernel jobs split by schedule (swb_bandwarp.cuh): 8 lanes / 32 lanes per alignment      // SWB_NF8 lists: forward sweep with 8 threads per lane pair (swb_fast.cuh, G = 8)
+       LIST_BANDQ_TMP = 156, LIST_BANDW_TMP = 157,
+       LIST_LATE = 158 };       // one-shot path: pairs whose records change after the first traceback round (early download)      // a round's warp-kernel jobs split by schedule (swb_bandwarp.cuh): 8 lanes / 32 lanes per alignment      // SWB_NF8 lists: forward sweep with 8 threads per lane pair (swb_fast.cuh, G = 8)
 enum { CNT_BYTE_FWD = 0, CNT_WORD_FWD = 1, CNT_BYTE_REV = 2, CNT_WORD_REV = 3,
        CNT_FAST_FWD = 8, CNT_FAST_REV = 16, CNT_BAND = 24, CNT_BAND_NEXT = 32,
        CNT_SW_FWD = 132, CNT_SW_REV = 140, CNT_F8_FWD = 150,

@@ -68,6 +68,9 @@ struct swb_ctx {
     DevBuf b_roff, b_woff, b_rlen, b_wlen, b_pmask, b_mode, b_res, b_lists, b_counters, b_colmax, b_band, b_cigar, b_bump;
     DevBuf b_tbw, b_tbest, b_rbad, b_wbad, b_state, b_csafe, b_fastcols;
     DevBuf b_ind_off, b_ind_cnt, b_ind_rend, b_ind_recs, b_ind_misc, b_ind_cig, b_ind_coff, b_ind_clen, b_ind_rs, b_ind_qs;   // indel extraction
+    // early download of the one-shot path: the caller's output arrays, known while the traceback rounds are still running
+    struct { bool active = false, started = false; swb_result* results = nullptr; uint32_t* arena = nullptr; int64_t cap = 0, arena_done = 0; } early;
+    cudaEvent_t ev_early = nullptr; DevBuf b_late; swb_result* h_late_rec = nullptr; int32_t* h_late_idx = nullptr; size_t h_late_cap = 0;
     Part parts[SWB_MAX_PARTS]; int nparts = 1, cur_part = 0, force_parts = 0;
     cudaEvent_t ev_part_fwd[SWB_MAX_PARTS] = {}; cudaEvent_t ev_fwd_end = nullptr;      // behind a part's forward sweeps / behind the last one (timed)
     int fastMaxCols[SWB_NFWD] = {};              // longest window per forward list family
