@@ -25,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE = os.environ.get("REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref_pipeline")
 STUB = os.path.join(HERE, "pysam_stub")
+SHIM = os.path.join(HERE, "ref_pileup_shim.pyx")   # our own four-line accessor of the cdef make_pileup
 
 SETUP = '''
 from setuptools import setup, Extension
@@ -37,6 +38,7 @@ for p in sorted(glob.glob("indelpost/*.pyx")):
     name = os.path.basename(p)[:-4]
     src = [p] + (["indelpost/ssw.c"] if name == "sswpy" else [])
     exts.append(Extension("indelpost." + name, src, include_dirs=["."], extra_compile_args=["-Wno-unused-function", "-w"]))
+exts.append(Extension("refshim", ["refshim.pyx"], include_dirs=["."], extra_compile_args=["-w"]))
 setup(ext_modules=cythonize(exts, language_level=3, include_path=["."], quiet=True))
 '''
 
@@ -49,6 +51,8 @@ def source_stamp():
                 h.update(p.encode())
                 with open(p, "rb") as fh:
                     h.update(fh.read())
+    with open(SHIM, "rb") as fh:
+        h.update(fh.read())
     h.update(sys.version.encode())
     return h.hexdigest()
 
@@ -65,6 +69,7 @@ def build(force=False):
     try:
         shutil.copytree(os.path.join(REFERENCE, "indelpost"), os.path.join(tmp, "indelpost"))
         shutil.copytree(os.path.join(STUB, "pysam"), os.path.join(tmp, "pysam"))
+        shutil.copy2(SHIM, os.path.join(tmp, "refshim.pyx"))
         with open(os.path.join(tmp, "setup.py"), "w") as fh:
             fh.write(SETUP)
         r = subprocess.run([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=tmp, capture_output=True, text=True)
@@ -79,6 +84,8 @@ def build(force=False):
                 # build products + what an installed package needs at run time; no C / Cython sources
                 if p.endswith(".so") or p.endswith(".py"):
                     shutil.copy2(p, os.path.join(OUT, pkg, os.path.basename(p)))
+        for p in glob.glob(os.path.join(tmp, "refshim*.so")):
+            shutil.copy2(p, os.path.join(OUT, os.path.basename(p)))
         with open(stamp_file, "w") as fh:
             fh.write(stamp + "\n")
         print("built", OUT)
