@@ -398,7 +398,22 @@ def pipeline_measurements():
         # the same at equal host parallelism: W worker processes in both arms (the wave arm's workers share GPU 0)
         w = max(2, min(8, host_cores() // 2))
         out["cfg3_%d_workers" % w] = BP.measure("cfg3", 6 * w, workers=w)
+        # BASELINE configs[0] / [2] "in a BAM": the same loci written to BAM + BAI / FASTA + FAI and read back through the native
+        # reader (indelpost_b200.bamio; pysam is absent) in BOTH arms
+        out["cfg1_from_bam"] = BP.measure("cfg1", 4, workers=1, repeats=2, from_files=True)
+        out["cfg3_from_bam"] = BP.measure("cfg3", 12, workers=1, from_files=True)
         return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
+def ingest_measurements():
+    """reads/s of pileup ingestion on one host core: the reference's make_pileup vs the native reader (tools/bench_ingest.py)"""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_ingest as BI
+
+        return BI.measure(budget=0.7)
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)}
 
@@ -563,6 +578,7 @@ def run_ours(args):
         result_line = line
     if world == 1 and rank == 0 and not args.no_extra and result_line is not None:
         result_line.setdefault("extra", {})["pipeline"] = pipeline_measurements()
+        result_line["extra"]["ingest"] = ingest_measurements()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -296,9 +296,9 @@ class ReadBatch:
         self.n_cigar = _view(b.n_cigar, n, "<i4"); self.next_tid = _view(b.next_tid, n, "<i4"); self.next_pos = _view(b.next_pos, n, "<i4")
         self.tlen = _view(b.tlen, n, "<i4"); self.name_off = _view(b.name_off, n, "<i8"); self.seq_off = _view(b.seq_off, n, "<i8")
         self.cigar_off = _view(b.cigar_off, n, "<i8")
-        self.names = _view(b.names, int(b.names_len), "u1").tobytes()
-        self.seq = _view(b.seq, int(b.seq_len), "u1").tobytes()          # ASCII bases, all records back to back
-        self.qual = _view(b.qual, int(b.seq_len), "u1").tobytes()
+        self.names = C.string_at(b.names, int(b.names_len))
+        self.seq = C.string_at(b.seq, int(b.seq_len))                     # ASCII bases, all records back to back
+        self.qual = C.string_at(b.qual, int(b.seq_len))
         self.cigar = _view(b.cigar, int(b.cigar_len), "<u4")
         self._seq_str = None
         self._cig_text = None
@@ -341,6 +341,15 @@ class ReadBatch:
         text, off = self._cig_text
         return text[int(off[i]): int(off[i + 1]) - 1]
 
+    def count_overlapping(self, start: int, stop: int, exclude: int = 0) -> int:
+        """records of the batch overlapping [start, stop) under htslib's rule (what AlignmentFile.count would report for a
+        region inside the fetched one) without another pass over the file"""
+        end = np.where(self.end < 0, self.pos + 1, np.maximum(self.end, self.pos + 1))
+        m = (self.pos < stop) & (end > start)
+        if exclude:
+            m &= (self.flag & exclude) == 0
+        return int(m.sum())
+
     def segment(self, i) -> AlignedSegment:
         return AlignedSegment(self, i)
 
@@ -373,7 +382,7 @@ class ReadBatch:
             reads = _view(c.reads, int(c.n), PILEUP_READ_DTYPE)
             sub = _view(c.subreads, 2 * int(c.n_subreads), "<i4").reshape(-1, 2)
             ind = _view(c.indels, int(c.n_indels), PILEUP_INDEL_DTYPE)
-            ref = _view(c.ref_seq, int(c.ref_seq_len), "u1").tobytes().decode("ascii", "replace")
+            ref = C.string_at(c.ref_seq, int(c.ref_seq_len)).decode("ascii", "replace")
             roff = _view(c.ref_seq_off, int(c.n) + 1, "<i8")
         finally:
             self._lib.swb_pileup_cols_free(pc)

@@ -37,12 +37,17 @@ typedef struct {
     uint64_t stamp;
     uint8_t* data;
 } bgzf_blk;
+/* a run of consecutive blocks inflated together (by several threads) for one region query */
+typedef struct { int64_t coff; int32_t clen, ulen; int64_t uoff; } span_blk;
+typedef struct { int n; span_blk* b; uint8_t* data; } bgzf_span;
 typedef struct {
     int fd;
     int64_t fsize;
     bgzf_blk cache[NCACHE];
     uint64_t tick;
     uint8_t* cbuf;
+    bgzf_span span;       /* consulted before the cache */
+    bgzf_blk span_view;   /* the span block last handed out, dressed as a cache entry */
 } bgzf_rd;
 
 static int bgzf_rd_init(bgzf_rd* z, const char* path) {
@@ -56,13 +61,24 @@ static int bgzf_rd_init(bgzf_rd* z, const char* path) {
     z->cbuf = (uint8_t*)malloc(BGZF_MAX + 64);
     return z->cbuf ? 0 : -1;
 }
+static void span_free(bgzf_rd* z) { free(z->span.b); free(z->span.data); z->span.b = NULL; z->span.data = NULL; z->span.n = 0; }
 static void bgzf_rd_free(bgzf_rd* z) {
+    span_free(z);
     for (int i = 0; i < NCACHE; i++) free(z->cache[i].data);
     free(z->cbuf);
     if (z->fd >= 0) close(z->fd);
 }
 /* the block at file offset coff, inflated (cached); NULL at end of file or on a damaged block */
 static bgzf_blk* bgzf_load(bgzf_rd* z, int64_t coff) {
+    if (z->span.n && coff >= z->span.b[0].coff && coff <= z->span.b[z->span.n - 1].coff) {
+        int lo = 0, hi = z->span.n - 1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (z->span.b[mid].coff < coff) lo = mid + 1; else hi = mid; }
+        if (z->span.b[lo].coff == coff) {
+            z->span_view.coff = coff; z->span_view.clen = z->span.b[lo].clen; z->span_view.ulen = z->span.b[lo].ulen;
+            z->span_view.data = z->span.data + z->span.b[lo].uoff;
+            return &z->span_view;
+        }
+    }
     int slot = 0;
     for (int i = 0; i < NCACHE; i++) {
         if (z->cache[i].coff == coff) { z->cache[i].stamp = ++z->tick; return &z->cache[i]; }
@@ -107,6 +123,83 @@ static bgzf_blk* bgzf_load(bgzf_rd* z, int64_t coff) {
     if ((uint32_t)crc32(crc32(0L, NULL, 0), b->data, isize) != crc) { set_err("BGZF CRC mismatch at %lld", (long long)coff); return NULL; }
     b->coff = coff; b->clen = clen; b->ulen = (int32_t)isize; b->stamp = ++z->tick;
     return b;
+}
+
+/* ---- parallel inflate of a block range: BGZF blocks are independent deflate streams, and every block states its compressed
+ * size in the header (BSIZE) and its inflated size in the trailer (ISIZE), so the output layout is known before inflating */
+#include <pthread.h>
+typedef struct { const uint8_t* craw; bgzf_span* sp; int64_t base; int t, nt; int fail; } span_job;
+static int inflate_one(const uint8_t* blk, int clen, uint8_t* dst, int ulen) {
+    int xlen = rd16(blk + 10);
+    z_stream s; memset(&s, 0, sizeof s);
+    if (inflateInit2(&s, -15) != Z_OK) return -1;
+    s.next_in = (Bytef*)(blk + 12 + xlen); s.avail_in = (uInt)(clen - 12 - xlen - 8);
+    s.next_out = dst; s.avail_out = (uInt)ulen;
+    int rc = inflate(&s, Z_FINISH);
+    inflateEnd(&s);
+    if (rc != Z_STREAM_END || (int)s.total_out != ulen) return -1;
+    if ((uint32_t)crc32(crc32(0L, NULL, 0), dst, (uInt)ulen) != rd32(blk + clen - 8)) return -1;
+    return 0;
+}
+static void* span_worker(void* a) {
+    span_job* j = (span_job*)a;
+    for (int i = j->t; i < j->sp->n; i += j->nt) {
+        span_blk* b = &j->sp->b[i];
+        if (inflate_one(j->craw + (b->coff - j->base), b->clen, j->sp->data + b->uoff, b->ulen) != 0) { j->fail = 1; return NULL; }
+    }
+    return NULL;
+}
+static int bam_threads(void) {
+    static int n = 0;
+    if (!n) {
+        const char* e = getenv("SWB_BAM_THREADS");
+        n = e ? atoi(e) : 4;
+        long c = sysconf(_SC_NPROCESSORS_ONLN);
+        if (n > c) n = (int)c;
+        if (n < 1) n = 1;
+        if (n > 32) n = 32;
+    }
+    return n;
+}
+/* inflate every block that starts in [c0, c1] (file offsets of block starts) into z->span; 0 = done, 1 = not worth it / not
+ * possible (the caller falls back to block-by-block reading), never an error by itself */
+#define SPAN_MAX_BYTES (256LL << 20)
+static int span_load(bgzf_rd* z, int64_t c0, int64_t c1) {
+    span_free(z);
+    if (c1 >= z->fsize) c1 = z->fsize - 1;
+    if (c1 < c0) return 1;
+    int64_t want = c1 - c0 + BGZF_MAX + 64;                   /* the last block starts at c1 and may be a full block long */
+    if (c0 + want > z->fsize) want = z->fsize - c0;
+    if (want > SPAN_MAX_BYTES || want < 4 * 1024) return 1;   /* tiny ranges: the per-block path and its cache do fine */
+    uint8_t* craw = (uint8_t*)malloc((size_t)want);
+    if (!craw) return 1;
+    if (pread(z->fd, craw, (size_t)want, c0) != want) { free(craw); return 1; }
+    int cap = 64, n = 0; span_blk* b = (span_blk*)malloc(sizeof(span_blk) * (size_t)cap);
+    int64_t o = 0, utot = 0;
+    while (c0 + o <= c1 && o + 18 <= want) {
+        const uint8_t* h = craw + o;
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4) || h[12] != 'B' || h[13] != 'C' || rd16(h + 14) != 2) { free(craw); free(b); return 1; }
+        int clen = rd16(h + 16) + 1;
+        if (o + clen > want || clen < 26) { free(craw); free(b); return 1; }
+        uint32_t isize = rd32(h + clen - 4);
+        if (isize > BGZF_MAX) { free(craw); free(b); return 1; }
+        if (n == cap) { cap *= 2; span_blk* q = (span_blk*)realloc(b, sizeof(span_blk) * (size_t)cap); if (!q) { free(craw); free(b); return 1; } b = q; }
+        b[n].coff = c0 + o; b[n].clen = clen; b[n].ulen = (int32_t)isize; b[n].uoff = utot; n++;
+        utot += isize; o += clen;
+    }
+    if (n < 2) { free(craw); free(b); return 1; }
+    z->span.b = b; z->span.n = n; z->span.data = (uint8_t*)malloc((size_t)utot + 1);
+    if (!z->span.data) { free(craw); span_free(z); return 1; }
+    int nt = bam_threads(); if (nt > n / 4) nt = n / 4 ? n / 4 : 1;
+    span_job jobs[32]; pthread_t th[32]; int started[32] = { 0 };
+    for (int t = 0; t < nt; t++) { jobs[t].craw = craw; jobs[t].sp = &z->span; jobs[t].base = c0; jobs[t].t = t; jobs[t].nt = nt; jobs[t].fail = 0; }
+    for (int t = 1; t < nt; t++) started[t] = pthread_create(&th[t], NULL, span_worker, &jobs[t]) == 0;
+    span_worker(&jobs[0]);
+    int fail = jobs[0].fail;
+    for (int t = 1; t < nt; t++) { if (started[t]) pthread_join(th[t], NULL); else span_worker(&jobs[t]); fail |= jobs[t].fail; }
+    free(craw);
+    if (fail) { span_free(z); return 1; }      /* the sequential path will meet the damaged block and report it */
+    return 0;
 }
 typedef struct { bgzf_rd* z; int64_t coff; int32_t uoff; } bgzf_cur;
 static inline uint64_t cur_voff(const bgzf_cur* c) { return ((uint64_t)c->coff << 16) | (uint32_t)c->uoff; }
@@ -362,8 +455,11 @@ static chunk_t* region_chunks(const swb_bam* b, int32_t tid, int64_t beg, int64_
     if (!n) { free(out); return NULL; }
     qsort(out, (size_t)n, sizeof(chunk_t), cmp_chunk);
     int m = 0;
+    /* chunks that overlap, touch, or start within one block's reach of the previous end become one run: a writer closes a
+       chunk at every block boundary, and reading the few records in between costs less than a seek (every record is
+       tested against the region anyway) */
     for (int i = 1; i < n; i++) {
-        if (out[i].beg <= out[m].end) { if (out[i].end > out[m].end) out[m].end = out[i].end; }
+        if (out[i].beg <= out[m].end || (out[i].beg >> 16) <= (out[m].end >> 16) + BGZF_MAX) { if (out[i].end > out[m].end) out[m].end = out[i].end; }
         else out[++m] = out[i];
     }
     *n_out = m + 1;
@@ -385,6 +481,8 @@ static int64_t scan_region(swb_bam* b, int32_t tid, int64_t beg, int64_t end, ui
     uint8_t* rec = NULL; int32_t cap = 0;
     for (int ci = 0; ci < nch && !stop; ci++) {
         bgzf_cur c = { &b->z, (int64_t)(chunks[ci].beg >> 16), (int32_t)(chunks[ci].beg & 0xffff) };
+        /* the chunk's blocks, inflated together by several threads (whole-file scans: everything up to the last block) */
+        span_load(&b->z, c.coff, chunks[ci].end == ~0ULL ? b->z.fsize - 1 : (int64_t)(chunks[ci].end >> 16));
         for (;;) {
             if (cur_voff(&c) >= chunks[ci].end) break;
             uint8_t h[4];
@@ -411,6 +509,7 @@ static int64_t scan_region(swb_bam* b, int32_t tid, int64_t beg, int64_t end, ui
         }
     }
     free(rec);
+    span_free(&b->z);
     if (owned) free(chunks);
     return rc ? -1 : count;
 }
@@ -587,7 +686,9 @@ swb_pileup_cols* swb_pileup_columns(const swb_bam_batch* q, int32_t pos, int32_t
                 /* UnsplicedLocalReference.get_ref_seq(aln_start - 1, aln_end): a Python slice of the local reference */
                 int64_t a = (int64_t)(R->aln_start - 1) - local_start, lo, hi;
                 py_slice(local_len, a, a + (R->aln_end - (R->aln_start - 1)), &lo, &hi);
-                for (int64_t x = lo; x < hi; x++) { int64_t g = local_start + x - contig_start; dst[w++] = (g >= 0 && g < contig_len) ? contig[g] : 'N'; }
+                int64_t g0 = local_start + lo - contig_start;
+                if (g0 >= 0 && g0 + (hi - lo) <= contig_len) { memcpy(dst, contig + g0, (size_t)(hi - lo)); w = hi - lo; }
+                else for (int64_t x = lo; x < hi; x++) { int64_t g = local_start + x - contig_start; dst[w++] = (g >= 0 && g < contig_len) ? contig[g] : 'N'; }
             } else {
                 int64_t cur = R->aln_start - 1;
                 for (int k = 0; k < nc; k++) {

@@ -16,6 +16,8 @@ import re
 from collections import namedtuple
 from typing import Callable, List, Optional, Tuple
 
+import numpy as np
+
 from . import bamio
 
 cigar_ptrn = re.compile(r"[0-9]+[MIDNSHPX=]")
@@ -54,7 +56,7 @@ def bam_chrom(chrom: str, bam) -> str:
 
 
 def fetch_reads(chrom, pos, bam, ref_len, window, exclude_duplicates):
-    """pileup.pyx:126-157 -> (ReadBatch of the region, indices of the records the reference keeps, in file order)"""
+    """pileup.pyx:126-157 -> (ReadBatch of the region, index array of the records the reference keeps, in file order)"""
     pos = pos - 1
     batch = bam.fetch_columns(chrom, max(0, pos - window), min(pos + 1 + window, ref_len))
     flag, ncig, start = batch.flag, batch.n_cigar, batch.pos
@@ -63,7 +65,7 @@ def fetch_reads(chrom, pos, bam, ref_len, window, exclude_duplicates):
     if exclude_duplicates:
         keep &= (flag & bamio.FDUP) == 0
         keep &= start != 0          # `and read.reference_start` (pileup.pyx:145): a read at position 0 is dropped
-    return batch, [int(i) for i in keep.nonzero()[0]]
+    return batch, keep.nonzero()[0]
 
 
 def is_within_intron(read, pos, window):
@@ -80,14 +82,16 @@ def _select(target, bam, window, downsamplethresh, exclude_duplicates):
     ref_len = reference.get_reference_length(chrom)
     _chrom = bam_chrom(chrom, bam)
     batch, keep = fetch_reads(_chrom, pos, bam, ref_len, window, exclude_duplicates)
-    orig_depth = bam.count(_chrom, pos - 1, pos, read_callback="all" if exclude_duplicates else "nofilter")
+    # bam.count(_chrom, pos - 1, pos, read_callback=...) (pileup.pyx:82-83): [pos - 1, pos) lies inside the fetched region, so
+    # the count is taken from the batch instead of a second pass over the file
+    orig_depth = batch.count_overlapping(pos - 1, pos, (bamio.FUNMAP | bamio.FSECONDARY | bamio.FQCFAIL | bamio.FDUP) if exclude_duplicates else 0)
     orig_read_num = len(keep)
     sample_factor = 1.0
     if orig_depth > downsamplethresh:
         random.seed(123)
         n_sample = int(orig_read_num * (downsamplethresh / orig_depth))
         if n_sample >= downsamplethresh / 2 > 0:
-            keep = random.sample(keep, n_sample)      # same draw as sampling the segment list: it depends on len() only
+            keep = np.array(random.sample(keep.tolist(), n_sample), dtype=np.int64)   # the draw depends on len() only: same reads as sampling the segment list
             sample_factor = orig_read_num / len(keep)
     return batch, keep, sample_factor, ref_len, rpos
 
@@ -97,10 +101,9 @@ def _columns(batch, keep, target, rpos, unspl_loc_ref, basequalthresh):
     chrom, reference = target.chrom, target.reference
     lo = unspl_loc_ref.local_ref_start
     hi = lo + len(unspl_loc_ref.unspliced_local_reference)
-    if keep:
-        ends = batch.end
-        lo = min(lo, min(int(batch.pos[i]) for i in keep))
-        hi = max(hi, max(int(ends[i]) for i in keep) + 1)
+    if len(keep):
+        lo = min(lo, int(batch.pos[keep].min()))
+        hi = max(hi, int(batch.end[keep].max()) + 1)
     lo = max(0, lo)
     contig = reference.fetch(chrom, lo, hi)
     return batch.pileup_columns(target.pos, rpos, basequalthresh, contig.encode("ascii"), lo, unspl_loc_ref.local_ref_start,
@@ -122,7 +125,7 @@ def make_pileup(target, bam, unspl_loc_ref, exclude_duplicates, window, downsamp
     ind = cols.indels.tolist()
     flag, mapq = batch.flag.tolist(), batch.mapq.tolist()
     pileup = []
-    for i in keep:
+    for i in keep.tolist():
         seg = batch.segment(i)
         read_seq, read_qual, cigar_string = seg.query_sequence, seg.query_qualities, seg.cigarstring
         ref_seq = cols.ref_seq(i)
@@ -202,19 +205,15 @@ class PileupBatch:
         """-> (table, off, len, index): SWB_SEQ_PACKED4 read table of the WHOLE region batch and the kept records' indices
         (pair_read entries for swb_align_batch): the bases never exist as Python strings"""
         table, off, length = self.batch.pack4()
-        return table, off, length, list(self.keep)
+        return table, off, length, self.keep
 
 
 def make_pileup_batch(target, bam, unspl_loc_ref, exclude_duplicates, window, downsamplethresh, basequalthresh) -> PileupBatch:
     """the columnar ingest: fetch_reads + down-sampling + dictize_read's integer core + is_within_intron, no dicts"""
     batch, keep, sample_factor, ref_len, rpos = _select(target, bam, window, downsamplethresh, exclude_duplicates)
     cols = _columns(batch, keep, target, rpos, unspl_loc_ref, basequalthresh)
-    r = cols.reads
+    r = cols.reads[keep]
     pos = target.pos
-    out = []
-    for i in keep:
-        s, e = int(r["intron_start"][i]), int(r["intron_end"][i])
-        if (s, e) != (0, 0) and s < pos - window and pos + window < e:
-            continue
-        out.append(i)
-    return PileupBatch(batch, out, cols, sample_factor)
+    s, e = r["intron_start"], r["intron_end"]
+    within = ((s != 0) | (e != 0)) & (s < pos - window) & (pos + window < e)
+    return PileupBatch(batch, keep[~within], cols, sample_factor)

@@ -71,6 +71,31 @@ def open_locus(locus, bam_cls=None):
     return fa, bam
 
 
+def file_backed_bam(src, base_cls=None):
+    """the stub's AlignmentFile TYPE (the compiled reference checks it) over a bamio.AlignmentFile's DATA: fetch / count go to
+    the native reader, every record becomes a stub AlignedSegment carrying the attributes pysam would report"""
+    pysam = load()[1]
+    base = base_cls or pysam.AlignmentFile
+
+    class FileBackedBam(base):
+        def fetch(self, contig=None, start=None, stop=None, until_eof=False):
+            for seg in src.fetch(contig, start, stop):
+                yield pysam.AlignedSegment(**seg.as_dict())
+
+        def count(self, contig=None, start=None, stop=None, read_callback="nofilter"):
+            return src.count(contig, start, stop, read_callback=read_callback)
+
+    return FileBackedBam
+
+
+def open_locus_files(locus, src_bam, src_fa, bam_cls=None):
+    """like open_locus, but the reads come out of a BAM file and the genome out of a FASTA file (indelpost_b200.bamio)"""
+    pysam = load()[1]
+    fa = pysam.FastaFile({locus["chrom"]: src_fa.fetch(locus["chrom"])}, filename=src_fa.filename)
+    bam = (bam_cls or file_backed_bam(src_bam))([], src_bam.references)
+    return fa, bam
+
+
 def _variant_tuple(v):
     return None if v is None else (v.chrom, v.pos, v.ref, v.alt)
 
@@ -131,18 +156,20 @@ class ThreadCalls:
         self._tl.dest.append(x)
 
 
-def run_locus(locus, ssw_cls=None, calls=None, swap=True, bam_cls=None):
+def run_locus(locus, ssw_cls=None, calls=None, swap=True, bam_cls=None, files=None):
     """-> summary dict; with `calls` (a list) every SW call is recorded into it.  swap=False: the caller has already
-    installed the SSW class (refpipe.swapped) -- required when several loci run concurrently."""
+    installed the SSW class (refpipe.swapped) -- required when several loci run concurrently.  files=(bamio.AlignmentFile,
+    bamio.FastaFile): read the locus from those files instead of the in-memory stub (bam_cls then wraps file_backed_bam)."""
     indelpost, pysam, localn, RefSSW = load()
+    opener = (lambda: open_locus(locus, bam_cls)) if files is None else (lambda: open_locus_files(locus, files[0], files[1], bam_cls))
     if not swap:
-        fa, bam = open_locus(locus, bam_cls)
+        fa, bam = opener()
         return analyse(locus, fa, bam)
     cls = ssw_cls or RefSSW
     if calls is not None:
         cls = recording(cls, calls)
     with swapped(cls):
-        fa, bam = open_locus(locus, bam_cls)
+        fa, bam = opener()
         return analyse(locus, fa, bam)
 
 

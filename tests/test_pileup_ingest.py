@@ -283,7 +283,7 @@ def test_make_pileup_batch_matches_dict_pileup(tmp_path):
     pb = pileup.make_pileup_batch(Target, bam, u, True, 50, 1000, 20)
     assert [pb.batch.name(i) for i in pb.keep] == [r["read_name"] for r in our_p]
     table, off, ln, idx = pb.read_table()
-    assert idx == pb.keep and len(off) == len(pb.batch)
+    assert list(idx) == list(pb.keep) and len(off) == len(pb.batch)
 
 
 @needs_ref
@@ -296,17 +296,5 @@ def test_reference_pipeline_from_files(tmp_path, spec_idx):
     locus["reads"].sort(key=lambda r: r["reference_start"])
     mem = refpipe.run_locus(locus)
     bam_p, fa_p = write_locus(str(tmp_path), locus)
-    src = bamio.AlignmentFile(bam_p)
-
-    class FileBackedBam(pysam.AlignmentFile):            # the stub's type (the compiled reference checks it), our reader's data
-        def fetch(self, contig=None, start=None, stop=None, until_eof=False):
-            for seg in src.fetch(contig, start, stop):
-                yield pysam.AlignedSegment(**seg.as_dict())
-
-        def count(self, contig=None, start=None, stop=None, read_callback="nofilter"):
-            return src.count(contig, start, stop, read_callback=read_callback)
-
-    fa_src = bamio.FastaFile(fa_p)
-    fa = pysam.FastaFile({locus["chrom"]: fa_src.fetch(locus["chrom"])})
-    bam = FileBackedBam([], src.references)
-    assert refpipe.analyse(locus, fa, bam) == mem
+    files = (bamio.AlignmentFile(bam_p), bamio.FastaFile(fa_p))
+    assert refpipe.run_locus(locus, files=files) == mem

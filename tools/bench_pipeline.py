@@ -9,7 +9,7 @@ and the check that both give identical outputs for every locus.  The host logic 
 single-threaded Python/Cython in both arms (out of scope), so the ratio is Amdahl-bounded by the
 SW share of a locus (54-64 %); scaling beyond one host core is by processes (loci are independent).
 
-    python tools/bench_pipeline.py [--config cfg3] [--loci N] [--workers P] [--arms reference,wave] [--devices 0,1,...]
+    python tools/bench_pipeline.py [--config cfg3] [--loci N] [--workers P] [--arms reference,wave] [--devices 0,1,...] [--from-files]
 
 Used by bench.py (`extra.pipeline`) on rank 0 with a bounded sample; standalone it prints one JSON line.
 """
@@ -52,7 +52,26 @@ def make_specs(config: str, n_loci: int, seed0: int = 5000):
     return specs
 
 
-def _worker(arm, specs, device, q):
+def write_loci_files(lcs, directory, tag="loci"):
+    """all loci of a worker into ONE coordinate-sorted BAM + BAI and ONE FASTA + FAI (every locus its own contig), written by
+    libswbbam -> (bamio.AlignmentFile, bamio.FastaFile).  BASELINE.json's configs are "written to BAM"; pysam is absent."""
+    from indelpost_b200 import bamio
+
+    reads, seqs = [], {}
+    for k, lc in enumerate(lcs):
+        name = f"locus{k:05d}"
+        lc["chrom"] = name
+        for r in lc["reads"]:
+            r["reference_name"] = name
+        seqs[name] = lc["genome"]
+        reads.extend(lc["reads"])
+    bam_p, fa_p = os.path.join(directory, tag + ".bam"), os.path.join(directory, tag + ".fa")
+    bamio.write_fasta(fa_p, seqs)
+    bamio.write_bam(bam_p, [(k, len(v)) for k, v in seqs.items()], reads)
+    return bamio.AlignmentFile(bam_p), bamio.FastaFile(fa_p)
+
+
+def _worker(arm, specs, device, q, from_files=False):
     """one host process: its share of the loci through one arm -> (seconds, summaries, stats)"""
     try:
         import loci
@@ -60,9 +79,17 @@ def _worker(arm, specs, device, q):
 
         lcs = [loci.make_locus(**sp) for sp in specs]          # generation is not part of the timed region
         refpipe.load()
+        files = None
+        base_bam = refpipe.load()[1].AlignmentFile
+        if from_files:
+            import tempfile
+
+            tmpdir = tempfile.mkdtemp(prefix="swb_loci_")
+            files = write_loci_files(lcs, tmpdir, f"w{os.getpid()}")
+            base_bam = refpipe.file_backed_bam(files[0])
         if arm == "reference":
             t0 = time.perf_counter()
-            outs = [refpipe.run_locus(lc) for lc in lcs]
+            outs = [refpipe.run_locus(lc, files=files) for lc in lcs]
             dt = time.perf_counter() - t0
             q.put((dt, outs, {}))
             return
@@ -70,15 +97,15 @@ def _worker(arm, specs, device, q):
         from indelpost_b200.sswpy import _aligner
 
         al = _aligner(device)
-        tee = wave.tee_alignment_file(refpipe.load()[1].AlignmentFile)
+        tee = wave.tee_alignment_file(base_bam)
         runner = wave.WaveRunner(device=device, aligner=al, max_inflight=256)
         with refpipe.swapped(SSW):
             # warm-up: context, kernels, staging buffers
-            runner.map(lambda lc: refpipe.run_locus(lc, swap=False, bam_cls=tee), lcs[:1])
+            runner.map(lambda lc: refpipe.run_locus(lc, swap=False, bam_cls=tee, files=files), lcs[:1])
             runner.stats = {k: 0 for k in runner.stats}
             clear_prefetched()
             t0 = time.perf_counter()
-            outs = runner.map(lambda lc: refpipe.run_locus(lc, swap=False, bam_cls=tee), lcs)
+            outs = runner.map(lambda lc: refpipe.run_locus(lc, swap=False, bam_cls=tee, files=files), lcs)
             dt = time.perf_counter() - t0
         q.put((dt, outs, dict(runner.stats)))
     except BaseException as e:  # noqa: BLE001
@@ -86,14 +113,14 @@ def _worker(arm, specs, device, q):
         q.put((None, traceback.format_exc(), {}))
 
 
-def run_arm(arm, specs, workers, devices):
+def run_arm(arm, specs, workers, devices, from_files=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     shards = [specs[k::workers] for k in range(workers)]
     procs = []
     t0 = time.perf_counter()
     for k, sh in enumerate(shards):
-        p = ctx.Process(target=_worker, args=(arm, sh, devices[k % len(devices)], q))
+        p = ctx.Process(target=_worker, args=(arm, sh, devices[k % len(devices)], q, from_files))
         p.start()
         procs.append(p)
     parts = [q.get() for _ in procs]
@@ -106,19 +133,19 @@ def run_arm(arm, specs, workers, devices):
     return parts, wall, shards
 
 
-def measure(config="cfg3", n_loci=32, workers=1, arms=("reference", "wave"), devices=(0,), repeats=1):
+def measure(config="cfg3", n_loci=32, workers=1, arms=("reference", "wave"), devices=(0,), repeats=1, from_files=False):
     specs = make_specs(config, n_loci)
     n_reads = sum(sp["n_reads"] for sp in specs)
     out = {"config": config, "loci": n_loci, "reads": n_reads, "workers": workers, "devices": list(devices),
-           "repeats": repeats,
+           "repeats": repeats, "input": "BAM + BAI / FASTA + FAI files written and read by libswbbam (one BAM per worker, one contig per locus)" if from_files else "in-memory stub pysam",
            "what": "unmodified reference VariantAlignment + count_alleles + phase per locus (stub pysam, synthetic loci); timed region = the pipeline calls, "
                    "max over worker processes; host logic above the SW calls is the reference's own in both arms"}
     by_arm = {}
     for arm in arms:
-        parts, wall, shards = run_arm(arm, specs, workers, devices)
+        parts, wall, shards = run_arm(arm, specs, workers, devices, from_files)
         dt = max(p[0] for p in parts)
         for _ in range(max(0, repeats - 1)):                 # the host is shared: keep the fastest of a few runs
-            parts2, wall2, _ = run_arm(arm, specs, workers, devices)
+            parts2, wall2, _ = run_arm(arm, specs, workers, devices, from_files)
             dt2 = max(p[0] for p in parts2)
             if dt2 < dt:
                 parts, wall, dt = parts2, wall2, dt2
@@ -151,8 +178,9 @@ def main():
     ap.add_argument("--workers", type=int, default=1)
     ap.add_argument("--arms", default="reference,wave")
     ap.add_argument("--devices", default="0")
+    ap.add_argument("--from-files", action="store_true", help="loci are written to BAM / FASTA files and read back through the native reader (indelpost_b200.bamio)")
     a = ap.parse_args()
-    print(json.dumps(measure(a.config, a.loci, a.workers, tuple(a.arms.split(",")), tuple(int(x) for x in a.devices.split(",")))))
+    print(json.dumps(measure(a.config, a.loci, a.workers, tuple(a.arms.split(",")), tuple(int(x) for x in a.devices.split(",")), from_files=a.from_files)))
 
 
 if __name__ == "__main__":
