@@ -402,6 +402,8 @@ def pipeline_measurements():
         # reader (indelpost_b200.bamio; pysam is absent) in BOTH arms
         out["cfg1_from_bam"] = BP.measure("cfg1", 4, workers=1, repeats=2, from_files=True)
         out["cfg3_from_bam"] = BP.measure("cfg3", 12, workers=1, from_files=True)
+        # ... and through the product's locus-parallel driver (indelpost_b200.locuspool): ONE BAM + FASTA with every locus, W workers
+        out["cfg3_pool_%d_workers" % w] = BP.measure_pool("cfg3", 6 * w, workers=w)
         return out
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)}

@@ -133,6 +133,85 @@ def run_arm(arm, specs, workers, devices, from_files=False):
     return parts, wall, shards
 
 
+# ---- the product's locus-parallel driver (indelpost_b200.locuspool) on ONE BAM + FASTA holding every locus -------------------------
+_POOL = {}
+
+
+def _pool_init(rank, device):
+    """in every worker: open the files, load the reference pipeline, install the SSW class of the arm"""
+    import types
+
+    import refpipe
+    from indelpost_b200 import bamio
+
+    refpipe.load()
+    bam, fa = bamio.AlignmentFile(os.environ["SWB_POOL_BAM"]), bamio.FastaFile(os.environ["SWB_POOL_FA"])
+    _POOL["files"] = (bam, fa)
+    base = refpipe.file_backed_bam(bam)
+    arm = os.environ["SWB_POOL_ARM"]
+    if arm == "pool_reference":
+        _POOL["bam_cls"] = base
+        return None
+    from indelpost_b200 import SSW, sswpy, wave
+
+    _POOL["bam_cls"] = wave.tee_alignment_file(base)
+    if os.environ.get("SWB_POOL_CPU_ORACLE"):            # host-logic check without a GPU: batches computed by the CPU oracle
+        import test_wave_cpu as W
+
+        sswpy.align_batch = W._oracle_align_batch([])
+        refpipe.load()[2].SSW = W._NoGpuSSW
+        return types.SimpleNamespace(aligner=object())
+    refpipe.load()[2].SSW = SSW
+    return types.SimpleNamespace(aligner=sswpy._aligner(device))
+
+
+def _pool_item(meta):
+    import refpipe
+
+    swap = os.environ["SWB_POOL_ARM"] == "pool_reference"
+    return refpipe.run_locus(meta, swap=swap, bam_cls=_POOL["bam_cls"], files=_POOL["files"])
+
+
+def measure_pool(config="cfg3", n_loci=64, workers=4, devices=(0,), arms=("pool_reference", "pool_wave"), cpu_oracle=False):
+    """loci/s through indelpost_b200.locuspool.LocusPool: every locus in ONE coordinate-sorted BAM + BAI and one FASTA + FAI
+    (written by libswbbam, not timed), a list of (chrom, pos, ref, alt) work items, `workers` processes over `devices`.
+    Timed region: pool.map() over all items in the parent (workers already started and warmed by one item each)."""
+    import tempfile
+
+    import loci
+    from indelpost_b200 import locuspool
+
+    specs = make_specs(config, n_loci)
+    lcs = [loci.make_locus(**sp) for sp in specs]
+    tmpdir = tempfile.mkdtemp(prefix="swb_pool_")
+    bam, fa = write_loci_files(lcs, tmpdir, "all_loci")
+    os.environ["SWB_POOL_BAM"], os.environ["SWB_POOL_FA"] = bam.filename, fa.filename
+    bam.close(); fa.close()
+    if cpu_oracle:
+        os.environ["SWB_POOL_CPU_ORACLE"] = "1"
+    metas = [dict(chrom=lc["chrom"], pos=lc["pos"], ref=lc["ref"], alt=lc["alt"], kwargs=lc["kwargs"]) for lc in lcs]
+    out = {"config": config, "loci": n_loci, "reads": sum(sp["n_reads"] for sp in specs), "workers": workers, "devices": list(devices),
+           "bam_bytes": os.path.getsize(os.environ["SWB_POOL_BAM"]),
+           "what": "indelpost_b200.locuspool.LocusPool over one BAM + FASTA holding every locus (native reader in both arms); timed region = pool.map() in the parent"}
+    outs = {}
+    for arm in arms:
+        os.environ["SWB_POOL_ARM"] = arm
+        with locuspool.LocusPool(_pool_item, workers=workers, devices=devices, init=_pool_init, mode="plain" if arm == "pool_reference" else "wave") as pool:
+            pool.map(metas[:workers])                    # warm-up: contexts, kernels, page cache
+            t0 = time.perf_counter()
+            res = pool.map(metas)
+            dt = time.perf_counter() - t0
+            outs[arm] = res
+            out[arm] = {"seconds": dt, "loci_per_s": n_loci / dt, "reads_per_s": out["reads"] / dt}
+            if pool.stats:
+                out[arm].update({"waves": pool.stats.get("waves"), "pairs_aligned": pool.stats.get("pairs")})
+    if len(outs) == 2:
+        a, b = (outs[k] for k in arms)
+        out["identical_outputs"] = a == b
+        out["speedup"] = out[arms[1]]["loci_per_s"] / out[arms[0]]["loci_per_s"]
+    return out
+
+
 def measure(config="cfg3", n_loci=32, workers=1, arms=("reference", "wave"), devices=(0,), repeats=1, from_files=False):
     specs = make_specs(config, n_loci)
     n_reads = sum(sp["n_reads"] for sp in specs)
@@ -179,7 +258,12 @@ def main():
     ap.add_argument("--arms", default="reference,wave")
     ap.add_argument("--devices", default="0")
     ap.add_argument("--from-files", action="store_true", help="loci are written to BAM / FASTA files and read back through the native reader (indelpost_b200.bamio)")
+    ap.add_argument("--pool", action="store_true", help="measure through indelpost_b200.locuspool.LocusPool on one BAM holding every locus")
+    ap.add_argument("--cpu-oracle", action="store_true", help="(--pool) merged batches computed by the CPU oracle: checks the host logic without a GPU")
     a = ap.parse_args()
+    if a.pool:
+        print(json.dumps(measure_pool(a.config, a.loci, a.workers, tuple(int(x) for x in a.devices.split(",")), cpu_oracle=a.cpu_oracle)))
+        return
     print(json.dumps(measure(a.config, a.loci, a.workers, tuple(a.arms.split(",")), tuple(int(x) for x in a.devices.split(",")), from_files=a.from_files)))
 
 
