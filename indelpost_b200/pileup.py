@@ -6,7 +6,7 @@ assembles the dicts from the columns.  `make_pileup_batch` is the same ingest wi
 SWB_SEQ_PACKED4 table ready for `BatchAligner` / `swb_align_batch`, plus the columns.
 
 The reference's `make_pileup` is a `cdef` function (`varaln.pyx:30` cimports it), so it cannot be swapped from Python; the
-patch a maintainer adds is in INTEGRATION.md §6.  Parity is pinned against the reference's own `make_pileup`, reached through
+patch a maintainer adds is in INTEGRATION.md §4.  Parity is pinned against the reference's own `make_pileup`, reached through
 a four-line Cython shim (oracle/ref_pileup_shim.pyx), on every locus of tests/loci.py: tests/test_pileup_ingest.py.
 """
 from __future__ import annotations
