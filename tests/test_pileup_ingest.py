@@ -298,3 +298,54 @@ def test_reference_pipeline_from_files(tmp_path, spec_idx):
     bam_p, fa_p = write_locus(str(tmp_path), locus)
     files = (bamio.AlignmentFile(bam_p), bamio.FastaFile(fa_p))
     assert refpipe.run_locus(locus, files=files) == mem
+
+
+def test_long_reads_unplaced_reads_and_foreign_blocks(tmp_path):
+    """records longer than a BGZF block (they span blocks), unplaced reads after the last contig, records without qualities
+    or CIGAR, and a file whose blocks were written by another gzip implementation with a different block size"""
+    rng = random.Random(17)
+    big = "".join(rng.choice("ACGTN") for _ in range(200_000))
+    reads = [
+        dict(query_name="long1", query_sequence=big, query_qualities=array_of(rng, len(big)), cigarstring="1000S198000M1000S", reference_name="chr1", reference_start=500, mapping_quality=7, is_reverse=True),
+        dict(query_name="short", query_sequence="ACGTACGTAC", query_qualities=None, cigarstring="10M", reference_name="chr1", reference_start=100_000, mapping_quality=60, is_reverse=False),
+        dict(query_name="long2", query_sequence=big[:70_000], query_qualities=None, cigarstring="70000M", reference_name="chr1", reference_start=150_000, mapping_quality=60, is_reverse=False),
+        dict(query_name="nocigar", query_sequence="ACGT", query_qualities=None, cigarstring=None, reference_name="chr1", reference_start=160_000, mapping_quality=0, is_reverse=False, is_unmapped=True),
+        dict(query_name="unplaced", query_sequence="TTTTGGGG", query_qualities=None, cigarstring=None, reference_name=None, reference_start=-1, mapping_quality=0, is_reverse=False, is_unmapped=True),
+    ]
+    bam = os.path.join(str(tmp_path), "long.bam")
+    bamio.write_bam(bam, [("chr1", 400_000)], reads, level=1)
+    _, _, recs = bam_oracle.read_bam(bam)
+    assert [r["name"] for r in recs] == ["long1", "short", "long2", "nocigar", "unplaced"]
+    assert recs[0]["seq"] == big and recs[0]["end"] == 500 + 198_000 and recs[4]["tid"] == -1 and recs[4]["pos"] == -1
+    f = bamio.AlignmentFile(bam)
+    b = f.fetch_columns()
+    assert len(b) == 5 and b.sequence(0) == big and b.qualities(1) is None and b.qualities(0) == reads[0]["query_qualities"]
+    assert b.segment(3).cigarstring is None and b.segment(3).reference_end is None and b.segment(4).reference_name is None
+    assert [s.query_name for s in f.fetch("chr1", 100_005, 100_006)] == ["long1", "short"]
+    assert [s.query_name for s in f.fetch("chr1", 198_499, 198_501)] == ["long1", "long2"]
+    assert [s.query_name for s in f.fetch("chr1", 198_500, 198_501)] == ["long2"]
+    assert [s.query_name for s in f.fetch("chr1", 160_000, 160_001)] == ["long1", "long2", "nocigar"]       # a record without CIGAR covers one base
+    assert f.count("chr1", 160_000, 160_001, read_callback="all") == 2
+    # the same uncompressed stream re-blocked by Python's zlib into 4 kB blocks with the BC subfield (still valid BGZF)
+    import gzip
+    import struct
+    import zlib
+    raw = gzip.open(bam, "rb").read()
+    out = bytearray()
+    for o in range(0, len(raw), 4096):
+        chunk = raw[o: o + 4096]
+        co = zlib.compressobj(9, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        out += struct.pack("<4BI2BH2BHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(body) + 25) + body + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    out += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    other = os.path.join(str(tmp_path), "reblocked.bam")
+    open(other, "wb").write(out)
+    g = bamio.AlignmentFile(other)                      # no index: scans
+    b2 = g.fetch_columns("chr1", 198_499, 198_501)
+    assert [b2.name(i) for i in range(len(b2))] == ["long1", "long2"] and b2.sequence(0) == big
+    assert len(g.fetch_columns()) == 5
+
+
+def array_of(rng, n):
+    import array
+    return array.array("B", [rng.choice((2, 20, 30, 40)) for _ in range(n)])
