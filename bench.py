@@ -383,6 +383,14 @@ def extra_measurements(al, L, T, peak_gcups):
                          "reads_per_s": n / dt, "ms": dt * 1e3, "us_per_materialised_alignment": dmat * 1e6, "sample_cigar": first[0].CIGAR}
     except Exception as e:  # noqa: BLE001
         ex["e2e_api"] = {"error": repr(e)}
+    # reads realigned per second FROM A BAM FILE: native columnar ingest on host threads + the six-point gap grid on the GPU
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_bam_realign as BR
+
+        ex["bam_realign"] = {"cfg3": BR.measure("cfg3", n_loci=600, chunk=200, aligner=al)}
+    except Exception as e:  # noqa: BLE001
+        ex["bam_realign"] = {"error": repr(e)}
     return ex
 
 

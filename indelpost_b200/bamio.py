@@ -592,6 +592,34 @@ def write_bam(path: str, references: Sequence[Tuple[str, int]], reads: Iterable[
     return n
 
 
+def write_bam_columns(path: str, references: Sequence[Tuple[str, int]], tid, pos, flag, mapq, l_seq, n_cigar, name_off, seq_off, cigar_off,
+                      names: bytes, seq: bytes, qual: Optional[bytes], cigar, index: bool = True, level: int = 6, header_text: Optional[str] = None) -> int:
+    """coordinate-sorted BAM (+ BAI) straight from columnar arrays (the layout of ReadBatch / swb_bam_write): no per-read Python
+    objects.  `names`: NUL-terminated names back to back; `seq` / `qual`: ASCII bases / phred bytes at seq_off; `cigar`: BAM words."""
+    lib = load()
+    n = int(len(pos))
+    arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)  # noqa: E731
+    tid, pos, flag, mapq = arr(tid, "<i4"), arr(pos, "<i4"), arr(flag, "<u2"), arr(mapq, "u1")
+    l_seq, n_cigar, name_off, seq_off, cigar_off = arr(l_seq, "<i4"), arr(n_cigar, "<i4"), arr(name_off, "<i8"), arr(seq_off, "<i8"), arr(cigar_off, "<i8")
+    cigar = arr(cigar, "<u4")
+    nbuf, sbuf = np.frombuffer(names or b"\0", "u1"), np.frombuffer(seq or b"\0", "u1")
+    qbuf = np.frombuffer(qual, "u1") if qual else None
+    if header_text is None:
+        header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{r}\tLN:{ln}\n" for r, ln in references)
+    cnames = (C.c_char_p * max(1, len(references)))(*[r.encode() for r, _ in references])
+    lens = np.array([ln for _, ln in references] or [0], "<i8")
+    w = lib.swb_bam_create(os.fsencode(path), header_text.encode(), len(references), cnames, _ptr(lens), level)
+    if not w:
+        raise OSError(_err(lib))
+    rc = lib.swb_bam_write(w, n, _ptr(tid), _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(l_seq), _ptr(n_cigar), _ptr(name_off), _ptr(seq_off), _ptr(cigar_off),
+                           _ptr(nbuf), _ptr(sbuf), _ptr(qbuf) if qbuf is not None else None, _ptr(cigar), None, None, None)
+    msg = _err(lib) if rc != 0 else ""
+    rc2 = lib.swb_bam_writer_close(w, 1 if index else 0)
+    if rc != 0 or rc2 != 0:
+        raise OSError(msg or _err(lib) or "BAM write failed")
+    return n
+
+
 def write_fasta(path: str, seqs, line_width: int = 60) -> None:
     """FASTA + .fai from {name: sequence} (or a list of pairs)"""
     lib = load()
