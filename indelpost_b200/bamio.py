@@ -287,21 +287,36 @@ class ReadBatch:
     """The records of one region, columnar (swb_bam_batch).  Columns are numpy arrays owned by Python; the C batch stays
     alive with the object for pack4 / pileup_columns."""
 
+    # columns are copied out of the C batch on first use: the columnar path touches four of them, the per-read path all
+    _COLS = {"tid": "<i4", "pos": "<i4", "end": "<i4", "flag": "<u2", "mapq": "u1", "l_seq": "<i4", "n_cigar": "<i4", "next_tid": "<i4",
+             "next_pos": "<i4", "tlen": "<i4", "name_off": "<i8", "seq_off": "<i8", "cigar_off": "<i8"}
+
     def __init__(self, lib, cb, references):
         self._lib, self._cb, self.references = lib, cb, references
-        b = cb.contents
-        n = self.n = int(b.n)
-        self.tid = _view(b.tid, n, "<i4"); self.pos = _view(b.pos, n, "<i4"); self.end = _view(b.end, n, "<i4")
-        self.flag = _view(b.flag, n, "<u2"); self.mapq = _view(b.mapq, n, "u1"); self.l_seq = _view(b.l_seq, n, "<i4")
-        self.n_cigar = _view(b.n_cigar, n, "<i4"); self.next_tid = _view(b.next_tid, n, "<i4"); self.next_pos = _view(b.next_pos, n, "<i4")
-        self.tlen = _view(b.tlen, n, "<i4"); self.name_off = _view(b.name_off, n, "<i8"); self.seq_off = _view(b.seq_off, n, "<i8")
-        self.cigar_off = _view(b.cigar_off, n, "<i8")
-        self.names = C.string_at(b.names, int(b.names_len))
-        self.seq = C.string_at(b.seq, int(b.seq_len))                     # ASCII bases, all records back to back
-        self.qual = C.string_at(b.qual, int(b.seq_len))
-        self.cigar = _view(b.cigar, int(b.cigar_len), "<u4")
+        self.n = int(cb.contents.n)
         self._seq_str = None
         self._cig_text = None
+
+    def __getattr__(self, name):
+        # only reached for attributes not materialised yet
+        cb = self.__dict__.get("_cb")
+        if cb is None:
+            raise AttributeError(name)
+        b = cb.contents
+        if name in ReadBatch._COLS:
+            v = _view(getattr(b, name), self.n, ReadBatch._COLS[name])
+        elif name == "names":
+            v = C.string_at(b.names, int(b.names_len))
+        elif name == "seq":
+            v = C.string_at(b.seq, int(b.seq_len))                 # ASCII bases, all records back to back
+        elif name == "qual":
+            v = C.string_at(b.qual, int(b.seq_len))
+        elif name == "cigar":
+            v = _view(b.cigar, int(b.cigar_len), "<u4")
+        else:
+            raise AttributeError(name)
+        self.__dict__[name] = v
+        return v
 
     def __del__(self):
         cb, self._cb = getattr(self, "_cb", None), None
@@ -360,10 +375,9 @@ class ReadBatch:
     def pack4(self):
         """-> (table uint8[], off int64[n], len int32[n]): the batch's reads as a SWB_SEQ_PACKED4 table (DNA_BASE_LUT codes,
         two per byte) straight from the BAM's own 4-bit bases: what BatchAligner / swb_align_batch take as the read table"""
-        nbytes = int(((self.l_seq.astype(np.int64) + 1) // 2).sum())
-        table = np.zeros(max(1, nbytes), "u1"); off = np.zeros(max(1, self.n), "<i8")
-        w = self._lib.swb_bam_batch_pack4(self._cb, _ptr(table), _ptr(off))
-        return table[:w], off[: self.n], self.l_seq.copy()
+        table = np.empty(max(1, int(self._cb.contents.seq4_len)), "u1"); off = np.empty(max(1, self.n), "<i8")
+        w = self._lib.swb_bam_batch_pack4(self._cb, table.ctypes.data, off.ctypes.data)
+        return table[:w], off[: self.n], self.l_seq
 
     def pileup_columns(self, pos, rpos, basequalthresh, contig: Optional[bytes] = None, contig_start=0, local_start=None, local_len=None) -> PileupColumns:
         """the integer core of dictize_read for every record (swb_pileup_columns); `contig` = reference bases from

@@ -164,7 +164,7 @@ def measure(config="cfg3", n_loci=1000, threads=None, chunk=250, device=0, align
             res, arena = aligner.align(b["reads"], b["read_off"], b["read_len"], b["windows"], b["win_off"], b["win_len"], b["pair_read"], b["pair_win"],
                                        b["gap_open"], b["gap_ext"], mat=mat, seq_encoding=2, copy=keep_results)
             n_pairs += res.shape[0]; n_kept += b["n_reads_kept"]
-            cells += int((b["read_len"][b["pair_read"]].astype(np.int64) * b["win_len"][b["pair_win"]]).sum())
+            cells += int(np.dot(np.bincount(b["pair_win"], weights=b["read_len"][b["pair_read"]], minlength=b["win_len"].shape[0]), b["win_len"]))   # bookkeeping for the GCUPS figure
             if keep_results:
                 out.append((b, res, arena))
         pool.shutdown()
