@@ -407,7 +407,7 @@ def pipeline_measurements():
         # BASELINE configs[0] / [2] "in a BAM": the same loci written to BAM + BAI / FASTA + FAI and read back through the native
         # reader (indelpost_b200.bamio; pysam is absent) in BOTH arms
         out["cfg1_from_bam"] = BP.measure("cfg1", 4, workers=1, repeats=2, from_files=True)
-        out["cfg3_from_bam"] = BP.measure("cfg3", 12, workers=1, from_files=True)
+        out["cfg3_from_bam"] = BP.measure("cfg3", 12, workers=1, repeats=2, from_files=True)
         # the same at equal host parallelism, through the product's locus-parallel driver (indelpost_b200.locuspool): ONE BAM +
         # FASTA with every locus, W worker processes in both arms (the wave arm's workers share GPU 0), started and warmed before
         # the timed map()
