@@ -94,6 +94,22 @@ int64_t swb_bam_count(swb_bam* b, int32_t tid, int64_t beg, int64_t end, uint32_
  * bytes (= seq4_len).  Returns the bytes written. */
 int64_t swb_bam_batch_pack4(const swb_bam_batch* batch, uint8_t* dst, int64_t* dst_off);
 
+/* Many regions in ONE call, on host threads: the records of every region that pass the flag masks (and, optionally, have a
+ * CIGAR / do not start at position 0: fetch_reads' conditions, pileup.pyx:138-155) as one SWB_SEQ_PACKED4 read table in region
+ * order -- the reads of region r are entries [region_first[r], region_first[r+1]).  Regions are dealt to `threads` workers
+ * (<= 0: one per core, at most 16), each with its own file handle and block cache over the shared header and index.  This is
+ * the ingest of a whole chunk of loci for swb_align_batch without a Python object per locus.  NULL on error. */
+typedef struct {
+    int64_t   n_regions, n_reads;
+    int64_t*  region_first;             /* n_regions + 1 */
+    int64_t*  read_off;   int32_t* read_len;   /* table entries: byte offset, length in bases */
+    uint8_t*  table;      int64_t table_len;
+    int32_t*  pos;  int32_t* end;  uint16_t* flag;  uint8_t* mapq;     /* per read, like swb_bam_batch */
+} swb_bam_pack;
+swb_bam_pack* swb_bam_fetch_pack4(swb_bam* b, int64_t n_regions, const int32_t* tid, const int64_t* beg, const int64_t* end,
+                                  uint32_t require, uint32_t exclude, int need_cigar, int drop_pos0, int threads);
+void swb_bam_pack_free(swb_bam_pack* p);
+
 /* CIGAR strings of the batch ("70M1D80M", what AlignedSegment.cigarstring returns): entry i NUL terminated at dst + off[i],
  * off has n + 1 entries.  Returns the bytes needed (an upper bound); nothing is written when cap is smaller or dst is NULL. */
 int64_t swb_bam_batch_cigar_text(const swb_bam_batch* batch, char* dst, int64_t cap, int64_t* off);
@@ -177,6 +193,9 @@ int64_t  swb_fai_len(const swb_fai* f, const char* name);     /* -1 if absent */
 /* bases [beg, end) of `name` (clamped to the sequence like pysam's fetch) into dst (end - beg bytes at most); returns the
  * number of bases written, -1 if the sequence is absent. */
 int64_t  swb_fai_fetch(const swb_fai* f, const char* name, int64_t beg, int64_t end, char* dst);
+/* n slices back to back: slice i at dst + off[i], off has n + 1 entries.  Returns the bytes written, -(bytes needed) when cap is
+ * too small, INT64_MIN when a sequence is absent. */
+int64_t  swb_fai_fetch_many(const swb_fai* f, int64_t n, const char* const* names, const int64_t* beg, const int64_t* end, char* dst, int64_t cap, int64_t* off);
 
 #ifdef __cplusplus
 }

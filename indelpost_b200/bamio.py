@@ -32,7 +32,7 @@ _OP_CODE = {c: i for i, c in enumerate(CIGAR_OPS)}
 EXPORTS = (
     "swb_bam_last_error", "swb_bam_version", "swb_bam_open", "swb_bam_close", "swb_bam_n_ref", "swb_bam_ref_name", "swb_bam_ref_len",
     "swb_bam_tid", "swb_bam_header_text", "swb_bam_has_index", "swb_bam_fetch", "swb_bam_batch_free", "swb_bam_count",
-    "swb_bam_batch_pack4", "swb_bam_batch_cigar_text", "swb_pileup_columns", "swb_pileup_cols_free", "swb_pileup_read_size",
+    "swb_bam_batch_pack4", "swb_bam_batch_cigar_text", "swb_bam_fetch_pack4", "swb_bam_pack_free", "swb_fai_fetch_many", "swb_pileup_columns", "swb_pileup_cols_free", "swb_pileup_read_size",
     "swb_bam_create", "swb_bam_write", "swb_bam_writer_close", "swb_fasta_write", "swb_fai_open", "swb_fai_close", "swb_fai_n",
     "swb_fai_name", "swb_fai_len", "swb_fai_fetch",
 )
@@ -49,6 +49,13 @@ class _CBatch(C.Structure):
         ("qual", C.c_void_p),
         ("seq4", C.c_void_p), ("seq4_len", C.c_int64), ("seq4_off", C.c_void_p),
         ("cigar", C.c_void_p), ("cigar_len", C.c_int64),
+    ]
+
+
+class _CPack(C.Structure):
+    _fields_ = [
+        ("n_regions", C.c_int64), ("n_reads", C.c_int64), ("region_first", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p),
+        ("table", C.c_void_p), ("table_len", C.c_int64), ("pos", C.c_void_p), ("end", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
     ]
 
 
@@ -95,6 +102,8 @@ def load():
         "swb_bam_fetch": (C.POINTER(_CBatch), [vp, i32, i64, i64, u32, u32]), "swb_bam_batch_free": (None, [C.POINTER(_CBatch)]),
         "swb_bam_count": (i64, [vp, i32, i64, i64, u32, u32]),
         "swb_bam_batch_pack4": (i64, [C.POINTER(_CBatch), vp, vp]), "swb_bam_batch_cigar_text": (i64, [C.POINTER(_CBatch), vp, i64, vp]),
+        "swb_bam_fetch_pack4": (C.POINTER(_CPack), [vp, i64, vp, vp, vp, u32, u32, C.c_int, C.c_int, C.c_int]), "swb_bam_pack_free": (None, [C.POINTER(_CPack)]),
+        "swb_fai_fetch_many": (i64, [vp, i64, C.POINTER(cp), vp, vp, vp, i64, vp]),
         "swb_pileup_columns": (C.POINTER(_CCols), [C.POINTER(_CBatch), i32, i32, i32, vp, i64, i64, i64, i64]),
         "swb_pileup_cols_free": (None, [C.POINTER(_CCols)]), "swb_pileup_read_size": (i32, []),
         "swb_bam_create": (vp, [cp, cp, i32, C.POINTER(cp), vp, C.c_int]),
@@ -270,6 +279,17 @@ class AlignedSegment:
 
     def __repr__(self):
         return f"<AlignedSegment {self.query_name} {self.reference_name}:{self.reference_start} {self.cigarstring}>"
+
+
+class PackedReads:
+    """swb_bam_fetch_pack4's output: the reads of many regions as ONE SWB_SEQ_PACKED4 table (`table`, `read_off`, `read_len`) in
+    region order -- region r holds reads [region_first[r], region_first[r+1]) -- with pos / end / flag / mapq per read"""
+
+    __slots__ = ("n_regions", "n_reads", "region_first", "read_off", "read_len", "table", "pos", "end", "flag", "mapq")
+
+    def region_of_read(self):
+        """int32[n_reads]: the region every read belongs to (pair_win of a locus-per-window batch)"""
+        return np.repeat(np.arange(self.n_regions, dtype=np.int32), np.diff(self.region_first))
 
 
 class PileupColumns:
@@ -469,6 +489,30 @@ class AlignmentFile:
             raise OSError(_err(self._lib))
         return ReadBatch(self._lib, cb, self.references)
 
+    def fetch_pack4(self, regions, require: int = 0, exclude: int = 0, need_cigar: bool = True, drop_pos0: bool = False, threads: int = 0) -> PackedReads:
+        """the reads of MANY regions -- [(contig, start, stop), ...] -- in one call on host threads, as one SWB_SEQ_PACKED4 read
+        table (swb_bam_fetch_pack4).  fetch_reads' filter (pileup.pyx:138-155) is exclude=FSECONDARY (| FDUP), need_cigar=True,
+        drop_pos0=exclude_duplicates."""
+        n = len(regions)
+        tid = np.empty(n, "<i4"); beg = np.empty(n, "<i8"); end = np.empty(n, "<i8")
+        for k, (contig, start, stop) in enumerate(regions):
+            tid[k], beg[k], end[k] = self._region(contig, start, stop)
+        pp = self._lib.swb_bam_fetch_pack4(self._h, n, _ptr(tid), _ptr(beg), _ptr(end), require, exclude, int(need_cigar), int(drop_pos0), int(threads))
+        if not pp:
+            raise OSError(_err(self._lib))
+        try:
+            c = pp.contents
+            out = PackedReads()
+            out.n_regions, out.n_reads = n, int(c.n_reads)
+            m = out.n_reads
+            out.region_first = _view(c.region_first, n + 1, "<i8")
+            out.read_off = _view(c.read_off, m, "<i8"); out.read_len = _view(c.read_len, m, "<i4")
+            out.table = _view(c.table, int(c.table_len), "u1")
+            out.pos = _view(c.pos, m, "<i4"); out.end = _view(c.end, m, "<i4"); out.flag = _view(c.flag, m, "<u2"); out.mapq = _view(c.mapq, m, "u1")
+        finally:
+            self._lib.swb_bam_pack_free(pp)
+        return out
+
     def fetch(self, contig=None, start=None, stop=None, until_eof: bool = False) -> Iterator[AlignedSegment]:
         """pysam semantics: with a region the records overlapping it in file order (`until_eof` only matters without one)"""
         return iter(self.fetch_columns(contig, start, stop))
@@ -537,6 +581,19 @@ class FastaFile:
 
     def fetch(self, reference=None, start=None, end=None) -> str:
         return self.fetch_bytes(reference, start, end).decode("ascii")
+
+    def fetch_many(self, regions):
+        """[(reference, start, end), ...] -> (uint8 blob, int64 off[n + 1]): the slices back to back (a window table)"""
+        n = len(regions)
+        names = (C.c_char_p * max(1, n))(*[r[0].encode() for r in regions])
+        beg = np.array([r[1] for r in regions] or [0], "<i8"); end = np.array([r[2] for r in regions] or [0], "<i8")
+        off = np.zeros(n + 1, "<i8")
+        cap = int(np.maximum(end - np.maximum(beg, 0), 0).sum()) if n else 0
+        buf = np.empty(max(1, cap), "u1")
+        w = self._lib.swb_fai_fetch_many(self._h, n, names, _ptr(beg), _ptr(end), _ptr(buf), cap, _ptr(off))
+        if w < 0:
+            raise OSError(_err(self._lib) or "fetch_many failed")
+        return buf[:w], off
 
 
 # ---------------------------------------------------------------------------------------------------------------- writing

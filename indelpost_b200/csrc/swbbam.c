@@ -228,6 +228,7 @@ struct swb_bam {
     int32_t n_ref; char** names; int64_t* lens;
     uint64_t first_rec;       /* virtual offset of the first record */
     int has_idx; int32_t idx_nref; refidx_t* idx;
+    char* path;               /* for the per-thread reader clones of swb_bam_fetch_pack4 */
 };
 
 static void free_index(swb_bam* b) {
@@ -279,6 +280,7 @@ swb_bam* swb_bam_open(const char* path) {
     swb_bam* b = (swb_bam*)calloc(1, sizeof *b);
     if (!b) return NULL;
     if (bgzf_rd_init(&b->z, path) != 0) { free(b); return NULL; }
+    b->path = strdup(path);
     bgzf_cur c = { &b->z, 0, 0 };
     uint8_t h[8];
     if (bgzf_read(&c, h, 8) != 8 || memcmp(h, "BAM\1", 4) != 0) { if (!g_err[0] || memcmp(h, "BAM\1", 4)) set_err("%s is not a BAM file", path); goto fail; }
@@ -319,7 +321,7 @@ void swb_bam_close(swb_bam* b) {
     if (!b) return;
     free_index(b);
     for (int i = 0; i < b->n_ref; i++) if (b->names) free(b->names[i]);
-    free(b->names); free(b->lens); free(b->text);
+    free(b->names); free(b->lens); free(b->text); free(b->path);
     bgzf_rd_free(&b->z);
     free(b);
 }
@@ -535,9 +537,9 @@ int64_t swb_bam_count(swb_bam* b, int32_t tid, int64_t beg, int64_t end, uint32_
     return scan_region(b, tid, beg, end, require, exclude, NULL, NULL);
 }
 
-int64_t swb_bam_batch_pack4(const swb_bam_batch* q, uint8_t* dst, int64_t* dst_off) {
-    /* BAM nibble -> DNA_BASE_LUT code (sswpy.pyx:16-29): A(1)->0 C(2)->1 G(4)->2 T(8)->3, every other symbol -> 4;
-       a BAM byte holds base k in its HIGH nibble, SWB_SEQ_PACKED4 in its LOW nibble */
+/* BAM nibble -> DNA_BASE_LUT code (sswpy.pyx:16-29): A(1)->0 C(2)->1 G(4)->2 T(8)->3, every other symbol -> 4;
+   a BAM byte holds base k in its HIGH nibble, SWB_SEQ_PACKED4 in its LOW nibble */
+static const uint8_t* pack4_lut(void) {
     static uint8_t lut[256]; static int ready = 0;
     if (!ready) {
         uint8_t code[16]; for (int i = 0; i < 16; i++) code[i] = 4;
@@ -545,6 +547,10 @@ int64_t swb_bam_batch_pack4(const swb_bam_batch* q, uint8_t* dst, int64_t* dst_o
         for (int v = 0; v < 256; v++) lut[v] = (uint8_t)(code[v >> 4] | code[v & 15] << 4);
         __sync_synchronize(); ready = 1;
     }
+    return lut;
+}
+int64_t swb_bam_batch_pack4(const swb_bam_batch* q, uint8_t* dst, int64_t* dst_off) {
+    const uint8_t* lut = pack4_lut();
     int64_t o = 0;
     for (int64_t i = 0; i < q->n; i++) {
         int32_t L = q->l_seq[i]; int64_t nb = (L + 1) / 2;
@@ -555,6 +561,121 @@ int64_t swb_bam_batch_pack4(const swb_bam_batch* q, uint8_t* dst, int64_t* dst_o
         o += nb;
     }
     return o;
+}
+
+/* ================================================================== many regions -> one packed read table, host threads */
+typedef struct {
+    uint8_t* tab; int64_t tab_len, tab_cap;
+    int32_t* len; int32_t* pos; int32_t* end; uint16_t* flag; uint8_t* mapq; int64_t n, cap;
+    int need_cigar, drop_pos0, oom;
+} reg_out;
+static int pack_cb(void* ctx, const uint8_t* r, int32_t bs) {
+    reg_out* o = (reg_out*)ctx;
+    int l_name = r[8], n_cig = rd16(r + 12); int32_t l_seq = (int32_t)rd32(r + 16), pos = (int32_t)rd32(r + 4);
+    if (l_seq < 0 || 32 + (int64_t)l_name + 4LL * n_cig + (l_seq + 1) / 2 > bs) { set_err("corrupt BAM record"); return -1; }
+    if ((o->need_cigar && n_cig == 0) || (o->drop_pos0 && pos == 0)) return 0;
+    if (o->n == o->cap) {
+        int64_t nc = o->cap ? o->cap * 2 : 512;
+        void *a = realloc(o->len, (size_t)nc * 4), *b = realloc(o->pos, (size_t)nc * 4), *c = realloc(o->end, (size_t)nc * 4), *d = realloc(o->flag, (size_t)nc * 2), *e = realloc(o->mapq, (size_t)nc);
+        if (a) o->len = (int32_t*)a;
+        if (b) o->pos = (int32_t*)b;
+        if (c) o->end = (int32_t*)c;
+        if (d) o->flag = (uint16_t*)d;
+        if (e) o->mapq = (uint8_t*)e;
+        if (!a || !b || !c || !d || !e) { o->oom = 1; return -1; }
+        o->cap = nc;
+    }
+    int64_t nb = (l_seq + 1) / 2;
+    if (o->tab_len + nb > o->tab_cap) {
+        int64_t nc = o->tab_cap ? o->tab_cap * 2 : 65536; while (nc < o->tab_len + nb) nc *= 2;
+        void* t = realloc(o->tab, (size_t)nc); if (!t) { o->oom = 1; return -1; }
+        o->tab = (uint8_t*)t; o->tab_cap = nc;
+    }
+    const uint8_t* lut = pack4_lut();
+    const uint8_t* sq = r + 32 + l_name + 4 * n_cig; uint8_t* dst = o->tab + o->tab_len;
+    for (int64_t k = 0; k < nb; k++) dst[k] = lut[sq[k]];
+    if (l_seq & 1) dst[nb - 1] &= 0x0f;
+    o->tab_len += nb;
+    uint16_t fl = rd16(r + 14);
+    o->len[o->n] = l_seq; o->pos[o->n] = pos; o->flag[o->n] = fl; o->mapq[o->n] = r[9];
+    o->end[o->n] = ((fl & SWB_BAM_FUNMAP) || n_cig == 0) ? -1 : pos + cigar_reflen(r + 32 + l_name, n_cig);
+    o->n++;
+    return 0;
+}
+typedef struct {
+    const swb_bam* src; int64_t n_regions; const int32_t* tid; const int64_t* beg; const int64_t* end; uint32_t require, exclude;
+    reg_out* out; volatile int64_t* next; int fail; char err[256];
+} pack_job;
+static void* pack_worker(void* a) {
+    pack_job* j = (pack_job*)a;
+    swb_bam local = *j->src;                       /* header and index are shared read-only; the file handle, caches and span are its own */
+    if (bgzf_rd_init(&local.z, j->src->path) != 0) { j->fail = 1; snprintf(j->err, sizeof j->err, "%s", g_err); return NULL; }
+    for (;;) {
+        int64_t r = __sync_fetch_and_add(j->next, 1);
+        if (r >= j->n_regions) break;
+        g_err[0] = 0;
+        if (j->tid[r] < 0 || scan_region(&local, j->tid[r], j->beg[r], j->end[r], j->require, j->exclude, pack_cb, &j->out[r]) < 0) {
+            j->fail = 1; snprintf(j->err, sizeof j->err, "region %lld: %s", (long long)r, j->tid[r] < 0 ? "unknown contig" : (j->out[r].oom ? "out of memory" : g_err));
+            break;
+        }
+    }
+    bgzf_rd_free(&local.z);
+    return NULL;
+}
+void swb_bam_pack_free(swb_bam_pack* p) {
+    if (!p) return;
+    free(p->region_first); free(p->read_off); free(p->read_len); free(p->table); free(p->pos); free(p->end); free(p->flag); free(p->mapq); free(p);
+}
+swb_bam_pack* swb_bam_fetch_pack4(swb_bam* b, int64_t n_regions, const int32_t* tid, const int64_t* beg, const int64_t* end,
+                                  uint32_t require, uint32_t exclude, int need_cigar, int drop_pos0, int threads) {
+    if (n_regions < 0) { set_err("negative region count"); return NULL; }
+    reg_out* out = (reg_out*)calloc((size_t)n_regions + 1, sizeof(reg_out));
+    swb_bam_pack* p = (swb_bam_pack*)calloc(1, sizeof *p);
+    if (!out || !p) { free(out); free(p); set_err("out of memory"); return NULL; }
+    for (int64_t r = 0; r < n_regions; r++) { out[r].need_cigar = need_cigar; out[r].drop_pos0 = drop_pos0; }
+    if (threads <= 0) { threads = (int)sysconf(_SC_NPROCESSORS_ONLN); if (threads > 16) threads = 16; }
+    if (threads > n_regions) threads = n_regions ? (int)n_regions : 1;
+    if (threads > 64) threads = 64;
+    volatile int64_t next = 0;
+    (void)pack4_lut(); (void)bam_threads();          /* one-time tables set up before the workers start */
+    pack_job jobs[64]; pthread_t th[64]; int started[64] = { 0 };
+    for (int t = 0; t < threads; t++) {
+        jobs[t].src = b; jobs[t].n_regions = n_regions; jobs[t].tid = tid; jobs[t].beg = beg; jobs[t].end = end; jobs[t].require = require; jobs[t].exclude = exclude;
+        jobs[t].out = out; jobs[t].next = &next; jobs[t].fail = 0; jobs[t].err[0] = 0;
+    }
+    for (int t = 1; t < threads; t++) started[t] = pthread_create(&th[t], NULL, pack_worker, &jobs[t]) == 0;
+    pack_worker(&jobs[0]);
+    int fail = jobs[0].fail; const char* msg = jobs[0].err;
+    for (int t = 1; t < threads; t++) { if (started[t]) pthread_join(th[t], NULL); if (jobs[t].fail && !fail) { fail = 1; msg = jobs[t].err; } }
+    if (!fail) {
+        int64_t n = 0, tb = 0;
+        for (int64_t r = 0; r < n_regions; r++) { n += out[r].n; tb += out[r].tab_len; }
+        p->n_regions = n_regions; p->n_reads = n; p->table_len = tb;
+        p->region_first = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_regions + 1));
+        p->read_off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1)); p->read_len = (int32_t*)malloc(4 * (size_t)(n + 1));
+        p->pos = (int32_t*)malloc(4 * (size_t)(n + 1)); p->end = (int32_t*)malloc(4 * (size_t)(n + 1));
+        p->flag = (uint16_t*)malloc(2 * (size_t)(n + 1)); p->mapq = (uint8_t*)malloc((size_t)n + 1); p->table = (uint8_t*)malloc((size_t)tb + 1);
+        if (!p->region_first || !p->read_off || !p->read_len || !p->pos || !p->end || !p->flag || !p->mapq || !p->table) { fail = 1; msg = "out of memory"; }
+        else {
+            int64_t i = 0, o = 0;
+            for (int64_t r = 0; r < n_regions; r++) {
+                p->region_first[r] = i;
+                if (out[r].tab_len) memcpy(p->table + o, out[r].tab, (size_t)out[r].tab_len);
+                int64_t oo = o;
+                for (int64_t k = 0; k < out[r].n; k++) { p->read_off[i + k] = oo; oo += (out[r].len[k] + 1) / 2; }
+                if (out[r].n) {
+                    memcpy(p->read_len + i, out[r].len, 4 * (size_t)out[r].n); memcpy(p->pos + i, out[r].pos, 4 * (size_t)out[r].n);
+                    memcpy(p->end + i, out[r].end, 4 * (size_t)out[r].n); memcpy(p->flag + i, out[r].flag, 2 * (size_t)out[r].n); memcpy(p->mapq + i, out[r].mapq, (size_t)out[r].n);
+                }
+                i += out[r].n; o += out[r].tab_len;
+            }
+            p->region_first[n_regions] = i;
+        }
+    }
+    for (int64_t r = 0; r < n_regions; r++) { free(out[r].tab); free(out[r].len); free(out[r].pos); free(out[r].end); free(out[r].flag); free(out[r].mapq); }
+    free(out);
+    if (fail) { char tmp[256]; snprintf(tmp, sizeof tmp, "%s", msg && msg[0] ? msg : "fetch failed"); swb_bam_pack_free(p); set_err("%s", tmp); return NULL; }
+    return p;
 }
 
 /* ================================================================== pileup columns (dictize_read's integer core) */
@@ -1029,3 +1150,25 @@ int64_t swb_bam_batch_cigar_text(const swb_bam_batch* q, char* dst, int64_t cap,
     return o;
 }
 int32_t swb_pileup_read_size(void) { return (int32_t)sizeof(swb_pileup_read); }
+
+/* n slices back to back into dst: slice i at dst + off[i] (off has n + 1 entries).  Returns the bytes written, or -(bytes needed) when
+ * cap is too small, or INT64_MIN on a missing sequence. */
+int64_t swb_fai_fetch_many(const swb_fai* f, int64_t n, const char* const* names, const int64_t* beg, const int64_t* end, char* dst, int64_t cap, int64_t* off) {
+    int64_t need = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const fai_ent* e = fai_find(f, names[i]);
+        if (!e) { set_err("sequence %s not in the FASTA index", names[i]); return INT64_MIN; }
+        int64_t b = beg[i] < 0 ? 0 : beg[i], x = end[i] > e->len ? e->len : end[i];
+        need += x > b ? x - b : 0;
+    }
+    if (need > cap) return -need;
+    int64_t o = 0;
+    for (int64_t i = 0; i < n; i++) {
+        off[i] = o;
+        int64_t w = swb_fai_fetch(f, names[i], beg[i], end[i], dst + o);
+        if (w < 0) return INT64_MIN;
+        o += w;
+    }
+    off[n] = o;
+    return o;
+}

@@ -349,3 +349,51 @@ def test_long_reads_unplaced_reads_and_foreign_blocks(tmp_path):
 def array_of(rng, n):
     import array
     return array.array("B", [rng.choice((2, 20, 30, 40)) for _ in range(n)])
+
+
+def test_fetch_pack4_many_regions_equals_per_region_fetches(tmp_path):
+    """swb_bam_fetch_pack4 (many regions, host threads, own file handle per thread) == one fetch_columns + pack4 per region with
+    fetch_reads' filter applied; swb_fai_fetch_many == one fetch per slice"""
+    rng = random.Random(23)
+    lcs, reads, seqs = [], [], {}
+    for k in range(24):
+        lc = L.make_locus(600 + k, kind=("del", "ins", "spliced")[k % 3], ev_len=1 + k % 7, n_reads=60 + 5 * k, read_len=(100, 150, 151)[k % 3], n_rate=0.01)
+        name = f"c{k:02d}"
+        for r in lc["reads"]:
+            r["reference_name"] = name
+            r["is_duplicate"] = rng.random() < 0.1
+            r["is_secondary"] = rng.random() < 0.05
+        lc["reads"][0]["reference_start"] = 0                     # dropped by `and read.reference_start`
+        lc["reads"][0]["reference_end"] = lc["reads"][0]["reference_end"] - lc["reads"][0]["reference_start"]
+        seqs[name] = lc["genome"]; reads.extend(lc["reads"]); lcs.append((name, lc["pos"]))
+    bam_p, fa_p = os.path.join(str(tmp_path), "m.bam"), os.path.join(str(tmp_path), "m.fa")
+    bamio.write_fasta(fa_p, seqs)
+    bamio.write_bam(bam_p, [(k, len(v)) for k, v in seqs.items()], reads)
+    bam, fa = bamio.AlignmentFile(bam_p), bamio.FastaFile(fa_p)
+    regions = [(name, pos - 51, pos + 50) for name, pos in lcs] + [("c03", 0, 10), ("c05", 3990, 4000), ("c07", 100, 101)]
+    for excl_dup in (True, False):
+        for threads in (1, 3, 8):
+            pk = bam.fetch_pack4(regions, exclude=bamio.FSECONDARY | (bamio.FDUP if excl_dup else 0), need_cigar=True, drop_pos0=excl_dup, threads=threads)
+            first = [0]; tabs = []; lens = []; poss = []; flags = []
+            for (name, a, e) in regions:
+                b = bam.fetch_columns(name, a, e)
+                keep = ((b.flag & bamio.FSECONDARY) == 0) & (b.n_cigar > 0)
+                if excl_dup:
+                    keep &= ((b.flag & bamio.FDUP) == 0) & (b.pos != 0)
+                t, o, ln = b.pack4()
+                for i in keep.nonzero()[0]:
+                    tabs.append(t[int(o[i]): int(o[i]) + (int(ln[i]) + 1) // 2]); lens.append(int(ln[i])); poss.append(int(b.pos[i])); flags.append(int(b.flag[i]))
+                first.append(len(lens))
+            assert pk.n_reads == len(lens) and list(pk.region_first) == first
+            assert list(pk.read_len) == lens and list(pk.pos) == poss and list(pk.flag) == flags
+            assert np.array_equal(pk.table, np.concatenate(tabs) if tabs else np.zeros(0, "u1"))
+            assert np.array_equal(pk.read_off, np.concatenate([[0], np.cumsum((np.array(lens) + 1) // 2)[:-1]]))
+            assert np.array_equal(pk.region_of_read(), np.repeat(np.arange(len(regions)), np.diff(first)))
+    empty = bam.fetch_pack4([])
+    assert empty.n_reads == 0 and list(empty.region_first) == [0]
+    with pytest.raises(ValueError):
+        bam.fetch_pack4([("nope", 0, 10)])
+    slices = [(name, pos - 150, pos + 150) for name, pos in lcs] + [("c00", 3900, 5000), ("c01", -5, 3), ("c02", 10, 10)]
+    blob, off = fa.fetch_many(slices)
+    assert blob.tobytes() == b"".join(fa.fetch_bytes(*s) for s in slices)
+    assert list(np.diff(off)) == [len(fa.fetch_bytes(*s)) for s in slices]

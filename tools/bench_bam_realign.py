@@ -122,7 +122,26 @@ def build_chunk(items):
                 win_len=wlen, pair_read=pr, pair_win=pw, gap_open=go, gap_ext=ge, n_reads_kept=n_kept)
 
 
-def measure(config="cfg3", n_loci=1000, threads=None, chunk=250, device=0, aligner=None, cpu_sample=24000):
+def ingest_chunk_bulk(bam, fa, part, window, threads):
+    """a whole chunk of loci in TWO C calls (swb_bam_fetch_pack4 on host threads + swb_fai_fetch_many) and a handful of numpy
+    operations: no Python work per locus or per read"""
+    from indelpost_b200 import bamio
+    from indelpost_b200.batch import pack_table
+
+    pk = bam.fetch_pack4([(name, max(0, pos - 1 - window), pos + window) for name, pos in part], exclude=bamio.FSECONDARY | bamio.FDUP, need_cigar=True,
+                         drop_pos0=True, threads=threads)                                                        # fetch_reads, pileup.pyx:138-147
+    wblob, woff = fa.fetch_many([(name, max(0, pos - 3 * window), pos + 3 * window) for name, pos in part])   # local_reference.pyx:22-30
+    wlen = np.diff(woff).astype("<i4")
+    wtab, wtoff = pack_table(wblob, woff[:-1], wlen, bits=4, ascii=True)
+    g = len(GRID)
+    pr = np.repeat(np.arange(pk.n_reads, dtype="<i4"), g)
+    pw = np.repeat(pk.region_of_read(), g)
+    go = np.tile(np.array([a for a, _ in GRID], "u1"), pk.n_reads); ge = np.tile(np.array([e for _, e in GRID], "u1"), pk.n_reads)
+    return dict(reads=pk.table.view(np.int8), read_off=pk.read_off, read_len=pk.read_len, windows=wtab.view(np.int8), win_off=wtoff, win_len=wlen,
+                pair_read=pr, pair_win=pw, gap_open=go, gap_ext=ge, n_reads_kept=pk.n_reads)
+
+
+def measure(config="cfg3", n_loci=1000, threads=None, chunk=250, device=0, aligner=None, cpu_sample=24000, mode="bulk"):
     import swbtest as T
     from indelpost_b200 import bamio
 
@@ -139,7 +158,33 @@ def measure(config="cfg3", n_loci=1000, threads=None, chunk=250, device=0, align
         aligner = BatchAligner(device)
     window = sh["window"]
 
-    def run(keep_results=False):
+    def align_chunk(b, keep_results):
+        return aligner.align(b["reads"], b["read_off"], b["read_len"], b["windows"], b["win_off"], b["win_len"], b["pair_read"], b["pair_win"],
+                             b["gap_open"], b["gap_ext"], mat=mat, seq_encoding=2, copy=keep_results)
+
+    def chunk_cells(b):       # bookkeeping for the GCUPS figure
+        return int(np.dot(np.bincount(b["pair_win"], weights=b["read_len"][b["pair_read"]], minlength=b["win_len"].shape[0]), b["win_len"]))
+
+    def run_bulk(keep_results=False):
+        bam, fa = bamio.AlignmentFile(bam_p), bamio.FastaFile(fa_p)
+        chunks = [meta[i: i + chunk] for i in range(0, len(meta), chunk)]
+        bg = ThreadPoolExecutor(max_workers=1)              # the next chunk's ingest (C calls, GIL released) beside this chunk's GPU call
+        n_pairs = n_kept = cells = 0
+        out = []
+        pending = bg.submit(ingest_chunk_bulk, bam, fa, chunks[0], window, threads)
+        for ci in range(len(chunks)):
+            b = pending.result()
+            if ci + 1 < len(chunks):
+                pending = bg.submit(ingest_chunk_bulk, bam, fa, chunks[ci + 1], window, threads)
+            res, arena = align_chunk(b, keep_results)
+            n_pairs += res.shape[0]; n_kept += b["n_reads_kept"]; cells += chunk_cells(b)
+            if keep_results:
+                out.append((b, res, arena))
+        bg.shutdown()
+        bam.close(); fa.close()
+        return n_pairs, n_kept, cells, out
+
+    def run_per_locus(keep_results=False):
         pool = ThreadPoolExecutor(max_workers=threads)
         chunks = [meta[i: i + chunk] for i in range(0, len(meta), chunk)]
         # a reader handle is not thread-safe (block cache, span buffer) and cheap to open: one per ingest thread
@@ -161,10 +206,8 @@ def measure(config="cfg3", n_loci=1000, threads=None, chunk=250, device=0, align
             if ci + 1 < len(chunks):
                 pending = submit(chunks[ci + 1])             # the next chunk's ingest runs beside this chunk's GPU call
             b = build_chunk(items)
-            res, arena = aligner.align(b["reads"], b["read_off"], b["read_len"], b["windows"], b["win_off"], b["win_len"], b["pair_read"], b["pair_win"],
-                                       b["gap_open"], b["gap_ext"], mat=mat, seq_encoding=2, copy=keep_results)
-            n_pairs += res.shape[0]; n_kept += b["n_reads_kept"]
-            cells += int(np.dot(np.bincount(b["pair_win"], weights=b["read_len"][b["pair_read"]], minlength=b["win_len"].shape[0]), b["win_len"]))   # bookkeeping for the GCUPS figure
+            res, arena = align_chunk(b, keep_results)
+            n_pairs += res.shape[0]; n_kept += b["n_reads_kept"]; cells += chunk_cells(b)
             if keep_results:
                 out.append((b, res, arena))
         pool.shutdown()
@@ -172,12 +215,13 @@ def measure(config="cfg3", n_loci=1000, threads=None, chunk=250, device=0, align
             hb.close(); hf.close()
         return n_pairs, n_kept, cells, out
 
+    run = run_bulk if mode == "bulk" else run_per_locus
     run()                                                    # warm-up: context, kernels, page cache
     t0 = time.perf_counter()
     n_pairs, n_kept, cells, _ = run()
     dt = time.perf_counter() - t0
     res = {"config": config, "loci": n_loci, "reads_in_bam": n_loci * sh["n_reads"], "reads_realigned": n_kept, "pairs": n_pairs, "grid_points": len(GRID),
-           "read_len": sh["read_len"], "window_len": 6 * window, "host_threads": threads, "chunk_loci": chunk, "bam_bytes": os.path.getsize(bam_p),
+           "read_len": sh["read_len"], "window_len": 6 * window, "host_threads": threads, "chunk_loci": chunk, "ingest": "one swb_bam_fetch_pack4 + one swb_fai_fetch_many call per chunk" if mode == "bulk" else "one fetch per locus on a Python thread pool", "bam_bytes": os.path.getsize(bam_p),
            "seconds": dt, "reads_per_s": n_kept / dt, "pairs_per_s": n_pairs / dt, "gcups": cells / dt / 1e9, "generate_and_write_s": t_gen,
            "what": "files closed -> every record and CIGAR on the host: native BAM ingest on host threads + swb_align_batch (PACKED4 tables straight from the BAM nibbles), "
                    "six gap-grid points per read against the locus window"}
@@ -218,8 +262,9 @@ def main():
     ap.add_argument("--loci", type=int, default=1000)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=250)
+    ap.add_argument("--mode", default="bulk", choices=("bulk", "per_locus"))
     a = ap.parse_args()
-    print(json.dumps(measure(a.config, a.loci, a.threads or None, a.chunk)))
+    print(json.dumps(measure(a.config, a.loci, a.threads or None, a.chunk, mode=a.mode)))
 
 
 if __name__ == "__main__":
