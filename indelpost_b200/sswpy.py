@@ -61,13 +61,28 @@ def cigar_to_string(ops: np.ndarray) -> str:
     return "".join(f"{int(v) >> 4}{_OPS[int(v) & 15] if (int(v) & 15) <= 8 else 'M'}" for v in ops)
 
 
+_MATRICES: dict = {}      # (match, mismatch) -> (5x5 int8 matrix, its bytes): built once, shared by every SSW with those scores
+
+
 class SSW:
-    """Drop-in for reference ``sswpy.SSW`` (sswpy.pyx:99-337)."""
+    """Drop-in for reference ``sswpy.SSW`` (sswpy.pyx:99-337).
+
+    indelPost builds a fresh aligner for almost every call (`make_aligner` + `align`, localn.pyx:464-472: thousands per locus), and
+    under prefetch / the wave scheduler nearly every `align()` is answered from a batch computed earlier.  So everything that is
+    only needed by the single-pair GPU path -- encoding the sequences, `ssw_init`, the profile -- is deferred until that path is
+    actually taken; `setRead` / `setReference` just record the sequence."""
+
+    __slots__ = ("_lib", "score_matrix", "_mkey", "_ms", "_mm", "_rid", "_wid", "_rkey", "_wkey", "read", "reference", "_read_arr", "_ref_arr",
+                 "_profile", "read_length", "ref_length", "_memo", "__dict__")
 
     def __init__(self, match_score: int = 2, mismatch_penalty: int = 2):
-        self._lib = L.load()
-        self.score_matrix = dna_score_matrix(_c_int(match_score), _c_int(mismatch_penalty))  # buildDNAScoreMatrix
-        self._mkey = self.score_matrix.tobytes()
+        self._lib = None
+        m = _MATRICES.get((match_score, mismatch_penalty))
+        if m is None:
+            mat = dna_score_matrix(_c_int(match_score), _c_int(mismatch_penalty))        # buildDNAScoreMatrix
+            mat.setflags(write=False)
+            m = _MATRICES[(match_score, mismatch_penalty)] = (mat, mat.tobytes())
+        self.score_matrix, self._mkey = m
         self._ms, self._mm = match_score, mismatch_penalty
         self._rid = self._wid = self._rkey = self._wkey = None
         self.read = None
@@ -79,74 +94,51 @@ class SSW:
         self.ref_length = 0
         # results of this aligner's recent calls: indelPost repeats alignments with identical inputs (update_read_info,
         # pileup.pyx:849, re-runs what retarget computed at pileup.pyx:647 -- SURVEY.md 8f item 1); a hit skips the GPU round trip
-        self._memo = {}
+        self._memo = None
 
     def __del__(self):  # __dealloc__, sswpy.pyx:135-147
         try:
-            if self._profile:
+            if self._profile and self._lib is not None:
                 self._lib.init_destroy(self._profile)
                 self._profile = None
         except Exception:
             pass
 
-    def setRead(self, read: STR_T):  # sswpy.pyx:149-178
-        raw = _to_bytes(read)
-        arr = np.ascontiguousarray(_LUT[np.frombuffer(raw, dtype=np.uint8)])
-        if self._profile:
+    def _drop_profile(self):
+        if self._profile and self._lib is not None:
             self._lib.init_destroy(self._profile)
-            self._profile = None
+        self._profile = None
+
+    def setRead(self, read: STR_T):  # sswpy.pyx:149-178
+        raw = read.encode("utf8") if type(read) is str else (read if type(read) is bytes else _to_bytes(read))
+        if self._profile:
+            self._drop_profile()
         self.read = read
-        self._read_arr = arr
+        self._read_arr = None
         self._rid = _SEQ_IDS.get(raw)            # None: this read is in no prefetched block
         self._rkey = raw
         self.read_length = len(raw)
-        self._profile = self._lib.ssw_init(arr.ctypes.data, len(raw), self.score_matrix.ctypes.data, 5, 2)
 
     def setReference(self, reference: STR_T):  # sswpy.pyx:180-197
-        raw = _to_bytes(reference)
-        self._ref_arr = np.ascontiguousarray(_LUT[np.frombuffer(raw, dtype=np.uint8)])
+        raw = reference.encode("utf8") if type(reference) is str else (reference if type(reference) is bytes else _to_bytes(reference))
+        self._ref_arr = None
         self._wid = _SEQ_IDS.get(raw)
         self._wkey = raw
         self.reference = reference
         self.ref_length = len(raw)
-        self._memo.clear()
+        self._memo = None
 
-    def align(self, gap_open: int = 3, gap_extension: int = 1, start_idx: int = 0, end_idx: int = 0) -> Alignment:
-        """sswpy.pyx:227-304 (same checks, same order, same messages)"""
-        gap_open = _c_int(gap_open, "gap_open")
-        gap_extension = _c_int(gap_extension, "gap_extension")
-        start_idx = int(start_idx)
-        end_idx = int(end_idx)
-        if start_idx < 0 or end_idx < 0:
-            raise ValueError("negative indexing not supported")
-        if end_idx > self.ref_length or start_idx > self.ref_length:
-            raise ValueError(
-                "start_idx: {} or end_idx: {} can't be greater than ref_length: {}".format(start_idx, end_idx, self.ref_length)
-            )
-        end_idx_final = self.ref_length if end_idx == 0 else end_idx
-        search_length = end_idx_final - start_idx
-        if self.reference is None:
-            raise ValueError("call setReference first")
+    def _single_pair(self, gap_open, gap_extension, start_idx, search_length):
+        """the per-call GPU path (ssw_init + ssw_align through the compatibility symbols): a one-pair round trip"""
+        if self._lib is None:
+            self._lib = L.load()
+        if self._ref_arr is None:
+            self._ref_arr = np.ascontiguousarray(_LUT[np.frombuffer(self._wkey, dtype=np.uint8)])
         if not self._profile:
-            raise ValueError("Must set profile first")
-        go8, ge8 = gap_open & 0xFF, gap_extension & 0xFF
-        key = (self._rkey, go8, ge8, start_idx, search_length)
-        hit = self._memo.get(key)
-        if hit is not None:
-            return hit
-        if _BLOCKS and start_idx == 0 and search_length == self.ref_length:
-            if self._rid is None:
-                self._rid = _SEQ_IDS.get(self._rkey)
-            if self._wid is None:
-                self._wid = _SEQ_IDS.get(self._wkey)
-            if self._rid is not None and self._wid is not None:
-                hit = prefetched(self._mkey, self._rid, self._wid, go8, ge8, self.read_length)      # filled by prefetch_alignments()
-                if hit is not None:
-                    return hit
-        if _RESOLVER is not None:
-            hit = _RESOLVER(self, go8, ge8, start_idx, search_length)                                 # wave scheduler (wave.py)
-            if hit is not None:
-                return hit
+            self._read_arr = np.ascontiguousarray(_LUT[np.frombuffer(self._rkey, dtype=np.uint8)])
+            self._profile = self._lib.ssw_init(self._read_arr.ctypes.data, self.read_length, self.score_matrix.ctypes.data, 5, 2)
+            if not self._profile:
+                raise ValueError("Must set profile first")
         mask_len = self.read_length // 2  # align_c, sswpy.pyx:209-211
         mask_len = 15 if mask_len < 15 else mask_len
         ref_ptr = self._ref_arr.ctypes.data + start_idx
@@ -161,9 +153,63 @@ class SSW:
             cigar = cigar_to_string(ops)
         out = Alignment(cigar, r.score1, r.score2, r.ref_begin1, r.ref_end1, r.read_begin1, r.read_end1)
         self._lib.align_destroy(res)
-        if len(self._memo) >= 256:
-            self._memo.clear()
-        self._memo[key] = out
+        return out
+
+    def align(self, gap_open: int = 3, gap_extension: int = 1, start_idx: int = 0, end_idx: int = 0) -> Alignment:
+        """sswpy.pyx:227-304 (same checks, same order, same messages)"""
+        if type(gap_open) is not int or type(gap_extension) is not int or not (-2147483648 <= gap_open < 2147483648) or not (-2147483648 <= gap_extension < 2147483648):
+            gap_open = _c_int(gap_open, "gap_open")
+            gap_extension = _c_int(gap_extension, "gap_extension")
+        ref_length = self.ref_length
+        if start_idx == 0 and end_idx == 0:
+            search_length = ref_length
+        else:
+            start_idx = int(start_idx)
+            end_idx = int(end_idx)
+            if start_idx < 0 or end_idx < 0:
+                raise ValueError("negative indexing not supported")
+            if end_idx > ref_length or start_idx > ref_length:
+                raise ValueError(
+                    "start_idx: {} or end_idx: {} can't be greater than ref_length: {}".format(start_idx, end_idx, ref_length)
+                )
+            search_length = (ref_length if end_idx == 0 else end_idx) - start_idx
+        if self.reference is None:
+            raise ValueError("call setReference first")
+        rkey = self._rkey
+        if rkey is None:
+            raise ValueError("Must set profile first")
+        go8, ge8 = gap_open & 0xFF, gap_extension & 0xFF
+        memo = self._memo
+        key = (rkey, go8, ge8, start_idx, search_length)
+        if memo is not None:
+            hit = memo.get(key)
+            if hit is not None:
+                return hit
+        if search_length == ref_length and start_idx == 0:
+            if _BLOCKS:
+                rid, wid = self._rid, self._wid
+                if rid is None:
+                    rid = self._rid = _SEQ_IDS.get(rkey)
+                if wid is None:
+                    wid = self._wid = _SEQ_IDS.get(self._wkey)
+                if rid is not None and wid is not None:
+                    blocks = _BLOCKS.get((self._mkey, wid))                                           # filled by prefetch_alignments()
+                    if blocks:
+                        rlen = self.read_length
+                        for b in blocks:
+                            hit = b.find(rid, wid, go8, ge8, rlen)
+                            if hit is not None:
+                                return hit
+        if _RESOLVER is not None:
+            hit = _RESOLVER(self, go8, ge8, start_idx, search_length)                                 # wave scheduler (wave.py)
+            if hit is not None:
+                return hit
+        out = self._single_pair(gap_open, gap_extension, start_idx, search_length)
+        if memo is None:
+            memo = self._memo = {}
+        elif len(memo) >= 256:
+            memo.clear()
+        memo[key] = out
         return out
 
 

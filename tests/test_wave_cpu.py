@@ -15,17 +15,8 @@ pytestmark = pytest.mark.skipif(not refpipe.available(), reason="oracle/_ref_pip
 class _NoGpuSSW(sswpy.SSW):
     """the product's SSW with the per-call GPU path closed: every answer must come from a wave"""
 
-    def __init__(self, match_score=2, mismatch_penalty=2):
-        super().__init__(match_score, mismatch_penalty)
-        self._lib = None
-
-    def setRead(self, read):
-        raw = sswpy._to_bytes(read)
-        self.read, self._rkey, self._rid, self.read_length = read, raw, sswpy._SEQ_IDS.get(raw), len(raw)
-        self._profile = 1                  # align() only checks that a profile exists before it consults memo / blocks / resolver
-
-    def __del__(self):
-        pass
+    def _single_pair(self, gap_open, gap_extension, start_idx, search_length):
+        raise AssertionError("the per-call GPU path was taken: a request was not served by a wave")
 
 
 def _oracle_align_batch(calls_log):
