@@ -397,3 +397,32 @@ def test_fetch_pack4_many_regions_equals_per_region_fetches(tmp_path):
     blob, off = fa.fetch_many(slices)
     assert blob.tobytes() == b"".join(fa.fetch_bytes(*s) for s in slices)
     assert list(np.diff(off)) == [len(fa.fetch_bytes(*s)) for s in slices]
+
+
+def test_bai_with_samtools_metadata(tmp_path):
+    """an index as samtools writes it: the metadata pseudo-bin 37450 inside every reference and the trailing n_no_coor count
+    (SAMv1 5.2) must not change any query"""
+    import struct
+    locus = L.make_locus(31, kind="ins", ev_len=5, n_reads=300)
+    bam, _ = write_locus(str(tmp_path), locus)
+    want = [s.query_name for s in bamio.AlignmentFile(bam).fetch("chr1", 1990, 2010)]
+    raw = open(bam + ".bai", "rb").read()
+    (n_ref,) = struct.unpack_from("<i", raw, 4)
+    out = bytearray(raw[:8]); o = 8
+    for _ in range(n_ref):
+        (n_bin,) = struct.unpack_from("<i", raw, o); o += 4
+        out += struct.pack("<i", n_bin + 1)
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", raw, o)
+            out += raw[o: o + 8 + 16 * n_chunk]; o += 8 + 16 * n_chunk
+        out += struct.pack("<IiQQQQ", 37450, 2, 0, 1 << 40, 300, 0)            # ref_beg, ref_end / n_mapped, n_unmapped
+        (n_intv,) = struct.unpack_from("<i", raw, o)
+        out += raw[o: o + 4 + 8 * n_intv]; o += 4 + 8 * n_intv
+    out += struct.pack("<Q", 7)                                                 # n_no_coor
+    open(bam + ".bai", "wb").write(out)
+    f = bamio.AlignmentFile(bam)
+    assert f.has_index() and [s.query_name for s in f.fetch("chr1", 1990, 2010)] == want
+    # a truncated index is refused (the reader then scans): same answer
+    open(bam + ".bai", "wb").write(out[: len(out) // 2])
+    g = bamio.AlignmentFile(bam)
+    assert not g.has_index() and [s.query_name for s in g.fetch("chr1", 1990, 2010)] == want
