@@ -609,13 +609,13 @@ typedef struct {
 static void* pack_worker(void* a) {
     pack_job* j = (pack_job*)a;
     swb_bam local = *j->src;                       /* header and index are shared read-only; the file handle, caches and span are its own */
-    if (bgzf_rd_init(&local.z, j->src->path) != 0) { j->fail = 1; snprintf(j->err, sizeof j->err, "%s", g_err); return NULL; }
+    if (bgzf_rd_init(&local.z, j->src->path) != 0) { j->fail = 1; snprintf(j->err, sizeof j->err, "%.250s", g_err); return NULL; }
     for (;;) {
         int64_t r = __sync_fetch_and_add(j->next, 1);
         if (r >= j->n_regions) break;
         g_err[0] = 0;
         if (j->tid[r] < 0 || scan_region(&local, j->tid[r], j->beg[r], j->end[r], j->require, j->exclude, pack_cb, &j->out[r]) < 0) {
-            j->fail = 1; snprintf(j->err, sizeof j->err, "region %lld: %s", (long long)r, j->tid[r] < 0 ? "unknown contig" : (j->out[r].oom ? "out of memory" : g_err));
+            j->fail = 1; snprintf(j->err, sizeof j->err, "region %lld: %.200s", (long long)r, j->tid[r] < 0 ? "unknown contig" : (j->out[r].oom ? "out of memory" : g_err));
             break;
         }
     }
