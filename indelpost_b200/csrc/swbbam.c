@@ -441,19 +441,20 @@ static chunk_t* region_chunks(const swb_bam* b, int32_t tid, int64_t beg, int64_
     uint64_t min_off = 0;
     if (r->n_intv > 0) { int64_t w = beg >> 14; min_off = r->ioff[w >= r->n_intv ? r->n_intv - 1 : w]; }
     static __thread uint16_t bins[40000];
+    static __thread uint8_t want[37450];             /* membership map of the region's bins (cleared again below) */
     int nb = reg2bins(beg, end, bins), cap = 16, n = 0;
+    for (int q = 0; q < nb; q++) if (bins[q] < 37450) want[bins[q]] = 1;
     chunk_t* out = (chunk_t*)malloc(sizeof(chunk_t) * (size_t)cap);
     for (int k = 0; k < r->n_bin; k++) {
         if (r->bins[k].bin >= 37450) continue;       /* pseudo-bin: metadata */
-        int hit = 0;
-        for (int q = 0; q < nb; q++) if (bins[q] == r->bins[k].bin) { hit = 1; break; }
-        if (!hit) continue;
+        if (!want[r->bins[k].bin]) continue;
         for (int c = 0; c < r->bins[k].n; c++) {
             if (r->bins[k].c[c].end <= min_off) continue;
             if (n == cap) { cap *= 2; out = (chunk_t*)realloc(out, sizeof(chunk_t) * (size_t)cap); }
             out[n++] = r->bins[k].c[c];
         }
     }
+    for (int q = 0; q < nb; q++) if (bins[q] < 37450) want[bins[q]] = 0;
     if (!n) { free(out); return NULL; }
     qsort(out, (size_t)n, sizeof(chunk_t), cmp_chunk);
     int m = 0;

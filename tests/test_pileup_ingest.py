@@ -426,3 +426,64 @@ def test_bai_with_samtools_metadata(tmp_path):
     open(bam + ".bai", "wb").write(out[: len(out) // 2])
     g = bamio.AlignmentFile(bam)
     assert not g.has_index() and [s.query_name for s in g.fetch("chr1", 1990, 2010)] == want
+
+
+def test_random_records_all_bin_levels(tmp_path):
+    """seeded fuzz: records with every CIGAR operation, IUPAC bases, arbitrary flags, on contigs up to 400 Mb (all six levels of the
+    binning scheme; introns that push a record into a coarse bin) -- writer vs the Python parser, indexed region queries vs the
+    linear scan rule"""
+    rng = random.Random(2026)
+    refs = [("big", 400_000_000), ("mid", 40_000_000), ("small", 20_000)]
+    reads = []
+    for k in range(6000):
+        name, ln = refs[rng.choice((0, 0, 0, 1, 1, 2))]
+        ops = []
+        if rng.random() < 0.2:
+            ops.append((rng.randint(1, 30), "S"))
+        ops.append((rng.randint(1, 120), "M"))
+        for _ in range(rng.randint(0, 4)):
+            ops.append((rng.randint(1, 12) if rng.random() < 0.8 else rng.choice((5_000, 200_000, 3_000_000, 40_000_000)), rng.choice("IDN=XP" if rng.random() < 0.5 else "ID")))
+            if ops[-1][1] not in "DN" and ops[-1][0] > 100:            # only reference-skipping operations get the long lengths
+                ops[-1] = (rng.randint(1, 20), ops[-1][1])
+            ops.append((rng.randint(1, 100), rng.choice("M=X")))
+        if rng.random() < 0.2:
+            ops.append((rng.randint(1, 30), "S"))
+        if rng.random() < 0.05:
+            ops = [(rng.randint(1, 5), "H")] + ops
+        qlen = sum(n for n, o in ops if o in "MIS=X")
+        rlen = sum(n for n, o in ops if o in "MDN=X")
+        if rlen >= ln - 2:
+            continue
+        pos = rng.randrange(0, ln - rlen) if rng.random() < 0.7 else rng.choice((0, (1 << 14) - 1, 1 << 14, (1 << 17) - 3, (1 << 20) - 1, (1 << 23) - 50, (1 << 26) - 10)) % max(1, ln - rlen)
+        seq = "".join(rng.choice("ACGTNRYKMSWBDHV=" if rng.random() < 0.05 else "ACGT") for _ in range(qlen))
+        flag = rng.choice((0, 16, 1024, 256, 512, 2048, 99, 147, 1 | 64 | 32))
+        reads.append(dict(query_name=f"f{k}", query_sequence=seq, query_qualities=None if k % 7 == 0 else array_of(rng, qlen), cigarstring="".join(f"{n}{o}" for n, o in ops),
+                          reference_name=name, reference_start=pos, mapping_quality=rng.randrange(0, 61), flag=flag))
+    bam = os.path.join(str(tmp_path), "fuzz.bam")
+    n = bamio.write_bam(bam, refs, reads)
+    _, prefs, recs = bam_oracle.read_bam(bam)
+    assert prefs == refs and len(recs) == n
+    by = {r["query_name"]: r for r in reads}
+    levels = set()
+    for r in recs:
+        s = by[r["name"]]
+        assert (r["seq"], r["cigarstring"], r["pos"], r["flag"], r["mapq"]) == (s["query_sequence"].upper(), s["cigarstring"], s["reference_start"], s["flag"], s["mapping_quality"])
+        b = bam_oracle.reg2bin(r["pos"], r["pos"] + max(1, r["reflen"]))
+        assert r["bin"] == b
+        levels.add(sum(b >= x for x in (1, 9, 73, 585, 4681)))
+    assert levels == {0, 1, 2, 3, 4, 5}, levels
+    f = bamio.AlignmentFile(bam)
+    whole = f.fetch_columns()
+    assert [whole.name(i) for i in range(len(whole))] == [r["name"] for r in recs]
+    assert [whole.cigarstring(i) for i in range(0, len(whole), 37)] == [recs[i]["cigarstring"] for i in range(0, len(recs), 37)]
+    for q in range(300):
+        t = rng.randrange(3)
+        ln = refs[t][1]
+        beg = rng.randrange(0, ln)
+        end = min(ln, beg + rng.choice((1, 100, 20_000, 1 << 14, 1 << 20, 50_000_000)))
+        if q % 10 == 0 and recs:
+            r = recs[rng.randrange(len(recs))]; t, beg = r["tid"], max(0, r["pos"] + rng.randint(-3, 3)); end = beg + rng.randint(1, 5)
+        exp = [r["name"] for r in bam_oracle.overlapping(recs, t, beg, end)]
+        b = f.fetch_columns(refs[t][0], beg, end)
+        assert [b.name(i) for i in range(len(b))] == exp, (refs[t][0], beg, end)
+        assert f.count(refs[t][0], beg, end) == len(exp)
