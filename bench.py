@@ -403,6 +403,8 @@ def pipeline_measurements():
         out = {}
         for cfg, loci in (("cfg1", 4), ("cfg3", 12)):
             out[cfg] = BP.measure(cfg, loci, workers=1, repeats=2)
+        # zero-change use (SSW class swapped, no prefetch line, no wave scheduler): every miss is a device round trip
+        out["cfg3_zero_change"] = BP.measure("cfg3", 4, workers=1, arms=("reference", "percall"))
         w = max(2, min(8, host_cores() // 2))
         # BASELINE configs[0] / [2] "in a BAM": the same loci written to BAM + BAI / FASTA + FAI and read back through the native
         # reader (indelpost_b200.bamio; pysam is absent) in BOTH arms

@@ -10,6 +10,8 @@ Same names, argument meaning and error behaviour as the reference's Cython modul
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import NamedTuple, Optional, Sequence, Union
 
@@ -202,6 +204,10 @@ class SSW:
                                 return hit
         if _RESOLVER is not None:
             hit = _RESOLVER(self, go8, ge8, start_idx, search_length)                                 # wave scheduler (wave.py)
+            if hit is not None:
+                return hit
+        if AUTO_BATCH and search_length == ref_length and start_idx == 0:
+            hit = _auto_get(self, go8, ge8)                                                            # implicit batching (below)
             if hit is not None:
                 return hit
         out = self._single_pair(gap_open, gap_extension, start_idx, search_length)
@@ -426,6 +432,16 @@ def seq_id(raw: bytes) -> int:
     return i
 
 
+def _grid_slot(grid: dict, go8: int, ge8: int, rlen: int):
+    """index of a (narrowed) penalty pair in a block's grid; "len" entries stand for len(read) (localn.pyx:253-255)"""
+    g = grid.get((go8, ge8))
+    if g is None and go8 == (rlen & 0xFF):
+        g = grid.get(("len", ge8))
+        if g is None and ge8 == (rlen & 0xFF):
+            g = grid.get(("len", "len"))
+    return g
+
+
 class _Block:
     __slots__ = ("alist", "n", "rows", "cols", "n_cols", "pairs", "grid", "made", "mkey", "wids")
 
@@ -438,11 +454,7 @@ class _Block:
             p = None if r is None or c is None else r * self.n_cols + c
         if p is None:
             return None
-        g = self.grid.get((go8, ge8))
-        if g is None and go8 == (rlen & 0xFF):
-            g = self.grid.get(("len", ge8))
-            if g is None and ge8 == (rlen & 0xFF):
-                g = self.grid.get(("len", "len"))
+        g = _grid_slot(self.grid, go8, ge8, rlen)
         if g is None:
             return None
         k = g * self.n + p
@@ -458,6 +470,7 @@ def clear_prefetched():
     _BLOCK_FIFO.clear()
     _SEQ_IDS.clear()
     _prefetched_pairs = 0
+    clear_auto_batches()
 
 
 def drop_block(b) -> None:
@@ -550,6 +563,118 @@ def prefetch_alignments(reads: Sequence[STR_T], references: Sequence[STR_T], pai
     mkey = dna_score_matrix(_c_int(match_score), _c_int(mismatch_penalty)).tobytes()
     register_block(alist, [seq_id(r) for r in raws_r], [seq_id(w) for w in raws_w], pr, pw, grid, mkey, cross)
     return len(alist)
+
+
+# ---------------------------------------------------------------------------------------------
+# implicit batching: what a ZERO-CHANGE caller gets (no prefetch line, no wave scheduler)
+# ---------------------------------------------------------------------------------------------
+# A single alignment through the GPU is a ~0.5 ms round trip against ~30 us for ssw.c, and it costs the same whether it carries
+# one pair or ten thousand.  So an `SSW.align()` nobody prepared for does not fetch one alignment: it fetches
+#   * every gap-penalty pair indelPost can ask about this (read, window) -- the six-point grid of varaln.pyx:1127-1143 and the
+#     `len(read)` penalties of localn.pyx:255 / varaln.pyx:1230 -- so grid_search's other five calls are answered from memory, and
+#   * the same for the reads this process aligned most recently against OTHER windows: indelPost walks the same pileup over one
+#     window after another (reference window, contig, retargeted windows), so the first call on a new window
+#     brings the whole pileup along.
+# What is computed is what the per-call path would compute (same kernels, same records); the cache is keyed by the sequences
+# themselves and spans aligner objects (indelPost builds a new SSW for almost every call), which also serves the repeats of
+# update_read_info (pileup.pyx:849).  The first window of a locus still costs one round trip per read: for batch throughput use
+# prefetch_alignments() or the wave scheduler.  SWB200_AUTO_BATCH=0 turns this off (one pair per call).
+
+AUTO_BATCH = os.environ.get("SWB200_AUTO_BATCH", "1") != "0"
+_AUTO_GRID = tuple(INDELPOST_GRID) + (("len", 1), ("len", 0), ("len", "len"))
+_AUTO_MAX_READS = 1024          # reads carried along per call ...
+_AUTO_MAX_BASES = 1 << 20       # ... and their total length
+_AUTO_RECENT = 2048             # distinct reads remembered per substitution matrix
+_AUTO_LIMIT = 4_000_000         # alignments kept before the cache is dropped
+_AUTO: dict = {}                # (matrix bytes, window bytes) -> {read bytes: (AlignmentList, row, n_rows, grid map, made)}
+_RECENT: dict = {}              # matrix bytes -> {read bytes: None}, oldest first
+_auto_pairs = 0
+auto_stats = {"batches": 0, "pairs": 0, "hits": 0}
+
+
+def clear_auto_batches():
+    global _auto_pairs
+    _AUTO.clear()
+    _RECENT.clear()
+    _auto_pairs = 0
+
+
+def _auto_hit(entry, go8, ge8, rlen):
+    alist, row, n_rows, gmap, made = entry
+    g = _grid_slot(gmap, go8, ge8, rlen)
+    if g is None:
+        return None
+    k = g * n_rows + row
+    hit = made.get(k)
+    if hit is None:
+        hit = made[k] = alist[k]
+    return hit
+
+
+def _auto_get(ssw: "SSW", go8: int, ge8: int):
+    """answer from the implicit cache, or compute this pair together with what is likely to be asked next; None = use the
+    single-pair path (the batch could not be run: its error is the single-pair path's to report)"""
+    global _auto_pairs
+    mkey, wkey, rkey, rlen = ssw._mkey, ssw._wkey, ssw._rkey, ssw.read_length
+    win = _AUTO.get((mkey, wkey))
+    if win is not None:
+        entry = win.get(rkey)
+        if entry is not None:
+            hit = _auto_hit(entry, go8, ge8, rlen)
+            if hit is not None:
+                auto_stats["hits"] += 1
+                return hit
+    else:
+        win = _AUTO[(mkey, wkey)] = {}
+    recent = _RECENT.get(mkey)
+    if recent is None:
+        recent = _RECENT[mkey] = {}
+    reads, bases = [rkey], rlen
+    if wkey and rkey:
+        for r in reversed(recent):
+            if r != rkey and r not in win:
+                reads.append(r)
+                bases += len(r)
+                if len(reads) >= _AUTO_MAX_READS or bases >= _AUTO_MAX_BASES:
+                    break
+    recent.pop(rkey, None)
+    recent[rkey] = None
+    if len(recent) > _AUTO_RECENT:
+        del recent[next(iter(recent))]
+    rlen8 = rlen & 0xFF
+    covered = any((o == go8 or (o == "len" and go8 == rlen8)) and (e == ge8 or (e == "len" and ge8 == rlen8)) for o, e in _AUTO_GRID)
+    grid = _AUTO_GRID if covered else _AUTO_GRID + ((go8, ge8),)
+    alist = None
+    for attempt in (reads, [rkey]):
+        try:
+            n = len(attempt)
+            rl = np.fromiter(map(len, attempt), dtype=np.int64, count=n)
+            go, ge = grid_penalties(grid, rl)
+            got = align_batch(attempt, [wkey], np.tile(np.arange(n, dtype=np.int32), len(grid)), np.zeros(n * len(grid), np.int32),
+                              go.reshape(-1), ge.reshape(-1), match_score=ssw._ms, mismatch_penalty=ssw._mm)
+            alist = AlignmentList(got.records.copy(), got.cigar_arena.copy())       # out of the pinned output buffers
+            reads = attempt
+            break
+        except (ValueError, L.SwbError):
+            if len(attempt) == 1 or len(reads) == 1:
+                return None                      # e.g. an empty sequence, or no device: the single-pair path raises the reference's error
+    if alist is None:
+        return None
+    gmap = {}
+    for g, (o, e) in enumerate(grid):
+        gmap.setdefault((o if o == "len" else int(o) & 0xFF, e if e == "len" else int(e) & 0xFF), g)
+    made: dict = {}
+    n = len(reads)
+    for row, r in enumerate(reads):
+        win[r] = (alist, row, n, gmap, made)
+    auto_stats["batches"] += 1
+    auto_stats["pairs"] += len(alist)
+    _auto_pairs += len(alist)
+    hit = _auto_hit(win[rkey], go8, ge8, rlen)
+    if _auto_pairs > _AUTO_LIMIT:
+        _AUTO.clear()
+        _auto_pairs = 0
+    return hit
 
 
 # ---------------------------------------------------------------------------------------------

@@ -96,6 +96,20 @@ def _worker(arm, specs, device, q, from_files=False):
         from indelpost_b200 import SSW, clear_prefetched, wave
         from indelpost_b200.sswpy import _aligner
 
+        if arm == "percall":
+            # ZERO-CHANGE use: the product's SSW class swapped in, nothing else -- no prefetch line, no wave scheduler; every miss
+            # is a device round trip (widened by the implicit batching of sswpy.py)
+            from indelpost_b200 import sswpy
+
+            refpipe.run_locus(lcs[0], ssw_cls=SSW, files=files)           # warm-up: context, kernels
+            clear_prefetched()
+            sswpy.auto_stats.update(batches=0, pairs=0, hits=0)
+            t0 = time.perf_counter()
+            outs = [refpipe.run_locus(lc, ssw_cls=SSW, files=files) for lc in lcs]
+            dt = time.perf_counter() - t0
+            q.put((dt, outs, {"waves": sswpy.auto_stats["batches"], "pairs": sswpy.auto_stats["pairs"], "requests": sswpy.auto_stats["hits"]}))
+            return
+
         al = _aligner(device)
         tee = wave.tee_alignment_file(base_bam)
         runner = wave.WaveRunner(device=device, aligner=al, max_inflight=256)
@@ -247,6 +261,9 @@ def measure(config="cfg3", n_loci=32, workers=1, arms=("reference", "wave"), dev
     if "reference" in by_arm and "wave" in by_arm:
         out["identical_outputs"] = by_arm["reference"] == by_arm["wave"]
         out["speedup"] = out["wave"]["loci_per_s"] / out["reference"]["loci_per_s"]
+    if "reference" in by_arm and "percall" in by_arm:
+        out["percall_identical_outputs"] = by_arm["reference"] == by_arm["percall"]
+        out["percall_vs_reference"] = out["percall"]["loci_per_s"] / out["reference"]["loci_per_s"]
     return out
 
 
