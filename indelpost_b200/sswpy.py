@@ -570,23 +570,28 @@ def prefetch_alignments(reads: Sequence[STR_T], references: Sequence[STR_T], pai
 # ---------------------------------------------------------------------------------------------
 # A single alignment through the GPU is a ~0.5 ms round trip against ~30 us for ssw.c, and it costs the same whether it carries
 # one pair or ten thousand.  So an `SSW.align()` nobody prepared for does not fetch one alignment: it fetches
-#   * every gap-penalty pair indelPost can ask about this (read, window) -- the six-point grid of varaln.pyx:1127-1143 and the
-#     `len(read)` penalties of localn.pyx:255 / varaln.pyx:1230 -- so grid_search's other five calls are answered from memory, and
+#   * every point of the gap grid indelPost can ask about this (read, window) (varaln.pyx:1127-1143), so grid_search's other five
+#     calls are answered from memory;
 #   * the same for the reads this process aligned most recently against OTHER windows: indelPost walks the same pileup over one
 #     window after another (reference window, contig, retargeted windows), so the first call on a new window
-#     brings the whole pileup along.
+#     brings the whole pileup along;
+#   * a first `gap_open = len(read)` call on a window (is_target_by_ssw, localn.pyx:255; is_perfect_match, varaln.pyx:1230)
+#     fetches those penalties for every read the window has been asked about -- in a batch of its own, because they run through
+#     the exact kernels, whose latency the grid batches should not pay.
 # What is computed is what the per-call path would compute (same kernels, same records); the cache is keyed by the sequences
 # themselves and spans aligner objects (indelPost builds a new SSW for almost every call), which also serves the repeats of
 # update_read_info (pileup.pyx:849).  The first window of a locus still costs one round trip per read: for batch throughput use
 # prefetch_alignments() or the wave scheduler.  SWB200_AUTO_BATCH=0 turns this off (one pair per call).
 
 AUTO_BATCH = os.environ.get("SWB200_AUTO_BATCH", "1") != "0"
-_AUTO_GRID = tuple(INDELPOST_GRID) + (("len", 1), ("len", 0), ("len", "len"))
+_AUTO_GRID = tuple(INDELPOST_GRID)                              # what a first call on a (read, window) brings along
+_AUTO_LEN_GRID = (("len", 1), ("len", 0), ("len", "len"))      # ... and a first `gap_open = len(read)` call (these take the exact kernels:
+                                                                #     a millisecond of latency per batch, so they travel separately)
 _AUTO_MAX_READS = 1024          # reads carried along per call ...
 _AUTO_MAX_BASES = 1 << 20       # ... and their total length
 _AUTO_RECENT = 2048             # distinct reads remembered per substitution matrix
 _AUTO_LIMIT = 4_000_000         # alignments kept before the cache is dropped
-_AUTO: dict = {}                # (matrix bytes, window bytes) -> {read bytes: (AlignmentList, row, n_rows, grid map, made)}
+_AUTO: dict = {}                # (matrix bytes, window bytes) -> {read bytes: [(AlignmentList, row, n_rows, grid map, made), ...]}
 _RECENT: dict = {}              # matrix bytes -> {read bytes: None}, oldest first
 _auto_pairs = 0
 auto_stats = {"batches": 0, "pairs": 0, "hits": 0}
@@ -599,16 +604,20 @@ def clear_auto_batches():
     _auto_pairs = 0
 
 
-def _auto_hit(entry, go8, ge8, rlen):
-    alist, row, n_rows, gmap, made = entry
-    g = _grid_slot(gmap, go8, ge8, rlen)
-    if g is None:
-        return None
-    k = g * n_rows + row
-    hit = made.get(k)
-    if hit is None:
-        hit = made[k] = alist[k]
-    return hit
+def _auto_hit(entries, go8, ge8, rlen):
+    for alist, row, n_rows, gmap, made, _tag in entries:
+        g = _grid_slot(gmap, go8, ge8, rlen)
+        if g is not None:
+            k = g * n_rows + row
+            hit = made.get(k)
+            if hit is None:
+                hit = made[k] = alist[k]
+            return hit
+    return None
+
+
+def _grid_covers(grid, go8, ge8, rlen8):
+    return any((o == go8 or (o == "len" and go8 == rlen8)) and (e == ge8 or (e == "len" and ge8 == rlen8)) for o, e in grid)
 
 
 def _auto_get(ssw: "SSW", go8: int, ge8: int):
@@ -618,9 +627,9 @@ def _auto_get(ssw: "SSW", go8: int, ge8: int):
     mkey, wkey, rkey, rlen = ssw._mkey, ssw._wkey, ssw._rkey, ssw.read_length
     win = _AUTO.get((mkey, wkey))
     if win is not None:
-        entry = win.get(rkey)
-        if entry is not None:
-            hit = _auto_hit(entry, go8, ge8, rlen)
+        entries = win.get(rkey)
+        if entries is not None:
+            hit = _auto_hit(entries, go8, ge8, rlen)
             if hit is not None:
                 auto_stats["hits"] += 1
                 return hit
@@ -629,10 +638,23 @@ def _auto_get(ssw: "SSW", go8: int, ge8: int):
     recent = _RECENT.get(mkey)
     if recent is None:
         recent = _RECENT[mkey] = {}
+    rlen8 = rlen & 0xFF
     reads, bases = [rkey], rlen
+    if _grid_covers(_AUTO_GRID, go8, ge8, rlen8):
+        # the first question about this (read, window): the whole grid, and the recent reads this window has not seen
+        grid, tag = _AUTO_GRID, 0
+        candidates = (r for r in reversed(recent) if r not in win)
+    elif _grid_covers(_AUTO_LEN_GRID, go8, ge8, rlen8):
+        # the first `gap_open = len(read)` question (is_target_by_ssw, is_perfect_match): those penalties for every read this
+        # window has been asked about
+        grid, tag = _AUTO_LEN_GRID, 1
+        candidates = (r for r, es in reversed(win.items()) if not any(e[5] == 1 for e in es))
+    else:
+        grid, tag = ((go8, ge8),), 2
+        candidates = ()
     if wkey and rkey:
-        for r in reversed(recent):
-            if r != rkey and r not in win:
+        for r in candidates:
+            if r != rkey:
                 reads.append(r)
                 bases += len(r)
                 if len(reads) >= _AUTO_MAX_READS or bases >= _AUTO_MAX_BASES:
@@ -641,9 +663,6 @@ def _auto_get(ssw: "SSW", go8: int, ge8: int):
     recent[rkey] = None
     if len(recent) > _AUTO_RECENT:
         del recent[next(iter(recent))]
-    rlen8 = rlen & 0xFF
-    covered = any((o == go8 or (o == "len" and go8 == rlen8)) and (e == ge8 or (e == "len" and ge8 == rlen8)) for o, e in _AUTO_GRID)
-    grid = _AUTO_GRID if covered else _AUTO_GRID + ((go8, ge8),)
     alist = None
     for attempt in (reads, [rkey]):
         try:
@@ -666,7 +685,7 @@ def _auto_get(ssw: "SSW", go8: int, ge8: int):
     made: dict = {}
     n = len(reads)
     for row, r in enumerate(reads):
-        win[r] = (alist, row, n, gmap, made)
+        win.setdefault(r, []).append((alist, row, n, gmap, made, tag))
     auto_stats["batches"] += 1
     auto_stats["pairs"] += len(alist)
     _auto_pairs += len(alist)

@@ -54,24 +54,30 @@ def test_auto_batch_details(monkeypatch):
         res, arena = T.oracle().align_batch(b)
         return sswpy.AlignmentList(res.view(sswpy.L.RESULT_DTYPE), arena)[0]
 
-    # first window: one batch per read, the other grid points and the len(read) penalties come from memory
+    # first window: one batch per read for the grid; the first len(read) question fetches those penalties for every read seen so far
     for r in reads:
         a = W._NoGpuSSW(3, 2); a.setReference(win1); a.setRead(r)
-        for go, ge in ((3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0), (len(r), 1), (len(r), len(r))):
+        for go, ge in ((3, 1), (3, 0), (5, 1), (5, 0), (4, 1), (4, 0)):
             assert a.align(gap_open=go, gap_extension=ge) == ref_result(r, win1, go, ge)
-    assert len(batches) == len(reads)
+    assert len(batches) == len(reads) and batches[-1] == len(sswpy._AUTO_GRID)
+    for k, r in enumerate(reads):
+        a = W._NoGpuSSW(3, 2); a.setReference(win1); a.setRead(r)
+        for go, ge in ((len(r), 1), (len(r), 0), (len(r), len(r))):
+            assert a.align(gap_open=go, gap_extension=ge) == ref_result(r, win1, go, ge)
+    assert len(batches) == len(reads) + 1 and batches[-1] == len(reads) * len(sswpy._AUTO_LEN_GRID)
     # a new window: the first call brings every recent read along; a fresh aligner object per call (like make_aligner) still hits
     for r in reads:
         a = W._NoGpuSSW(3, 2); a.setReference(win2); a.setRead(r)
         assert a.align(gap_open=4, gap_extension=1) == ref_result(r, win2, 4, 1)
-    assert len(batches) == len(reads) + 1 and batches[-1] == len(reads) * len(sswpy._AUTO_GRID)
-    # a penalty pair outside the grid joins its batch; another matrix has its own cache; sub-range searches are not batched
+    assert len(batches) == len(reads) + 2 and batches[-1] == len(reads) * len(sswpy._AUTO_GRID)
+    # a penalty pair outside both grids travels alone; another matrix has its own cache; sub-range searches are not batched
     a = W._NoGpuSSW(3, 2); a.setReference(win2); a.setRead(reads[0])
     assert a.align(gap_open=7, gap_extension=2) == ref_result(reads[0], win2, 7, 2)
-    assert len(batches) == len(reads) + 2
+    assert len(batches) == len(reads) + 3 and batches[-1] == 1
+    assert a.align(gap_open=7, gap_extension=2) is a.align(gap_open=7, gap_extension=2) and len(batches) == len(reads) + 3
     b = W._NoGpuSSW(2, 2); b.setReference(win2); b.setRead(reads[0])
     assert b.align(gap_open=3, gap_extension=1) == ref_result(reads[0], win2, 3, 1, 2, 2)
-    assert len(batches) == len(reads) + 3
+    assert len(batches) == len(reads) + 4
     with pytest.raises(AssertionError, match="per-call GPU path"):
         a.align(gap_open=3, gap_extension=1, start_idx=10, end_idx=200)
     # a failing batch falls back to the single-pair path (which reports the error the reference's way)
