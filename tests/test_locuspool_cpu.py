@@ -55,3 +55,21 @@ def test_locus_pool_start_failure():
         raise RuntimeError("x")
     with pytest.raises(Exception):
         locuspool.LocusPool(_run, workers=1, init=_bad_init, start_timeout=30)
+
+
+def test_pool_on_one_bam_file_matches_plain_arm():
+    """tools/bench_pipeline.py --pool: every locus in ONE BAM + FASTA, work items are (chrom, pos, ref, alt); the wave arm (batches by the
+    CPU oracle here) and the plain reference arm must give identical outputs"""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_pipeline as BP
+
+    BP.CONFIGS["tiny"] = dict(kinds=[("del", 2), ("ins", 3)], n_reads=40, read_len=150, window=50)
+    try:
+        out = BP.measure_pool("tiny", n_loci=4, workers=2, cpu_oracle=True)
+    finally:
+        for k in ("SWB_POOL_CPU_ORACLE", "SWB_POOL_ARM", "SWB_POOL_BAM", "SWB_POOL_FA"):
+            os.environ.pop(k, None)
+    assert out["identical_outputs"] is True and out["pool_wave"]["waves"] >= 2 and out["bam_bytes"] > 0
