@@ -45,6 +45,12 @@ def test_exports_and_layout():
     hdr = open(os.path.join(os.path.dirname(HERE), "include", "swbbam.h")).read()
     for s in bamio.EXPORTS:
         assert s + "(" in hdr, f"{s} is not declared in include/swbbam.h"
+    # ... and every function the header declares is exported by the library
+    import re
+    declared = set(re.findall(r"\b(swb_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)))
+    assert declared == set(bamio.EXPORTS), declared ^ set(bamio.EXPORTS)
+    for s in declared:
+        assert hasattr(lib, s), s
 
 
 @pytest.mark.parametrize("seed,kind", [(7, "del"), (8, "spliced"), (9, "complex")])
