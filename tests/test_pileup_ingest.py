@@ -493,3 +493,43 @@ def test_random_records_all_bin_levels(tmp_path):
         b = f.fetch_columns(refs[t][0], beg, end)
         assert [b.name(i) for i in range(len(b))] == exp, (refs[t][0], beg, end)
         assert f.count(refs[t][0], beg, end) == len(exp)
+
+
+def test_records_with_aux_tags(tmp_path):
+    """real BAMs carry optional fields after the qualities (NM, MD, RG, ...): the reader must step over them by block_size"""
+    import gzip
+    import struct
+    import zlib
+    locus = L.make_locus(41, kind="del", ev_len=3, n_reads=80)
+    bam, _ = write_locus(str(tmp_path), locus)
+    raw = gzip.open(bam, "rb").read()
+    (l_text,) = struct.unpack_from("<i", raw, 4)
+    o = 8 + l_text
+    (n_ref,) = struct.unpack_from("<i", raw, o); o += 4
+    for _ in range(n_ref):
+        (ln,) = struct.unpack_from("<i", raw, o); o += 4 + ln + 4
+    out = bytearray(raw[:o])
+    k = 0
+    while o < len(raw):
+        (bs,) = struct.unpack_from("<i", raw, o)
+        aux = b"NMC" + bytes([k % 7]) + b"MDZ" + (b"%dA%d" % (k, 150 - k)) + b"\0" + b"RGZgrp1\0" + b"XSi" + struct.pack("<i", -k) + b"ZBBs\x02\x00\x00\x00\x01\x00\x02\x00"
+        out += struct.pack("<i", bs + len(aux)) + raw[o + 4: o + 4 + bs] + aux
+        o += 4 + bs; k += 1
+    blocks = bytearray()
+    for p in range(0, len(out), 30000):
+        chunk = bytes(out[p: p + 30000])
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        blocks += struct.pack("<4BI2BH2BHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(body) + 25) + body + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    blocks += bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    tagged = os.path.join(str(tmp_path), "tagged.bam")
+    open(tagged, "wb").write(blocks)
+    a, b = bamio.AlignmentFile(bam).fetch_columns(), bamio.AlignmentFile(tagged).fetch_columns()
+    assert len(a) == len(b) == k == 80
+    for i in range(len(a)):
+        assert (a.name(i), a.sequence(i), a.cigarstring(i), int(a.pos[i]), int(a.end[i]), int(a.flag[i])) == (b.name(i), b.sequence(i), b.cigarstring(i), int(b.pos[i]), int(b.end[i]), int(b.flag[i]))
+        assert a.qualities(i) == b.qualities(i)
+    _, _, recs = bam_oracle.read_bam(tagged)
+    assert recs[5]["aux"].startswith(b"NMC") and len(recs) == 80
+    sub = bamio.AlignmentFile(tagged).fetch_columns("chr1", 1999, 2000)
+    assert len(sub) == len(bamio.AlignmentFile(bam).fetch_columns("chr1", 1999, 2000))
