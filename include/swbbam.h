@@ -22,6 +22,11 @@
  * The library also WRITES coordinate-sorted BAM + BAI and FASTA + FAI (BASELINE.json's configs are "written to BAM"; pysam
  * is absent from the image), so the measured pipeline reads real files.  Plain pointers and sizes only; no GPU code, links zlib.
  * Every function that can fail returns NULL / a negative value and leaves a message in swb_bam_last_error().
+ *
+ * Limits (by design, none of indelPost's inputs needs more): BAM with a BAI index (no CRAM, SAM text or CSI); optional fields are
+ * stepped over, not decoded, so a CIGAR of more than 65 535 operations kept in a CG tag is reported as the record's in-line
+ * placeholder; the writer emits no optional fields and expects its input in coordinate order.  A handle is not thread-safe (block
+ * cache); open one per thread -- swb_bam_fetch_pack4 does that internally.
  */
 #ifndef SWBBAM_H
 #define SWBBAM_H
