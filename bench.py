@@ -15,8 +15,10 @@ A "step" is one pass of the whole hot path (prepare, forward, reverse, banded tr
           `e2e_codes` is the same call with one-byte-per-base tables (the round-1 figure), `extra.e2e_api` the Python entry
           `align_batch` from lists of ASCII sequences (host gather included)
   extra : (1 GPU only) the other BASELINE configs and mixes, each resident + e2e with its own stage split: cfg4 / cfg5 shapes,
-          cfg2 with shared windows, indelPost's penalty mix, short reads, and the reference pipeline's loci/s on ssw.c vs
-          under the wave scheduler (tools/bench_pipeline.py)
+          cfg2 with shared windows, indelPost's penalty mix, short reads; reads realigned per second from BAM + FASTA files
+          (tools/bench_bam_realign.py); pileup ingestion rates (tools/bench_ingest.py); and the reference pipeline's loci/s on
+          ssw.c vs under the wave scheduler, from memory and from BAM files, zero-change use, and eight workers through LocusPool
+          (tools/bench_pipeline.py)
 Multi-GPU (torchrun, one rank per GPU): the pairs shard across ranks with no collective in the data
 path (weak scaling: every rank aligns its own P pairs); torch.distributed is only the barrier and the
 max-over-ranks of the timed region.
