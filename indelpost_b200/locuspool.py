@@ -88,13 +88,19 @@ class LocusPool:
             p = ctx.Process(target=_worker_main, args=(k, self.devices[k % len(self.devices)], fn, init, mode, max_inflight, self._tasks, self._results), daemon=True)
             p.start()
             self._procs.append(p)
-        ready = 0
+        import queue
+        import time
+
+        ready, deadline = 0, time.monotonic() + start_timeout
         while ready < self.workers:
             try:
-                kind, rank, _, payload = self._results.get(timeout=start_timeout)
-            except Exception:
-                self.close()
-                raise LocusPoolError("a worker did not start") from None
+                kind, rank, _, payload = self._results.get(timeout=1.0)
+            except queue.Empty:
+                dead = [k for k, p in enumerate(self._procs) if not p.is_alive()]
+                if dead or time.monotonic() > deadline:
+                    self.close()
+                    raise LocusPoolError(f"worker(s) {dead} exited before they were ready" if dead else "a worker did not start in time") from None
+                continue
             if kind == "fatal":
                 self.close()
                 raise LocusPoolError(f"worker {rank} failed to start:\n{payload}")
@@ -115,7 +121,7 @@ class LocusPool:
         failure = None
         totals = {}
         for _ in range(jobs):
-            kind, rank, base, payload = self._results.get()
+            kind, rank, base, payload = self._next_result()
             if kind == "ok":
                 res, st = payload
                 out[base: base + len(res)] = res
@@ -129,6 +135,21 @@ class LocusPool:
         if failure is not None:
             raise LocusPoolError(f"worker {failure[0]} failed on the chunk starting at item {failure[1]}:\n{failure[2]}")
         return out
+
+    def _next_result(self):
+        """the next message of a worker; a worker that died without one (killed, out of memory, a crashed driver) must not leave
+        the caller waiting forever"""
+        import queue
+
+        while True:
+            try:
+                return self._results.get(timeout=1.0)
+            except queue.Empty:
+                dead = [k for k, p in enumerate(self._procs) if not p.is_alive()]
+                if dead:
+                    codes = [self._procs[k].exitcode for k in dead]
+                    self.close()
+                    raise LocusPoolError(f"worker(s) {dead} exited without a result (exit codes {codes}); the pool is closed") from None
 
     def close(self):
         procs, self._procs = self._procs, []

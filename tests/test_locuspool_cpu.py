@@ -50,6 +50,20 @@ def test_locus_pool_equals_serial_reference():
         assert pool.map(range(4)) == want[:4]
 
 
+def _dies(k):
+    import os
+    if k == 2:
+        os._exit(7)              # a worker killed mid-item (out of memory, a crashed driver ...)
+    return k
+
+
+def test_locus_pool_reports_a_dead_worker():
+    pool = locuspool.LocusPool(_dies, workers=2, mode="plain", chunk=1)
+    with pytest.raises(locuspool.LocusPoolError, match="exited without a result"):
+        pool.map(range(4))
+    pool.close()
+
+
 def test_locus_pool_start_failure():
     def _bad_init(rank, device):          # not picklable by reference from a spawned worker -> start failure is reported
         raise RuntimeError("x")
