@@ -137,7 +137,15 @@ def run_arm(arm, specs, workers, devices, from_files=False):
         p = ctx.Process(target=_worker, args=(arm, sh, devices[k % len(devices)], q, from_files))
         p.start()
         procs.append(p)
-    parts = [q.get() for _ in procs]
+    import queue
+
+    parts = []
+    while len(parts) < len(procs):
+        try:
+            parts.append(q.get(timeout=1.0))
+        except queue.Empty:                                   # a worker that died without reporting must not hang the bench
+            if all(not p.is_alive() for p in procs) and q.empty():
+                raise RuntimeError(f"{arm}: a worker exited without a result (exit codes {[p.exitcode for p in procs]})")
     for p in procs:
         p.join()
     wall = time.perf_counter() - t0
