@@ -533,3 +533,41 @@ def test_records_with_aux_tags(tmp_path):
     assert recs[5]["aux"].startswith(b"NMC") and len(recs) == 80
     sub = bamio.AlignmentFile(tagged).fetch_columns("chr1", 1999, 2000)
     assert len(sub) == len(bamio.AlignmentFile(bam).fetch_columns("chr1", 1999, 2000))
+
+
+def test_make_pileup_reproduces_golden(tmp_path):
+    """tests/golden/pileup_dicts.json.gz: 447 read dicts the REFERENCE's own make_pileup produced (tests/golden/make_pileup_golden.py);
+    the native ingest reproduces every key of every dict from BAM / FASTA files, without the reference build being present"""
+    import gzip
+    import json
+
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_pileup_golden as MG
+
+    doc = json.load(gzip.open(os.path.join(HERE, "golden", "pileup_dicts.json.gz"), "rt"))
+    assert len(doc) == len(MG.CASES)
+    n = 0
+    for entry, case in zip(doc, MG.CASES):
+        assert entry["case"] == json.loads(json.dumps(case))
+        locus = MG.prepare(case)
+        bam_p, fa_p = write_locus(str(tmp_path), locus)
+        bam, fa = bamio.AlignmentFile(bam_p), bamio.FastaFile(fa_p)
+        rpos = entry["rpos"]
+
+        class Target:
+            chrom, pos, reference = locus["chrom"], locus["pos"], fa
+
+            @staticmethod
+            def generate_equivalents(p=rpos):
+                return [type("V", (), {"pos": p})]
+
+        u = pileup.UnsplicedLocalReference(locus["chrom"], locus["pos"], len(locus["genome"]), entry["window"], fa)
+        random.seed(99)
+        got, sf = pileup.make_pileup(Target, bam, u, case["excl"], entry["window"], case["down"], case["thresh"])
+        assert sf == entry["sample_factor"], case
+        got = json.loads(json.dumps([MG.plain(d) for d in got]))
+        assert len(got) == len(entry["pileup"]), case
+        for a, b in zip(got, entry["pileup"]):
+            assert a == b, (case, a["read_name"], [k for k in b if a.get(k) != b[k]])
+        n += len(got)
+    assert n == 447
