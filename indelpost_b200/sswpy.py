@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import os
 
-import ctypes as C
 from typing import NamedTuple, Optional, Sequence, Union
 
 import numpy as np
